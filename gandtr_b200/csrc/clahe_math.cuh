@@ -1,0 +1,283 @@
+// Per-pixel arithmetic of the CLAHE path (K1). Every function here is `__host__ __device__` so the
+// exact same source is (a) inlined into the sm_100a kernels of clahe_sm100.cu and (b) compiled by
+// g++ into a test-only harness (tests/host_harness) that checks the arithmetic against live cv2 on
+// a machine without a GPU. The product never runs the host instantiation.
+//
+// Reference behaviour restated here (OpenCV 4.13.0 float paths reached from
+// mdir/components/data/transform/functional.py:35,63,148 -- see SURVEY.md App. A):
+//   RGB2Lab : int16 LUT (33^3 lattice) + integer trilinear interpolation, Q14 fixed point
+//   CLAHE   : bilinear blend of four tile LUTs, separate f32 roundings, cvRound
+//   Lab2RGB : f32, SIMD-body / scalar-tail op sequences, cubic-spline inverse gamma
+// All float ops are single IEEE-754 roundings: no FMA contraction (intrinsics on the device,
+// -ffp-contract=off on the host).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define GDT_HD __host__ __device__ __forceinline__
+#else
+#define GDT_HD inline
+#endif
+
+namespace gdt {
+
+GDT_HD float f_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+GDT_HD float f_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+GDT_HD float f_sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+GDT_HD float f_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+// cvRound: round half to even
+GDT_HD int f_rint(float a) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rn(a);
+#else
+    return (int)lrintf(a);
+#endif
+}
+GDT_HD int f_floor(float a) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rd(a);
+#else
+    return (int)floorf(a);
+#endif
+}
+GDT_HD int f_trunc(float a) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(a);
+#else
+    return (int)a;
+#endif
+}
+GDT_HD float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+
+// ---- RGB -> Lab (Q14 integer LUT path) ----------------------------------------------------------
+
+// Quantise a [0,1] float channel to the LUT cell `t` (0..31) and 4-bit fraction `f` (0..16).
+// OpenCV: c = cvRound(x * 16384); t = c >> 9; f = (c >> 5) & 15, neighbour index clamped to 32.
+// c == 16384 (t == 32, f == 0) is folded into (t = 31, f = 16): identical weights on identical
+// lattice points, and keeps every cell inside a 32^3 packed table.
+GDT_HD void lab_cell(float x01, int& t, int& f) {
+    int c = f_rint(f_mul(x01, 16384.0f));
+    t = c >> 9;
+    f = (c >> 5) & 15;
+    if (t >= 32) { t = 31; f = 16; }
+}
+
+// One channel of the trilinear interpolation. `w` holds the four (dx,dy) corner pairs of the cell,
+// each 32-bit word = value(dz=0) | value(dz=1) << 16 (values in [0,16384]).
+GDT_HD int lab_trilinear(uint32_t w00, uint32_t w01, uint32_t w10, uint32_t w11, int fr, int fg, int fb) {
+    const int wz1 = fb, wz0 = 16 - fb;
+    const int i00 = (int)(w00 & 0xffffu) * wz0 + (int)(w00 >> 16) * wz1;
+    const int i01 = (int)(w01 & 0xffffu) * wz0 + (int)(w01 >> 16) * wz1;
+    const int i10 = (int)(w10 & 0xffffu) * wz0 + (int)(w10 >> 16) * wz1;
+    const int i11 = (int)(w11 & 0xffffu) * wz0 + (int)(w11 >> 16) * wz1;
+    const int wx1 = fr, wx0 = 16 - fr, wy1 = fg, wy0 = 16 - fg;
+    const int acc = i00 * (wx0 * wy0) + i01 * (wx0 * wy1) + i10 * (wx1 * wy0) + i11 * (wx1 * wy1);
+    return (acc + 2048) >> 12;
+}
+
+// Q14 lightness -> the uint8 the reference hands to cv2 CLAHE:
+//   L = (float(o0) * 2^-14) * 100 ; spc = (L + 0) / 100 ; L8 = uint8(trunc(spc * 255))
+// (functional.py:35 and :148 -- truncation, not rounding).
+GDT_HD int lab_l8(int o0) {
+    const float L = f_mul(f_mul((float)o0, 1.0f / 16384.0f), 100.0f);
+    const float spc = f_div(L, 100.0f);
+    return f_trunc(f_mul(spc, 255.0f));
+}
+
+// Q14 chroma -> the a (or b) value handed to LAB2RGB after the reference's normalise/denormalise
+// round trip:  a = o*2^-14*256 - 128 ; spc = (a + 128) / 255 ; a' = spc*255 - 128.
+GDT_HD float lab_chroma(int o) {
+    const float a = f_sub(f_mul(f_mul((float)o, 1.0f / 16384.0f), 256.0f), 128.0f);
+    const float spc = f_div(f_add(a, 128.0f), 255.0f);
+    return f_sub(f_mul(spc, 255.0f), 128.0f);
+}
+
+// CLAHE output byte -> L handed to LAB2RGB:  (float(v) / 255) * 100 - 0.
+GDT_HD float lab_l_from_u8(int v) { return f_mul(f_div((float)v, 255.0f), 100.0f); }
+
+// ---- CLAHE bilinear blend -----------------------------------------------------------------------
+
+struct ClaheAxis {
+    int i1, i2;      // clamped tile indices
+    float a, a1;     // weights (computed before clamping)
+};
+
+GDT_HD ClaheAxis clahe_axis(int coord, float inv_tile, int ntiles) {
+    ClaheAxis r;
+    const float tf = f_sub(f_mul((float)coord, inv_tile), 0.5f);
+    const int t1 = f_floor(tf);
+    r.a = f_sub(tf, (float)t1);
+    r.a1 = f_sub(1.0f, r.a);
+    const int t2 = t1 + 1;
+    r.i1 = t1 < 0 ? 0 : t1;
+    r.i2 = t2 > ntiles - 1 ? ntiles - 1 : t2;
+    return r;
+}
+
+GDT_HD int clahe_blend(int l11, int l12, int l21, int l22, float xa, float xa1, float ya, float ya1) {
+    const float top = f_add(f_mul((float)l11, xa1), f_mul((float)l12, xa));
+    const float bot = f_add(f_mul((float)l21, xa1), f_mul((float)l22, xa));
+    const float res = f_add(f_mul(top, ya1), f_mul(bot, ya));
+    int v = f_rint(res);
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// ---- Lab -> RGB (f32) ---------------------------------------------------------------------------
+
+struct Lab2RgbConst {
+    float C[9];        // float32(XYZ2sRGB_D65[k][j] * whitePt[j]), row-major
+};
+
+// `tail` selects OpenCV's scalar-tail sequence (last W % 8 pixels of every row): true divisions and
+// ((C0*X + C1*y) + C2*Z); the SIMD body multiplies by f32 reciprocals and uses C0*X + (C1*y + C2*Z).
+// Returns the three *linear* channels, unclipped.
+GDT_HD void lab2lin(float L, float a, float b, bool tail, const Lab2RgbConst& K, float& r, float& g, float& bl) {
+    const float c16 = 16.0f / 116.0f;
+    const float fth = 6.0f / 29.0f;
+    float y, fy, fx, fz, X, Z;
+    if (!tail) {
+        const float r903 = 1.0f / 903.3f, r116 = 1.0f / 116.0f, r500 = 1.0f / 500.0f, r200 = 1.0f / 200.0f,
+                    r7787 = 1.0f / 7.787f;
+        if (L <= 8.0f) {
+            y = f_mul(L, r903);
+            fy = f_add(f_mul(y, 7.787f), c16);
+        } else {
+            fy = f_mul(f_add(L, 16.0f), r116);
+            y = f_mul(f_mul(fy, fy), fy);
+        }
+        fx = f_add(f_mul(a, r500), fy);
+        fz = f_sub(fy, f_mul(b, r200));
+        X = fx <= fth ? f_mul(f_sub(fx, c16), r7787) : f_mul(f_mul(fx, fx), fx);
+        Z = fz <= fth ? f_mul(f_sub(fz, c16), r7787) : f_mul(f_mul(fz, fz), fz);
+        r = f_add(f_mul(K.C[0], X), f_add(f_mul(K.C[1], y), f_mul(K.C[2], Z)));
+        g = f_add(f_mul(K.C[3], X), f_add(f_mul(K.C[4], y), f_mul(K.C[5], Z)));
+        bl = f_add(f_mul(K.C[6], X), f_add(f_mul(K.C[7], y), f_mul(K.C[8], Z)));
+    } else {
+        if (L <= 8.0f) {
+            y = f_div(L, 903.3f);
+            fy = f_add(f_mul(y, 7.787f), c16);
+        } else {
+            fy = f_div(f_add(L, 16.0f), 116.0f);
+            y = f_mul(f_mul(fy, fy), fy);
+        }
+        fx = f_add(f_div(a, 500.0f), fy);
+        fz = f_sub(fy, f_div(b, 200.0f));
+        X = fx <= fth ? f_div(f_sub(fx, c16), 7.787f) : f_mul(f_mul(fx, fx), fx);
+        Z = fz <= fth ? f_div(f_sub(fz, c16), 7.787f) : f_mul(f_mul(fz, fz), fz);
+        r = f_add(f_add(f_mul(K.C[0], X), f_mul(K.C[1], y)), f_mul(K.C[2], Z));
+        g = f_add(f_add(f_mul(K.C[3], X), f_mul(K.C[4], y)), f_mul(K.C[5], Z));
+        bl = f_add(f_add(f_mul(K.C[6], X), f_mul(K.C[7], y)), f_mul(K.C[8], Z));
+    }
+}
+
+// sRGB inverse gamma through the 1024-segment cubic spline: `seg` = {f, b, c, d} of segment ix.
+GDT_HD float spline_index(float lin, int& ix) {
+    float x = f_mul(clamp01(lin), 1024.0f);
+    ix = f_trunc(x);
+    ix = ix < 0 ? 0 : (ix > 1023 ? 1023 : ix);
+    return f_sub(x, (float)ix);
+}
+GDT_HD float spline_eval(float x, float s0, float s1, float s2, float s3) {
+    return f_add(f_mul(f_add(f_mul(f_add(f_mul(s3, x), s2), x), s1), x), s0);
+}
+
+// Normalize: (x - mean) / std, sub then true division (core_transforms.py:64-67).
+GDT_HD float normalize_px(float x, float mean, float std) { return f_div(f_sub(x, mean), std); }
+
+// ---- host-side table builders (used by gdt_init; plain C++) --------------------------------------
+
+// Natural cubic spline of the sRGB inverse gamma, built exactly like OpenCV's splineBuild on
+// float32 samples f[i] evaluated in double (color_lab.cpp). tab: 1024*4 floats.
+inline void build_inv_gamma_spline(float* tab) {
+    const int n = 1024;
+    static float f[1025];
+    for (int i = 0; i <= n; ++i) {
+        const double xi = (double)i / n;
+        f[i] = (float)(xi <= 0.0031308 ? xi * 12.92 : 1.055 * pow(xi, 1.0 / 2.4) - 0.055);
+    }
+    tab[0] = tab[1] = 0.0f;
+    for (int i = 1; i < n; ++i) {
+        volatile float t0 = f[i] * 2.0f;
+        volatile float t1 = f[i + 1] - t0;
+        volatile float t2 = t1 + f[i - 1];
+        volatile float t = t2 * 3.0f;
+        volatile float den = 4.0f - tab[(i - 1) * 4];
+        volatile float l = 1.0f / den;
+        tab[i * 4] = l;
+        volatile float num = t - tab[(i - 1) * 4 + 1];
+        tab[i * 4 + 1] = num * l;
+    }
+    float cn = 0.0f;
+    for (int i = n - 1; i >= 0; --i) {
+        volatile float p0 = tab[i * 4] * cn;
+        volatile float c = tab[i * 4 + 1] - p0;
+        volatile float d0 = f[i + 1] - f[i];
+        volatile float c2 = c * 2.0f;
+        volatile float s0 = cn + c2;
+        volatile float s1 = s0 / 3.0f;
+        volatile float b = d0 - s1;
+        volatile float e0 = cn - c;
+        volatile float d = e0 / 3.0f;
+        tab[i * 4] = f[i];
+        tab[i * 4 + 1] = b;
+        tab[i * 4 + 2] = c;
+        tab[i * 4 + 3] = d;
+        cn = c;
+    }
+}
+
+inline void build_lab2rgb_const(Lab2RgbConst& K) {
+    static const double M[9] = {3.240479, -1.53715, -0.498535, -0.969256, 1.875991, 0.041556,
+                                0.055648, -0.204043, 1.057311};
+    static const double wp[3] = {0.950456, 1.0, 1.088754};
+    for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j) K.C[k * 3 + j] = (float)(M[k * 3 + j] * wp[j]);
+}
+
+// Re-pack the 33^3 x 3 lattice table into per-cell words (see lab_trilinear):
+//   lutL [cell][dxdy]        4 words  = 16 B per cell   (pass A: lightness only)
+//   lutAB[cell][ch(a,b)][dxdy] 8 words = 32 B per cell  (pass B: chroma)
+// cell = (tr*32 + tg)*32 + tb, tr/tg/tb in 0..31.
+inline void pack_lab_lut(const int16_t* lut33, uint32_t* lutL, uint32_t* lutAB) {
+    for (int tr = 0; tr < 32; ++tr)
+        for (int tg = 0; tg < 32; ++tg)
+            for (int tb = 0; tb < 32; ++tb) {
+                const int cell = (tr * 32 + tg) * 32 + tb;
+                for (int dx = 0; dx < 2; ++dx)
+                    for (int dy = 0; dy < 2; ++dy) {
+                        const int16_t* p0 = lut33 + (((tr + dx) * 33 + (tg + dy)) * 33 + tb) * 3;
+                        const int16_t* p1 = p0 + 3;
+                        const int q = dx * 2 + dy;
+                        lutL[cell * 4 + q] = (uint32_t)(uint16_t)p0[0] | ((uint32_t)(uint16_t)p1[0] << 16);
+                        lutAB[cell * 8 + q] = (uint32_t)(uint16_t)p0[1] | ((uint32_t)(uint16_t)p1[1] << 16);
+                        lutAB[cell * 8 + 4 + q] = (uint32_t)(uint16_t)p0[2] | ((uint32_t)(uint16_t)p1[2] << 16);
+                    }
+            }
+}
+
+}  // namespace gdt

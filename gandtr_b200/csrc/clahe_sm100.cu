@@ -1,0 +1,503 @@
+// K1 -- CLAHE preprocessing for sm_100a: fused `pil2np | apply_clahe | totensor | normalize`
+// (mdir/components/data/transform/{core_transforms.py:35-100, photometric_transforms.py:28-36,
+// functional.py:28-35,55-63,81-85,140-161}) and the ClahePost wrapper
+// (mdir/components/data/wrapper.py:325-348), bit-exact against the reference's OpenCV 4.13.0 path.
+//
+// Two launches per batch, both HBM-streaming with coalesced 16-byte accesses:
+//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> Q14 lightness (one 16 B gather from
+//           the L2-resident packed lattice table) -> uint8 L8 scratch + 256-bin shared-memory histogram
+//           (warp-aggregated atomics: __match_any_sync elects one lane per distinct bin) -> clip,
+//           redistribute, prefix sum -> 256-byte tile LUT.
+//   pass B  clahe_apply_kernel  one CTA per (image, row band, 1024-px column chunk): tile LUTs of the
+//           band staged in shared memory, per pixel: bilinear LUT blend -> chroma (32 B gather) ->
+//           Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
+// Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 1 B/px
+// written by A and read by B (L2-resident for batches up to ~100 MB).
+#include "clahe_math.cuh"
+#include "common.cuh"
+
+namespace gdt {
+
+struct ClaheTables {
+    uint4* lutL = nullptr;     // [32768]      packed lightness corners
+    uint4* lutAB = nullptr;    // [32768][2]   packed chroma corners (a words, b words)
+    float4* spline = nullptr;  // [1024]
+    uint16_t* q8 = nullptr;    // [256]  uint8 channel -> (t << 5) | f
+    float* lnew = nullptr;     // [256]  CLAHE byte -> L handed to LAB2RGB
+    Lab2RgbConst K;
+    float spline_host[4096];
+    bool ready = false;
+};
+
+static ClaheTables g_tables[32];
+
+const ClaheTables* clahe_tables_for_current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+    return g_tables[dev].ready ? &g_tables[dev] : nullptr;
+}
+
+struct Norm3 {
+    float mean[3];
+    float std[3];
+};
+
+// ---- pixel helpers ------------------------------------------------------------------------------
+
+template <bool U8>
+struct PixelIn;
+
+// One input pixel -> (cell, fr, fg, fb)
+__device__ __forceinline__ void cell_from_q8(const uint16_t* q8s, int r, int g, int b, int& cell, int& fr, int& fg,
+                                             int& fb) {
+    const int qr = q8s[r], qg = q8s[g], qb = q8s[b];
+    cell = ((qr >> 5) << 10) | ((qg >> 5) << 5) | (qb >> 5);
+    fr = qr & 31;
+    fg = qg & 31;
+    fb = qb & 31;
+}
+
+__device__ __forceinline__ void cell_from_f32(float r, float g, float b, const Norm3& in, int& cell, int& fr, int& fg,
+                                              int& fb) {
+    // ClahePost: tensor.mul(std).add(mean) (wrapper.py:342), then cv2 clips to [0,1]
+    int tr, tg, tb;
+    lab_cell(clamp01(f_add(f_mul(r, in.std[0]), in.mean[0])), tr, fr);
+    lab_cell(clamp01(f_add(f_mul(g, in.std[1]), in.mean[1])), tg, fg);
+    lab_cell(clamp01(f_add(f_mul(b, in.std[2]), in.mean[2])), tb, fb);
+    cell = (tr << 10) | (tg << 5) | tb;
+}
+
+__device__ __forceinline__ int l8_from_cell(const uint4* __restrict__ lutL, int cell, int fr, int fg, int fb) {
+    const uint4 w = __ldg(lutL + cell);
+    return lab_l8(lab_trilinear(w.x, w.y, w.z, w.w, fr, fg, fb));
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+// warp-aggregated shared-memory histogram increment; `key` > 255 means "no pixel"
+__device__ __forceinline__ void hist_add(int* hist, int key) {
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int lane = threadIdx.x & 31;
+    if (key < 256 && lane == (__ffs(peers) - 1)) atomicAdd(&hist[key], __popc(peers));
+}
+
+// ---- pass A -------------------------------------------------------------------------------------
+
+template <bool U8>
+__global__ void __launch_bounds__(256)
+clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_t* __restrict__ tile_luts, int h, int w,
+                  int grid, int th, int tw, int clip, float lut_scale, int vec_ok, const uint4* __restrict__ lutL,
+                  const uint16_t* __restrict__ q8, Norm3 in_norm) {
+    __shared__ int hist[256];
+    __shared__ uint16_t q8s[256];
+    __shared__ int warp_tmp[8];
+    const int tid = threadIdx.x;
+    const int img = blockIdx.y;
+    const int ty = blockIdx.x / grid, tx = blockIdx.x % grid;
+    hist[tid] = 0;
+    if (U8) q8s[tid] = q8[tid];
+    __syncthreads();
+
+    const size_t plane = (size_t)h * w;
+    const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
+    const float* inf = (const float*)in_ + (size_t)img * plane * 3;
+    uint8_t* l8img = L8 + (size_t)img * plane;
+
+    if (vec_ok) {
+        // tile fully inside the image, 4 consecutive pixels per thread
+        const int gw = tw >> 2;
+        const int ngroups = th * gw;
+        for (int base = 0; base < ngroups; base += 256) {
+            const int gidx = base + tid;
+            const bool valid = gidx < ngroups;
+            int v[4] = {256, 256, 256, 256};
+            if (valid) {
+                const int row = gidx / gw, c4 = gidx - row * gw;
+                const int y = ty * th + row, x0 = tx * tw + (c4 << 2);
+                const size_t p = (size_t)y * w + x0;
+                if (U8) {
+                    const uint32_t* src = (const uint32_t*)(in8 + p * 3);
+                    const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+                    const int rr[4] = {(int)(a0 & 255), (int)(a0 >> 24), (int)((a1 >> 16) & 255), (int)((a2 >> 8) & 255)};
+                    const int gg[4] = {(int)((a0 >> 8) & 255), (int)(a1 & 255), (int)(a1 >> 24), (int)((a2 >> 16) & 255)};
+                    const int bb[4] = {(int)((a0 >> 16) & 255), (int)((a1 >> 8) & 255), (int)(a2 & 255), (int)(a2 >> 24)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int cell, fr, fg, fb;
+                        cell_from_q8(q8s, rr[i], gg[i], bb[i], cell, fr, fg, fb);
+                        v[i] = l8_from_cell(lutL, cell, fr, fg, fb);
+                    }
+                } else {
+                    const float4 r4 = __ldg((const float4*)(inf + p));
+                    const float4 g4 = __ldg((const float4*)(inf + plane + p));
+                    const float4 b4 = __ldg((const float4*)(inf + 2 * plane + p));
+                    const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w},
+                                bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int cell, fr, fg, fb;
+                        cell_from_f32(rr[i], gg[i], bb[i], in_norm, cell, fr, fg, fb);
+                        v[i] = l8_from_cell(lutL, cell, fr, fg, fb);
+                    }
+                }
+                *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hist_add(hist, v[i]);
+        }
+    } else {
+        // generic: extended (REFLECT_101-padded) tile, one pixel per thread per step
+        const int npx = th * tw;
+        for (int base = 0; base < npx; base += 256) {
+            const int pidx = base + tid;
+            int v = 256;
+            if (pidx < npx) {
+                const int row = pidx / tw, col = pidx - row * tw;
+                const int ey = ty * th + row, ex = tx * tw + col;
+                const int sy = reflect101(ey, h), sx = reflect101(ex, w);
+                const size_t p = (size_t)sy * w + sx;
+                int cell, fr, fg, fb;
+                if (U8) {
+                    cell_from_q8(q8s, in8[p * 3], in8[p * 3 + 1], in8[p * 3 + 2], cell, fr, fg, fb);
+                } else {
+                    cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
+                }
+                v = l8_from_cell(lutL, cell, fr, fg, fb);
+                if (ey < h && ex < w) l8img[p] = (uint8_t)v;
+            }
+            hist_add(hist, v);
+        }
+    }
+    __syncthreads();
+
+    // ---- clip, redistribute, prefix sum -> tile LUT (OpenCV clahe.cpp CLAHE_CalcLut_Body) ----
+    int hv = hist[tid];
+    const int lane = tid & 31, wid = tid >> 5;
+    if (clip > 0) {
+        int excess = hv > clip ? hv - clip : 0;
+        hv = hv > clip ? clip : hv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, o);
+        if (lane == 0) warp_tmp[wid] = excess;
+        __syncthreads();
+        int clipped = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) clipped += warp_tmp[i];
+        __syncthreads();
+        const int batch = clipped / 256;
+        int resid = clipped - batch * 256;
+        hv += batch;
+        if (resid != 0) {
+            const int step = max(256 / resid, 1);
+            if ((tid % step) == 0 && (tid / step) < resid) hv += 1;
+        }
+    }
+    int sum = hv;  // inclusive scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, sum, o);
+        if (lane >= o) sum += t;
+    }
+    if (lane == 31) warp_tmp[wid] = sum;
+    __syncthreads();
+    for (int i = 0; i < wid; ++i) sum += warp_tmp[i];
+    int lv = f_rint(f_mul((float)sum, lut_scale));
+    lv = lv < 0 ? 0 : (lv > 255 ? 255 : lv);
+    tile_luts[((size_t)img * grid * grid + blockIdx.x) * 256 + tid] = (uint8_t)lv;
+}
+
+// ---- pass B -------------------------------------------------------------------------------------
+
+template <bool U8>
+__global__ void __launch_bounds__(256)
+clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ tile_luts,
+                   float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
+                   int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline,
+                   const uint16_t* __restrict__ q8, const float* __restrict__ lnew_tab, Lab2RgbConst K, Norm3 in_norm,
+                   Norm3 out_norm) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* luts = smem;  // [(ty_hi - ty_lo + 1) * grid][256]
+    __shared__ uint16_t q8s[256];
+    __shared__ float lnews[256];
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z;
+    const int y0 = blockIdx.y * rows_per_cta;
+    const int y1 = min(y0 + rows_per_cta, h);
+    const int ty_lo = clahe_axis(y0, inv_th, grid).i1;
+    const int ty_hi = clahe_axis(y1 - 1, inv_th, grid).i2;
+
+    {
+        const int nbytes = (ty_hi - ty_lo + 1) * grid * 256;
+        const uint4* src = (const uint4*)(tile_luts + ((size_t)img * grid * grid + (size_t)ty_lo * grid) * 256);
+        uint4* dst = (uint4*)luts;
+        for (int i = tid; i < (nbytes >> 4); i += 256) dst[i] = __ldg(src + i);
+        if (U8) q8s[tid] = q8[tid];
+        lnews[tid] = lnew_tab[tid];
+    }
+    __syncthreads();
+
+    const int x0 = (blockIdx.x * 256 + tid) * 4;
+    if (x0 >= w) return;
+    const int npx = min(4, w - x0);
+    const int wbody = (w >> 3) << 3;  // pixels >= wbody take OpenCV's scalar-tail op sequence
+
+    ClaheAxis ax[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ax[i] = clahe_axis(x0 + i, inv_tw, grid);
+
+    const size_t plane = (size_t)h * w;
+    const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
+    const float* inf = (const float*)in_ + (size_t)img * plane * 3;
+    const uint8_t* l8img = L8 + (size_t)img * plane;
+    float* outimg = out + (size_t)img * plane * 3;
+
+    for (int y = y0; y < y1; ++y) {
+        const ClaheAxis ay = clahe_axis(y, inv_th, grid);
+        const uint8_t* lrow1 = luts + (size_t)(ay.i1 - ty_lo) * grid * 256;
+        const uint8_t* lrow2 = luts + (size_t)(ay.i2 - ty_lo) * grid * 256;
+        const size_t p = (size_t)y * w + x0;
+
+        int cell[4], fr[4], fg[4], fb[4], v[4];
+        if (vec_ok) {
+            const uint32_t lw = __ldg((const uint32_t*)(l8img + p));
+            v[0] = lw & 255; v[1] = (lw >> 8) & 255; v[2] = (lw >> 16) & 255; v[3] = lw >> 24;
+            if (U8) {
+                const uint32_t* src = (const uint32_t*)(in8 + p * 3);
+                const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+                cell_from_q8(q8s, a0 & 255, (a0 >> 8) & 255, (a0 >> 16) & 255, cell[0], fr[0], fg[0], fb[0]);
+                cell_from_q8(q8s, a0 >> 24, a1 & 255, (a1 >> 8) & 255, cell[1], fr[1], fg[1], fb[1]);
+                cell_from_q8(q8s, (a1 >> 16) & 255, a1 >> 24, a2 & 255, cell[2], fr[2], fg[2], fb[2]);
+                cell_from_q8(q8s, (a2 >> 8) & 255, (a2 >> 16) & 255, a2 >> 24, cell[3], fr[3], fg[3], fb[3]);
+            } else {
+                const float4 r4 = __ldg((const float4*)(inf + p));
+                const float4 g4 = __ldg((const float4*)(inf + plane + p));
+                const float4 b4 = __ldg((const float4*)(inf + 2 * plane + p));
+                cell_from_f32(r4.x, g4.x, b4.x, in_norm, cell[0], fr[0], fg[0], fb[0]);
+                cell_from_f32(r4.y, g4.y, b4.y, in_norm, cell[1], fr[1], fg[1], fb[1]);
+                cell_from_f32(r4.z, g4.z, b4.z, in_norm, cell[2], fr[2], fg[2], fb[2]);
+                cell_from_f32(r4.w, g4.w, b4.w, in_norm, cell[3], fr[3], fg[3], fb[3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < npx) {
+                    v[i] = l8img[p + i];
+                    if (U8) {
+                        cell_from_q8(q8s, in8[(p + i) * 3], in8[(p + i) * 3 + 1], in8[(p + i) * 3 + 2], cell[i], fr[i],
+                                     fg[i], fb[i]);
+                    } else {
+                        cell_from_f32(inf[p + i], inf[plane + p + i], inf[2 * plane + p + i], in_norm, cell[i], fr[i],
+                                      fg[i], fb[i]);
+                    }
+                } else {
+                    v[i] = 0; cell[i] = 0; fr[i] = fg[i] = fb[i] = 0;
+                }
+            }
+        }
+
+        float o[3][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // chroma
+            const uint4 wa = __ldg(lutAB + cell[i] * 2);
+            const uint4 wb = __ldg(lutAB + cell[i] * 2 + 1);
+            const float a2 = lab_chroma(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
+            const float b2 = lab_chroma(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
+            // lightness through CLAHE
+            const int l11 = lrow1[ax[i].i1 * 256 + v[i]], l12 = lrow1[ax[i].i2 * 256 + v[i]];
+            const int l21 = lrow2[ax[i].i1 * 256 + v[i]], l22 = lrow2[ax[i].i2 * 256 + v[i]];
+            const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
+            const float Ln = lnews[dst];
+            float lr, lg, lb;
+            lab2lin(Ln, a2, b2, (x0 + i) >= wbody, K, lr, lg, lb);
+            int ir, ig, ib;
+            const float xr = spline_index(lr, ir), xg = spline_index(lg, ig), xb = spline_index(lb, ib);
+            const float4 sr = __ldg(spline + ir), sg = __ldg(spline + ig), sb = __ldg(spline + ib);
+            o[0][i] = normalize_px(spline_eval(xr, sr.x, sr.y, sr.z, sr.w), out_norm.mean[0], out_norm.std[0]);
+            o[1][i] = normalize_px(spline_eval(xg, sg.x, sg.y, sg.z, sg.w), out_norm.mean[1], out_norm.std[1]);
+            o[2][i] = normalize_px(spline_eval(xb, sb.x, sb.y, sb.z, sb.w), out_norm.mean[2], out_norm.std[2]);
+        }
+        if (vec_ok) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                __stcs((float4*)(outimg + c * plane + p), make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < npx) outimg[c * plane + p + i] = o[c][i];
+        }
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+
+struct ClaheGeom {
+    int eh, ew, th, tw, clip, rows_per_cta;
+    float lut_scale, inv_th, inv_tw;
+};
+
+static int clahe_geometry(int n, int h, int w, double clip_limit, int grid, ClaheGeom& g) {
+    if (n <= 0 || h <= 0 || w <= 0 || grid < 1 || grid > 16) return GDT_ERR_INVALID_ARGUMENT;
+    if (h % grid == 0 && w % grid == 0) {
+        g.eh = h; g.ew = w;
+    } else {  // OpenCV quirk: a dimension that IS divisible still gets +grid
+        g.eh = h + (grid - h % grid);
+        g.ew = w + (grid - w % grid);
+        if (g.eh - h >= h || g.ew - w >= w) return GDT_ERR_UNSUPPORTED;  // REFLECT_101 needs pad < size
+    }
+    g.th = g.eh / grid; g.tw = g.ew / grid;
+    const int area = g.th * g.tw;
+    g.lut_scale = 255.0f / (float)area;
+    g.clip = 0;
+    if (clip_limit > 0.0) {
+        g.clip = (int)(clip_limit * area / 256);
+        if (g.clip < 1) g.clip = 1;
+    }
+    g.inv_th = 1.0f / (float)g.th;
+    g.inv_tw = 1.0f / (float)g.tw;
+    return GDT_OK;
+}
+
+template <bool U8>
+static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, int grid, const Norm3& in_norm,
+                        const Norm3& out_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    const ClaheTables* T = clahe_tables_for_current_device();
+    if (!T) return GDT_ERR_NOT_INITIALISED;
+    if (!in || !out || !ws) return GDT_ERR_INVALID_ARGUMENT;
+    ClaheGeom g;
+    int rc = clahe_geometry(n, h, w, clip_limit, grid, g);
+    if (rc != GDT_OK) return rc;
+    if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    Workspace W(ws, ws_bytes);
+    uint8_t* L8 = W.take<uint8_t>((size_t)n * h * w);
+    uint8_t* luts = W.take<uint8_t>((size_t)n * grid * grid * 256);
+    if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
+
+    const bool aligned = (((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0;
+    const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
+    const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
+
+    dim3 gridA(grid * grid, n);
+    clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
+                                                      vec_hist, T->lutL, T->q8, in_norm);
+    GDT_LAUNCH_CHECK();
+
+    // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
+    const int sms = sm_count_current_device();
+    int rows = 16;
+    const int xchunks = ceil_div(w, 1024);
+    while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 4LL * sms) rows >>= 1;
+    dim3 gridB(xchunks, ceil_div(h, rows), n);
+    const size_t smem = (size_t)grid * grid * 256;
+    static bool attr_set[2] = {false, false};
+    if (smem > 48 * 1024 && !attr_set[U8 ? 1 : 0]) {
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[U8 ? 1 : 0] = true;
+    }
+    clahe_apply_kernel<U8><<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
+                                                          vec_apply, T->lutAB, T->spline, T->q8, T->lnew, T->K, in_norm,
+                                                          out_norm);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
+}  // namespace gdt
+
+using namespace gdt;
+
+extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
+    if (!host_rgb2lab_lut) return GDT_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return GDT_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    GDT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) return GDT_ERR_UNSUPPORTED;
+    ClaheTables& T = g_tables[dev];
+    if (T.ready) return GDT_OK;
+
+    const size_t ncell = 32 * 32 * 32;
+    uint32_t* hL = (uint32_t*)malloc(ncell * 4 * sizeof(uint32_t));
+    uint32_t* hAB = (uint32_t*)malloc(ncell * 8 * sizeof(uint32_t));
+    if (!hL || !hAB) { free(hL); free(hAB); return GDT_ERR_INVALID_ARGUMENT; }
+    pack_lab_lut(host_rgb2lab_lut, hL, hAB);
+    build_inv_gamma_spline(T.spline_host);
+    build_lab2rgb_const(T.K);
+    uint16_t q8[256];
+    float lnew[256];
+    for (int v = 0; v < 256; ++v) {
+        int t, f;
+        // Pil2Numpy: float32(u8) / 255.0 (core_transforms.py:83); already inside [0,1]
+        volatile float x = (float)v / 255.0f;
+        volatile float xs = x * 16384.0f;
+        int c = (int)lrintf(xs);
+        t = c >> 9; f = (c >> 5) & 15;
+        if (t >= 32) { t = 31; f = 16; }
+        q8[v] = (uint16_t)((t << 5) | f);
+        volatile float s = (float)v / 255.0f;
+        volatile float L = s * 100.0f;
+        lnew[v] = L;
+    }
+    int rc = GDT_OK;
+    auto up = [&](void** dptr, const void* src, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(dptr, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(tables)", __FILE__, __LINE__);
+        e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tables)", __FILE__, __LINE__);
+        return GDT_OK;
+    };
+    if (rc == GDT_OK) rc = up((void**)&T.lutL, hL, ncell * 16);
+    if (rc == GDT_OK) rc = up((void**)&T.lutAB, hAB, ncell * 32);
+    if (rc == GDT_OK) rc = up((void**)&T.spline, T.spline_host, 4096 * sizeof(float));
+    if (rc == GDT_OK) rc = up((void**)&T.q8, q8, sizeof(q8));
+    if (rc == GDT_OK) rc = up((void**)&T.lnew, lnew, sizeof(lnew));
+    free(hL);
+    free(hAB);
+    if (rc == GDT_OK) T.ready = true;
+    return rc;
+}
+
+extern "C" int gdt_is_initialised(void) { return clahe_tables_for_current_device() ? 1 : 0; }
+
+extern "C" int gdt_debug_get_spline_table(float* host_out_4096) {
+    if (!host_out_4096) return GDT_ERR_INVALID_ARGUMENT;
+    static float tab[4096];
+    static bool built = false;
+    if (!built) { build_inv_gamma_spline(tab); built = true; }
+    memcpy(host_out_4096, tab, sizeof(tab));
+    return GDT_OK;
+}
+
+extern "C" size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid) {
+    if (n <= 0 || h <= 0 || w <= 0 || grid < 1) return 0;
+    return align_up((size_t)n * h * w, 256) + align_up((size_t)n * grid * grid * 256, 256) + 256;
+}
+
+extern "C" int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,
+                            const float* host_mean, const float* host_std, float* out_chw, void* ws, size_t ws_bytes,
+                            void* stream) {
+    if (!host_mean || !host_std) return GDT_ERR_INVALID_ARGUMENT;
+    Norm3 o, i;
+    for (int c = 0; c < 3; ++c) { o.mean[c] = host_mean[c]; o.std[c] = host_std[c]; i.mean[c] = 0.f; i.std[c] = 1.f; }
+    return clahe_launch<true>(rgb_hwc, n, h, w, clip_limit, grid, i, o, out_chw, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, int grid,
+                             const float* host_in_mean, const float* host_in_std, const float* host_out_mean,
+                             const float* host_out_std, float* out_chw, void* ws, size_t ws_bytes, void* stream) {
+    if (!host_in_mean || !host_in_std || !host_out_mean || !host_out_std) return GDT_ERR_INVALID_ARGUMENT;
+    Norm3 o, i;
+    for (int c = 0; c < 3; ++c) {
+        o.mean[c] = host_out_mean[c]; o.std[c] = host_out_std[c];
+        i.mean[c] = host_in_mean[c]; i.std[c] = host_in_std[c];
+    }
+    return clahe_launch<false>(in_chw, n, h, w, clip_limit, grid, i, o, out_chw, ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,182 @@
+/*
+ * gandtr_b200 -- C ABI of the B200-native retrieval hot path (libgandtr_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types. Every entry point
+ * cites the reference interface it replaces (paths relative to the mohwald/gandtr checkout).
+ * The reference is pure Python, so its "FFI" is ctypes: gandtr_b200/_lib.py is the binding,
+ * INTEGRATION.md shows the stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every `const T* x` / `T* x` argument named without a `host_` prefix is a DEVICE pointer
+ *     owned by the caller (in practice: torch tensors); `host_*` arguments are read on the host
+ *     during the call.
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the device, nothing allocates device memory: scratch comes from the
+ *     caller-provided workspace (`ws`, `ws_bytes`; query the size with the matching
+ *     gdt_*_workspace_bytes call). Workspaces must be 256-byte aligned.
+ *   - return value: GDT_OK (0) or a negative gdt_status. Functions never throw.
+ *   - thread-safe for distinct streams; tables are immutable after gdt_init.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     GDT_ERR_NO_DEVICE / GDT_ERR_NOT_INITIALISED.
+ */
+#ifndef GANDTR_B200_H
+#define GANDTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDT_ABI_VERSION 1
+
+typedef enum gdt_status {
+    GDT_OK = 0,
+    GDT_ERR_INVALID_ARGUMENT = -1,
+    GDT_ERR_NOT_INITIALISED = -2,
+    GDT_ERR_NO_DEVICE = -3,
+    GDT_ERR_WORKSPACE_TOO_SMALL = -4,
+    GDT_ERR_CUDA = -5,          /* a CUDA runtime / driver call failed; see gdt_last_cuda_error */
+    GDT_ERR_UNSUPPORTED = -6,
+    GDT_ERR_CANDIDATE_OVERFLOW = -7 /* score_topk: a query exceeded its candidate capacity (reported
+                                       through the device status word, see gdt_score_topk) */
+} gdt_status;
+
+/* ---- library ----------------------------------------------------------------------------- */
+
+int gdt_abi_version(void);
+const char* gdt_status_string(int status);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* gdt_last_cuda_error(void);
+
+/*
+ * Upload the immutable tables of the CLAHE path to the *current* CUDA device:
+ *   host_rgb2lab_lut : 33*33*33*3 int16, the lattice table of OpenCV's float RGB2Lab
+ *                      (color_lab.cpp RGB2LabLUT_s16), layout [r][g][b][L,a,b]
+ *                      (shipped as gandtr_b200/data/rgb2lab_lut_s16.bin).
+ * The sRGB inverse-gamma spline (1024x4 f32) and the Lab->RGB coefficients are built inside.
+ * Replaces: the implicit table initialisation inside cv2.cvtColor, reached from
+ * mdir/components/data/transform/functional.py:35,63.
+ */
+int gdt_init(const int16_t* host_rgb2lab_lut);
+int gdt_is_initialised(void);
+/* debug/test hook: copy the 1024x4 inverse-gamma spline table built by gdt_init to host memory */
+int gdt_debug_get_spline_table(float* host_out_4096);
+
+/* ---- K1: CLAHE preprocessing ------------------------------------------------------------------
+ * Fused `pil2np | apply_clahe:clip:grid:lab | totensor | normalize`
+ * (mdir/components/data/transform/core_transforms.py:35-100,
+ *  mdir/components/data/transform/photometric_transforms.py:28-36,
+ *  mdir/components/data/transform/functional.py:28-35,55-63,81-85,140-161).
+ * rgb_hwc : n images, uint8, [n][h][w][3]          out_chw : float32 [n][3][h][w]
+ * host_mean/host_std : 3 floats each (Normalize). Bit-exact against the reference's OpenCV path.
+ */
+size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid);
+int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,
+                 const float* host_mean, const float* host_std, float* out_chw,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* `ClahePost.postprocess` (mdir/components/data/wrapper.py:325-348): CLAHE on a normalised float
+ * CHW device tensor without the device->host->device round trip.
+ * in_chw : float32 [n][3][h][w] normalised with (in_mean, in_std); result re-normalised with
+ * (out_mean, out_std) (the reference uses the same pair for both). */
+int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, int grid,
+                  const float* host_in_mean, const float* host_in_std,
+                  const float* host_out_mean, const float* host_out_std, float* out_chw,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K2: GeM + L2N + multi-scale aggregation + learned whitening ---------------------------------
+ * Replaces LF.gem / LF.l2n (mdir/external/cirtorch/layers/functional.py:21-22,130-131),
+ * CirMultiscaleAggregation.aggregate_tensor/postprocess (mdir/components/data/wrapper.py:235-260)
+ * and CirtorchWhiten.postprocess (mdir/components/data/wrapper.py:320-322).
+ *
+ * host_fmaps[s] : device pointer to the backbone's final feature map of scale s,
+ *                 float32 [n][c][host_h[s]][host_w[s]] contiguous, s < scales (<= GDT_MAX_SCALES)
+ * p_dev         : device pointer to GeM's 1-element exponent `pool.p` (read on the device: no sync)
+ * eps           : GeM clamp (1e-6)
+ * flags         : GDT_GEM_AGGREGATE   apply the multi-scale generalised mean + eps-free renorm
+ *                                    (cirmultiscale wrapper present; also valid for scales == 1)
+ *                 GDT_GEM_MSP_IS_P    exponent of that mean is p (wrapper.py:248-251), else 1
+ * P, m          : whitening projection [dim][c] row-major (row stride ldP) and mean [c], or NULL
+ * desc          : float32 [n][dim] row-major (dim == c when P == NULL)
+ */
+#define GDT_MAX_SCALES 8
+#define GDT_GEM_AGGREGATE 1
+#define GDT_GEM_MSP_IS_P 2
+size_t gdt_gem_whiten_workspace_bytes(int n, int c, int scales, int dim);
+int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h, const int* host_w,
+                   int n, int c, int scales, const float* p_dev, float eps, int flags,
+                   const float* P, int ldP, const float* m, int dim,
+                   float* desc, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K3: query x database scoring fused with streaming top-k ----------------------------------------
+ * Replaces `scores = np.dot(vecs.T, qvecs); ranks = np.argsort(-scores, axis=0)` restricted to the
+ * first k ranks (mdir/components/optim/score/cirscore.py:71-72).
+ *
+ * Database shards are prepared once (gdt_db_prepare): a bf16 shadow copy feeds the tcgen05 coarse
+ * pass, the fp32 rows feed the exact re-scoring of the few survivors, so the returned scores are
+ * fp32-exact (fp64-accumulated dot, rounded once) and the ranking is exact:
+ * ordering = (score descending, global index ascending).
+ *
+ * q        : float32 [nq][d] row-major queries            db : float32 [ndb][d] row-major shard
+ * db_bf16  : shadow written by gdt_db_prepare, [ndb][d] bf16
+ * db_norm_max : device float, max L2 norm over the shard's rows (written by gdt_db_prepare)
+ * top_scores/top_idx : [nq][k]; top_idx holds index_base + local row; when ndb < k the tail is
+ *            filled with (-inf, -1)
+ * status_dev : device int32[4], zero on success; [0] = GDT_ERR_CANDIDATE_OVERFLOW if a query's
+ *            candidate set did not fit (results for that query are then not trustworthy),
+ *            [1] = worst-case number of candidates re-scored for one query (diagnostic)
+ */
+size_t gdt_db_prepare_workspace_bytes(long long ndb, int d);
+int gdt_db_prepare(const float* db, long long ndb, int d, void* db_bf16, float* db_norm_max,
+                   void* ws, size_t ws_bytes, void* stream);
+size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k);
+int gdt_score_topk(const float* q, const float* db, const void* db_bf16, const float* db_norm_max,
+                   int nq, long long ndb, int d, int k, long long index_base,
+                   float* top_scores, int64_t* top_idx, int32_t* status_dev,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* Exact CUDA-core variant of the same contract (no bf16 shadow, no tensor cores); used for small
+ * problems and as an on-device cross-check of the tcgen05 path. */
+size_t gdt_score_topk_exact_workspace_bytes(int nq, long long ndb, int d, int k);
+int gdt_score_topk_exact(const float* q, const float* db, int nq, long long ndb, int d, int k,
+                         long long index_base, float* top_scores, int64_t* top_idx,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Merge g per-shard top-k lists (after the NCCL allgather) into one:
+ * scores/idx : [g][nq][k] -> out : [nq][k], same ordering rule; entries with idx < 0 are padding. */
+int gdt_topk_merge(const float* scores, const int64_t* idx, int g, int nq, int k,
+                   float* out_scores, int64_t* out_idx, void* stream);
+
+/* ---- K4: ranks of ground-truth ids + mAP ------------------------------------------------------------
+ * Replaces the use of the full `ranks` matrix inside compute_map
+ * (mdir/external/cirtorch/utils/evaluate.py:39-111): for every query and every probe id (its
+ * positives and junk), the 0-based position the id would have in the full descending ranking
+ * = number of database rows that sort before it.
+ *
+ * probe_idx  : int64 [nq][pmax] global ids (index_base-relative rows live on this shard), -1 = pad
+ * probe_score: float32 [nq][pmax] exact score of each probe (gdt_probe_scores on the owning shard,
+ *              summed across shards by the caller since non-owners contribute 0)
+ * before     : int64 [nq][pmax], += number of rows of THIS shard that sort before the probe
+ *              (caller zero-initialises and sums across shards)
+ */
+int gdt_probe_scores(const float* q, const float* db, int nq, long long ndb, int d,
+                     long long index_base, const int64_t* probe_idx, int pmax,
+                     float* probe_score, void* stream);
+int gdt_rank_counts(const float* q, const float* db, int nq, long long ndb, int d,
+                    long long index_base, const int64_t* probe_idx, const float* probe_score,
+                    int pmax, int64_t* before, void* stream);
+
+/* compute_ap / compute_map body (evaluate.py:3-37,60-106) for nq queries:
+ * pos_rank [nq][pmax_pos], junk_rank [nq][pmax_junk] : 0-based full-ranking positions (any order,
+ * first npos[q] / njunk[q] entries valid). kappas [nk] (device). Outputs (float64, as the
+ * reference): ap [nq] (NaN when npos == 0), prk [nq][nk]. */
+int gdt_map_eval(const int64_t* pos_rank, int pmax_pos, const int64_t* junk_rank, int pmax_junk,
+                 const int32_t* npos, const int32_t* njunk, int nq,
+                 const int32_t* kappas, int nk, double* ap, double* prk, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANDTR_B200_H */
