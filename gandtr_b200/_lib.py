@@ -1,0 +1,360 @@
+"""ctypes binding of libgandtr_b200.so -- the C ABI declared in include/gandtr_b200.h.
+
+The reference is pure Python, so this file *is* the reference-side FFI stub.
+PyTorch is used only for device memory and streams: every function takes torch CUDA tensors, checks
+dtype / contiguity / device, and passes raw pointers and the current CUDA stream to the library.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is visible, calls raise.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libgandtr_b200.so")
+LUT_PATH = os.path.join(_PKG_DIR, "data", "rgb2lab_lut_s16.bin")
+
+GDT_OK = 0
+GDT_ERR_CANDIDATE_OVERFLOW = -7
+GDT_MAX_SCALES = 8
+GDT_GEM_AGGREGATE = 1
+GDT_GEM_MSP_IS_P = 2
+
+# every symbol include/gandtr_b200.h declares: (name, restype, argtypes)
+_c = ctypes
+_P = _c.c_void_p
+SYMBOLS = [
+    ("gdt_abi_version", _c.c_int, []),
+    ("gdt_status_string", _c.c_char_p, [_c.c_int]),
+    ("gdt_last_cuda_error", _c.c_char_p, []),
+    ("gdt_init", _c.c_int, [_P]),
+    ("gdt_is_initialised", _c.c_int, []),
+    ("gdt_debug_get_spline_table", _c.c_int, [_P]),
+    ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    ("gdt_clahe_u8", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _c.c_size_t, _P]),
+    ("gdt_clahe_f32", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P,
+                                 _c.c_size_t, _P]),
+    ("gdt_gem_whiten_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    ("gdt_gem_whiten", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P,
+                                  _c.c_int, _P, _P, _c.c_size_t, _P]),
+    ("gdt_db_prepare_workspace_bytes", _c.c_size_t, [_c.c_longlong, _c.c_int]),
+    ("gdt_db_prepare", _c.c_int, [_P, _c.c_longlong, _c.c_int, _P, _P, _P, _c.c_size_t, _P]),
+    ("gdt_score_topk_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_longlong, _c.c_int, _c.c_int]),
+    ("gdt_score_topk", _c.c_int, [_P, _P, _P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P,
+                                  _P, _P, _c.c_size_t, _P]),
+    ("gdt_score_topk_exact_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_longlong, _c.c_int, _c.c_int]),
+    ("gdt_score_topk_exact", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P, _P,
+                                        _c.c_size_t, _P]),
+    ("gdt_topk_merge", _c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
+    ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
+    ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P]),
+    ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
+]
+
+_lib = None
+_lock = threading.Lock()
+_initialised_devices = set()
+launch_count = 0  # number of library compute calls made by this process (bench.py reports kernel launches from it)
+
+# kernels launched by each entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"clahe": 2, "gem": 2, "gem_whiten": 4, "db_prepare": 1, "score_topk": 3, "score_topk_exact": 2,
+                    "topk_merge": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1}
+
+
+class GdtError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library (once). Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise GdtError("%s is missing: run `python -m gandtr_b200._build` (or __graft_entry__.build()); "
+                               "gandtr_b200 has no CPU fallback" % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, restype, argtypes in SYMBOLS:
+                fn = getattr(lib, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != GDT_OK:
+        lib = load()
+        msg = lib.gdt_status_string(rc).decode()
+        cuda = lib.gdt_last_cuda_error().decode()
+        raise GdtError("%s failed: %s (%d)%s" % (what, msg, rc, (" -- " + cuda) if rc == -5 and cuda else ""))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _require(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise GdtError("%s must be a CUDA tensor (gandtr_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise GdtError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise GdtError("%s must be contiguous" % name)
+    return t
+
+
+def _workspace(nbytes, device):
+    # torch's caching allocator returns 512-byte aligned blocks
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def ensure_init(device):
+    """gdt_init on `device` (uploads the CLAHE tables) once per process and device."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise GdtError("gandtr_b200 kernels need a CUDA device, got %s" % dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx in _initialised_devices:
+        return
+    lib = load()
+    lut = np.fromfile(LUT_PATH, dtype="<i2")
+    if lut.size != 33 * 33 * 33 * 3:
+        raise GdtError("corrupt table file %s" % LUT_PATH)
+    with torch.cuda.device(idx):
+        torch.cuda.current_stream().synchronize()
+        check(lib.gdt_init(lut.ctypes.data_as(ctypes.c_void_p)), "gdt_init")
+    _initialised_devices.add(idx)
+
+
+def _f3(v):
+    a = (ctypes.c_float * 3)(*[float(x) for x in v])
+    return a
+
+
+def _count(kind):
+    global launch_count
+    launch_count += KERNELS_PER_CALL[kind]
+
+
+# ---- K1 ----------------------------------------------------------------------------------------------
+
+def clahe_u8(rgb_hwc, mean, std, clip_limit=1.0, grid=8, out=None):
+    """[n,h,w,3] uint8 CUDA -> [n,3,h,w] float32: fused pil2np | apply_clahe | totensor | normalize."""
+    _require(rgb_hwc, torch.uint8, "rgb_hwc")
+    if rgb_hwc.dim() != 4 or rgb_hwc.shape[3] != 3:
+        raise GdtError("rgb_hwc must be [n, h, w, 3]")
+    n, h, w, _ = rgb_hwc.shape
+    ensure_init(rgb_hwc.device)
+    lib = load()
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=rgb_hwc.device)
+    else:
+        _require(out, torch.float32, "out")
+    with torch.cuda.device(rgb_hwc.device):
+        ws = _workspace(lib.gdt_clahe_workspace_bytes(n, h, w, grid), rgb_hwc.device)
+        check(lib.gdt_clahe_u8(_ptr(rgb_hwc), n, h, w, float(clip_limit), int(grid), _f3(mean), _f3(std), _ptr(out),
+                               _ptr(ws), ws.numel(), _stream()), "gdt_clahe_u8")
+    _count("clahe")
+    return out
+
+
+def clahe_f32(x_chw, in_mean, in_std, out_mean, out_std, clip_limit=1.0, grid=8, out=None):
+    """[n,3,h,w] float32 CUDA normalised with (in_mean, in_std) -> same shape, CLAHE applied, re-normalised."""
+    _require(x_chw, torch.float32, "x_chw")
+    if x_chw.dim() != 4 or x_chw.shape[1] != 3:
+        raise GdtError("x_chw must be [n, 3, h, w]")
+    n, _, h, w = x_chw.shape
+    ensure_init(x_chw.device)
+    lib = load()
+    if out is None:
+        out = torch.empty_like(x_chw)
+    with torch.cuda.device(x_chw.device):
+        ws = _workspace(lib.gdt_clahe_workspace_bytes(n, h, w, grid), x_chw.device)
+        check(lib.gdt_clahe_f32(_ptr(x_chw), n, h, w, float(clip_limit), int(grid), _f3(in_mean), _f3(in_std),
+                                _f3(out_mean), _f3(out_std), _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_clahe_f32")
+    _count("clahe")
+    return out
+
+
+# ---- K2 ----------------------------------------------------------------------------------------------
+
+def gem_whiten(fmaps, p, eps=1e-6, aggregate=False, msp_is_p=False, P=None, m=None, dim=None):
+    """fmaps: list (one per scale) of [n,c,h,w] float32 CUDA feature maps -> descriptors [n, dim] float32.
+    p: 1-element float32 CUDA tensor (GeM exponent, read on the device)."""
+    if isinstance(fmaps, torch.Tensor):
+        fmaps = [fmaps]
+    scales = len(fmaps)
+    if not 1 <= scales <= GDT_MAX_SCALES:
+        raise GdtError("1..%d scales supported" % GDT_MAX_SCALES)
+    fmaps = [_require(f, torch.float32, "fmap") for f in fmaps]
+    n, c = fmaps[0].shape[0], fmaps[0].shape[1]
+    for f in fmaps:
+        if f.dim() != 4 or f.shape[0] != n or f.shape[1] != c:
+            raise GdtError("all feature maps must be [n, c, h, w] with equal n and c")
+    dev = fmaps[0].device
+    _require(p, torch.float32, "p")
+    lib = load()
+    flags = (GDT_GEM_AGGREGATE if aggregate else 0) | (GDT_GEM_MSP_IS_P if msp_is_p else 0)
+    if P is not None:
+        _require(P, torch.float32, "P")
+        _require(m, torch.float32, "m")
+        dim = int(dim or P.shape[0])
+        if P.dim() != 2 or P.shape[1] != c or dim > P.shape[0] or m.numel() != c:
+            raise GdtError("whitening shapes do not match the feature maps")
+        ldP = P.stride(0)
+    else:
+        dim, ldP = c, 0
+    desc = torch.empty((n, dim), dtype=torch.float32, device=dev)
+    ptrs = (ctypes.c_void_p * scales)(*[f.data_ptr() for f in fmaps])
+    hs = (ctypes.c_int * scales)(*[int(f.shape[2]) for f in fmaps])
+    ws_ = (ctypes.c_int * scales)(*[int(f.shape[3]) for f in fmaps])
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_gem_whiten_workspace_bytes(n, c, scales, dim), dev)
+        check(lib.gdt_gem_whiten(ptrs, hs, ws_, n, c, scales, _ptr(p), float(eps), flags,
+                                 _ptr(P) if P is not None else None, int(ldP), _ptr(m) if m is not None else None,
+                                 dim, _ptr(desc), _ptr(ws), ws.numel(), _stream()), "gdt_gem_whiten")
+    _count("gem_whiten" if P is not None else "gem")
+    return desc
+
+
+# ---- K3 ----------------------------------------------------------------------------------------------
+
+def db_prepare(db):
+    """[ndb, d] float32 CUDA database shard -> (bf16 shadow [ndb, d], max row norm [1])."""
+    _require(db, torch.float32, "db")
+    ndb, d = db.shape
+    lib = load()
+    shadow = torch.empty((ndb, d), dtype=torch.bfloat16, device=db.device)
+    norm_max = torch.empty(1, dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        ws = _workspace(lib.gdt_db_prepare_workspace_bytes(ndb, d), db.device)
+        check(lib.gdt_db_prepare(_ptr(db), ndb, d, _ptr(shadow), _ptr(norm_max), _ptr(ws), ws.numel(), _stream()),
+              "gdt_db_prepare")
+    _count("db_prepare")
+    return shadow, norm_max
+
+
+def score_topk_workspace_bytes(nq, ndb, d, k):
+    return load().gdt_score_topk_workspace_bytes(nq, ndb, d, k)
+
+
+def score_topk(q, db, shadow, norm_max, k, index_base=0, ws=None, out=None):
+    """tcgen05 path. Returns (scores [nq,k] f32, idx [nq,k] i64, status [4] i32), all on the device, async."""
+    _require(q, torch.float32, "q")
+    _require(db, torch.float32, "db")
+    _require(shadow, torch.bfloat16, "shadow")
+    _require(norm_max, torch.float32, "norm_max")
+    nq, d = q.shape
+    ndb = db.shape[0]
+    if db.shape[1] != d or tuple(shadow.shape) != (ndb, d):
+        raise GdtError("q, db and shadow shapes do not match")
+    lib = load()
+    dev = q.device
+    if out is None:
+        scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        status = torch.empty(4, dtype=torch.int32, device=dev)
+    else:
+        scores, idx, status = out
+    with torch.cuda.device(dev):
+        if ws is None:
+            ws = _workspace(lib.gdt_score_topk_workspace_bytes(nq, ndb, d, k), dev)
+        check(lib.gdt_score_topk(_ptr(q), _ptr(db), _ptr(shadow), _ptr(norm_max), nq, ndb, d, k, int(index_base),
+                                 _ptr(scores), _ptr(idx), _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_score_topk")
+    _count("score_topk")
+    return scores, idx, status
+
+
+def score_topk_exact(q, db, k, index_base=0):
+    """CUDA-core exact path (fp64-accumulated). Materialises [nq, ndb] scores in the workspace."""
+    _require(q, torch.float32, "q")
+    _require(db, torch.float32, "db")
+    nq, d = q.shape
+    ndb = db.shape[0]
+    if db.shape[1] != d:
+        raise GdtError("q and db dimensions differ")
+    lib = load()
+    dev = q.device
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_score_topk_exact_workspace_bytes(nq, ndb, d, k), dev)
+        check(lib.gdt_score_topk_exact(_ptr(q), _ptr(db), nq, ndb, d, k, int(index_base), _ptr(scores), _ptr(idx),
+                                       _ptr(ws), ws.numel(), _stream()), "gdt_score_topk_exact")
+    _count("score_topk_exact")
+    return scores, idx
+
+
+def topk_merge(scores, idx):
+    """[g, nq, k] per-shard lists -> merged [nq, k]."""
+    _require(scores, torch.float32, "scores")
+    _require(idx, torch.int64, "idx")
+    g, nq, k = scores.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(load().gdt_topk_merge(_ptr(scores), _ptr(idx), g, nq, k, _ptr(out_s), _ptr(out_i), _stream()),
+              "gdt_topk_merge")
+    _count("topk_merge")
+    return out_s, out_i
+
+
+# ---- K4 ----------------------------------------------------------------------------------------------
+
+def probe_scores(q, db, probe_idx, index_base=0, out=None):
+    _require(q, torch.float32, "q")
+    _require(db, torch.float32, "db")
+    _require(probe_idx, torch.int64, "probe_idx")
+    nq, d = q.shape
+    pmax = probe_idx.shape[1]
+    if out is None:
+        out = torch.zeros((nq, pmax), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(load().gdt_probe_scores(_ptr(q), _ptr(db), nq, db.shape[0], d, int(index_base), _ptr(probe_idx), pmax,
+                                      _ptr(out), _stream()), "gdt_probe_scores")
+    _count("probe_scores")
+    return out
+
+
+def rank_counts(q, db, probe_idx, probe_score, index_base=0, out=None):
+    _require(q, torch.float32, "q")
+    _require(db, torch.float32, "db")
+    _require(probe_idx, torch.int64, "probe_idx")
+    _require(probe_score, torch.float32, "probe_score")
+    nq, d = q.shape
+    pmax = probe_idx.shape[1]
+    if out is None:
+        out = torch.zeros((nq, pmax), dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        check(load().gdt_rank_counts(_ptr(q), _ptr(db), nq, db.shape[0], d, int(index_base), _ptr(probe_idx),
+                                     _ptr(probe_score), pmax, _ptr(out), _stream()), "gdt_rank_counts")
+    _count("rank_counts")
+    return out
+
+
+def map_eval(pos_rank, junk_rank, npos, njunk, kappas):
+    _require(pos_rank, torch.int64, "pos_rank")
+    _require(junk_rank, torch.int64, "junk_rank")
+    _require(npos, torch.int32, "npos")
+    _require(njunk, torch.int32, "njunk")
+    nq = pos_rank.shape[0]
+    dev = pos_rank.device
+    kap = torch.tensor(list(kappas) or [1], dtype=torch.int32, device=dev)
+    nk = len(kappas)
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    prk = torch.empty((nq, max(nk, 1)), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(load().gdt_map_eval(_ptr(pos_rank), pos_rank.shape[1], _ptr(junk_rank), junk_rank.shape[1], _ptr(npos),
+                                  _ptr(njunk), nq, _ptr(kap), nk, _ptr(ap), _ptr(prk), _stream()), "gdt_map_eval")
+    _count("map_eval")
+    return ap, prk[:, :nk]
