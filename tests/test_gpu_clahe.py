@@ -1,0 +1,86 @@
+"""K1 parity (through the C ABI): bit-exact against the oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clahe_np as O
+from tests.util import MEAN, STD, golden, load_lut, synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_u8(imgs, clip=1.0, grid=8):
+    from gandtr_b200 import _lib
+    x = torch.from_numpy(np.stack(imgs)).cuda()
+    out = _lib.clahe_u8(x, MEAN, STD, clip, grid)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _assert_bits(a, b, what):
+    assert a.shape == b.shape and a.dtype == b.dtype == np.float32
+    bad = int((a.view(np.uint32) != b.view(np.uint32)).sum())
+    assert bad == 0, "%s: %d of %d floats differ (max abs %g)" % (what, bad, a.size, np.abs(a - b).max())
+
+
+def test_reference_golden_bit_exact():
+    g = golden("clahe_transform.npz")
+    n = len([k for k in g.files if k.startswith("img")])
+    for i in range(n):
+        out = _run_u8([g["img%d" % i]])[0]
+        _assert_bits(out, g["out%d" % i], "golden case %d %s" % (i, g["img%d" % i].shape))
+
+
+@pytest.mark.parametrize("kind,h,w", [("smooth", 96, 128), ("noise", 64, 64), ("dark", 120, 160), ("smooth", 61, 77),
+                                      ("noise", 37, 53), ("smooth", 100, 130), ("smooth", 8, 8), ("smooth", 72, 100),
+                                      ("dark", 50, 1100)])
+def test_oracle_bit_exact_shapes(kind, h, w):
+    lut = load_lut()
+    img = synth_image(100 + h + w, h, w, kind)
+    out = _run_u8([img])[0]
+    _assert_bits(out, O.transform_u8(img, lut, MEAN, STD), "%s %dx%d" % (kind, h, w))
+
+
+def test_batch_and_clip_limits():
+    lut = load_lut()
+    imgs = [synth_image(200 + i, 80, 120, k) for i, k in enumerate(["smooth", "noise", "dark"])]
+    for clip in (1.0, 4.0, 0.0):
+        out = _run_u8(imgs, clip=clip)
+        for i, img in enumerate(imgs):
+            _assert_bits(out[i], O.transform_u8(img, lut, MEAN, STD, clip_limit=clip), "clip %g img %d" % (clip, i))
+
+
+def test_full_size_image_bit_exact():
+    """BASELINE config size (1024x768)."""
+    lut = load_lut()
+    img = synth_image(7, 768, 1024, "smooth")
+    out = _run_u8([img])[0]
+    _assert_bits(out, O.transform_u8(img, lut, MEAN, STD), "768x1024")
+
+
+def test_clahe_post_float_variant_bit_exact():
+    from gandtr_b200 import _lib
+    g = golden("clahe_post.npz")
+    x0 = torch.from_numpy(g["x0"][None]).cuda()
+    y0 = _lib.clahe_f32(x0, [0.5] * 3, [0.5] * 3, [0.5] * 3, [0.5] * 3, 1.0, 8)[0].cpu().numpy()
+    _assert_bits(y0, g["y0"], "clahepost 0.5/0.5")
+    x1 = torch.from_numpy(g["x1"][None]).cuda()
+    y1 = _lib.clahe_f32(x1, MEAN, STD, MEAN, STD, 4.0, 8)[0].cpu().numpy()
+    _assert_bits(y1, g["y1"], "clahepost imagenet clip 4")
+
+
+def test_idempotent_properties_full_batch():
+    """Size-independent properties at bench scale: determinism and batch independence."""
+    imgs = [synth_image(300 + i, 768, 1024, "smooth" if i % 4 else "noise") for i in range(4)]
+    a = _run_u8(imgs)
+    b = _run_u8(imgs[::-1])[::-1]
+    assert np.array_equal(a, b)
+    assert np.isfinite(a).all()
+
+
+def test_errors_are_loud():
+    from gandtr_b200 import _lib
+    with pytest.raises(_lib.GdtError):
+        _lib.clahe_u8(torch.zeros((1, 8, 8, 3), dtype=torch.uint8), MEAN, STD)      # CPU tensor: no fallback
+    with pytest.raises(_lib.GdtError):
+        _lib.clahe_u8(torch.zeros((1, 8, 8, 3), dtype=torch.float32).cuda(), MEAN, STD)

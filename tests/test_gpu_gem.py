@@ -1,0 +1,71 @@
+"""K2 parity (through the C ABI) against the oracle and the reference's golden outputs; tolerance 1e-5 relative
+(north_star), plus an absolute floor of 1e-7 for near-zero components."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import descriptors_np as D
+from tests.util import golden
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 2e-7
+
+
+def _run(fmaps, p, **kw):
+    from gandtr_b200 import _lib
+    fm = [torch.from_numpy(np.ascontiguousarray(f)).cuda() for f in fmaps]
+    pt = torch.tensor([p], dtype=torch.float32, device="cuda")
+    P, m = kw.pop("P", None), kw.pop("m", None)
+    if P is not None:
+        P = torch.tensor(P, dtype=torch.float32, device="cuda")
+        m = torch.tensor(m, dtype=torch.float32, device="cuda").reshape(-1)
+    out = _lib.gem_whiten(fm, pt, 1e-6, P=P, m=m, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_reference_golden():
+    g = golden("descriptors.npz")
+    ci = 0
+    while "c%d_p" % ci in g.files:
+        fm = []
+        while "c%d_fmap%d" % (ci, len(fm)) in g.files:
+            fm.append(g["c%d_fmap%d" % (ci, len(fm))])
+        p = float(g["c%d_p" % ci])
+        np.testing.assert_allclose(_run(fm[:1], p), g["c%d_plain" % ci], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(_run(fm, p, aggregate=True, msp_is_p=True), g["c%d_agg" % ci], rtol=RTOL, atol=ATOL)
+        wh = _run(fm, p, aggregate=True, msp_is_p=True, P=g["c%d_P" % ci], m=g["c%d_m" % ci], dim=int(g["c%d_dim" % ci]))
+        np.testing.assert_allclose(wh, g["c%d_whiten" % ci], rtol=2e-5, atol=2e-6)
+        ci += 1
+    assert ci == 3
+
+
+@pytest.mark.parametrize("n,c,sizes,p", [(3, 512, [(48, 64)], 3.0), (2, 2048, [(24, 32), (17, 23), (12, 16)], 3.0),
+                                         (2, 512, [(48, 64), (33, 45), (24, 32)], 2.92), (1, 96, [(5, 7)], 1.0),
+                                         (4, 64, [(3, 3)], 2.0), (2, 40, [(1, 1)], 3.0)])
+def test_oracle_shapes(n, c, sizes, p):
+    rs = np.random.RandomState(n * 1000 + c)
+    fm = [(np.abs(rs.normal(0, 1, (n, c, h, w))) * (rs.rand(n, c, 1, 1) > 0.1)).astype(np.float32) for h, w in sizes]
+    multi = len(sizes) > 1
+    P = (rs.normal(0, 1, (c, c)) / np.sqrt(c))
+    m = 0.05 * rs.rand(c, 1)
+    np.testing.assert_allclose(_run(fm[:1], p), D.descriptor_pipeline(fm[:1], p=p), rtol=RTOL, atol=ATOL)
+    agg = _run(fm, p, aggregate=True, msp_is_p=multi)
+    np.testing.assert_allclose(agg, D.descriptor_pipeline(fm, p=p, aggregate=True, msp_is_p=multi), rtol=RTOL, atol=ATOL)
+    dim = c - 8
+    wh = _run(fm, p, aggregate=True, msp_is_p=multi, P=P, m=m, dim=dim)
+    ref = D.descriptor_pipeline(fm, p=p, aggregate=True, msp_is_p=multi, P=P, m=m, dimensions=dim)
+    np.testing.assert_allclose(wh, ref, rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(np.linalg.norm(wh, axis=1), 1.0, atol=1e-5)
+
+
+def test_unaligned_rows_and_offsets():
+    """Feature-map rows that do not start on 16-byte boundaries (odd h*w) and a sliced storage offset."""
+    rs = np.random.RandomState(5)
+    base = torch.from_numpy(np.abs(rs.normal(0, 1, (1 + 2 * 40 * 7 * 9,))).astype(np.float32)).cuda()
+    fm = base[1:].view(2, 40, 7, 9)
+    from gandtr_b200 import _lib
+    with pytest.raises(_lib.GdtError):
+        _lib.gem_whiten([fm.permute(0, 1, 3, 2)], torch.tensor([3.0], device="cuda"))   # non-contiguous
+    out = _lib.gem_whiten([fm], torch.tensor([3.0], device="cuda")).cpu().numpy()
+    np.testing.assert_allclose(out, D.descriptor_pipeline([fm.cpu().numpy()], p=3.0), rtol=RTOL, atol=ATOL)

@@ -1,0 +1,77 @@
+"""K4 parity (through the C ABI): ranks of ground-truth ids and AP / P@k against the reference's golden numbers."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_np as R
+from tests.util import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad(lists, fill=-1):
+    n = max(1, max(len(x) for x in lists))
+    return np.array([np.pad(np.asarray(x, dtype=np.int64), (0, n - len(x)), constant_values=fill) for x in lists])
+
+
+def _ap_on_gpu(q, db, ok, junk, kappas, shards=1):
+    from gandtr_b200 import _lib
+    nq = q.shape[0]
+    probes = _pad([np.concatenate([o, j]) for o, j in zip(ok, junk)])
+    pd = torch.from_numpy(probes).cuda()
+    qd = torch.from_numpy(q).cuda()
+    bounds = np.linspace(0, db.shape[0], shards + 1).astype(int)
+    dbs = [torch.from_numpy(db[a:b]).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+    ps = torch.zeros(probes.shape, dtype=torch.float32, device="cuda")
+    for a, dbd in zip(bounds[:-1], dbs):
+        _lib.probe_scores(qd, dbd, pd, index_base=int(a), out=ps)
+    before = torch.zeros(probes.shape, dtype=torch.int64, device="cuda")
+    for a, dbd in zip(bounds[:-1], dbs):
+        _lib.rank_counts(qd, dbd, pd, ps, index_base=int(a), out=before)
+    before = before.cpu().numpy()
+    pos = _pad([before[i, :len(o)] for i, o in enumerate(ok)], 0)
+    jnk = _pad([before[i, len(o):len(o) + len(j)] for i, (o, j) in enumerate(zip(ok, junk))], 0)
+    npos = torch.tensor([len(o) for o in ok], dtype=torch.int32, device="cuda")
+    njunk = torch.tensor([len(j) for j in junk], dtype=torch.int32, device="cuda")
+    ap, prk = _lib.map_eval(torch.from_numpy(pos).cuda(), torch.from_numpy(jnk).cuda(), npos, njunk, kappas)
+    return ap.cpu().numpy(), prk.cpu().numpy(), before
+
+
+@pytest.mark.parametrize("shards", [1, 3])
+def test_revisited_protocol_matches_reference_golden(shards):
+    g = golden("map_eval.npz")
+    q, db = g["q"], g["db"]
+    easy = [x[x >= 0] for x in g["easy"]]
+    hard = [x[x >= 0] for x in g["hard"]]
+    junk = [x[x >= 0] for x in g["junk"]]
+    # our total order vs the oracle's full ranking
+    ranks = R.full_ranks(R.scores_exact(q, db))
+    for name, ok, jk in (("easy", easy, [np.concatenate([j, h]) for j, h in zip(junk, hard)]),
+                         ("medium", [np.concatenate([e, h]) for e, h in zip(easy, hard)], junk),
+                         ("hard", hard, [np.concatenate([j, e]) for j, e in zip(junk, easy)])):
+        ap, prk, before = _ap_on_gpu(q, db, ok, jk, [1, 5, 10], shards)
+        m, aps, mpr, prs = R.compute_map(ranks, [{"ok": o, "junk": j} for o, j in zip(ok, jk)], [1, 5, 10])
+        np.testing.assert_array_equal(ap, aps)                 # float64, same op order: bit-equal incl. NaN
+        np.testing.assert_array_equal(prk, prs)
+        # and against the unmodified reference (its ranks come from a float32 sgemm: allow near-tie swaps)
+        np.testing.assert_allclose(ap, g["ap_" + name], rtol=0, atol=1e-6, equal_nan=True)
+        valid = ~np.isnan(ap)
+        assert abs(ap[valid].sum() / valid.sum() - float(g["map_" + name])) < 1e-6
+        # positions themselves
+        for i, o in enumerate(ok):
+            inv = np.empty(db.shape[0], dtype=np.int64)
+            inv[ranks[:, i]] = np.arange(db.shape[0])
+            assert np.array_equal(before[i, :len(o)], inv[o])
+
+
+def test_old_protocol_with_empty_query():
+    g = golden("map_eval.npz")
+    q, db = g["q"], g["db"]
+    ok = [np.concatenate([e[e >= 0], h[h >= 0]]) for e, h in zip(g["easy"], g["hard"])]
+    junk = [x[x >= 0] for x in g["junk"]]
+    ok[3] = np.array([], dtype=np.int64)
+    ap, _, _ = _ap_on_gpu(q, db, ok, junk, [])
+    assert np.isnan(ap[3])
+    np.testing.assert_allclose(ap, g["old_ap"], rtol=0, atol=1e-6, equal_nan=True)
+    valid = ~np.isnan(ap)
+    assert abs(ap[valid].sum() / valid.sum() - float(g["old_map"])) < 1e-6
