@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Benchmark of the gandtr retrieval hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (oracle/reference_cpu.py)
+
+Headline metric (BASELINE.json): images/sec of CLAHE + GeM + whitening. One step = one batch of `--batch` synthetic
+1024x768 uint8 images through K1 (fused pil2np|apply_clahe:1.0|totensor|normalize) plus the matching batch of
+ResNet-101 final feature maps [B,2048,24,32] through K2 (GeM + L2N + aggregation + learned whitening 2048->2048).
+The conv backbone between the two is stock PyTorch and outside the path (BASELINE.json north_star), so the feature maps
+are synthetic resident tensors. Images are independent: ranks shard them with no collective (weak scaling).
+`retrieval` (second half of the metric): top-100 queries/sec of 10k queries against a 1M x 2048 database, row-sharded
+over the ranks, per-shard lists merged after one NCCL all_gather.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 768, 1024                    # 1024 px synthetic images (BASELINE configs[1])
+C_FEAT, FH, FW = 2048, 24, 32       # ResNet-101 final feature map at 1024x768
+MS_SIZES = [(24, 32), (17, 23), (12, 16)]   # scales 1, 1/sqrt2, 1/2
+DB_ROWS, DB_DIM, N_QUERIES, TOPK = 1_000_000, 2048, 10_000, 100
+MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+K1_BYTES_PER_IMG = 15 * H * W
+K2_BYTES_PER_IMG = 4 * C_FEAT * FH * FW + 4 * C_FEAT
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU")
+    ap.add_argument("--db-rows", type=int, default=DB_ROWS)
+    ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=48, help="images in the bounded CPU sample")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- inputs
+
+def synth_images_torch(n, seed, device):
+    """Smooth sinusoid + noise family of SURVEY 8(d), generated with torch (host or device)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    yy = torch.arange(H, device=device, dtype=torch.float32).view(1, H, 1, 1)
+    xx = torch.arange(W, device=device, dtype=torch.float32).view(1, 1, W, 1)
+    cc = torch.arange(3, device=device, dtype=torch.float32).view(1, 1, 1, 3)
+    base = 128 + 70 * (torch.sin(xx / (37.0 + 5 * cc)) + torch.cos(yy / (23.0 + 3 * cc)))
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=device)
+    for i in range(n):
+        noise = torch.randn((1, H, W, 3), generator=g, device=device) * 8.0
+        gain = 0.6 + 0.8 * torch.rand((1, 1, 1, 1), generator=g, device=device)
+        out[i] = (base * gain + noise).clamp_(0, 255).to(torch.uint8)[0]
+    return out
+
+
+def synth_db_rows(lo, hi, d, device, block=65536):
+    """Unit-norm database rows [lo, hi): generated per 64k-row block keyed by the block id, so the data do not depend
+    on how the rows are sharded."""
+    import torch
+    out = torch.empty((hi - lo, d), dtype=torch.float32, device=device)
+    b = lo // block
+    while b * block < hi:
+        g = torch.Generator(device=device).manual_seed(1000 + b)
+        rows = torch.randn((block, d), generator=g, device=device)
+        rows /= rows.norm(dim=1, keepdim=True)
+        a0, a1 = max(lo, b * block), min(hi, (b + 1) * block)
+        out[a0 - lo:a1 - lo] = rows[a0 - b * block:a1 - b * block]
+        b += 1
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = str(index), [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for t, r in self.rows:
+            if len(r) < 9 or not any(a - 0.05 <= t <= b + 0.25 for a, b in windows):
+                continue
+            try:
+                sm.append(float(r[1])); smax = float(r[2]); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_extract_sample(n_images, seed=7):
+    """Reference CPU implementation (oracle/reference_cpu.py: cv2 + torch CPU ops, as the reference calls them) on a
+    bounded sample of the bench workload. Returns (images/sec, threads, description)."""
+    import numpy as np
+    import torch
+    from oracle import reference_cpu as RC
+    try:
+        import cv2
+        cv_threads = cv2.getNumThreads()
+    except Exception:
+        cv_threads = 1
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    imgs = synth_images_torch(min(n_images, 8), seed, "cpu").numpy()
+    rs = np.random.RandomState(seed)
+    P = torch.from_numpy((rs.normal(0, 1, (C_FEAT, C_FEAT)) / np.sqrt(C_FEAT)).astype(np.float32))
+    m = torch.from_numpy((0.05 * rs.rand(C_FEAT, 1)).astype(np.float32))
+    fm = torch.rand((min(n_images, 8), C_FEAT, FH, FW))
+    RC.transform_cv2(imgs[0], MEAN, STD)                                    # warm-up (table init inside cv2)
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        RC.transform_cv2(imgs[i % len(imgs)], MEAN, STD)
+    t_k1 = time.perf_counter() - t0
+    with torch.no_grad():
+        RC.whiten_torch(RC.aggregate_torch([RC.gem_l2n_torch(fm[:1], 3.0)], 1.0), P, m)
+        t0 = time.perf_counter()
+        for i in range(n_images):                                           # batch size 1, as the reference (8a16)
+            j = i % fm.shape[0]
+            RC.whiten_torch(RC.aggregate_torch([RC.gem_l2n_torch(fm[j:j + 1], 3.0)], 1.0), P, m)
+        t_k2 = time.perf_counter() - t0
+    desc = ("%d synthetic 1024x768 images through cv2 CLAHE transform (%.1f ms/img) + torch-CPU GeM/L2N/whiten on "
+            "[1,2048,24,32] maps (%.1f ms/img); cv2 threads=%d torch threads=%d"
+            % (n_images, 1e3 * t_k1 / n_images, 1e3 * t_k2 / n_images, cv_threads, threads))
+    return n_images / (t_k1 + t_k2), max(threads, cv_threads), desc
+
+
+def cpu_retrieval_sample(db_rows, nq=32):
+    import numpy as np
+    from oracle import reference_cpu as RC
+    rg = np.random.default_rng(3)
+    rows = min(db_rows, 250_000)
+    db = rg.standard_normal((rows, DB_DIM), dtype=np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    q = rg.standard_normal((nq, DB_DIM), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t0 = time.perf_counter()
+    RC.rank_numpy(db.T, q.T, TOPK)
+    dt = (time.perf_counter() - t0) * (db_rows / rows)                      # linear in rows (argsort: n log n, ~+10%)
+    return nq / dt, "np.dot + np.argsort, %d queries x %d rows x %d (scaled linearly to %d rows)" % (nq, rows, DB_DIM, db_rows)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(args.steps, 1), args.warmup
+    per_step = max(2, args.cpu_images // max(steps, 1))
+    for _ in range(min(warm, 1)):
+        cpu_extract_sample(2)
+    t0 = time.perf_counter()
+    vals = [cpu_extract_sample(per_step) for _ in range(steps)]
+    dt = time.perf_counter() - t0
+    ips = statistics.median(v[0] for v in vals)
+    line = {"impl": "reference", "metric": "images/sec CLAHE+GeM+whiten", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, per_step),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": vals[0][1], "kind": "port", "sample": vals[0][2]},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if not args.no_retrieval:
+        qps, what = cpu_retrieval_sample(args.db_rows)
+        line["retrieval"] = {"metric": "1M-db top-100 queries/sec", "value": qps, "unit": "queries/s", "sample": what}
+    print(json.dumps(line))
+
+
+def workload_config(args, batch):
+    return {"workload": "gem_resnet101_cyclegan descriptor extraction, synthetic 1024x768 batch, single-scale: "
+                        "K1 CLAHE transform on [B,768,1024,3] u8 + K2 GeM+L2N+whiten(2048->2048) on [B,2048,24,32] f32 "
+                        "(stock conv backbone between them excluded)",
+            "batch_per_gpu": batch, "image": "1024x768", "feature_map": [C_FEAT, FH, FW], "whiten_dim": C_FEAT,
+            "l2_policy": "inputs larger than L2 (u8 batch + feature maps + f32 output > 1 GB per step)",
+            "retrieval": {"db_rows": args.db_rows, "dim": DB_DIM, "queries": args.queries, "k": TOPK,
+                          "sharding": "row-wise over ranks, all_gather + merge"}}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gandtr_b200 import _lib
+    from gandtr_b200.retrieval import ShardedIndex, shard_bounds
+    from gandtr_b200.transforms import initialize_transforms
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (gandtr_b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    tc_peak, tc_src = (peaks["bf16_tflops"], "measured") if "bf16_tflops" in peaks else (1590.0, "fallback")
+
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    transform = initialize_transforms("pil2np | apply_clahe:1.0 | totensor | normalize", [MEAN, STD], device=dev)
+    imgs = synth_images_torch(B, 100 + rank, dev)
+    imgs_host = imgs.cpu().pin_memory()
+    fmap = torch.rand((B, C_FEAT, FH, FW), device=dev)
+    fmaps_ms = [fmap] + [torch.rand((B, C_FEAT, h, w), device=dev) for h, w in MS_SIZES[1:]]
+    p = torch.tensor([3.0], device=dev)
+    gP = torch.Generator(device=dev).manual_seed(5)
+    Pm = torch.randn((C_FEAT, C_FEAT), generator=gP, device=dev) / C_FEAT ** 0.5
+    mm = torch.rand(C_FEAT, generator=gP, device=dev) * 0.05
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    desc_host = torch.empty((B, C_FEAT), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step(ev=None):
+        transform.batch(imgs, out=out)
+        if ev is not None:
+            ev.record()
+        return _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm)
+
+    def step_e2e():
+        x = imgs_host.to(dev, non_blocking=True)
+        transform.batch(x, out=out)
+        d = _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm)
+        desc_host.copy_(d, non_blocking=True)
+
+    def timed(fn, steps, warm, mids=None):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_a = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(*(() if mids is None else (mids[i],)))
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), (t_a, time.time())
+
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    windows = []
+
+    # ---- headline: device-resident steps, K1 / K2 split by one event between them ----
+    launches0 = _lib.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+
+    def step_split(i):
+        starts[i].record()
+        step(mids[i])
+        ends[i].record()
+
+    for _ in range(Wm):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_before = _lib.launch_count
+    t_a = time.time()
+    e0.record()
+    for i in range(K):
+        step_split(i)
+    e1.record()
+    barrier()
+    windows.append((t_a, time.time()))
+    gpu_launches = _lib.launch_count - launches_before
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    k1_ms = statistics.mean(starts[i].elapsed_time(mids[i]) for i in range(K))
+    k2_ms = statistics.mean(mids[i].elapsed_time(ends[i]) for i in range(K))
+    value = world * B * K / (total_ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host u8 in, descriptors back to pinned host ----
+    e2e_ms, w = timed(step_e2e, K, Wm)
+    windows.append(w)
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+
+    # ---- multi-scale variant of K2 (reported, not the headline) ----
+    def step_ms():
+        return _lib.gem_whiten(fmaps_ms, p, aggregate=True, msp_is_p=True, P=Pm, m=mm)
+    ms_ms, w = timed(step_ms, K, Wm)
+    windows.append(w)
+
+    line = {
+        "metric": "images/sec CLAHE+GeM+whiten", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
+        "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
+                "d2h_bytes_per_step": B * C_FEAT * 4, "ms_per_step": e2e_ms / K},
+        "gpu_launches": gpu_launches,
+        "roofline": {"kernel": "K1 clahe_hist_kernel + clahe_apply_kernel (one gdt_clahe_u8 call)", "bound": "hbm",
+                     "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "peak_source": hbm_src, "traffic": None, "ms_per_launch_pair": k1_ms,
+                     "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
+        "roofline_k2": {"kernel": "K2 gem_pool + finalize + whiten (one gdt_gem_whiten call, single-scale)",
+                        "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "ms_per_call": k2_ms,
+                        "multi_scale": {"ms_per_call": ms_ms / K, "achieved": B * (4 * C_FEAT * sum(h * w for h, w in MS_SIZES) + 4 * C_FEAT) / (ms_ms / K * 1e-3) / 1e9}},
+    }
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / hbm_peak
+    line["roofline_k2"]["frac"] = line["roofline_k2"]["achieved"] / hbm_peak
+
+    # ---- retrieval: 10k queries vs the row-sharded 1M x 2048 database ----
+    if not args.no_retrieval:
+        del out, fmaps_ms
+        torch.cuda.empty_cache()
+        lo, hi = shard_bounds(args.db_rows, world, rank)
+        index = ShardedIndex(synth_db_rows(lo, hi, DB_DIM, dev), n_total=args.db_rows, index_base=lo)
+        gq = torch.Generator(device="cpu").manual_seed(3)
+        q_host = torch.randn((args.queries, DB_DIM), generator=gq)
+        q_host = (q_host / q_host.norm(dim=1, keepdim=True)).pin_memory()
+        q = q_host.to(dev)
+        res_s = torch.empty((args.queries, TOPK), dtype=torch.float32).pin_memory()
+        res_i = torch.empty((args.queries, TOPK), dtype=torch.int64).pin_memory()
+        rK, rW = max(3, min(K, 5)), 3
+        l0 = _lib.launch_count
+        r_ms, w = timed(lambda: index.search(q, TOPK), rK, rW)
+        windows.append(w)
+        r_launches = (_lib.launch_count - l0) * rK // (rK + rW)
+
+        def search_e2e():
+            s, i = index.search(q_host.to(dev, non_blocking=True), TOPK)
+            res_s.copy_(s, non_blocking=True)
+            res_i.copy_(i, non_blocking=True)
+        re_ms, w = timed(search_e2e, rK, rW)
+        windows.append(w)
+        flops = 2.0 * args.queries * args.db_rows * DB_DIM
+        line["retrieval"] = {
+            "metric": "1M-db top-100 queries/sec", "value": args.queries * rK / (r_ms * 1e-3), "unit": "queries/s",
+            "ms_per_search": r_ms / rK, "steps": rK, "warmup": rW, "gpu_launches": r_launches,
+            "e2e": {"value": args.queries * rK / (re_ms * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": args.queries * DB_DIM * 4, "d2h_bytes_per_step": args.queries * TOPK * 12},
+            "status": index.shard.last_status,
+            "roofline": {"kernel": "K3 score_filter_kernel (tcgen05 bf16 coarse pass) + exact re-score/finalise",
+                         "bound": "tensor", "achieved": flops / world / (r_ms / rK * 1e-3) / 1e12, "peak": tc_peak,
+                         "unit": "TFLOP/s", "peak_source": tc_src + " bf16 burst", "note": "per GPU; algorithmic flops 2*nq*ndb*d"}}
+        line["retrieval"]["roofline"]["frac"] = line["retrieval"]["roofline"]["achieved"] / tc_peak
+        del index
+
+    if rank == 0:
+        line["clocks"] = sampler.stop(windows)
+        if world == 1 and not args.no_cpu_baseline:
+            ips, cores, what = cpu_extract_sample(args.cpu_images)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": what}
+            if not args.no_retrieval:
+                qps, what = cpu_retrieval_sample(args.db_rows)
+                line["retrieval"]["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(),
+                                                     "kind": "port", "sample": what}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

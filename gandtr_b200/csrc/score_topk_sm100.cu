@@ -52,10 +52,16 @@ struct QMeta {
     float pad;
 };
 
-__host__ __device__ inline int cand_capacity(int k) {
-    int c = 16 * k;
+// Per-query candidate capacity. Every database stripe of a query tile starts from the threshold published
+// so far (initially -inf), so its first tile can insert all kBlockN rows and a few multiples of k follow
+// before its histogram threshold bites: capacity grows with the number of concurrently started stripes.
+__host__ __device__ inline int cand_capacity(int k, int n_stripes) {
+    long long c = 16LL * k;
+    const long long per_stripe = (long long)n_stripes * (kBlockN + 4LL * k);
+    if (c < per_stripe) c = per_stripe;
     if (c < 4096) c = 4096;
-    return next_pow2(c);
+    if (c > (1 << 22)) c = 1 << 22;
+    return next_pow2((int)c);
 }
 __host__ __device__ inline int survivor_capacity(int k) {
     int c = 4 * k;
@@ -560,11 +566,11 @@ struct TopkLayout {
     int cap;
 };
 
-static TopkLayout topk_layout(int nq, int d, int k) {
+static TopkLayout topk_layout(int nq, int d, int k, int n_stripes) {
     TopkLayout L;
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); const size_t r = off; off += bytes; return r; };
-    L.cap = cand_capacity(k);
+    L.cap = cand_capacity(k, n_stripes);
     L.qb = take((size_t)nq * d * 2);
     L.meta = take((size_t)nq * sizeof(QMeta));
     L.tau = take((size_t)nq * 4);
@@ -621,9 +627,10 @@ extern "C" int gdt_db_prepare(const float* db, long long ndb, int d, void* db_bf
 }
 
 extern "C" size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k) {
-    (void)ndb;
-    if (nq <= 0 || d <= 0 || k <= 0) return 0;
-    return topk_layout(nq, d, k).total + 256;
+    if (nq <= 0 || ndb <= 0 || d <= 0 || k <= 0) return 0;
+    int n_stripes, stripe_len;
+    plan_items(ceil_div(nq, kBlockM), (int)ceil_div_ll(ndb, kBlockN), sm_count_current_device(), n_stripes, stripe_len);
+    return topk_layout(nq, d, k, n_stripes).total + 256;
 }
 
 extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_bf16, const float* db_norm_max, int nq,
@@ -641,7 +648,12 @@ extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_bf
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
     if (ws_bytes < gdt_score_topk_workspace_bytes(nq, ndb, d, k) || (((uintptr_t)ws) & 255)) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
-    const TopkLayout L = topk_layout(nq, d, k);
+    FilterParams P;
+    P.n_qtiles = ceil_div(nq, kBlockM);
+    P.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
+    const int sms = sm_count_current_device();
+    plan_items(P.n_qtiles, P.n_dtiles, sms, P.n_stripes, P.stripe_len);
+    const TopkLayout L = topk_layout(nq, d, k, P.n_stripes);
     char* base = (char*)ws;
     __nv_bfloat16* qb = (__nv_bfloat16*)(base + L.qb);
     QMeta* meta = (QMeta*)(base + L.meta);
@@ -659,12 +671,7 @@ extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_bf
     rc = make_bf16_map(&map_db, db_bf16, ndb, d, kBlockN);
     if (rc != GDT_OK) return rc;
 
-    FilterParams P;
     P.nq = nq; P.d = d; P.k = k; P.cap = L.cap; P.ndb = ndb;
-    P.n_qtiles = ceil_div(nq, kBlockM);
-    P.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
-    const int sms = sm_count_current_device();
-    plan_items(P.n_qtiles, P.n_dtiles, sms, P.n_stripes, P.stripe_len);
     P.n_items = P.n_stripes * P.n_qtiles;
     P.n_kblocks = ceil_div(d, kBlockK);
     P.meta = meta; P.tau = tau; P.cnt = cnt; P.hist = hist; P.cand = cand;

@@ -1,0 +1,253 @@
+"""Query x database scoring, ranking and mAP on row-sharded databases.
+
+Replaces the tail of `CirDatasetAp.__call__` (mdir/components/optim/score/cirscore.py:66-73):
+    scores = np.dot(vecs.T, qvecs); ranks = np.argsort(-scores, axis=0); compute_map_and_print(dataset, ranks, gnd)
+and the consumers of `ranks` inside mdir/external/cirtorch/utils/evaluate.py:39-152.
+
+Layout: the database is sharded ROW-WISE over the ranks of a torch.distributed group (rank r owns the global rows
+[lo_r, hi_r) of `shard_bounds`), queries are replicated (broadcast from rank 0), every rank runs the fused
+score + top-k kernel on its shard, the per-shard (score, global index) lists are exchanged with ONE all_gather of
+[nq, k] and merged by `gdt_topk_merge`. mAP needs the full-ranking positions of the ground-truth ids only: per-shard
+"rows that sort before" counts are summed with one all_reduce and fed to `gdt_map_eval`. The full ndb x nq score /
+rank matrices of the reference are never materialised.
+
+The compute callables are injectable (`ops=`) so the collective plumbing can be exercised on CPU/gloo in the tests;
+the default `CudaOps` calls libgandtr_b200.so and raises when it is missing -- there is no CPU fallback in the
+product.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_bounds", "CudaOps", "DatabaseShard", "ShardedIndex", "evaluate_map", "compute_map_and_print",
+           "TC_MIN_WORK"]
+
+# below this many multiply-adds the exact CUDA-core kernel is used instead of the tcgen05 pipeline
+TC_MIN_WORK = 1 << 24
+
+
+def shard_bounds(n_total, world_size, rank):
+    """Contiguous block partition of `n_total` rows: rank r owns [lo, hi). Sizes differ by at most one."""
+    base, rem = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+class CudaOps:
+    """The product's compute: every method is one or more launches of libgandtr_b200.so kernels."""
+
+    def prepare(self, db):
+        from . import _lib
+        d = db.shape[1]
+        if d % 8 == 0 and d <= 8192 and db.shape[0] > 0:
+            shadow, norm_max = _lib.db_prepare(db)
+            return {"shadow": shadow, "norm_max": norm_max}
+        return {}
+
+    def local_topk(self, q, shard, k):
+        """(scores [nq,k], global idx [nq,k]) of one shard; exact ordering (score desc, index asc)."""
+        from . import _lib
+        db, aux, base = shard.db, shard.aux, shard.index_base
+        nq, d = q.shape
+        ndb = db.shape[0]
+        if ndb == 0:
+            return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device),
+                    torch.full((nq, k), -1, dtype=torch.int64, device=q.device))
+        use_tc = "shadow" in aux and k <= 1024 and nq * ndb * d >= TC_MIN_WORK and base + ndb <= 0xFFFFFFFF
+        if not use_tc:
+            return self._exact_chunked(q, db, k, base)
+        s, i, st = _lib.score_topk(q, db, aux["shadow"], aux["norm_max"], k, index_base=base)
+        status = st.cpu()  # one small sync per search: the status word decides whether a repair pass is needed
+        shard.last_status = status.tolist()
+        if int(status[0]) != 0:
+            # candidate overflow (massive ties / adversarial data): re-score exactly the flagged queries
+            bad = torch.nonzero(i[:, 0] == -2).flatten()
+            if bad.numel():
+                se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
+                s[bad] = se
+                i[bad] = ie
+        return s, i
+
+    @staticmethod
+    def _exact_chunked(q, db, k, base):
+        from . import _lib
+        # the exact kernel materialises [nq_chunk, ndb] scores in its workspace: bound it to ~1 GiB
+        ndb = db.shape[0]
+        step = max(1, min(q.shape[0], (1 << 28) // max(ndb, 1)))
+        outs = [_lib.score_topk_exact(q[a:a + step].contiguous(), db, k, index_base=base)
+                for a in range(0, q.shape[0], step)]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+    def merge(self, scores, idx):
+        from . import _lib
+        return _lib.topk_merge(scores.contiguous(), idx.contiguous())
+
+    def probe_scores(self, q, shard, probe_idx, out):
+        from . import _lib
+        if shard.db.shape[0]:
+            _lib.probe_scores(q, shard.db, probe_idx, index_base=shard.index_base, out=out)
+        return out
+
+    def rank_counts(self, q, shard, probe_idx, probe_score, out):
+        from . import _lib
+        if shard.db.shape[0]:
+            _lib.rank_counts(q, shard.db, probe_idx, probe_score, index_base=shard.index_base, out=out)
+        return out
+
+    def map_eval(self, pos_rank, junk_rank, npos, njunk, kappas):
+        from . import _lib
+        return _lib.map_eval(pos_rank, junk_rank, npos, njunk, kappas)
+
+
+class DatabaseShard:
+    """Rows [index_base, index_base + n) of the database, resident in HBM: fp32 rows + the bf16 shadow used by the
+    tcgen05 coarse pass (6 bytes per element in total)."""
+
+    def __init__(self, db, index_base=0, ops=None):
+        self.ops = ops or CudaOps()
+        self.db = db.contiguous()
+        self.index_base = int(index_base)
+        self.aux = self.ops.prepare(self.db)
+        self.last_status = None
+
+    @property
+    def rows(self):
+        return self.db.shape[0]
+
+
+class ShardedIndex:
+    """Row-sharded database over a process group. `search` is the drop-in for
+    `np.argsort(-np.dot(vecs.T, qvecs), axis=0)[:k]` (cirscore.py:71-72), returned query-major."""
+
+    def __init__(self, local_db, n_total=None, group=None, ops=None, index_base=None):
+        self.group = group
+        self.world, self.rank = _world(group)
+        self.ops = ops or CudaOps()
+        if n_total is None:
+            n_total = self._sum_int(local_db.shape[0])
+        self.n_total = int(n_total)
+        if index_base is None:
+            index_base = shard_bounds(self.n_total, self.world, self.rank)[0]
+            if self.world > 1:
+                assert local_db.shape[0] == shard_bounds(self.n_total, self.world, self.rank)[1] - index_base, \
+                    "local shard does not match shard_bounds(); pass index_base explicitly for custom partitions"
+        self.shard = DatabaseShard(local_db, index_base, self.ops)
+
+    @classmethod
+    def from_full(cls, db, group=None, ops=None):
+        """Every rank holds (or can produce) the full [ndb, d] matrix: keep only this rank's rows."""
+        world, rank = _world(group)
+        lo, hi = shard_bounds(db.shape[0], world, rank)
+        return cls(db[lo:hi].contiguous(), n_total=db.shape[0], group=group, ops=ops, index_base=lo)
+
+    def _sum_int(self, v):
+        if self.world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], dtype=torch.int64)
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def broadcast_queries(self, q, src=0):
+        if self.world > 1:
+            dist.broadcast(q, src=src, group=self.group)
+        return q
+
+    def search(self, q, k, broadcast=False):
+        """q: [nq, d] float32 (identical on every rank, or rank 0's copy with broadcast=True).
+        Returns (scores [nq, k], global indices [nq, k] int64) on every rank."""
+        if broadcast:
+            q = self.broadcast_queries(q)
+        s, i = self.ops.local_topk(q, self.shard, k)
+        if self.world == 1:
+            return s, i
+        all_s = torch.empty((self.world,) + tuple(s.shape), dtype=s.dtype, device=s.device)
+        all_i = torch.empty((self.world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+        # list-of-views form: one collective on NCCL (equal sizes), and also supported by gloo (CPU tests)
+        dist.all_gather(list(all_s.unbind(0)), s.contiguous(), group=self.group)
+        dist.all_gather(list(all_i.unbind(0)), i.contiguous(), group=self.group)
+        return self.ops.merge(all_s, all_i)
+
+    def positions(self, q, probe_idx):
+        """0-based position every probe id would take in the full descending ranking of its query
+        (= what `np.flatnonzero(np.in1d(ranks[:, i], ids))` reads, evaluate.py:75-76). probe_idx: [nq, pmax] int64, -1 pad."""
+        ps = torch.zeros(probe_idx.shape, dtype=torch.float32, device=q.device)
+        self.ops.probe_scores(q, self.shard, probe_idx, ps)
+        if self.world > 1:
+            dist.all_reduce(ps, group=self.group)       # non-owners contributed exact zeros
+        before = torch.zeros(probe_idx.shape, dtype=torch.int64, device=q.device)
+        self.ops.rank_counts(q, self.shard, probe_idx, ps, before)
+        if self.world > 1:
+            dist.all_reduce(before, group=self.group)
+        return before
+
+
+def _pad_ids(lists, device, fill=-1):
+    n = max(1, max((len(x) for x in lists), default=1))
+    arr = np.full((len(lists), n), fill, dtype=np.int64)
+    for r, x in enumerate(lists):
+        arr[r, :len(x)] = np.asarray(x, dtype=np.int64)
+    return torch.from_numpy(arr).to(device)
+
+
+def evaluate_map(index, q, gnd, kappas=()):
+    """compute_map (evaluate.py:39-111) on the GPU. gnd: list of {'ok': ids, 'junk': ids}.
+    Returns (map, aps [nq] float64, mean P@k, P@k [nq, nk]) as NumPy, NaN rows for queries without positives."""
+    ops = index.ops
+    ok = [np.asarray(g["ok"], dtype=np.int64).reshape(-1) for g in gnd]
+    junk = [np.asarray(g.get("junk", []), dtype=np.int64).reshape(-1) for g in gnd]
+    probes = _pad_ids([np.concatenate([o, j]) for o, j in zip(ok, junk)], q.device)
+    before = index.positions(q, probes)
+    npos_h = [len(o) for o in ok]
+    njunk_h = [len(j) for j in junk]
+    pp, pj = max(1, max(npos_h)), max(1, max(njunk_h))
+    # split the [ok | junk] probe columns into the two padded matrices gdt_map_eval takes
+    cols = torch.arange(max(pp, pj), device=q.device)
+    npos = torch.tensor(npos_h, dtype=torch.int32, device=q.device)
+    njunk = torch.tensor(njunk_h, dtype=torch.int32, device=q.device)
+    pos_rank = before[:, :pp].contiguous()
+    jidx = (npos.long()[:, None] + cols[None, :pj]).clamp_(max=before.shape[1] - 1)
+    junk_rank = torch.gather(before, 1, jidx).contiguous()
+    ap, prk = ops.map_eval(pos_rank, junk_rank, npos, njunk, list(kappas))
+    ap, prk = ap.cpu().numpy(), prk.cpu().numpy()
+    # same accumulation order as the reference loop (evaluate.py:98,106,108-109): sequential, empty queries skipped
+    total, pr, nempty = 0.0, np.zeros(len(kappas)), 0
+    for i in range(len(gnd)):
+        if npos_h[i] == 0:
+            nempty += 1
+            continue
+        total = total + ap[i]
+        pr = pr + prk[i, :]
+    nvalid = len(gnd) - nempty
+    return (total / nvalid if nvalid else float("nan")), ap, (pr / nvalid if nvalid else pr * np.nan), prk
+
+
+def compute_map_and_print(dataset, index, q, gnd, kappas=(1, 5, 10), printer=print):
+    """Same protocol split, rounding and output dictionaries as evaluate.py:114-152, with (index, q) in place of
+    the precomputed `ranks` matrix."""
+    if "ok" in gnd[0]:                                            # old protocol (Oxford/Paris/Tokyo), :117-120
+        m, aps, _, _ = evaluate_map(index, q, gnd)
+        printer(">> {}: mAP {:.2f}".format(dataset, np.around(m * 100, decimals=2)))
+        return {"map": m}, {"ap": aps}
+    if not (dataset.startswith("roxford5k") or dataset.startswith("rparis6k")):
+        raise ValueError("Unsupported ground-truth format for dataset %s" % dataset)
+    out_avg, out_aps, mprs = {}, {}, {}
+    for name, ok_keys, junk_keys in (("easy", ("easy",), ("junk", "hard")),        # :125-131
+                                     ("medium", ("easy", "hard"), ("junk",)),       # :133-139
+                                     ("hard", ("hard",), ("junk", "easy"))):        # :141-147
+        g = [{"ok": np.concatenate([np.asarray(x[k_], dtype=np.int64).reshape(-1) for k_ in ok_keys]),
+              "junk": np.concatenate([np.asarray(x[k_], dtype=np.int64).reshape(-1) for k_ in junk_keys])} for x in gnd]
+        m, aps, mpr, _ = evaluate_map(index, q, g, kappas)
+        out_avg["map_" + name], out_aps["ap_" + name], mprs[name] = m, aps, mpr
+    printer(">> {}: mAP E: {}, M: {}, H: {}".format(dataset, *[np.around(out_avg["map_" + n] * 100, decimals=2)
+                                                               for n in ("easy", "medium", "hard")]))
+    printer(">> {}: mP@k{} E: {}, M: {}, H: {}".format(dataset, list(kappas), *[np.around(mprs[n] * 100, decimals=2)
+                                                                                   for n in ("easy", "medium", "hard")]))
+    return out_avg, out_aps

@@ -1,0 +1,36 @@
+"""Short driver for ncu captures: a few launches of every hot kernel at bench shapes (smaller batch)."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+from gandtr_b200 import _lib
+from bench import synth_images_torch, MEAN, STD
+
+which = sys.argv[1:] or ["clahe", "gem", "topk"]
+dev = torch.device("cuda", 0)
+reps = 3
+if "clahe" in which:
+    x = synth_images_torch(32, 1, dev)
+    out = torch.empty((32, 3, 768, 1024), dtype=torch.float32, device=dev)
+    for _ in range(reps):
+        _lib.clahe_u8(x, MEAN, STD, out=out)
+if "gem" in which:
+    c = 2048
+    fm = [torch.rand((32, c, h, w), device=dev) for h, w in ((24, 32), (17, 23), (12, 16))]
+    p = torch.tensor([3.0], device=dev)
+    P = torch.randn((c, c), device=dev) / c ** 0.5
+    m = torch.rand(c, device=dev) * 0.05
+    for _ in range(reps):
+        _lib.gem_whiten(fm[:1], p, aggregate=True, P=P, m=m)
+    _lib.gem_whiten(fm, p, aggregate=True, msp_is_p=True, P=P, m=m)
+    fv = torch.rand((32, 512, 48, 64), device=dev)
+    _lib.gem_whiten([fv], torch.tensor([2.92], device=dev), aggregate=True)
+if "topk" in which:
+    nq, ndb, d = 4096, 262144, 2048
+    db = torch.randn((ndb, d), device=dev); db /= db.norm(dim=1, keepdim=True)
+    q = torch.randn((nq, d), device=dev); q /= q.norm(dim=1, keepdim=True)
+    shadow, nmax = _lib.db_prepare(db)
+    for _ in range(reps):
+        s, i, st = _lib.score_topk(q, db, shadow, nmax, 100)
+    print("status", st.cpu().tolist())
+torch.cuda.synchronize()
+print("done")
