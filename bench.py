@@ -389,9 +389,9 @@ def main():
             "e2e": {"value": args.queries * rK / (re_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": args.queries * DB_DIM * 4, "d2h_bytes_per_step": args.queries * TOPK * 12},
             "status": index.shard.last_status,
-            "roofline": {"kernel": "K3 score_filter_kernel (tcgen05 bf16 coarse pass) + exact re-score/finalise",
+            "roofline": {"kernel": "K3 score_filter_kernel (tcgen05 fp16 coarse pass) + exact re-score/finalise",
                          "bound": "tensor", "achieved": flops / world / (r_ms / rK * 1e-3) / 1e12, "peak": tc_peak,
-                         "unit": "TFLOP/s", "peak_source": tc_src + " bf16 burst", "note": "per GPU; algorithmic flops 2*nq*ndb*d"}}
+                         "unit": "TFLOP/s", "peak_source": tc_src + " bf16-GEMM burst (fp16 runs at the same tensor rate)", "note": "per GPU; algorithmic flops 2*nq*ndb*d"}}
         line["retrieval"]["roofline"]["frac"] = line["retrieval"]["roofline"]["achieved"] / tc_peak
         del index
 

@@ -33,6 +33,7 @@ SYMBOLS = [
     ("gdt_init", _c.c_int, [_P]),
     ("gdt_is_initialised", _c.c_int, []),
     ("gdt_debug_get_spline_table", _c.c_int, [_P]),
+    ("gdt_debug_div_check", _c.c_int, [_c.c_float, _c.c_uint32, _c.c_uint32, _P, _P]),
     ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_clahe_u8", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _c.c_size_t, _P]),
     ("gdt_clahe_f32", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P,
@@ -40,6 +41,11 @@ SYMBOLS = [
     ("gdt_gem_whiten_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_gem_whiten", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P,
                                   _c.c_int, _P, _P, _c.c_size_t, _P]),
+    ("gdt_gem_pool", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _P, _P]),
+    ("gdt_l2n_rows", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _P, _P]),
+    ("gdt_desc_post_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int]),
+    ("gdt_desc_post", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P, _c.c_int,
+                                 _P, _P, _c.c_size_t, _P]),
     ("gdt_db_prepare_workspace_bytes", _c.c_size_t, [_c.c_longlong, _c.c_int]),
     ("gdt_db_prepare", _c.c_int, [_P, _c.c_longlong, _c.c_int, _P, _P, _P, _c.c_size_t, _P]),
     ("gdt_score_topk_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_longlong, _c.c_int, _c.c_int]),
@@ -60,7 +66,7 @@ _initialised_devices = set()
 launch_count = 0  # number of library compute calls made by this process (bench.py reports kernel launches from it)
 
 # kernels launched by each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"clahe": 2, "gem": 2, "gem_whiten": 4, "db_prepare": 1, "score_topk": 3, "score_topk_exact": 2,
+KERNELS_PER_CALL = {"clahe": 2, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
                     "topk_merge": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1}
 
 
@@ -227,15 +233,84 @@ def gem_whiten(fmaps, p, eps=1e-6, aggregate=False, msp_is_p=False, P=None, m=No
     return desc
 
 
+def gem_pool(fmap, p, eps=1e-6):
+    """GeM.forward: [n,c,h,w] float32 CUDA -> pooled [n,c] (not normalised)."""
+    _require(fmap, torch.float32, "fmap")
+    _require(p, torch.float32, "p")
+    if fmap.dim() != 4:
+        raise GdtError("fmap must be [n, c, h, w]")
+    n, c, h, w = fmap.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=fmap.device)
+    with torch.cuda.device(fmap.device):
+        check(load().gdt_gem_pool(_ptr(fmap), n, c, h, w, _ptr(p), float(eps), _ptr(out), _stream()), "gdt_gem_pool")
+    _count("gem_pool")
+    return out
+
+
+def l2n_rows(x, eps=1e-6):
+    """L2N.forward on [n, dim] rows."""
+    _require(x, torch.float32, "x")
+    if x.dim() != 2:
+        raise GdtError("x must be [n, dim]")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(load().gdt_l2n_rows(_ptr(x), x.shape[0], x.shape[1], float(eps), _ptr(out), _stream()), "gdt_l2n_rows")
+    _count("l2n_rows")
+    return out
+
+
+def desc_post(descs, msp, P=None, m=None, dim=None):
+    """Aggregation (msp: None = none, float, or 1-element CUDA tensor read on the device) and / or whitening of
+    already L2-normalised per-scale descriptors, each [n, c] -> [n, dim]."""
+    descs = [_require(d, torch.float32, "desc") for d in descs]
+    scales = len(descs)
+    n, c = descs[0].shape
+    for d in descs:
+        if tuple(d.shape) != (n, c):
+            raise GdtError("all per-scale descriptors must be [n, c]")
+    dev = descs[0].device
+    flags, msp_dev, msp_host = 0, None, 1.0
+    if msp is not None:
+        flags |= GDT_GEM_AGGREGATE
+        if isinstance(msp, torch.Tensor):
+            _require(msp, torch.float32, "msp")
+            flags |= GDT_GEM_MSP_IS_P
+            msp_dev = msp
+        else:
+            msp_host = float(msp)
+    elif scales != 1:
+        raise GdtError("several scales need an aggregation exponent")
+    if P is not None:
+        _require(P, torch.float32, "P")
+        _require(m, torch.float32, "m")
+        dim = int(dim or P.shape[0])
+        if P.dim() != 2 or P.shape[1] != c or dim > P.shape[0] or m.numel() != c:
+            raise GdtError("whitening shapes do not match the descriptors")
+        ldP = P.stride(0)
+    else:
+        dim, ldP = c, 0
+    out = torch.empty((n, dim), dtype=torch.float32, device=dev)
+    ptrs = (ctypes.c_void_p * scales)(*[d.data_ptr() for d in descs])
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_desc_post_workspace_bytes(n, c, dim), dev)
+        check(lib.gdt_desc_post(ptrs, n, c, scales, _ptr(msp_dev) if msp_dev is not None else None, msp_host, flags,
+                                _ptr(P) if P is not None else None, int(ldP), _ptr(m) if m is not None else None, dim,
+                                _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_desc_post")
+    _count("desc_post_whiten" if P is not None else "desc_post")
+    return out
+
+
 # ---- K3 ----------------------------------------------------------------------------------------------
 
 def db_prepare(db):
-    """[ndb, d] float32 CUDA database shard -> (bf16 shadow [ndb, d], max row norm [1])."""
+    """[ndb, d] float32 CUDA database shard -> (fp16 shadow [ndb, d], stats [4] float32: max row norm, power-of-two
+    scale, max rounding-residual norm, max shadow-row norm)."""
     _require(db, torch.float32, "db")
     ndb, d = db.shape
     lib = load()
-    shadow = torch.empty((ndb, d), dtype=torch.bfloat16, device=db.device)
-    norm_max = torch.empty(1, dtype=torch.float32, device=db.device)
+    shadow = torch.empty((ndb, d), dtype=torch.float16, device=db.device)
+    norm_max = torch.empty(4, dtype=torch.float32, device=db.device)
     with torch.cuda.device(db.device):
         ws = _workspace(lib.gdt_db_prepare_workspace_bytes(ndb, d), db.device)
         check(lib.gdt_db_prepare(_ptr(db), ndb, d, _ptr(shadow), _ptr(norm_max), _ptr(ws), ws.numel(), _stream()),
@@ -252,7 +327,7 @@ def score_topk(q, db, shadow, norm_max, k, index_base=0, ws=None, out=None):
     """tcgen05 path. Returns (scores [nq,k] f32, idx [nq,k] i64, status [4] i32), all on the device, async."""
     _require(q, torch.float32, "q")
     _require(db, torch.float32, "db")
-    _require(shadow, torch.bfloat16, "shadow")
+    _require(shadow, torch.float16, "shadow")
     _require(norm_max, torch.float32, "norm_max")
     nq, d = q.shape
     ndb = db.shape[0]
@@ -271,7 +346,9 @@ def score_topk(q, db, shadow, norm_max, k, index_base=0, ws=None, out=None):
             ws = _workspace(lib.gdt_score_topk_workspace_bytes(nq, ndb, d, k), dev)
         check(lib.gdt_score_topk(_ptr(q), _ptr(db), _ptr(shadow), _ptr(norm_max), nq, ndb, d, k, int(index_base),
                                  _ptr(scores), _ptr(idx), _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_score_topk")
-    _count("score_topk")
+    global launch_count
+    seed = max(8, (4 * k + 255) // 256)
+    launch_count += 3 + (1 if (ndb + 255) // 256 > seed else 0)   # q_prepare, seed (+ main) filter pass, finalize
     return scores, idx, status
 
 

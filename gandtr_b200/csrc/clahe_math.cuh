@@ -13,6 +13,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GDT_HD __host__ __device__ __forceinline__
@@ -73,6 +74,38 @@ GDT_HD int f_trunc(float a) {
 #endif
 }
 GDT_HD float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+GDT_HD float f_fma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
+// ---- IEEE division by a constant without the divider ---------------------------------------------
+// a / b == RN-correct result of  q = a*r; { e = fma(-b, q, a); q = fma(e, r, q); } x ITERS  with r = RN(1/b)
+// (Markstein's correction step: the residual e is exact, each step at least squares the error). ITERS = 2 is what
+// the hardware division sequence itself runs and is correctly rounded for every normal a (b's significand not all
+// ones, no under/overflow); ITERS = 1 is used only on small enumerated domains that tests/ check exhaustively.
+template <int ITERS>
+GDT_HD float div_by_const(float a, float b, float r) {
+    float q = f_mul(a, r);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int i = 0; i < ITERS; ++i) {
+        const float e = f_fma(-b, q, a);
+        q = f_fma(e, r, q);
+    }
+    return q;
+}
+// true when div_by_const<2>(a, b, RN(1/b)) is guaranteed for all a in [-4, 4] with |a| >= 2^-40 or a == 0
+inline bool div_by_const_ok(float b) {
+    uint32_t u;
+    memcpy(&u, &b, 4);
+    const uint32_t man = u & 0x7fffffu, ex = (u >> 23) & 0xffu;
+    return man != 0x7fffffu && ex >= 127 - 20 && ex <= 127 + 20;
+}
 
 // ---- RGB -> Lab (Q14 integer LUT path) ----------------------------------------------------------
 
@@ -82,6 +115,16 @@ GDT_HD float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); 
 // lattice points, and keeps every cell inside a 32^3 packed table.
 GDT_HD void lab_cell(float x01, int& t, int& f) {
     int c = f_rint(f_mul(x01, 16384.0f));
+    t = c >> 9;
+    f = (c >> 5) & 15;
+    if (t >= 32) { t = 31; f = 16; }
+}
+
+// 8-bit input channel: c = cvRound((float(v) / 255.0f) * 16384) == (v * 32768 + 255) / 510 for every v in [0, 255]
+// (v * 16384 / 255 is never within 1/510 of a half-integer, far outside the float rounding error; all 256 values are
+// checked in tests/test_clahe_fastmath.py).
+GDT_HD void lab_cell_u8(int v, int& t, int& f) {
+    const int c = (v * 32768 + 255) / 510;
     t = c >> 9;
     f = (c >> 5) & 15;
     if (t >= 32) { t = 31; f = 16; }
@@ -109,6 +152,13 @@ GDT_HD int lab_l8(int o0) {
     return f_trunc(f_mul(spc, 255.0f));
 }
 
+// lab_l8 without the divider: bit-identical for every o0 in [0, 16384] (exhaustively tested).
+GDT_HD int lab_l8_fast(int o0) {
+    const float L = f_mul(f_mul((float)o0, 1.0f / 16384.0f), 100.0f);
+    const float spc = div_by_const<1>(L, 100.0f, 1.0f / 100.0f);
+    return f_trunc(f_mul(spc, 255.0f));
+}
+
 // Q14 chroma -> the a (or b) value handed to LAB2RGB after the reference's normalise/denormalise
 // round trip:  a = o*2^-14*256 - 128 ; spc = (a + 128) / 255 ; a' = spc*255 - 128.
 GDT_HD float lab_chroma(int o) {
@@ -116,6 +166,15 @@ GDT_HD float lab_chroma(int o) {
     const float spc = f_div(f_add(a, 128.0f), 255.0f);
     return f_sub(f_mul(spc, 255.0f), 128.0f);
 }
+
+// lab_chroma without the divider: (o * 2^-14) * 256 - 128 == o / 64 - 128 exactly, so (a + 128) == o / 64 exactly;
+// bit-identical for every o in [0, 16384] (exhaustively tested).
+GDT_HD float lab_chroma_fast(int o) {
+    const float x = f_mul((float)o, 1.0f / 64.0f);
+    const float spc = div_by_const<1>(x, 255.0f, 1.0f / 255.0f);
+    return f_sub(f_mul(spc, 255.0f), 128.0f);
+}
+GDT_HD float lab_l_from_u8_fast(int v) { return f_mul(div_by_const<1>((float)v, 255.0f, 1.0f / 255.0f), 100.0f); }
 
 // CLAHE output byte -> L handed to LAB2RGB:  (float(v) / 255) * 100 - 0.
 GDT_HD float lab_l_from_u8(int v) { return f_mul(f_div((float)v, 255.0f), 100.0f); }
@@ -208,6 +267,9 @@ GDT_HD float spline_eval(float x, float s0, float s1, float s2, float s3) {
 
 // Normalize: (x - mean) / std, sub then true division (core_transforms.py:64-67).
 GDT_HD float normalize_px(float x, float mean, float std) { return f_div(f_sub(x, mean), std); }
+GDT_HD float normalize_px_fast(float x, float mean, float std, float rstd) {
+    return div_by_const<2>(f_sub(x, mean), std, rstd);
+}
 
 // ---- host-side table builders (used by gdt_init; plain C++) --------------------------------------
 

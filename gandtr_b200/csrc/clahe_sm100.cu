@@ -44,17 +44,13 @@ struct Norm3 {
 
 // ---- pixel helpers ------------------------------------------------------------------------------
 
-template <bool U8>
-struct PixelIn;
-
-// One input pixel -> (cell, fr, fg, fb)
-__device__ __forceinline__ void cell_from_q8(const uint16_t* q8s, int r, int g, int b, int& cell, int& fr, int& fg,
-                                             int& fb) {
-    const int qr = q8s[r], qg = q8s[g], qb = q8s[b];
-    cell = ((qr >> 5) << 10) | ((qg >> 5) << 5) | (qb >> 5);
-    fr = qr & 31;
-    fg = qg & 31;
-    fb = qb & 31;
+// One 8-bit pixel -> (cell, fr, fg, fb), pure integer arithmetic (no table)
+__device__ __forceinline__ void cell_from_u8(int r, int g, int b, int& cell, int& fr, int& fg, int& fb) {
+    int tr, tg, tb;
+    lab_cell_u8(r, tr, fr);
+    lab_cell_u8(g, tg, fg);
+    lab_cell_u8(b, tb, fb);
+    cell = (tr << 10) | (tg << 5) | tb;
 }
 
 __device__ __forceinline__ void cell_from_f32(float r, float g, float b, const Norm3& in, int& cell, int& fr, int& fg,
@@ -69,7 +65,7 @@ __device__ __forceinline__ void cell_from_f32(float r, float g, float b, const N
 
 __device__ __forceinline__ int l8_from_cell(const uint4* __restrict__ lutL, int cell, int fr, int fg, int fb) {
     const uint4 w = __ldg(lutL + cell);
-    return lab_l8(lab_trilinear(w.x, w.y, w.z, w.w, fr, fg, fb));
+    return lab_l8_fast(lab_trilinear(w.x, w.y, w.z, w.w, fr, fg, fb));
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -86,20 +82,21 @@ __device__ __forceinline__ void hist_add(int* hist, int key) {
 }
 
 // ---- pass A -------------------------------------------------------------------------------------
+// tile LUT layout written by pass A and read by pass B: lutT[img][ty][v][tx] with kLutRow bytes per (ty, v) row, so
+// the four tile LUT values a pixel blends sit in two 16-byte rows (one per tile row).
+constexpr int kLutRow = 16;   // >= max grid
 
 template <bool U8>
 __global__ void __launch_bounds__(256)
-clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_t* __restrict__ tile_luts, int h, int w,
+clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_t* __restrict__ lutT, int h, int w,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, const uint4* __restrict__ lutL,
-                  const uint16_t* __restrict__ q8, Norm3 in_norm) {
+                  Norm3 in_norm) {
     __shared__ int hist[256];
-    __shared__ uint16_t q8s[256];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
     const int img = blockIdx.y;
     const int ty = blockIdx.x / grid, tx = blockIdx.x % grid;
     hist[tid] = 0;
-    if (U8) q8s[tid] = q8[tid];
     __syncthreads();
 
     const size_t plane = (size_t)h * w;
@@ -125,12 +122,15 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
                     const int rr[4] = {(int)(a0 & 255), (int)(a0 >> 24), (int)((a1 >> 16) & 255), (int)((a2 >> 8) & 255)};
                     const int gg[4] = {(int)((a0 >> 8) & 255), (int)(a1 & 255), (int)(a1 >> 24), (int)((a2 >> 16) & 255)};
                     const int bb[4] = {(int)((a0 >> 16) & 255), (int)((a1 >> 8) & 255), (int)(a2 & 255), (int)(a2 >> 24)};
+                    int cell[4], fr[4], fg[4], fb[4];
+                    uint4 wv[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        int cell, fr, fg, fb;
-                        cell_from_q8(q8s, rr[i], gg[i], bb[i], cell, fr, fg, fb);
-                        v[i] = l8_from_cell(lutL, cell, fr, fg, fb);
-                    }
+                    for (int i = 0; i < 4; ++i) cell_from_u8(rr[i], gg[i], bb[i], cell[i], fr[i], fg[i], fb[i]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) wv[i] = __ldg(lutL + cell[i]);      // four gathers in flight
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        v[i] = lab_l8_fast(lab_trilinear(wv[i].x, wv[i].y, wv[i].z, wv[i].w, fr[i], fg[i], fb[i]));
                 } else {
                     const float4 r4 = __ldg((const float4*)(inf + p));
                     const float4 g4 = __ldg((const float4*)(inf + plane + p));
@@ -162,7 +162,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
                 const size_t p = (size_t)sy * w + sx;
                 int cell, fr, fg, fb;
                 if (U8) {
-                    cell_from_q8(q8s, in8[p * 3], in8[p * 3 + 1], in8[p * 3 + 2], cell, fr, fg, fb);
+                    cell_from_u8(in8[p * 3], in8[p * 3 + 1], in8[p * 3 + 2], cell, fr, fg, fb);
                 } else {
                     cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
                 }
@@ -207,36 +207,36 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
     for (int i = 0; i < wid; ++i) sum += warp_tmp[i];
     int lv = f_rint(f_mul((float)sum, lut_scale));
     lv = lv < 0 ? 0 : (lv > 255 ? 255 : lv);
-    tile_luts[((size_t)img * grid * grid + blockIdx.x) * 256 + tid] = (uint8_t)lv;
+    lutT[(((size_t)img * grid + ty) * 256 + tid) * kLutRow + tx] = (uint8_t)lv;
 }
 
 // ---- pass B -------------------------------------------------------------------------------------
 
+struct NormFast {
+    float mean[3], std[3], rstd[3];
+    int fast;   // div_by_const_ok() for all three std
+};
+
 template <bool U8>
 __global__ void __launch_bounds__(256)
-clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ tile_luts,
+clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
-                   int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline,
-                   const uint16_t* __restrict__ q8, const float* __restrict__ lnew_tab, Lab2RgbConst K, Norm3 in_norm,
-                   Norm3 out_norm) {
+                   int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
+                   Norm3 in_norm, NormFast on) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* luts = smem;  // [(ty_hi - ty_lo + 1) * grid][256]
-    __shared__ uint16_t q8s[256];
-    __shared__ float lnews[256];
+    float4* spl = (float4*)smem;                 // [1024] inverse-gamma spline segments
+    uint4* luts = (uint4*)(smem + 1024 * 16);    // [(ty_hi - ty_lo + 1)][256] rows of kLutRow bytes
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const int y0 = blockIdx.y * rows_per_cta;
     const int y1 = min(y0 + rows_per_cta, h);
     const int ty_lo = clahe_axis(y0, inv_th, grid).i1;
     const int ty_hi = clahe_axis(y1 - 1, inv_th, grid).i2;
-
     {
-        const int nbytes = (ty_hi - ty_lo + 1) * grid * 256;
-        const uint4* src = (const uint4*)(tile_luts + ((size_t)img * grid * grid + (size_t)ty_lo * grid) * 256);
-        uint4* dst = (uint4*)luts;
-        for (int i = tid; i < (nbytes >> 4); i += 256) dst[i] = __ldg(src + i);
-        if (U8) q8s[tid] = q8[tid];
-        lnews[tid] = lnew_tab[tid];
+        const int nrows = (ty_hi - ty_lo + 1) * 256;
+        const uint4* src = (const uint4*)(lutT + ((size_t)img * grid + ty_lo) * 256 * kLutRow);
+        for (int i = tid; i < nrows; i += 256) luts[i] = __ldg(src + i);
+        for (int i = tid; i < 1024; i += 256) spl[i] = __ldg(spline + i);
     }
     __syncthreads();
 
@@ -254,11 +254,12 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
     const float* inf = (const float*)in_ + (size_t)img * plane * 3;
     const uint8_t* l8img = L8 + (size_t)img * plane;
     float* outimg = out + (size_t)img * plane * 3;
+    const uint8_t* lut_bytes = (const uint8_t*)luts;
 
     for (int y = y0; y < y1; ++y) {
         const ClaheAxis ay = clahe_axis(y, inv_th, grid);
-        const uint8_t* lrow1 = luts + (size_t)(ay.i1 - ty_lo) * grid * 256;
-        const uint8_t* lrow2 = luts + (size_t)(ay.i2 - ty_lo) * grid * 256;
+        const uint8_t* lrow1 = lut_bytes + (size_t)(ay.i1 - ty_lo) * 256 * kLutRow;
+        const uint8_t* lrow2 = lut_bytes + (size_t)(ay.i2 - ty_lo) * 256 * kLutRow;
         const size_t p = (size_t)y * w + x0;
 
         int cell[4], fr[4], fg[4], fb[4], v[4];
@@ -268,10 +269,10 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
             if (U8) {
                 const uint32_t* src = (const uint32_t*)(in8 + p * 3);
                 const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
-                cell_from_q8(q8s, a0 & 255, (a0 >> 8) & 255, (a0 >> 16) & 255, cell[0], fr[0], fg[0], fb[0]);
-                cell_from_q8(q8s, a0 >> 24, a1 & 255, (a1 >> 8) & 255, cell[1], fr[1], fg[1], fb[1]);
-                cell_from_q8(q8s, (a1 >> 16) & 255, a1 >> 24, a2 & 255, cell[2], fr[2], fg[2], fb[2]);
-                cell_from_q8(q8s, (a2 >> 8) & 255, (a2 >> 16) & 255, a2 >> 24, cell[3], fr[3], fg[3], fb[3]);
+                cell_from_u8(a0 & 255, (a0 >> 8) & 255, (a0 >> 16) & 255, cell[0], fr[0], fg[0], fb[0]);
+                cell_from_u8(a0 >> 24, a1 & 255, (a1 >> 8) & 255, cell[1], fr[1], fg[1], fb[1]);
+                cell_from_u8((a1 >> 16) & 255, a1 >> 24, a2 & 255, cell[2], fr[2], fg[2], fb[2]);
+                cell_from_u8((a2 >> 8) & 255, (a2 >> 16) & 255, a2 >> 24, cell[3], fr[3], fg[3], fb[3]);
             } else {
                 const float4 r4 = __ldg((const float4*)(inf + p));
                 const float4 g4 = __ldg((const float4*)(inf + plane + p));
@@ -287,8 +288,7 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
                 if (i < npx) {
                     v[i] = l8img[p + i];
                     if (U8) {
-                        cell_from_q8(q8s, in8[(p + i) * 3], in8[(p + i) * 3 + 1], in8[(p + i) * 3 + 2], cell[i], fr[i],
-                                     fg[i], fb[i]);
+                        cell_from_u8(in8[(p + i) * 3], in8[(p + i) * 3 + 1], in8[(p + i) * 3 + 2], cell[i], fr[i], fg[i], fb[i]);
                     } else {
                         cell_from_f32(inf[p + i], inf[plane + p + i], inf[2 * plane + p + i], in_norm, cell[i], fr[i],
                                       fg[i], fb[i]);
@@ -305,21 +305,31 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
             // chroma
             const uint4 wa = __ldg(lutAB + cell[i] * 2);
             const uint4 wb = __ldg(lutAB + cell[i] * 2 + 1);
-            const float a2 = lab_chroma(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
-            const float b2 = lab_chroma(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
-            // lightness through CLAHE
-            const int l11 = lrow1[ax[i].i1 * 256 + v[i]], l12 = lrow1[ax[i].i2 * 256 + v[i]];
-            const int l21 = lrow2[ax[i].i1 * 256 + v[i]], l22 = lrow2[ax[i].i2 * 256 + v[i]];
+            const float a2 = lab_chroma_fast(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
+            const float b2 = lab_chroma_fast(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
+            // lightness through CLAHE: the two 16-byte rows hold the LUT value of every tile column at level v
+            const uint8_t* r1 = lrow1 + v[i] * kLutRow;
+            const uint8_t* r2 = lrow2 + v[i] * kLutRow;
+            const int l11 = r1[ax[i].i1], l12 = r1[ax[i].i2];
+            const int l21 = r2[ax[i].i1], l22 = r2[ax[i].i2];
             const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
-            const float Ln = lnews[dst];
+            const float Ln = lab_l_from_u8_fast(dst);
             float lr, lg, lb;
             lab2lin(Ln, a2, b2, (x0 + i) >= wbody, K, lr, lg, lb);
             int ir, ig, ib;
             const float xr = spline_index(lr, ir), xg = spline_index(lg, ig), xb = spline_index(lb, ib);
-            const float4 sr = __ldg(spline + ir), sg = __ldg(spline + ig), sb = __ldg(spline + ib);
-            o[0][i] = normalize_px(spline_eval(xr, sr.x, sr.y, sr.z, sr.w), out_norm.mean[0], out_norm.std[0]);
-            o[1][i] = normalize_px(spline_eval(xg, sg.x, sg.y, sg.z, sg.w), out_norm.mean[1], out_norm.std[1]);
-            o[2][i] = normalize_px(spline_eval(xb, sb.x, sb.y, sb.z, sb.w), out_norm.mean[2], out_norm.std[2]);
+            const float4 sr = spl[ir], sg = spl[ig], sb = spl[ib];
+            const float er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w), eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w),
+                        eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
+            if (on.fast) {
+                o[0][i] = normalize_px_fast(er, on.mean[0], on.std[0], on.rstd[0]);
+                o[1][i] = normalize_px_fast(eg, on.mean[1], on.std[1], on.rstd[1]);
+                o[2][i] = normalize_px_fast(eb, on.mean[2], on.std[2], on.rstd[2]);
+            } else {
+                o[0][i] = normalize_px(er, on.mean[0], on.std[0]);
+                o[1][i] = normalize_px(eg, on.mean[1], on.std[1]);
+                o[2][i] = normalize_px(eb, on.mean[2], on.std[2]);
+            }
         }
         if (vec_ok) {
 #pragma unroll
@@ -376,7 +386,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
     Workspace W(ws, ws_bytes);
     uint8_t* L8 = W.take<uint8_t>((size_t)n * h * w);
-    uint8_t* luts = W.take<uint8_t>((size_t)n * grid * grid * 256);
+    uint8_t* luts = W.take<uint8_t>((size_t)n * grid * 256 * kLutRow);
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
     const bool aligned = (((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0;
@@ -385,31 +395,63 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
 
     dim3 gridA(grid * grid, n);
     clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
-                                                      vec_hist, T->lutL, T->q8, in_norm);
+                                                      vec_hist, T->lutL, in_norm);
     GDT_LAUNCH_CHECK();
 
     // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
     const int sms = sm_count_current_device();
-    int rows = 16;
+    int rows = 32;
     const int xchunks = ceil_div(w, 1024);
     while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 4LL * sms) rows >>= 1;
     dim3 gridB(xchunks, ceil_div(h, rows), n);
-    const size_t smem = (size_t)grid * grid * 256;
+    // spline table + the LUT rows of every tile row a band can touch (all of them when tiles are shorter than a band)
+    const size_t smem = 1024 * 16 + (size_t)grid * 256 * kLutRow;
     static bool attr_set[2] = {false, false};
     if (smem > 48 * 1024 && !attr_set[U8 ? 1 : 0]) {
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      1024 * 16 + 16 * 256 * kLutRow));
         attr_set[U8 ? 1 : 0] = true;
     }
+    NormFast on;
+    on.fast = 1;
+    for (int c = 0; c < 3; ++c) {
+        on.mean[c] = out_norm.mean[c];
+        on.std[c] = out_norm.std[c];
+        volatile float r = 1.0f / out_norm.std[c];
+        on.rstd[c] = r;
+        if (!div_by_const_ok(out_norm.std[c])) on.fast = 0;
+    }
     clahe_apply_kernel<U8><<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
-                                                          vec_apply, T->lutAB, T->spline, T->q8, T->lnew, T->K, in_norm,
-                                                          out_norm);
+                                                          vec_apply, T->lutAB, T->spline, T->K, in_norm, on);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
+}
+
+// debug: count floats a in the bit range [lo_bits, hi_bits] (both signs) for which div_by_const<2> != a / b
+__global__ void __launch_bounds__(256)
+div_check_kernel(float b, float r, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    const unsigned long long n = (unsigned long long)hi_bits - lo_bits + 1;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256) {
+        const float a = __uint_as_float(lo_bits + (uint32_t)i);
+        if (__float_as_uint(div_by_const<2>(a, b, r)) != __float_as_uint(f_div(a, b))) ++bad;
+        if (__float_as_uint(div_by_const<2>(-a, b, r)) != __float_as_uint(f_div(-a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace gdt
 
 using namespace gdt;
+
+extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches_dev,
+                                   void* stream) {
+    if (!mismatches_dev || hi_bits < lo_bits) return GDT_ERR_INVALID_ARGUMENT;
+    volatile float r = 1.0f / b;
+    div_check_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(b, r, lo_bits, hi_bits, mismatches_dev);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
 
 extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     if (!host_rgb2lab_lut) return GDT_ERR_INVALID_ARGUMENT;
@@ -478,7 +520,7 @@ extern "C" int gdt_debug_get_spline_table(float* host_out_4096) {
 
 extern "C" size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid) {
     if (n <= 0 || h <= 0 || w <= 0 || grid < 1) return 0;
-    return align_up((size_t)n * h * w, 256) + align_up((size_t)n * grid * grid * 256, 256) + 256;
+    return align_up((size_t)n * h * w, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 256;
 }
 
 extern "C" int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,

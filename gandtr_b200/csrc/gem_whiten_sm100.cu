@@ -34,7 +34,8 @@ __device__ __forceinline__ float gem_pow(float x, float p) {
     if (MODE == 3) return x * x * x;
     if (MODE == 2) return x * x;
     if (MODE == 1) return x;
-    return exp2f(p * log2f(x));
+    // x >= eps > 0: lg2.approx (abs. error 2^-22 on the logarithm) and ex2.approx (2 ulp) give x^p to ~5e-7 relative
+    return exp2f(p * __log2f(x));
 }
 
 template <int MODE>
@@ -46,23 +47,23 @@ __device__ __forceinline__ float gem_row_sum(const float* __restrict__ row, int 
     if (lane < head) acc0 += gem_pow<MODE>(fmaxf(row[lane], eps), p);
     const float4* body = (const float4*)(row + head);
     const int nvec = (hw - head) >> 2;
-    int i = lane;
-    for (; i + 96 < nvec; i += 128) {
-        const float4 a = ld_stream_f4(body + i), b = ld_stream_f4(body + i + 32), c = ld_stream_f4(body + i + 64),
-                     d = ld_stream_f4(body + i + 96);
-        acc0 += gem_pow<MODE>(fmaxf(a.x, eps), p) + gem_pow<MODE>(fmaxf(a.y, eps), p);
-        acc1 += gem_pow<MODE>(fmaxf(a.z, eps), p) + gem_pow<MODE>(fmaxf(a.w, eps), p);
-        acc2 += gem_pow<MODE>(fmaxf(b.x, eps), p) + gem_pow<MODE>(fmaxf(b.y, eps), p);
-        acc3 += gem_pow<MODE>(fmaxf(b.z, eps), p) + gem_pow<MODE>(fmaxf(b.w, eps), p);
-        acc0 += gem_pow<MODE>(fmaxf(c.x, eps), p) + gem_pow<MODE>(fmaxf(c.y, eps), p);
-        acc1 += gem_pow<MODE>(fmaxf(c.z, eps), p) + gem_pow<MODE>(fmaxf(c.w, eps), p);
-        acc2 += gem_pow<MODE>(fmaxf(d.x, eps), p) + gem_pow<MODE>(fmaxf(d.y, eps), p);
-        acc3 += gem_pow<MODE>(fmaxf(d.z, eps), p) + gem_pow<MODE>(fmaxf(d.w, eps), p);
-    }
-    for (; i < nvec; i += 32) {
-        const float4 a = ld_stream_f4(body + i);
-        acc0 += gem_pow<MODE>(fmaxf(a.x, eps), p) + gem_pow<MODE>(fmaxf(a.y, eps), p);
-        acc1 += gem_pow<MODE>(fmaxf(a.z, eps), p) + gem_pow<MODE>(fmaxf(a.w, eps), p);
+    // up to 8 independent 16-byte loads per lane in flight (a 3 KB ResNet row is covered by one batch)
+    for (int base = 0; base < nvec; base += 256) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * 32 + lane;
+            v[j] = i < nvec ? ld_stream_f4(body + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (base + j * 32 + lane < nvec) {
+                acc0 += gem_pow<MODE>(fmaxf(v[j].x, eps), p);
+                acc1 += gem_pow<MODE>(fmaxf(v[j].y, eps), p);
+                acc2 += gem_pow<MODE>(fmaxf(v[j].z, eps), p);
+                acc3 += gem_pow<MODE>(fmaxf(v[j].w, eps), p);
+            }
+        }
     }
     const int tail0 = head + (nvec << 2);
     if (tail0 + lane < hw) acc2 += gem_pow<MODE>(fmaxf(row[tail0 + lane], eps), p);
@@ -77,22 +78,27 @@ __global__ void __launch_bounds__(256)
 gem_pool_kernel(GemScales S, long long rows_per_scale, long long total_rows, const float* __restrict__ p_dev, float eps,
                 float* __restrict__ g) {
     const int lane = threadIdx.x & 31;
-    const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (warp >= total_rows) return;
-    const int s = (int)(warp / rows_per_scale);
-    const long long r = warp - (long long)s * rows_per_scale;
-    const int hw = S.hw[s];
-    const float* row = S.ptr[s] + r * hw;
     const float p = __ldg(p_dev);
-    float sum;
-    if (p == 3.0f) sum = gem_row_sum<3>(row, hw, eps, p, lane);
-    else if (p == 2.0f) sum = gem_row_sum<2>(row, hw, eps, p, lane);
-    else if (p == 1.0f) sum = gem_row_sum<1>(row, hw, eps, p, lane);
-    else sum = gem_row_sum<0>(row, hw, eps, p, lane);
-    if (lane == 0) {
-        const float mean = sum / (float)hw;
-        g[warp] = powf(mean, 1.0f / p);
+    const float inv_p = 1.0f / p;
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); warp < total_rows; warp += nwarps) {
+        const int s = (int)(warp / rows_per_scale);
+        const long long r = warp - (long long)s * rows_per_scale;
+        const int hw = S.hw[s];
+        const float* row = S.ptr[s] + r * hw;
+        float sum;
+        if (p == 3.0f) sum = gem_row_sum<3>(row, hw, eps, p, lane);
+        else if (p == 2.0f) sum = gem_row_sum<2>(row, hw, eps, p, lane);
+        else if (p == 1.0f) sum = gem_row_sum<1>(row, hw, eps, p, lane);
+        else sum = gem_row_sum<0>(row, hw, eps, p, lane);
+        if (lane == 0) g[warp] = powf(sum / (float)hw, inv_p);
     }
+}
+
+static unsigned gem_pool_grid(long long total_rows) {
+    const long long want = ceil_div_ll(total_rows, 8);
+    const long long cap = (long long)sm_count_current_device() * 16;   // 8 resident CTAs/SM x 2 for load balance
+    return (unsigned)(want < cap ? want : cap);
 }
 
 __device__ __forceinline__ float block_sum_256(float v, float* red) {
@@ -107,16 +113,26 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return t;
 }
 
-// one CTA per image: per-scale L2N(+eps), optional multi-scale power mean + eps-free renorm,
-// optional centring for the whitening projection.
+struct DescScales {
+    const float* ptr[GDT_MAX_SCALES];   // per-scale [n][c] pooled vectors / descriptors
+};
+
+// one CTA per image: per-scale L2N(+eps) (skipped for already-normalised descriptors), optional multi-scale
+// power mean + eps-free renorm, optional centring for the whitening projection.
+// msp = p_dev[0] when GDT_GEM_MSP_IS_P, else msp_host.
 __global__ void __launch_bounds__(256)
-gem_finalize_kernel(const float* __restrict__ g, int n, int c, int scales, const float* __restrict__ p_dev, int flags,
+gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restrict__ p_dev, float msp_host, int flags,
                     const float* __restrict__ m, float* __restrict__ out /* [n][c] */) {
     __shared__ float red[8];
     __shared__ float inv_norm[GDT_MAX_SCALES];
     const int img = blockIdx.x, tid = threadIdx.x;
+    const bool normalised = (flags & GDT_DESC_NORMALISED) != 0;
     for (int s = 0; s < scales; ++s) {
-        const float* gs = g + ((size_t)s * n + img) * c;
+        if (normalised) {
+            if (tid == 0) inv_norm[s] = 1.0f;
+            continue;
+        }
+        const float* gs = D.ptr[s] + (size_t)img * c;
         float ss = 0.f;
         for (int i = tid; i < c; i += 256) { const float v = gs[i]; ss += v * v; }
         ss = block_sum_256(ss, red);
@@ -124,12 +140,12 @@ gem_finalize_kernel(const float* __restrict__ g, int n, int c, int scales, const
     }
     __syncthreads();
     const bool aggregate = (flags & GDT_GEM_AGGREGATE) != 0;
-    const float msp = (flags & GDT_GEM_MSP_IS_P) ? __ldg(p_dev) : 1.0f;
+    const float msp = (flags & GDT_GEM_MSP_IS_P) ? __ldg(p_dev) : msp_host;
     float* o = out + (size_t)img * c;
     if (!aggregate) {
-        const float* gs = g + (size_t)img * c;
+        const float* gs = D.ptr[0] + (size_t)img * c;
         for (int i = tid; i < c; i += 256) {
-            float v = gs[i] / inv_norm[0];
+            float v = normalised ? gs[i] : gs[i] / inv_norm[0];
             if (m) v -= m[i];
             o[i] = v;
         }
@@ -141,7 +157,8 @@ gem_finalize_kernel(const float* __restrict__ g, int n, int c, int scales, const
     for (int i = tid; i < c; i += 256) {
         float v = 0.f;
         for (int s = 0; s < scales; ++s) {
-            const float d = g[((size_t)s * n + img) * c + i] / inv_norm[s];
+            const float g = D.ptr[s][(size_t)img * c + i];
+            const float d = normalised ? g : g / inv_norm[s];
             v += (msp == 1.0f) ? d : powf(d, msp);
         }
         v = v / (float)scales;
@@ -158,14 +175,18 @@ gem_finalize_kernel(const float* __restrict__ g, int n, int c, int scales, const
     }
 }
 
-// X[n][dim] = V[n][c] . P[dim][c]^T   (fp32 SIMT, 64x64 tile, BK = 16, 4x4 outputs per thread)
+// Xpart[z][n][dim] = V[n][kz] . P[dim][kz]^T over the K-slice kz = [z*klen, (z+1)*klen)
+// (fp32 SIMT, 64x64 tile, BK = 16, 4x4 outputs per thread). Split-K fills the machine when n is small: the
+// slices are summed in a fixed order by whiten_reduce_l2n_kernel, so results are run-to-run deterministic.
 __global__ void __launch_bounds__(256)
-whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int ldP, int n, int c, int dim,
-                   float* __restrict__ X) {
+whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int ldP, int n, int c, int dim, int klen,
+                   float* __restrict__ Xpart) {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int tid = threadIdx.x;
     const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+    const int kbeg = blockIdx.z * klen, kend = min(c, kbeg + klen);
+    float* X = Xpart + (size_t)blockIdx.z * n * dim;
     const int tr = (tid >> 4) << 2, tc = (tid & 15) << 2;
     float acc[4][4];
 #pragma unroll
@@ -173,14 +194,21 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int lr = tid >> 2, lk = (tid & 3) << 2;  // each thread loads 4 consecutive k of one row
-    for (int k0 = 0; k0 < c; k0 += 16) {
+    const bool vec = (c & 3) == 0 && (ldP & 3) == 0 && ((((uintptr_t)V) | ((uintptr_t)P)) & 15) == 0;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
         float a[4], b[4];
+        const int ar = row0 + lr, br = col0 + lr, k = k0 + lk;
+        if (vec && k + 3 < kend) {
+            const float4 av = ar < n ? __ldg((const float4*)(V + (size_t)ar * c + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bv = br < dim ? __ldg((const float4*)(P + (size_t)br * ldP + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+            b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = k0 + lk + q;
-            const int ar = row0 + lr, br = col0 + lr;
-            a[q] = (ar < n && k < c) ? V[(size_t)ar * c + k] : 0.f;
-            b[q] = (br < dim && k < c) ? P[(size_t)br * ldP + k] : 0.f;
+            for (int q = 0; q < 4; ++q) {
+                a[q] = (ar < n && k + q < kend) ? V[(size_t)ar * c + k + q] : 0.f;
+                b[q] = (br < dim && k + q < kend) ? P[(size_t)br * ldP + k + q] : 0.f;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -206,15 +234,61 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
         }
 }
 
-// rows /= (||row||_2 + eps)
-__global__ void __launch_bounds__(256) l2n_rows_kernel(float* __restrict__ X, int dim, float eps) {
+// desc[r] = x / (||x||_2 + eps) with x = sum_z Xpart[z][r] (fixed order); one CTA per row
+__global__ void __launch_bounds__(256)
+whiten_reduce_l2n_kernel(const float* __restrict__ Xpart, int n, int dim, int splitk, float eps, float* __restrict__ desc) {
     __shared__ float red[8];
-    float* x = X + (size_t)blockIdx.x * dim;
+    const int r = blockIdx.x;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < dim; i += 256) {
+        float v = 0.f;
+        for (int z = 0; z < splitk; ++z) v += Xpart[((size_t)z * n + r) * dim + i];
+        desc[(size_t)r * dim + i] = v;
+        ss += v * v;
+    }
+    ss = block_sum_256(ss, red);
+    const float den = sqrtf(ss) + eps;
+    for (int i = threadIdx.x; i < dim; i += 256) desc[(size_t)r * dim + i] = desc[(size_t)r * dim + i] / den;
+}
+
+static int whiten_splitk(int n, int c, int dim) {
+    const int tiles = ceil_div(dim, 64) * ceil_div(n, 64);
+    int z = ceil_div(2 * sm_count_current_device(), tiles);
+    const int zmax = c / 128 > 1 ? c / 128 : 1;          // at least 128 of K per slice
+    if (z > zmax) z = zmax;
+    if (z > 32) z = 32;
+    return z < 1 ? 1 : z;
+}
+
+// out = in / (||row||_2 + eps), one CTA per row (in == out allowed)
+__global__ void __launch_bounds__(256) l2n_rows_kernel(const float* X, float* Y, int dim, float eps) {
+    __shared__ float red[8];
+    const float* x = X + (size_t)blockIdx.x * dim;
+    float* y = Y + (size_t)blockIdx.x * dim;
     float ss = 0.f;
     for (int i = threadIdx.x; i < dim; i += 256) { const float v = x[i]; ss += v * v; }
     ss = block_sum_256(ss, red);
     const float den = sqrtf(ss) + eps;
-    for (int i = threadIdx.x; i < dim; i += 256) x[i] = x[i] / den;
+    for (int i = threadIdx.x; i < dim; i += 256) y[i] = x[i] / den;
+}
+
+// finalize (+ whitening projection + final L2N) shared by gdt_gem_whiten and gdt_desc_post
+static int desc_tail(const DescScales& D, int n, int c, int scales, const float* p_dev, float msp_host, int flags,
+                     const float* P, int ldP, const float* m, int dim, float* desc, float* V, float* Xpart,
+                     cudaStream_t stream) {
+    float* fin_out = P ? V : desc;
+    gem_finalize_kernel<<<n, 256, 0, stream>>>(D, n, c, scales, p_dev, msp_host, flags, P ? m : nullptr, fin_out);
+    GDT_LAUNCH_CHECK();
+    if (P) {
+        const int splitk = whiten_splitk(n, c, dim);
+        const int klen = ceil_div(ceil_div(c, splitk), 16) * 16;
+        dim3 grid(ceil_div(dim, 64), ceil_div(n, 64), ceil_div(c, klen));
+        whiten_gemm_kernel<<<grid, 256, 0, stream>>>(V, P, ldP, n, c, dim, klen, Xpart);
+        GDT_LAUNCH_CHECK();
+        whiten_reduce_l2n_kernel<<<n, 256, 0, stream>>>(Xpart, n, dim, (int)grid.z, 1e-6f, desc);
+        GDT_LAUNCH_CHECK();
+    }
+    return GDT_OK;
 }
 
 }  // namespace gdt
@@ -223,8 +297,8 @@ using namespace gdt;
 
 extern "C" size_t gdt_gem_whiten_workspace_bytes(int n, int c, int scales, int dim) {
     if (n <= 0 || c <= 0 || scales <= 0) return 0;
-    (void)dim;
-    return align_up((size_t)scales * n * c * sizeof(float), 256) + align_up((size_t)n * c * sizeof(float), 256) + 256;
+    return align_up((size_t)scales * n * c * sizeof(float), 256) + align_up((size_t)n * c * sizeof(float), 256) +
+           align_up((size_t)whiten_splitk(n, c, dim > 0 ? dim : c) * n * (dim > 0 ? dim : c) * sizeof(float), 256) + 256;
 }
 
 extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h, const int* host_w, int n, int c,
@@ -243,6 +317,7 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
     Workspace W(ws, ws_bytes);
     float* g = W.take<float>((size_t)scales * n * c);
     float* V = W.take<float>((size_t)n * c);
+    float* Xpart = W.take<float>((size_t)whiten_splitk(n, c, dim) * n * dim);
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
     GemScales S;
@@ -256,17 +331,70 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
     }
     const long long rows_per_scale = (long long)n * c;
     const long long total_rows = rows_per_scale * scales;
-    gem_pool_kernel<<<(unsigned)ceil_div_ll(total_rows, 8), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, g);
+    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, g);
     GDT_LAUNCH_CHECK();
-    float* fin_out = P ? V : desc;
-    gem_finalize_kernel<<<n, 256, 0, stream>>>(g, n, c, scales, p_dev, flags, P ? m : nullptr, fin_out);
+    DescScales D;
+    for (int s = 0; s < GDT_MAX_SCALES; ++s) D.ptr[s] = s < scales ? g + (size_t)s * n * c : nullptr;
+    return desc_tail(D, n, c, scales, p_dev, 1.0f, flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P), P, ldP, m, dim, desc, V,
+                     Xpart, stream);
+}
+
+extern "C" int gdt_gem_pool(const float* fmap, int n, int c, int h, int w, const float* p_dev, float eps, float* pooled,
+                            void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!fmap || !p_dev || !pooled || n <= 0 || c <= 0 || h <= 0 || w <= 0) return GDT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)fmap) & 3) return GDT_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
+    GemScales S;
+    S.nscales = 1;
+    for (int s = 0; s < GDT_MAX_SCALES; ++s) { S.ptr[s] = nullptr; S.hw[s] = 0; }
+    S.ptr[0] = fmap;
+    S.hw[0] = h * w;
+    const long long rows = (long long)n * c;
+    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, pooled);
     GDT_LAUNCH_CHECK();
-    if (P) {
-        dim3 grid(ceil_div(dim, 64), ceil_div(n, 64));
-        whiten_gemm_kernel<<<grid, 256, 0, stream>>>(V, P, ldP, n, c, dim, desc);
-        GDT_LAUNCH_CHECK();
-        l2n_rows_kernel<<<n, 256, 0, stream>>>(desc, dim, 1e-6f);
-        GDT_LAUNCH_CHECK();
-    }
     return GDT_OK;
+}
+
+extern "C" int gdt_l2n_rows(const float* x, int n, int dim, float eps, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x || !out || n <= 0 || dim <= 0) return GDT_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
+    l2n_rows_kernel<<<n, 256, 0, stream>>>(x, out, dim, eps);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
+extern "C" size_t gdt_desc_post_workspace_bytes(int n, int c, int dim) {
+    if (n <= 0 || c <= 0) return 0;
+    return align_up((size_t)n * c * sizeof(float), 256) + align_up((size_t)whiten_splitk(n, c, dim > 0 ? dim : c) * n * (dim > 0 ? dim : c) * sizeof(float), 256) + 256;
+}
+
+extern "C" int gdt_desc_post(const float* const* host_descs, int n, int c, int scales, const float* msp_dev, float msp_host,
+                             int flags, const float* P, int ldP, const float* m, int dim, float* out, void* ws,
+                             size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!host_descs || !out || !ws || n <= 0 || c <= 0 || scales <= 0 || scales > GDT_MAX_SCALES)
+        return GDT_ERR_INVALID_ARGUMENT;
+    if (!(flags & GDT_GEM_AGGREGATE) && scales != 1) return GDT_ERR_INVALID_ARGUMENT;
+    if ((flags & GDT_GEM_MSP_IS_P) && !msp_dev) return GDT_ERR_INVALID_ARGUMENT;
+    if (P && (!m || dim <= 0 || ldP < c)) return GDT_ERR_INVALID_ARGUMENT;
+    if (!P && dim != c) return GDT_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < gdt_desc_post_workspace_bytes(n, c, dim)) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
+    Workspace W(ws, ws_bytes);
+    float* V = W.take<float>((size_t)n * c);
+    float* Xpart = W.take<float>((size_t)whiten_splitk(n, c, dim) * n * dim);
+    if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    DescScales D;
+    for (int s = 0; s < GDT_MAX_SCALES; ++s) {
+        D.ptr[s] = s < scales ? host_descs[s] : nullptr;
+        if (s < scales && !host_descs[s]) return GDT_ERR_INVALID_ARGUMENT;
+    }
+    return desc_tail(D, n, c, scales, msp_dev, msp_host,
+                     (flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P)) | GDT_DESC_NORMALISED, P, ldP, m, dim, out, V, Xpart,
+                     stream);
 }

@@ -3,28 +3,34 @@
 // first k ranks (mdir/components/optim/score/cirscore.py:71-72). The score matrix never reaches HBM.
 //
 // Pipeline (all on the caller's stream):
-//   db_prepare_kernel      once per database shard: bf16 shadow copy + max row norm.
-//   q_prepare_kernel       per call: bf16 copy of the queries, per-query scale and error bound, state reset.
-//   score_filter_kernel    the hot kernel. Persistent, warp-specialised, one CTA per SM:
-//        warp 0      TMA producer   cp.async.bulk.tensor (128B-swizzled [128 x 64] query and
-//                                   [256 x 64] database boxes) into a 4-stage mbarrier ring
-//        warp 1      MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                                   (bf16 x bf16 -> fp32, M=128, N=256, K=16) into a double-buffered
-//                                   TMEM accumulator (2 x 256 of the 512 columns)
-//        warps 2..5  epilogue       tcgen05.ld 32 lanes x 32 columns; thread == query row, so the running
-//                                   threshold of a query lives in one register and filtering needs no
-//                                   cross-thread traffic. Survivors (rare after warm-up) are appended to a
-//                                   per-query candidate list in global memory and counted in a per-query
-//                                   256-bin score histogram from which the threshold is tightened.
+//   db_norm_kernel / db_convert_kernel   once per database shard: max row norm, then the fp16 shadow copy (rows scaled by
+//                          an exact power of two so that the largest norm is in (0.5, 1]) and the largest norm of the
+//                          rounding residual x*s - fp16(x*s).
+//   q_prepare_kernel       per call: fp16 copy of the (power-of-two scaled) queries, per-query error bound, state reset.
+//   score_filter_kernel    the hot kernel, launched twice (a short "seed" range of database tiles that establishes
+//                          per-query thresholds, then the rest striped over the machine). Persistent, warp-specialised,
+//                          one CTA per SM:
+//        warp 0      TMA producer   cp.async.bulk.tensor (128B-swizzled [128 x 64] query and [256 x 64] database boxes)
+//                                   into a 4-stage mbarrier ring
+//        warp 1      MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (fp16 x fp16 -> fp32,
+//                                   M=128, N=256, K=16) into a double-buffered TMEM accumulator (2 x 256 of 512 columns)
+//        warps 2..5  epilogue       tcgen05.ld 32 lanes x 32 columns; thread == query row, so the running threshold of a
+//                                   query lives in one register and filtering needs no cross-thread traffic. Survivors
+//                                   (rare after warm-up) go to a candidate segment PRIVATE to (query, stripe) -- the slot
+//                                   counter is a register, no returning atomics -- and are counted in a per-query 256-bin
+//                                   score histogram (fire-and-forget reductions) from which the threshold is tightened.
 //   topk_finalize_kernel   one CTA per query: final threshold from the histogram, exact fp32 re-scoring
 //                          (fp64-accumulated) of the few survivors, bitonic sort by (score desc, index asc).
 //
-// Exactness. The bf16 pass only *filters*. With d_q = ||q||*max||x|| * (2^-8 + d*2^-22) (operand rounding
-// plus fp32 accumulation, worst case) every row whose exact score could reach the top k has a coarse score
-// >= t - 2*d_q where t is any value that >= k coarse scores are known to reach. Survivors are re-scored
-// exactly, so returned scores and ranking are those of the exact kernel (score_exact_sm100.cu).
+// Exactness. The fp16 pass only *filters*. With q~ = fp16(q*sq), x~ = fp16(x*sx) (sq, sx exact powers of two) the coarse
+// score c = <q~, x~> (fp32-accumulated on the tensor cores) differs from the exact scaled score sq*sx*<q, x> by at most
+//     E_q = ||q*sq - q~|| * max||x*sx||  +  ||q~|| * max||x*sx - x~||  +  acc(d) * ||q~|| * max||x~||
+// (Cauchy-Schwarz on the two MEASURED rounding residuals; acc(d) bounds the fp32 accumulation of d products, one rounding
+// per K=16 MMA plus the alignment error inside it). Every row whose exact score can reach the top k therefore has a coarse
+// score >= t - 2*E_q, where t is any value that >= k coarse scores are known to reach. Survivors are re-scored exactly
+// from the fp32 rows, so the returned scores and ranking are those of the exact kernel (score_exact_sm100.cu).
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "select.cuh"
@@ -34,7 +40,7 @@ namespace gdt {
 // ---- geometry -----------------------------------------------------------------------------------
 constexpr int kBlockM = 128;   // queries per tile (TMEM lanes)
 constexpr int kBlockN = 256;   // database rows per tile (TMEM columns)
-constexpr int kBlockK = 64;    // bf16 elements per k-block == one 128-byte swizzle span
+constexpr int kBlockK = 64;    // fp16 elements per k-block == one 128-byte swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
@@ -52,16 +58,16 @@ struct QMeta {
     float pad;
 };
 
-// Per-query candidate capacity. Every database stripe of a query tile starts from the threshold published
-// so far (initially -inf), so its first tile can insert all kBlockN rows and a few multiples of k follow
-// before its histogram threshold bites: capacity grows with the number of concurrently started stripes.
-__host__ __device__ inline int cand_capacity(int k, int n_stripes) {
-    long long c = 16LL * k;
-    const long long per_stripe = (long long)n_stripes * (kBlockN + 4LL * k);
-    if (c < per_stripe) c = per_stripe;
-    if (c < 4096) c = 4096;
-    if (c > (1 << 22)) c = 1 << 22;
-    return next_pow2((int)c);
+// Candidate segments. Segment 0 belongs to the seed pass (its capacity covers every row of the seed range, so it
+// cannot overflow); segments 1..n_stripes belong to the stripes of the main pass, which start from the seed threshold.
+__host__ __device__ inline int seed_tiles_for(int k) {
+    int t = (4 * k + kBlockN - 1) / kBlockN;
+    return t < 8 ? 8 : t;
+}
+__host__ __device__ inline int stripe_capacity(int k) {
+    int c = 4 * k;
+    if (c < 512) c = 512;
+    return next_pow2(c);
 }
 __host__ __device__ inline int survivor_capacity(int k) {
     int c = 4 * k;
@@ -133,8 +139,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -163,90 +169,162 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-// kind::f16 instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
-                                ((uint32_t)(kBlockM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (1<<4), A=B=fp16 (format 0 at [7,10) and [10,13)), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 
 // ---- preparation kernels ------------------------------------------------------------------------
 
-// one warp per row: bf16 (round-to-nearest-even) copy + atomic max of the row norm (positive floats
-// order like their bit patterns)
+// db_stats layout (device float[4]): [0] max row norm, [1] power-of-two scale sx, [2] max ||x*sx - fp16(x*sx)||,
+// [3] max ||fp16(x*sx)||
+__device__ __forceinline__ float pow2_scale_for(float norm_max) {
+    // largest power of two s with norm_max * s <= 1 (1 for empty / zero data)
+    if (!(norm_max > 0.f)) return 1.0f;
+    int e;
+    const float m = frexpf(norm_max, &e);      // norm_max = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, (m == 0.5f) ? -(e - 1) : -e);
+}
+
+// one warp per row: max of the row norms (positive floats order like their bit patterns)
 __global__ void __launch_bounds__(256)
-db_prepare_kernel(const float* __restrict__ db, long long ndb, int d, __nv_bfloat16* __restrict__ out,
-                  float* __restrict__ norm_max) {
+db_norm_kernel(const float* __restrict__ db, long long ndb, int d, float* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const long long warps = (long long)gridDim.x * 8;
     float wmax = 0.f;
     for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < ndb; r += warps) {
         const float* x = db + (size_t)r * d;
-        __nv_bfloat16* o = out + (size_t)r * d;
         float ss = 0.f;
-        if ((d & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)o)) & 15) == 0) {
+        if ((d & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
             for (int i = lane; i < (d >> 2); i += 32) {
                 const float4 v = __ldg((const float4*)x + i);
                 ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                uint2 pk;
-                pk.x = *(uint32_t*)&lo;
-                pk.y = *(uint32_t*)&hi;
-                *((uint2*)o + i) = pk;
             }
         } else {
-            for (int i = lane; i < d; i += 32) {
-                const float v = x[i];
-                ss += v * v;
-                o[i] = __float2bfloat16_rn(v);
-            }
+            for (int i = lane; i < d; i += 32) { const float v = x[i]; ss += v * v; }
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
         wmax = fmaxf(wmax, sqrtf(ss));
     }
-    if (lane == 0 && wmax > 0.f) atomicMax((int*)norm_max, __float_as_int(wmax));
+    if (lane == 0 && wmax > 0.f) atomicMax((int*)stats, __float_as_int(wmax));
 }
 
-// one warp per query: bf16 copy, scale / margin, state reset
+// one warp per row: fp16 (round-to-nearest-even) copy of x*sx + maxima of the residual and shadow norms
 __global__ void __launch_bounds__(256)
-q_prepare_kernel(const float* __restrict__ q, int nq, int d, const float* __restrict__ db_norm_max,
-                 __nv_bfloat16* __restrict__ qb, QMeta* __restrict__ meta, uint32_t* __restrict__ tau,
-                 uint32_t* __restrict__ cnt, uint32_t* __restrict__ hist, int32_t* __restrict__ status) {
+db_convert_kernel(const float* __restrict__ db, long long ndb, int d, __half* __restrict__ out, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * 8;
+    const float sx = pow2_scale_for(__ldcg(stats));
+    float rmax = 0.f, hmax = 0.f;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < ndb; r += warps) {
+        const float* x = db + (size_t)r * d;
+        __half* o = out + (size_t)r * d;
+        float rr = 0.f, hh = 0.f;
+        if ((d & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)o)) & 15) == 0) {
+            for (int i = lane; i < (d >> 2); i += 32) {
+                const float4 v = __ldg((const float4*)x + i);
+                const float a[4] = {v.x * sx, v.y * sx, v.z * sx, v.w * sx};
+                __half hv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hv[j] = __float2half_rn(a[j]);
+                    const float f = __half2float(hv[j]), e = a[j] - f;
+                    rr += e * e;
+                    hh += f * f;
+                }
+                uint2 pk;
+                pk.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
+                pk.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
+                *((uint2*)o + i) = pk;
+            }
+        } else {
+            for (int i = lane; i < d; i += 32) {
+                const float a = x[i] * sx;
+                const __half hv = __float2half_rn(a);
+                const float f = __half2float(hv), e = a - f;
+                rr += e * e;
+                hh += f * f;
+                o[i] = hv;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            rr += __shfl_xor_sync(0xffffffffu, rr, s);
+            hh += __shfl_xor_sync(0xffffffffu, hh, s);
+        }
+        rmax = fmaxf(rmax, sqrtf(rr));
+        hmax = fmaxf(hmax, sqrtf(hh));
+    }
+    if (lane == 0) {
+        if (rmax > 0.f) atomicMax((int*)stats + 2, __float_as_int(rmax));
+        if (hmax > 0.f) atomicMax((int*)stats + 3, __float_as_int(hmax));
+        if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] = sx;
+    }
+}
+
+// one warp per query: fp16 copy of q*sq, scale / error bound, state reset
+__global__ void __launch_bounds__(256)
+q_prepare_kernel(const float* __restrict__ q, int nq, int d, const float* __restrict__ db_stats,
+                 __half* __restrict__ qb, QMeta* __restrict__ meta, uint32_t* __restrict__ tau,
+                 uint32_t* __restrict__ cnt, int n_segs, uint32_t* __restrict__ hist, int32_t* __restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x < 4) status[threadIdx.x] = 0;
     if (r >= nq) return;
     const float* x = q + (size_t)r * d;
     float ss = 0.f;
-    for (int i = lane; i < d; i += 32) {
-        const float v = x[i];
-        ss += v * v;
-        qb[(size_t)r * d + i] = __float2bfloat16_rn(v);
-    }
+    for (int i = lane; i < d; i += 32) { const float v = x[i]; ss += v * v; }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    const float sq = pow2_scale_for(sqrtf(ss) * 1.0001f);
+    float rr = 0.f, hh = 0.f;
+    for (int i = lane; i < d; i += 32) {
+        const float a = x[i] * sq;
+        const __half hv = __float2half_rn(a);
+        const float f = __half2float(hv), e = a - f;
+        rr += e * e;
+        hh += f * f;
+        qb[(size_t)r * d + i] = hv;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, s);
+        hh += __shfl_xor_sync(0xffffffffu, hh, s);
+    }
     for (int i = lane; i < kHistBins; i += 32) hist[(size_t)r * kHistBins + i] = 0;
+    for (int i = lane; i < n_segs; i += 32) cnt[(size_t)r * n_segs + i] = 0;
     if (lane == 0) {
+        const float xs_max = __ldg(db_stats) * __ldg(db_stats + 1);          // max ||x * sx||  (<= 1)
+        const float dx_max = __ldg(db_stats + 2), hx_max = __ldg(db_stats + 3);
+        const float dq = sqrtf(rr), hq = sqrtf(hh);
+        // fp32 accumulation on the tensor cores: one rounding per K=16 MMA plus the alignment error inside it
+        const float acc = ((float)(d / 16 + 16)) * 4.76837158203125e-07f;    // * 2^-21
+        const float eq = (dq * xs_max + hq * dx_max + acc * hq * hx_max) * 1.001f;
         QMeta m;
-        m.scale = sqrtf(ss) * __ldg(db_norm_max) * 1.00001f;
+        m.scale = hq * hx_max * 1.0001f;                                     // |coarse score| <= scale
         m.inv_scale = m.scale > 0.f ? 1.0f / m.scale : 0.f;
-        m.margin = 2.0f * m.scale * (0.00390625f + (float)d * 2.384185791015625e-07f) * 1.001f;
-        m.pad = 0.f;
+        m.margin = 2.0f * eq;
+        m.pad = sq;
         meta[r] = m;
         tau[r] = ordered_bits(__int_as_float(0xff800000));
-        cnt[r] = 0;
     }
 }
 
 // ---- the hot kernel -----------------------------------------------------------------------------
 
 struct FilterParams {
-    int nq, d, k, cap;
+    int nq, d, k;
     long long ndb;
-    int n_qtiles, n_dtiles, n_stripes, stripe_len, n_items, n_kblocks;
+    int n_qtiles, n_kblocks;
+    int tile_begin, tile_end;          // database tile range of this launch
+    int n_stripes, stripe_len, n_items;
+    int seg_first;                     // candidate segment of stripe 0 of this launch
+    int n_segs, cap0, cap1;            // segments per query; capacity of segment 0 and of the others
     const QMeta* meta;
     uint32_t* tau;
-    uint32_t* cnt;
+    uint32_t* cnt;                     // [nq][n_segs]
     uint32_t* hist;
-    uint64_t* cand;
+    uint64_t* cand;                    // [nq][cap0 + (n_segs - 1) * cap1]
 };
 
 // per-query threshold from the global histogram (scanned from the top, 128-bit loads through L2)
@@ -316,7 +394,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             uint32_t stage = 0, phase = 0;
             for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
                 const int stripe = item / P.n_qtiles, qt = item - stripe * P.n_qtiles;
-                const int t0 = stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.n_dtiles);
+                const int t0 = P.tile_begin + stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.tile_end);
                 for (int t = t0; t < t1; ++t) {
                     for (int kb = 0; kb < P.n_kblocks; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -335,7 +413,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
                 const int stripe = item / P.n_qtiles;
-                const int t0 = stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.n_dtiles);
+                const int t0 = P.tile_begin + stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.tile_end);
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                     tc_fence_after();
@@ -348,8 +426,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             // +32 bytes along K inside the swizzle span == +2 in the (>>4) address field
-                            umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), kInstrDesc,
-                                      (kb | kk) != 0 ? 1u : 0u);
+                            umma_f16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), kInstrDesc,
+                                     (kb | kk) != 0 ? 1u : 0u);
                         }
                         umma_commit(bar_empty + 8 * stage);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -367,9 +445,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         uint32_t acc = 0, acc_phase = 0;
         for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
             const int stripe = item / P.n_qtiles, qt = item - stripe * P.n_qtiles;
-            const int t0 = stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.n_dtiles);
+            const int t0 = P.tile_begin + stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.tile_end);
             const int qrow = qt * kBlockM + quarter * 32 + lane;
             const bool valid = qrow < P.nq;
+            const int seg = P.seg_first + stripe;
+            const uint32_t segcap = seg == 0 ? (uint32_t)P.cap0 : (uint32_t)P.cap1;
             QMeta m;
             m.scale = 0.f; m.inv_scale = 0.f; m.margin = 0.f; m.pad = 0.f;
             float tau = pos_inf;
@@ -377,9 +457,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 m = P.meta[qrow];
                 tau = from_ordered_bits(__ldcg(P.tau + qrow));
             }
-            uint32_t* hist_row = P.hist + (size_t)(valid ? qrow : 0) * kHistBins;
-            uint64_t* cand_row = P.cand + (size_t)(valid ? qrow : 0) * P.cap;
-            uint32_t inserted = 0;
+            const size_t qv = valid ? (size_t)qrow : 0;
+            uint32_t* hist_row = P.hist + qv * kHistBins;
+            uint64_t* seg_row = P.cand + qv * ((size_t)P.cap0 + (size_t)(P.n_segs - 1) * P.cap1) +
+                                (seg == 0 ? (size_t)0 : (size_t)P.cap0 + (size_t)(seg - 1) * P.cap1);
+            uint32_t slot = 0, inserted = 0;
             int tiles_done = 0;
             for (int t = t0; t < t1; ++t) {
                 if (valid && t != t0) tau = fmaxf(tau, from_ordered_bits(__ldcg(P.tau + qrow)));
@@ -392,25 +474,32 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_addr + acc * kBlockN + c * 32, v);
                     tmem_ld_wait();
-                    float mx = __uint_as_float(v[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    if (mx >= tau) {
-                        uint32_t mask = 0;
+                    if (c * 32 + 32 > ncols) {      // ragged last tile: rows past the end of the shard never qualify
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (__uint_as_float(v[j]) >= tau && c * 32 + j < ncols) mask |= 1u << j;
-                        if (mask) {
-                            const uint32_t n = __popc(mask);
-                            uint32_t slot = atomicAdd(P.cnt + qrow, n);
-                            inserted += n;
+                            if (c * 32 + j >= ncols) v[j] = 0xff800000u;
+                    }
+                    float mg[4];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (mask & (1u << j)) {
-                                    if (slot < (uint32_t)P.cap)
-                                        cand_row[slot] = ((uint64_t)v[j] << 32) | (uint32_t)(col0 + c * 32 + j);
-                                    ++slot;
-                                    atomicAdd(hist_row + score_bin(__uint_as_float(v[j]), m.inv_scale), 1u);
+                    for (int g = 0; g < 4; ++g) {
+                        float x = __uint_as_float(v[g * 8]);
+#pragma unroll
+                        for (int j = 1; j < 8; ++j) x = fmaxf(x, __uint_as_float(v[g * 8 + j]));
+                        mg[g] = x;
+                    }
+                    if (fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3])) >= tau) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (mg[g] >= tau) {
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj) {
+                                    const int j = g * 8 + jj;
+                                    if (__uint_as_float(v[j]) >= tau) {
+                                        if (slot < segcap)
+                                            seg_row[slot] = ((uint64_t)v[j] << 32) | (uint32_t)(col0 + c * 32 + j);
+                                        ++slot;
+                                        atomicAdd(hist_row + score_bin(__uint_as_float(v[j]), m.inv_scale), 1u);
+                                    }
                                 }
                             }
                         }
@@ -423,15 +512,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 ++tiles_done;
                 // tighten the threshold: on a doubling schedule while warming up, whenever many candidates
                 // went in, and when leaving the stripe
-                if (valid && inserted != 0 &&
-                    ((tiles_done & (tiles_done - 1)) == 0 || inserted >= 64 || t + 1 == t1)) {
+                const uint32_t fresh = slot - inserted;
+                if (valid && fresh != 0 && ((tiles_done & (tiles_done - 1)) == 0 || fresh >= 32 || t + 1 == t1)) {
                     __threadfence();
                     const float nt = scan_threshold(hist_row, P.k, m);
                     if (nt > tau) tau = nt;
                     atomicMax(P.tau + qrow, ordered_bits(tau));
-                    inserted = 0;
+                    inserted = slot;
                 }
             }
+            if (valid) P.cnt[(size_t)qrow * P.n_segs + seg] = slot;
         }
         (void)neg_inf;
     }
@@ -447,10 +537,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // ---- finalisation -------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
-topk_finalize_kernel(const float* __restrict__ q, const float* __restrict__ db, int d, int dpad, int k, int cap, int scap,
-                     long long index_base, const QMeta* __restrict__ meta, const uint32_t* __restrict__ cnt,
-                     const uint32_t* __restrict__ hist, const uint64_t* __restrict__ cand, float* __restrict__ out_s,
-                     int64_t* __restrict__ out_i, int32_t* __restrict__ status) {
+topk_finalize_kernel(const float* __restrict__ q, const float* __restrict__ db, int d, int dpad, int k, int n_segs, int cap0,
+                     int cap1, int scap, long long index_base, const QMeta* __restrict__ meta,
+                     const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ hist, const uint64_t* __restrict__ cand,
+                     float* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t fsm[];
     uint64_t* keys = (uint64_t*)fsm;                      // [scap]
     float* qrow = (float*)(fsm + (size_t)scap * 8);       // [dpad]
@@ -479,15 +569,23 @@ topk_finalize_kernel(const float* __restrict__ q, const float* __restrict__ db, 
     __syncthreads();
     const float thr = bin_threshold(s_bin, m);
 
-    const uint32_t total = cnt[qi];
-    bool overflow = total > (uint32_t)cap;
-    const uint32_t n = overflow ? (uint32_t)cap : total;
-    const uint64_t* crow = cand + (size_t)qi * cap;
-    for (uint32_t i = tid; i < n; i += 256) {
-        const uint64_t c = __ldg(crow + i);
-        if (__uint_as_float((uint32_t)(c >> 32)) >= thr) {
-            const uint32_t pos = atomicAdd(&s_ns, 1u);
-            if (pos < (uint32_t)scap) keys[pos] = c;
+    // gather the candidates that pass the final threshold from every segment of this query
+    bool overflow = false;
+    uint32_t total = 0;
+    const uint64_t* qcand = cand + (size_t)qi * ((size_t)cap0 + (size_t)(n_segs - 1) * cap1);
+    for (int sgm = 0; sgm < n_segs; ++sgm) {
+        const uint32_t cap = sgm == 0 ? (uint32_t)cap0 : (uint32_t)cap1;
+        const uint32_t have = cnt[(size_t)qi * n_segs + sgm];
+        total += have;
+        if (have > cap) overflow = true;
+        const uint32_t n = have > cap ? cap : have;
+        const uint64_t* crow = qcand + (sgm == 0 ? (size_t)0 : (size_t)cap0 + (size_t)(sgm - 1) * cap1);
+        for (uint32_t i = tid; i < n; i += 256) {
+            const uint64_t c = __ldg(crow + i);
+            if (__uint_as_float((uint32_t)(c >> 32)) >= thr) {
+                const uint32_t pos = atomicAdd(&s_ns, 1u);
+                if (pos < (uint32_t)scap) keys[pos] = c;
+            }
         }
     }
     __syncthreads();
@@ -541,7 +639,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-static int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows) {
+static int make_f16_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) {
         snprintf(tls_error_buf(), 512, "cuTensorMapEncodeTiled entry point not found");
@@ -551,7 +649,7 @@ static int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int
     const cuuint64_t strides[1] = {(cuuint64_t)d * 2};
     const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -561,30 +659,11 @@ static int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int
     return GDT_OK;
 }
 
-struct TopkLayout {
-    size_t qb, meta, tau, cnt, hist, cand, total;
-    int cap;
-};
-
-static TopkLayout topk_layout(int nq, int d, int k, int n_stripes) {
-    TopkLayout L;
-    size_t off = 0;
-    auto take = [&](size_t bytes) { off = align_up(off, 256); const size_t r = off; off += bytes; return r; };
-    L.cap = cand_capacity(k, n_stripes);
-    L.qb = take((size_t)nq * d * 2);
-    L.meta = take((size_t)nq * sizeof(QMeta));
-    L.tau = take((size_t)nq * 4);
-    L.cnt = take((size_t)nq * 4);
-    L.hist = take((size_t)nq * kHistBins * 4);
-    L.cand = take((size_t)nq * L.cap * 8);
-    L.total = align_up(off, 256);
-    return L;
-}
-
 // pick the number of database stripes so that items fill whole waves of the persistent grid
 static void plan_items(int n_qtiles, int n_dtiles, int sms, int& n_stripes, int& stripe_len) {
     double best = -1.0;
     n_stripes = 1;
+    if (n_dtiles <= 0) { n_stripes = 0; stripe_len = 1; return; }
     for (int s = 1; s <= n_dtiles && s <= 4096; ++s) {
         const int len = ceil_div(n_dtiles, s);
         const int s_eff = ceil_div(n_dtiles, len);
@@ -601,6 +680,32 @@ static void plan_items(int n_qtiles, int n_dtiles, int sms, int& n_stripes, int&
     n_stripes = ceil_div(n_dtiles, stripe_len);
 }
 
+struct TopkPlan {
+    int n_qtiles, n_dtiles, seed_tiles, n_stripes, stripe_len, n_segs, cap0, cap1;
+    size_t qb, meta, tau, cnt, hist, cand, total;
+};
+
+static TopkPlan topk_plan(int nq, long long ndb, int d, int k) {
+    TopkPlan L;
+    L.n_qtiles = ceil_div(nq, kBlockM);
+    L.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
+    L.seed_tiles = seed_tiles_for(k) < L.n_dtiles ? seed_tiles_for(k) : L.n_dtiles;
+    plan_items(L.n_qtiles, L.n_dtiles - L.seed_tiles, sm_count_current_device(), L.n_stripes, L.stripe_len);
+    L.n_segs = 1 + L.n_stripes;
+    L.cap0 = L.seed_tiles * kBlockN;
+    L.cap1 = stripe_capacity(k);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = align_up(off, 256); const size_t r = off; off += bytes; return r; };
+    L.qb = take((size_t)nq * d * 2);
+    L.meta = take((size_t)nq * sizeof(QMeta));
+    L.tau = take((size_t)nq * 4);
+    L.cnt = take((size_t)nq * L.n_segs * 4);
+    L.hist = take((size_t)nq * kHistBins * 4);
+    L.cand = take((size_t)nq * ((size_t)L.cap0 + (size_t)L.n_stripes * L.cap1) * 8);
+    L.total = align_up(off, 256);
+    return L;
+}
+
 }  // namespace gdt
 
 using namespace gdt;
@@ -610,80 +715,85 @@ extern "C" size_t gdt_db_prepare_workspace_bytes(long long ndb, int d) {
     return 256;
 }
 
-extern "C" int gdt_db_prepare(const float* db, long long ndb, int d, void* db_bf16, float* db_norm_max, void* ws,
+extern "C" int gdt_db_prepare(const float* db, long long ndb, int d, void* db_f16, float* db_stats, void* ws,
                               size_t ws_bytes, void* stream_) {
     (void)ws; (void)ws_bytes;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!db || !db_bf16 || !db_norm_max || ndb <= 0 || d <= 0) return GDT_ERR_INVALID_ARGUMENT;
+    if (!db || !db_f16 || !db_stats || ndb <= 0 || d <= 0) return GDT_ERR_INVALID_ARGUMENT;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
-    GDT_CUDA(cudaMemsetAsync(db_norm_max, 0, sizeof(float), stream));
+    GDT_CUDA(cudaMemsetAsync(db_stats, 0, 4 * sizeof(float), stream));
     const int sms = sm_count_current_device();
     long long blocks = ceil_div_ll(ndb, 8);
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-    db_prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, (__nv_bfloat16*)db_bf16, db_norm_max);
+    db_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, db_stats);
+    GDT_LAUNCH_CHECK();
+    db_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, (__half*)db_f16, db_stats);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
 
 extern "C" size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k) {
     if (nq <= 0 || ndb <= 0 || d <= 0 || k <= 0) return 0;
-    int n_stripes, stripe_len;
-    plan_items(ceil_div(nq, kBlockM), (int)ceil_div_ll(ndb, kBlockN), sm_count_current_device(), n_stripes, stripe_len);
-    return topk_layout(nq, d, k, n_stripes).total + 256;
+    return topk_plan(nq, ndb, d, k).total + 256;
 }
 
-extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_bf16, const float* db_norm_max, int nq,
+extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_f16, const float* db_stats, int nq,
                               long long ndb, int d, int k, long long index_base, float* top_scores, int64_t* top_idx,
                               int32_t* status_dev, void* ws, size_t ws_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!q || !db || !db_bf16 || !db_norm_max || !top_scores || !top_idx || !status_dev || !ws)
+    if (!q || !db || !db_f16 || !db_stats || !top_scores || !top_idx || !status_dev || !ws)
         return GDT_ERR_INVALID_ARGUMENT;
     if (nq <= 0 || ndb <= 0 || d <= 0 || k <= 0) return GDT_ERR_INVALID_ARGUMENT;
     if ((d & 7) != 0 || d > 8192 || k > 1024 || ndb > 0x7fffffffLL || index_base < 0 ||
         index_base + ndb > 0xffffffffLL)
         return GDT_ERR_UNSUPPORTED;
-    if ((((uintptr_t)db_bf16) & 15) != 0) return GDT_ERR_INVALID_ARGUMENT;
+    if ((((uintptr_t)db_f16) & 15) != 0) return GDT_ERR_INVALID_ARGUMENT;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
     if (ws_bytes < gdt_score_topk_workspace_bytes(nq, ndb, d, k) || (((uintptr_t)ws) & 255)) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
-    FilterParams P;
-    P.n_qtiles = ceil_div(nq, kBlockM);
-    P.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
-    const int sms = sm_count_current_device();
-    plan_items(P.n_qtiles, P.n_dtiles, sms, P.n_stripes, P.stripe_len);
-    const TopkLayout L = topk_layout(nq, d, k, P.n_stripes);
+    const TopkPlan L = topk_plan(nq, ndb, d, k);
     char* base = (char*)ws;
-    __nv_bfloat16* qb = (__nv_bfloat16*)(base + L.qb);
+    __half* qb = (__half*)(base + L.qb);
     QMeta* meta = (QMeta*)(base + L.meta);
     uint32_t* tau = (uint32_t*)(base + L.tau);
     uint32_t* cnt = (uint32_t*)(base + L.cnt);
     uint32_t* hist = (uint32_t*)(base + L.hist);
     uint64_t* cand = (uint64_t*)(base + L.cand);
 
-    q_prepare_kernel<<<ceil_div(nq, 8), 256, 0, stream>>>(q, nq, d, db_norm_max, qb, meta, tau, cnt, hist, status_dev);
+    q_prepare_kernel<<<ceil_div(nq, 8), 256, 0, stream>>>(q, nq, d, db_stats, qb, meta, tau, cnt, L.n_segs, hist, status_dev);
     GDT_LAUNCH_CHECK();
 
     CUtensorMap map_q, map_db;
-    int rc = make_bf16_map(&map_q, qb, nq, d, kBlockM);
+    int rc = make_f16_map(&map_q, qb, nq, d, kBlockM);
     if (rc != GDT_OK) return rc;
-    rc = make_bf16_map(&map_db, db_bf16, ndb, d, kBlockN);
+    rc = make_f16_map(&map_db, db_f16, ndb, d, kBlockN);
     if (rc != GDT_OK) return rc;
-
-    P.nq = nq; P.d = d; P.k = k; P.cap = L.cap; P.ndb = ndb;
-    P.n_items = P.n_stripes * P.n_qtiles;
-    P.n_kblocks = ceil_div(d, kBlockK);
-    P.meta = meta; P.tau = tau; P.cnt = cnt; P.hist = hist; P.cand = cand;
 
     static bool attr_set = false;
     if (!attr_set) {
         GDT_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set = true;
     }
-    const int grid = P.n_items < sms ? P.n_items : sms;
-    score_filter_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
+    const int sms = sm_count_current_device();
+    FilterParams P;
+    P.nq = nq; P.d = d; P.k = k; P.ndb = ndb;
+    P.n_qtiles = L.n_qtiles;
+    P.n_kblocks = ceil_div(d, kBlockK);
+    P.n_segs = L.n_segs; P.cap0 = L.cap0; P.cap1 = L.cap1;
+    P.meta = meta; P.tau = tau; P.cnt = cnt; P.hist = hist; P.cand = cand;
+    // seed pass: the first tiles of the shard against every query tile establish the thresholds
+    P.tile_begin = 0; P.tile_end = L.seed_tiles;
+    P.n_stripes = 1; P.stripe_len = L.seed_tiles; P.n_items = L.n_qtiles; P.seg_first = 0;
+    score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
     GDT_LAUNCH_CHECK();
+    if (L.n_stripes > 0) {
+        P.tile_begin = L.seed_tiles; P.tile_end = L.n_dtiles;
+        P.n_stripes = L.n_stripes; P.stripe_len = L.stripe_len; P.n_items = L.n_stripes * L.n_qtiles; P.seg_first = 1;
+        score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
+        GDT_LAUNCH_CHECK();
+    }
 
     const int scap = survivor_capacity(k);
     const int dpad = (d + 3) & ~3;
@@ -693,8 +803,8 @@ extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_bf
         GDT_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fattr = fsmem;
     }
-    topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.cap, scap, index_base, meta, cnt, hist, cand,
-                                                     top_scores, top_idx, status_dev);
+    topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.n_segs, L.cap0, L.cap1, scap, index_base, meta,
+                                                     cnt, hist, cand, top_scores, top_idx, status_dev);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

@@ -106,7 +106,7 @@ class CudaOps:
 
 
 class DatabaseShard:
-    """Rows [index_base, index_base + n) of the database, resident in HBM: fp32 rows + the bf16 shadow used by the
+    """Rows [index_base, index_base + n) of the database, resident in HBM: fp32 rows + the fp16 shadow used by the
     tcgen05 coarse pass (6 bytes per element in total)."""
 
     def __init__(self, db, index_base=0, ops=None):

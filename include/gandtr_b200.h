@@ -64,6 +64,11 @@ int gdt_is_initialised(void);
 /* debug/test hook: copy the 1024x4 inverse-gamma spline table built by gdt_init to host memory */
 int gdt_debug_get_spline_table(float* host_out_4096);
 
+/* debug/test hook: K1 replaces `(x - mean) / std` by a divider-free, correctly rounded sequence; this counts (into the
+ * device counter, which the caller zeroes) the floats a with bit pattern in [lo_bits, hi_bits], both signs, for which
+ * that sequence differs from IEEE a / b. Expected: 0. */
+int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches_dev, void* stream);
+
 /* ---- K1: CLAHE preprocessing ------------------------------------------------------------------
  * Fused `pil2np | apply_clahe:clip:grid:lab | totensor | normalize`
  * (mdir/components/data/transform/core_transforms.py:35-100,
@@ -104,40 +109,63 @@ int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, i
 #define GDT_MAX_SCALES 8
 #define GDT_GEM_AGGREGATE 1
 #define GDT_GEM_MSP_IS_P 2
+#define GDT_DESC_NORMALISED 4 /* internal to gdt_desc_post: inputs are already L2-normalised descriptors */
 size_t gdt_gem_whiten_workspace_bytes(int n, int c, int scales, int dim);
 int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h, const int* host_w,
                    int n, int c, int scales, const float* p_dev, float eps, int flags,
                    const float* P, int ldP, const float* m, int dim,
                    float* desc, void* ws, size_t ws_bytes, void* stream);
 
+/* The module-level pieces of the same path, for callers that drive the reference's objects one by one:
+ *   gdt_gem_pool  `GeM.forward` / LF.gem (layers/pooling.py:36-47, layers/functional.py:21-22):
+ *                 fmap [n][c][h][w] -> pooled [n][c] (no normalisation)
+ *   gdt_l2n_rows  `L2N.forward` / LF.l2n (layers/normalization.py:10-20, layers/functional.py:130-131):
+ *                 out[r] = x[r] / (||x[r]||_2 + eps), x/out [n][dim] (in place allowed)
+ *   gdt_desc_post `CirMultiscaleAggregation.aggregate_tensor` (wrapper.py:235-245) and/or
+ *                 `CirtorchWhiten.postprocess` (wrapper.py:320-322) on already L2-normalised descriptors:
+ *                 host_descs[s] : device pointers to [n][c] per-scale descriptors; exponent of the
+ *                 generalised mean = msp_dev[0] when flags has GDT_GEM_MSP_IS_P (device read, no sync), else
+ *                 msp_host; GDT_GEM_AGGREGATE as in gdt_gem_whiten; P/m/dim as in gdt_gem_whiten. */
+int gdt_gem_pool(const float* fmap, int n, int c, int h, int w, const float* p_dev, float eps, float* pooled,
+                 void* stream);
+int gdt_l2n_rows(const float* x, int n, int dim, float eps, float* out, void* stream);
+size_t gdt_desc_post_workspace_bytes(int n, int c, int dim);
+int gdt_desc_post(const float* const* host_descs, int n, int c, int scales, const float* msp_dev, float msp_host,
+                  int flags, const float* P, int ldP, const float* m, int dim, float* out,
+                  void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K3: query x database scoring fused with streaming top-k ----------------------------------------
  * Replaces `scores = np.dot(vecs.T, qvecs); ranks = np.argsort(-scores, axis=0)` restricted to the
  * first k ranks (mdir/components/optim/score/cirscore.py:71-72).
  *
- * Database shards are prepared once (gdt_db_prepare): a bf16 shadow copy feeds the tcgen05 coarse
- * pass, the fp32 rows feed the exact re-scoring of the few survivors, so the returned scores are
- * fp32-exact (fp64-accumulated dot, rounded once) and the ranking is exact:
- * ordering = (score descending, global index ascending).
+ * Database shards are prepared once (gdt_db_prepare): an fp16 shadow copy (rows scaled by an exact power of
+ * two) feeds the tcgen05 coarse pass, the fp32 rows feed the exact re-scoring of the few survivors, so the
+ * returned scores are fp32-exact (fp64-accumulated dot, rounded once) and the ranking is exact:
+ * ordering = (score descending, global index ascending). The coarse pass only filters, with a margin derived
+ * from the measured fp16 rounding residuals (see score_topk_sm100.cu).
  *
  * q        : float32 [nq][d] row-major queries            db : float32 [ndb][d] row-major shard
- * db_bf16  : shadow written by gdt_db_prepare, [ndb][d] bf16
- * db_norm_max : device float, max L2 norm over the shard's rows (written by gdt_db_prepare)
+ * db_f16   : shadow written by gdt_db_prepare, [ndb][d] fp16 (16-byte aligned)
+ * db_stats : device float[4] written by gdt_db_prepare: max row norm, power-of-two scale, max norm of the
+ *            rounding residual, max norm of the shadow rows
  * top_scores/top_idx : [nq][k]; top_idx holds index_base + local row; when ndb < k the tail is
  *            filled with (-inf, -1)
  * status_dev : device int32[4], zero on success; [0] = GDT_ERR_CANDIDATE_OVERFLOW if a query's
- *            candidate set did not fit (results for that query are then not trustworthy),
- *            [1] = worst-case number of candidates re-scored for one query (diagnostic)
+ *            candidate set did not fit (that query's top_idx[0] is -2 and its results must be recomputed with
+ *            gdt_score_topk_exact), [1] = largest number of candidates re-scored for one query,
+ *            [2] = number of overflowed queries, [3] = largest number of coarse candidates of one query
+ * Requirements: d % 8 == 0, d <= 8192, k <= 1024, index_base + ndb <= 2^32.
  */
 size_t gdt_db_prepare_workspace_bytes(long long ndb, int d);
-int gdt_db_prepare(const float* db, long long ndb, int d, void* db_bf16, float* db_norm_max,
+int gdt_db_prepare(const float* db, long long ndb, int d, void* db_f16, float* db_stats,
                    void* ws, size_t ws_bytes, void* stream);
 size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k);
-int gdt_score_topk(const float* q, const float* db, const void* db_bf16, const float* db_norm_max,
+int gdt_score_topk(const float* q, const float* db, const void* db_f16, const float* db_stats,
                    int nq, long long ndb, int d, int k, long long index_base,
                    float* top_scores, int64_t* top_idx, int32_t* status_dev,
                    void* ws, size_t ws_bytes, void* stream);
 
-/* Exact CUDA-core variant of the same contract (no bf16 shadow, no tensor cores); used for small
+/* Exact CUDA-core variant of the same contract (no fp16 shadow, no tensor cores); used for small
  * problems and as an on-device cross-check of the tcgen05 path. */
 size_t gdt_score_topk_exact_workspace_bytes(int nq, long long ndb, int d, int k);
 int gdt_score_topk_exact(const float* q, const float* db, int nq, long long ndb, int d, int k,

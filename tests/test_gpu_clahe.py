@@ -84,3 +84,17 @@ def test_errors_are_loud():
         _lib.clahe_u8(torch.zeros((1, 8, 8, 3), dtype=torch.uint8), MEAN, STD)      # CPU tensor: no fallback
     with pytest.raises(_lib.GdtError):
         _lib.clahe_u8(torch.zeros((1, 8, 8, 3), dtype=torch.float32).cuda(), MEAN, STD)
+
+
+@pytest.mark.parametrize("std", [0.229, 0.224, 0.225, 0.5, 1.0, 0.3333333])
+def test_divider_free_normalisation_is_ieee_division_exhaustive(std):
+    """K1's `(x - mean) / std` uses a divider-free sequence: check EVERY float a with 2^-30 <= |a| <= 8 against a / std."""
+    import ctypes
+    from gandtr_b200 import _lib
+    lib = _lib.load()
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lo = np.float32(2.0 ** -30).view(np.uint32)
+    hi = np.float32(8.0).view(np.uint32)
+    _lib.check(lib.gdt_debug_div_check(ctypes.c_float(std), int(lo), int(hi), ctypes.c_void_p(cnt.data_ptr()),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gdt_debug_div_check")
+    assert int(cnt.item()) == 0

@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference interface, on the GPU: hub entry points, transform registry, modules, wrappers,
+the fused eval stack and the retrieval-evaluation entry points. Goldens come from the unmodified reference
+(tools/gen_golden.py); tolerances: CLAHE bit-exact, descriptors 1e-5 relative (conv backbone: cuDNN fp32 vs the
+reference's CPU convs, tolerance stated per test)."""
+import io
+import numpy as np
+import pytest
+import torch
+
+from oracle import descriptors_np as D
+from oracle import retrieval_np as R
+from tests.util import MEAN, STD, golden, load_lut, synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vgg():
+    from gandtr_b200 import hub
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)                        # same seed and constructor order as tools/gen_golden.py
+    return hub.gem_vgg16_hedngan(pretrained=False)
+
+
+def test_hub_model_surface(vgg):
+    assert repr(vgg.transform) == ("Compose(\n    Pil2Numpy()\n    ApplyClahe(clip_limit=1.0, grid_size=8, colorspace=lab)\n"
+                                   "    ToTensor()\n    Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225], "
+                                   "strict_shape=True)\n)")
+    assert vgg.meta["architecture"] == "vgg16" and vgg.meta["out_channels"] == 512 and vgg.meta["pooling"] == "gem"
+    assert "pool.p" in vgg.model.state_dict()
+    assert vgg.network_params.runtime["data"]["mean_std"] == [MEAN, STD]
+    assert vgg.stage == "eval" and not vgg.model.training
+
+
+def test_hub_transform_and_descriptor_match_reference_golden(vgg):
+    from PIL import Image
+    from oracle import clahe_np
+    g = golden("hub_vgg16_tiny.npz")
+    x = vgg.transform(Image.fromarray(g["img"]))
+    assert x.is_cuda and tuple(x.shape) == (3,) + g["img"].shape[:2]
+    ref = clahe_np.transform_u8(g["img"], load_lut(), MEAN, STD)
+    assert np.array_equal(x.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    with torch.no_grad():
+        vec = vgg(x.unsqueeze(0))
+    assert tuple(vec.shape) == (512, 1)
+    v = vec.cpu().numpy()
+    assert abs(np.linalg.norm(v) - 1.0) < 1e-5
+    # conv stack differs (cuDNN vs the reference's CPU kernels): 16 conv layers of fp32 round-off
+    np.testing.assert_allclose(v, g["desc"], rtol=0, atol=2e-4)
+
+
+def test_modules_match_oracle():
+    from gandtr_b200.network import GeM, L2N
+    rs = np.random.RandomState(3)
+    f = np.abs(rs.normal(0, 1, (3, 40, 9, 13))).astype(np.float32)
+    for p in (3.0, 2.92):
+        pool = GeM(p=p).cuda()
+        y = pool(torch.from_numpy(f).cuda())
+        assert tuple(y.shape) == (3, 40, 1, 1)
+        np.testing.assert_allclose(y.cpu().numpy()[:, :, 0, 0], D.gem(f, p), rtol=2e-6)
+        z = L2N()(y)
+        np.testing.assert_allclose(z.cpu().numpy()[:, :, 0, 0], D.l2n(D.gem(f, p)), rtol=3e-6, atol=1e-8)
+    assert repr(GeM()) == "GeM(p=3.0000, eps=1e-06)" and repr(L2N()) == "L2N(eps=1e-06)"
+
+
+def test_wrappers_standalone_match_reference_goldens():
+    from gandtr_b200.network import CirMultiscaleAggregation, CirtorchWhiten
+    g = golden("descriptors.npz")
+    for ci in range(2):
+        fm = [g[k] for k in sorted(k for k in g.files if k.startswith("c%d_fmap" % ci))]
+        p = float(g["c%d_p" % ci])
+        c = fm[0].shape[1]
+        per_scale = [torch.from_numpy(D.forward_descriptor(f, p)).cuda() for f in fm]          # N x D, oracle
+        wh = CirtorchWhiten({"P": g["c%d_P" % ci], "m": g["c%d_m" % ci]}, int(g["c%d_dim" % ci]), device="cuda")
+        for i in range(fm[0].shape[0]):
+            cols = [ps[i].reshape(c, 1).clone() for ps in per_scale]                            # D x 1 per scale
+            agg = CirMultiscaleAggregation.aggregate_tensor(cols, len(cols), c, p)
+            assert tuple(agg.shape) == (c,)
+            np.testing.assert_allclose(agg.cpu().numpy(), g["c%d_agg" % ci][i], rtol=2e-5, atol=2e-7)
+            w = wh.postprocess(agg.clone(), None, None)
+            assert tuple(w.shape) == (int(g["c%d_dim" % ci]),)
+            np.testing.assert_allclose(w.cpu().numpy(), g["c%d_whiten" % ci][i], rtol=1e-4, atol=2e-6)
+        # device-resident exponent (no host sync)
+        agg2 = CirMultiscaleAggregation.aggregate_tensor([ps[0].reshape(c, 1) for ps in per_scale], len(fm), c,
+                                                         torch.tensor([p], device="cuda"))
+        np.testing.assert_allclose(agg2.cpu().numpy(), g["c%d_agg" % ci][0], rtol=2e-5, atol=2e-7)
+
+
+def test_fused_eval_stack_equals_wrapper_by_wrapper_path(vgg):
+    """{0_cirwhiten, 1_cirmultiscale} (mdir/hub/embedding.yml:24-25): the fused K2 path against (a) the same wrappers run
+    one by one through the Compose protocol and (b) a float64 restatement on the same feature maps."""
+    from gandtr_b200 import network as N
+    rs = np.random.RandomState(9)
+    c = 512
+    whit = {"P": rs.normal(0, 1, (c, c)) / np.sqrt(c), "m": 0.05 * rs.rand(c, 1)}
+    runtime = {"data": vgg.network_params.runtime["data"],
+               "wrappers": {"train": None, "eval": {"0_cirwhiten": {"whitening": whit, "dimensions": 128},
+                                                    "1_cirmultiscale": {"scales": True}}}}
+    net = N.SingleNetwork(vgg.model, N.SingleNetwork.NetworkParams(vgg.network_params.model, runtime), "cuda", frozen=True)
+    img = synth_image(77, 160, 224, "smooth")
+    x = vgg.transform(img).unsqueeze(0)
+    with torch.no_grad():
+        fused = net(x)
+        assert tuple(fused.shape) == (128,)
+        generic = net.wrappers["eval"](x, net.forward_batch, outputmodel=net.model)
+        fmaps = [net.model.feature_map(N.CirMultiscaleAggregation.interpolate(x, s)).cpu().numpy()
+                 for s in net.wrappers["eval"].wrappers[1].scales]
+    ref = D.descriptor_pipeline(fmaps, p=3.0, aggregate=True, msp_is_p=True, P=whit["P"], m=whit["m"], dimensions=128)[0]
+    np.testing.assert_allclose(fused.cpu().numpy(), ref, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(generic.cpu().numpy(), fused.cpu().numpy(), rtol=1e-4, atol=2e-6)
+    assert abs(float(fused.norm()) - 1.0) < 1e-5
+    # batches are an extension over the reference (which is batch-size-1 here): D x N
+    with torch.no_grad():
+        both = net(torch.cat([x, x.flip(-1)]))
+    assert tuple(both.shape) == (128, 2)
+    np.testing.assert_allclose(both[:, 0].cpu().numpy(), fused.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_clahepost_wrapper_matches_reference_golden():
+    from gandtr_b200.network import ClahePost
+    g = golden("clahe_post.npz")
+    post = ClahePost("[[0.5,0.5,0.5],[0.5,0.5,0.5]]", "1.0", device="cuda")
+    y = post.postprocess(torch.from_numpy(g["x0"]).cuda(), None, None)
+    assert np.array_equal(y.cpu().numpy().view(np.uint32), g["y0"].view(np.uint32))
+
+
+def test_retrieval_evaluation_entry_points_match_reference_golden():
+    from gandtr_b200.retrieval import ShardedIndex, compute_map_and_print
+    g = golden("map_eval.npz")
+    q, db = torch.from_numpy(g["q"]).cuda(), torch.from_numpy(g["db"]).cuda()
+    index = ShardedIndex(db)
+    s, i = index.search(q, 100)
+    os_, oi = R.topk(R.scores_exact(g["q"], g["db"]), 100)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    gnd = [{"bbx": None, "easy": e[e >= 0], "hard": h[h >= 0], "junk": j[j >= 0]}
+           for e, h, j in zip(g["easy"], g["hard"], g["junk"])]
+    lines = []
+    avg, per = compute_map_and_print("roxford5k", index, q, gnd, printer=lines.append)
+    for name in ("easy", "medium", "hard"):
+        assert abs(avg["map_" + name] - float(g["map_" + name])) < 1e-6            # "identical mAP to 0.1" with margin
+        np.testing.assert_allclose(per["ap_" + name], g["ap_" + name], rtol=0, atol=1e-6, equal_nan=True)
+    assert lines[0].startswith(">> roxford5k: mAP E: ") and "mP@k[1, 5, 10]" in lines[1]
+    gnd_old = [{"ok": np.concatenate([x["easy"], x["hard"]]), "junk": x["junk"]} for x in gnd]
+    gnd_old[3]["ok"] = np.array([], dtype=np.int64)
+    avg_old, per_old = compute_map_and_print("tokyo", index, q, gnd_old, printer=lines.append)
+    assert abs(avg_old["map"] - float(g["old_map"])) < 1e-6 and np.isnan(per_old["ap"][3])
+
+
+def test_generators_build_in_stock_pytorch():
+    from gandtr_b200 import hub
+    gen = hub.cyclegan(pretrained=False)
+    x = gen.transform(synth_image(5, 64, 64, "smooth")).unsqueeze(0)
+    with torch.no_grad():
+        y = gen(x)
+    assert tuple(y.shape) == (1, 3, 64, 64) and float(y.abs().max()) <= 1.0
+    with pytest.raises(NotImplementedError):
+        hub.gem_vgg16_cyclegan(pretrained=True, weights_dir=None)
