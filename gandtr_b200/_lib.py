@@ -347,7 +347,7 @@ def score_topk(q, db, shadow, norm_max, k, index_base=0, ws=None, out=None):
         check(lib.gdt_score_topk(_ptr(q), _ptr(db), _ptr(shadow), _ptr(norm_max), nq, ndb, d, k, int(index_base),
                                  _ptr(scores), _ptr(idx), _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_score_topk")
     global launch_count
-    seed = max(8, (4 * k + 255) // 256)
+    seed = max(32, (16 * k + 255) // 256)
     launch_count += 3 + (1 if (ndb + 255) // 256 > seed else 0)   # q_prepare, seed (+ main) filter pass, finalize
     return scores, idx, status
 

@@ -124,20 +124,30 @@ GDT_HD void lab_cell(float x01, int& t, int& f) {
 // (v * 16384 / 255 is never within 1/510 of a half-integer, far outside the float rounding error; all 256 values are
 // checked in tests/test_clahe_fastmath.py).
 GDT_HD void lab_cell_u8(int v, int& t, int& f) {
-    const int c = (v * 32768 + 255) / 510;
-    t = c >> 9;
-    f = (c >> 5) & 15;
-    if (t >= 32) { t = 31; f = 16; }
+    // (c >> 5) with c = (v*32768 + 255) / 510 is one division: floor(floor(X / 510) / 32) == floor(X / 16320)
+    const unsigned tf = ((unsigned)v * 32768u + 255u) / 16320u;   // t << 4 | f, 512 only for v == 255
+    t = (int)(tf >> 4);
+    f = (int)(tf & 15u);
+    if (tf == 512u) { t = 31; f = 16; }
 }
 
 // One channel of the trilinear interpolation. `w` holds the four (dx,dy) corner pairs of the cell,
 // each 32-bit word = value(dz=0) | value(dz=1) << 16 (values in [0,16384]).
 GDT_HD int lab_trilinear(uint32_t w00, uint32_t w01, uint32_t w10, uint32_t w11, int fr, int fg, int fb) {
     const int wz1 = fb, wz0 = 16 - fb;
+#if defined(__CUDA_ARCH__)
+    // value(dz=0) * wz0 + value(dz=1) * wz1 is one 2-way dot product of the packed 16-bit pair with two 8-bit weights
+    const unsigned wz = (unsigned)wz0 | ((unsigned)wz1 << 8);
+    const int i00 = (int)__dp2a_lo(w00, wz, 0u);
+    const int i01 = (int)__dp2a_lo(w01, wz, 0u);
+    const int i10 = (int)__dp2a_lo(w10, wz, 0u);
+    const int i11 = (int)__dp2a_lo(w11, wz, 0u);
+#else
     const int i00 = (int)(w00 & 0xffffu) * wz0 + (int)(w00 >> 16) * wz1;
     const int i01 = (int)(w01 & 0xffffu) * wz0 + (int)(w01 >> 16) * wz1;
     const int i10 = (int)(w10 & 0xffffu) * wz0 + (int)(w10 >> 16) * wz1;
     const int i11 = (int)(w11 & 0xffffu) * wz0 + (int)(w11 >> 16) * wz1;
+#endif
     const int wx1 = fr, wx0 = 16 - fr, wy1 = fg, wy0 = 16 - fg;
     const int acc = i00 * (wx0 * wy0) + i01 * (wx0 * wy1) + i10 * (wx1 * wy0) + i11 * (wx1 * wy1);
     return (acc + 2048) >> 12;
@@ -256,9 +266,13 @@ GDT_HD void lab2lin(float L, float a, float b, bool tail, const Lab2RgbConst& K,
 
 // sRGB inverse gamma through the 1024-segment cubic spline: `seg` = {f, b, c, d} of segment ix.
 GDT_HD float spline_index(float lin, int& ix) {
+#if defined(__CUDA_ARCH__)
+    float x = f_mul(__saturatef(lin), 1024.0f);     // == clamp01 for every non-NaN input (-0 -> +0 changes no result)
+#else
     float x = f_mul(clamp01(lin), 1024.0f);
-    ix = f_trunc(x);
-    ix = ix < 0 ? 0 : (ix > 1023 ? 1023 : ix);
+#endif
+    ix = f_trunc(x);                                // x in [0, 1024]
+    ix = ix > 1023 ? 1023 : ix;
     return f_sub(x, (float)ix);
 }
 GDT_HD float spline_eval(float x, float s0, float s1, float s2, float s3) {

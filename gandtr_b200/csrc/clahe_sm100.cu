@@ -74,11 +74,13 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// warp-aggregated shared-memory histogram increment; `key` > 255 means "no pixel"
-__device__ __forceinline__ void hist_add(int* hist, int key) {
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int lane = threadIdx.x & 31;
-    if (key < 256 && lane == (__ffs(peers) - 1)) atomicAdd(&hist[key], __popc(peers));
+// Shared-memory histogram increment. Neighbouring pixels of a tile share few grey levels, so a single histogram would
+// serialise same-address atomics inside a warp: every warp owns kHistCopies copies (lane & 3 picks one; the copy stride
+// is padded by 8 words so equal levels in different copies fall into different banks). `key` > 255 means "no pixel".
+constexpr int kHistCopies = 4;
+constexpr int kHistStride = 256 + 8;
+__device__ __forceinline__ void hist_add(int* my_hist, int key) {
+    if (key < 256) atomicAdd(&my_hist[key], 1);
 }
 
 // ---- pass A -------------------------------------------------------------------------------------
@@ -91,12 +93,13 @@ __global__ void __launch_bounds__(256)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_t* __restrict__ lutT, int h, int w,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, const uint4* __restrict__ lutL,
                   Norm3 in_norm) {
-    __shared__ int hist[256];
+    __shared__ int hist_all[8 * kHistCopies * kHistStride];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
     const int img = blockIdx.y;
     const int ty = blockIdx.x / grid, tx = blockIdx.x % grid;
-    hist[tid] = 0;
+    for (int i = tid; i < 8 * kHistCopies * kHistStride; i += 256) hist_all[i] = 0;
+    int* hist = hist_all + ((tid >> 5) * kHistCopies + (tid & (kHistCopies - 1))) * kHistStride;
     __syncthreads();
 
     const size_t plane = (size_t)h * w;
@@ -175,7 +178,9 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
     __syncthreads();
 
     // ---- clip, redistribute, prefix sum -> tile LUT (OpenCV clahe.cpp CLAHE_CalcLut_Body) ----
-    int hv = hist[tid];
+    int hv = 0;
+#pragma unroll 8
+    for (int c = 0; c < 8 * kHistCopies; ++c) hv += hist_all[c * kHistStride + tid];
     const int lane = tid & 31, wid = tid >> 5;
     if (clip > 0) {
         int excess = hv > clip ? hv - clip : 0;
@@ -218,7 +223,7 @@ struct NormFast {
 };
 
 template <bool U8>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
@@ -256,6 +261,14 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
     float* outimg = out + (size_t)img * plane * 3;
     const uint8_t* lut_bytes = (const uint8_t*)luts;
 
+    // software prefetch (vectorised u8 path): the next row's pixel words are requested before this row's arithmetic
+    uint32_t nx0 = 0, nx1 = 0, nx2 = 0, nxl = 0;
+    if (U8 && vec_ok) {
+        const size_t p = (size_t)y0 * w + x0;
+        const uint32_t* src = (const uint32_t*)(in8 + p * 3);
+        nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2);
+        nxl = __ldg((const uint32_t*)(l8img + p));
+    }
     for (int y = y0; y < y1; ++y) {
         const ClaheAxis ay = clahe_axis(y, inv_th, grid);
         const uint8_t* lrow1 = lut_bytes + (size_t)(ay.i1 - ty_lo) * 256 * kLutRow;
@@ -264,11 +277,15 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
 
         int cell[4], fr[4], fg[4], fb[4], v[4];
         if (vec_ok) {
-            const uint32_t lw = __ldg((const uint32_t*)(l8img + p));
+            const uint32_t lw = U8 ? nxl : __ldg((const uint32_t*)(l8img + p));
             v[0] = lw & 255; v[1] = (lw >> 8) & 255; v[2] = (lw >> 16) & 255; v[3] = lw >> 24;
             if (U8) {
-                const uint32_t* src = (const uint32_t*)(in8 + p * 3);
-                const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+                const uint32_t a0 = nx0, a1 = nx1, a2 = nx2;
+                if (y + 1 < y1) {
+                    const uint32_t* nsrc = (const uint32_t*)(in8 + (p + w) * 3);
+                    nx0 = __ldg(nsrc); nx1 = __ldg(nsrc + 1); nx2 = __ldg(nsrc + 2);
+                    nxl = __ldg((const uint32_t*)(l8img + p + w));
+                }
                 cell_from_u8(a0 & 255, (a0 >> 8) & 255, (a0 >> 16) & 255, cell[0], fr[0], fg[0], fb[0]);
                 cell_from_u8(a0 >> 24, a1 & 255, (a1 >> 8) & 255, cell[1], fr[1], fg[1], fb[1]);
                 cell_from_u8((a1 >> 16) & 255, a1 >> 24, a2 & 255, cell[2], fr[2], fg[2], fb[2]);
@@ -404,8 +421,10 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int xchunks = ceil_div(w, 1024);
     while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 4LL * sms) rows >>= 1;
     dim3 gridB(xchunks, ceil_div(h, rows), n);
-    // spline table + the LUT rows of every tile row a band can touch (all of them when tiles are shorter than a band)
-    const size_t smem = 1024 * 16 + (size_t)grid * 256 * kLutRow;
+    // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
+    int span = (rows + g.th - 1) / g.th + 2;
+    if (span > grid) span = grid;
+    const size_t smem = 1024 * 16 + (size_t)span * 256 * kLutRow;
     static bool attr_set[2] = {false, false};
     if (smem > 48 * 1024 && !attr_set[U8 ? 1 : 0]) {
         GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,

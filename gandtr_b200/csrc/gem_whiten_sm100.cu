@@ -181,8 +181,8 @@ gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restr
 __global__ void __launch_bounds__(256)
 whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int ldP, int n, int c, int dim, int klen,
                    float* __restrict__ Xpart) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
+    __shared__ float As[2][16][64 + 4];
+    __shared__ float Bs[2][16][64 + 4];
     const int tid = threadIdx.x;
     const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
     const int kbeg = blockIdx.z * klen, kend = min(c, kbeg + klen);
@@ -195,9 +195,10 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int lr = tid >> 2, lk = (tid & 3) << 2;  // each thread loads 4 consecutive k of one row
     const bool vec = (c & 3) == 0 && (ldP & 3) == 0 && ((((uintptr_t)V) | ((uintptr_t)P)) & 15) == 0;
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
-        float a[4], b[4];
-        const int ar = row0 + lr, br = col0 + lr, k = k0 + lk;
+    const int ar = row0 + lr, br = col0 + lr;
+    float a[4], b[4];
+    auto fetch = [&](int k0) {
+        const int k = k0 + lk;
         if (vec && k + 3 < kend) {
             const float4 av = ar < n ? __ldg((const float4*)(V + (size_t)ar * c + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 bv = br < dim ? __ldg((const float4*)(P + (size_t)br * ldP + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -210,14 +211,19 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
                 b[q] = (br < dim && k + q < kend) ? P[(size_t)br * ldP + k + q] : 0.f;
             }
         }
-        __syncthreads();
+    };
+    // double-buffered shared tiles, next K-step prefetched into registers while the current one is multiplied
+    fetch(kbeg);
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += 16, buf ^= 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { As[lk + q][lr] = a[q]; Bs[lk + q][lr] = b[q]; }
+        for (int q = 0; q < 4; ++q) { As[buf][lk + q][lr] = a[q]; Bs[buf][lk + q][lr] = b[q]; }
         __syncthreads();
+        if (k0 + 16 < kend) fetch(k0 + 16);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const float4 av = *(const float4*)&As[k][tr];
-            const float4 bv = *(const float4*)&Bs[k][tc];
+            const float4 av = *(const float4*)&As[buf][k][tr];
+            const float4 bv = *(const float4*)&Bs[buf][k][tc];
             const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -234,12 +240,39 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
         }
 }
 
-// desc[r] = x / (||x||_2 + eps) with x = sum_z Xpart[z][r] (fixed order); one CTA per row
+// desc[r] = x / (||x||_2 + eps) with x = sum_z Xpart[z][r] (fixed order); one CTA per row, the row kept in registers
+constexpr int kReduceMaxPerThread = 8;   // rows up to 256 * 4 * 8 = 8192 wide stay in registers
 __global__ void __launch_bounds__(256)
 whiten_reduce_l2n_kernel(const float* __restrict__ Xpart, int n, int dim, int splitk, float eps, float* __restrict__ desc) {
     __shared__ float red[8];
     const int r = blockIdx.x;
+    const bool vec = (dim & 3) == 0 && ((((uintptr_t)Xpart) | ((uintptr_t)desc)) & 15) == 0 && dim <= 256 * 4 * kReduceMaxPerThread;
     float ss = 0.f;
+    if (vec) {
+        float4 acc[kReduceMaxPerThread];
+        const int nv = dim >> 2;
+#pragma unroll
+        for (int j = 0; j < kReduceMaxPerThread; ++j) {
+            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int i = threadIdx.x + j * 256;
+            if (i < nv) {
+                for (int z = 0; z < splitk; ++z) {
+                    const float4 v = __ldg((const float4*)(Xpart + ((size_t)z * n + r) * dim) + i);
+                    acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+                }
+                ss += acc[j].x * acc[j].x + acc[j].y * acc[j].y + acc[j].z * acc[j].z + acc[j].w * acc[j].w;
+            }
+        }
+        ss = block_sum_256(ss, red);
+        const float den = sqrtf(ss) + eps;
+#pragma unroll
+        for (int j = 0; j < kReduceMaxPerThread; ++j) {
+            const int i = threadIdx.x + j * 256;
+            if (i < nv)
+                *((float4*)(desc + (size_t)r * dim) + i) = make_float4(acc[j].x / den, acc[j].y / den, acc[j].z / den, acc[j].w / den);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < dim; i += 256) {
         float v = 0.f;
         for (int z = 0; z < splitk; ++z) v += Xpart[((size_t)z * n + r) * dim + i];

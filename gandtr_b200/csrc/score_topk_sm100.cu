@@ -61,12 +61,12 @@ struct QMeta {
 // Candidate segments. Segment 0 belongs to the seed pass (its capacity covers every row of the seed range, so it
 // cannot overflow); segments 1..n_stripes belong to the stripes of the main pass, which start from the seed threshold.
 __host__ __device__ inline int seed_tiles_for(int k) {
-    int t = (4 * k + kBlockN - 1) / kBlockN;
-    return t < 8 ? 8 : t;
+    int t = (16 * k + kBlockN - 1) / kBlockN;
+    return t < 32 ? 32 : t;
 }
 __host__ __device__ inline int stripe_capacity(int k) {
-    int c = 4 * k;
-    if (c < 512) c = 512;
+    int c = 8 * k;
+    if (c < 1024) c = 1024;
     return next_pow2(c);
 }
 __host__ __device__ inline int survivor_capacity(int k) {
@@ -159,6 +159,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+// fire-and-forget global reductions (no destination register, no scoreboard to wait on)
+__device__ __forceinline__ void red_add_u32(uint32_t* addr, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u32(uint32_t* addr, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -498,7 +505,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                         if (slot < segcap)
                                             seg_row[slot] = ((uint64_t)v[j] << 32) | (uint32_t)(col0 + c * 32 + j);
                                         ++slot;
-                                        atomicAdd(hist_row + score_bin(__uint_as_float(v[j]), m.inv_scale), 1u);
+                                        // bin 0 (everything below 2^-8 of the scale) never yields a threshold:
+                                        // not counting it keeps the same-address reductions off the L2 atomic units
+                                        const int bin = score_bin(__uint_as_float(v[j]), m.inv_scale);
+                                        if (bin) red_add_u32(hist_row + bin, 1u);
                                     }
                                 }
                             }
@@ -517,7 +527,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     __threadfence();
                     const float nt = scan_threshold(hist_row, P.k, m);
                     if (nt > tau) tau = nt;
-                    atomicMax(P.tau + qrow, ordered_bits(tau));
+                    red_max_u32(P.tau + qrow, ordered_bits(tau));
                     inserted = slot;
                 }
             }
