@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="images per step per GPU")
     ap.add_argument("--db-rows", type=int, default=DB_ROWS)
     ap.add_argument("--queries", type=int, default=N_QUERIES)
     ap.add_argument("--no-retrieval", action="store_true")
@@ -385,6 +385,7 @@ def main():
         flops = 2.0 * args.queries * args.db_rows * DB_DIM
         line["retrieval"] = {
             "metric": "1M-db top-100 queries/sec", "value": args.queries * rK / (r_ms * 1e-3), "unit": "queries/s",
+            "scaling": "strong (fixed database, row-sharded over the ranks)",
             "ms_per_search": r_ms / rK, "steps": rK, "warmup": rW, "gpu_launches": r_launches,
             "e2e": {"value": args.queries * rK / (re_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": args.queries * DB_DIM * 4, "d2h_bytes_per_step": args.queries * TOPK * 12},

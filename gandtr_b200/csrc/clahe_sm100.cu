@@ -84,9 +84,17 @@ __device__ __forceinline__ void hist_add(int* my_hist, int key) {
 }
 
 // ---- pass A -------------------------------------------------------------------------------------
-// tile LUT layout written by pass A and read by pass B: lutT[img][ty][v][tx] with kLutRow bytes per (ty, v) row, so
+// tile LUT layout written by pass A and read by pass B: lutT[img][ty][v][tx] with 8 or 16 bytes per (ty, v) row, so
 // the four tile LUT values a pixel blends sit in two 16-byte rows (one per tile row).
-constexpr int kLutRow = 16;   // >= max grid
+// Row stride: 8 bytes for grids up to 8x8 (the default), 16 bytes up to 16x16 -- `lsh` = log2(stride).
+__host__ __device__ inline int lut_row_shift(int grid) { return grid <= 8 ? 3 : 4; }
+
+// 32-byte gather of one chroma cell record (a words then b words) as a single 256-bit read-only load
+__device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int cell, uint4& wa, uint4& wb) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(wa.x), "=r"(wa.y), "=r"(wa.z), "=r"(wa.w), "=r"(wb.x), "=r"(wb.y), "=r"(wb.z), "=r"(wb.w)
+                 : "l"(lutAB + cell * 2));
+}
 
 template <bool U8>
 __global__ void __launch_bounds__(256)
@@ -212,7 +220,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
     for (int i = 0; i < wid; ++i) sum += warp_tmp[i];
     int lv = f_rint(f_mul((float)sum, lut_scale));
     lv = lv < 0 ? 0 : (lv > 255 ? 255 : lv);
-    lutT[(((size_t)img * grid + ty) * 256 + tid) * kLutRow + tx] = (uint8_t)lv;
+    lutT[((((size_t)img * grid + ty) * 256 + tid) << lut_row_shift(grid)) + tx] = (uint8_t)lv;
 }
 
 // ---- pass B -------------------------------------------------------------------------------------
@@ -229,8 +237,12 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
                    int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
                    Norm3 in_norm, NormFast on) {
     extern __shared__ __align__(16) uint8_t smem[];
-    float4* spl = (float4*)smem;                 // [1024] inverse-gamma spline segments
-    uint4* luts = (uint4*)(smem + 1024 * 16);    // [(ty_hi - ty_lo + 1)][256] rows of kLutRow bytes
+    // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
+    // less than 16-byte ones
+    float2* spl_fb = (float2*)smem;              // [1024] (f, b)
+    float2* spl_cd = (float2*)(smem + 1024 * 8); // [1024] (c, d)
+    uint2* luts = (uint2*)(smem + 1024 * 16);    // [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
+    const int lsh = lut_row_shift(grid);
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const int y0 = blockIdx.y * rows_per_cta;
@@ -238,10 +250,14 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
     const int ty_lo = clahe_axis(y0, inv_th, grid).i1;
     const int ty_hi = clahe_axis(y1 - 1, inv_th, grid).i2;
     {
-        const int nrows = (ty_hi - ty_lo + 1) * 256;
-        const uint4* src = (const uint4*)(lutT + ((size_t)img * grid + ty_lo) * 256 * kLutRow);
-        for (int i = tid; i < nrows; i += 256) luts[i] = __ldg(src + i);
-        for (int i = tid; i < 1024; i += 256) spl[i] = __ldg(spline + i);
+        const int nwords = ((ty_hi - ty_lo + 1) * 256) << (lsh - 3);
+        const uint2* src = (const uint2*)(lutT + ((((size_t)img * grid + ty_lo) * 256) << lsh));
+        for (int i = tid; i < nwords; i += 256) luts[i] = __ldg(src + i);
+        for (int i = tid; i < 1024; i += 256) {
+            const float4 sgm = __ldg(spline + i);
+            spl_fb[i] = make_float2(sgm.x, sgm.y);
+            spl_cd[i] = make_float2(sgm.z, sgm.w);
+        }
     }
     __syncthreads();
 
@@ -271,8 +287,8 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
     }
     for (int y = y0; y < y1; ++y) {
         const ClaheAxis ay = clahe_axis(y, inv_th, grid);
-        const uint8_t* lrow1 = lut_bytes + (size_t)(ay.i1 - ty_lo) * 256 * kLutRow;
-        const uint8_t* lrow2 = lut_bytes + (size_t)(ay.i2 - ty_lo) * 256 * kLutRow;
+        const uint8_t* lrow1 = lut_bytes + (((size_t)(ay.i1 - ty_lo) * 256) << lsh);
+        const uint8_t* lrow2 = lut_bytes + (((size_t)(ay.i2 - ty_lo) * 256) << lsh);
         const size_t p = (size_t)y * w + x0;
 
         int cell[4], fr[4], fg[4], fb[4], v[4];
@@ -320,13 +336,13 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             // chroma
-            const uint4 wa = __ldg(lutAB + cell[i] * 2);
-            const uint4 wb = __ldg(lutAB + cell[i] * 2 + 1);
+            uint4 wa, wb;
+            ld_cell_ab(lutAB, cell[i], wa, wb);
             const float a2 = lab_chroma_fast(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
             const float b2 = lab_chroma_fast(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
             // lightness through CLAHE: the two 16-byte rows hold the LUT value of every tile column at level v
-            const uint8_t* r1 = lrow1 + v[i] * kLutRow;
-            const uint8_t* r2 = lrow2 + v[i] * kLutRow;
+            const uint8_t* r1 = lrow1 + (v[i] << lsh);
+            const uint8_t* r2 = lrow2 + (v[i] << lsh);
             const int l11 = r1[ax[i].i1], l12 = r1[ax[i].i2];
             const int l21 = r2[ax[i].i1], l22 = r2[ax[i].i2];
             const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
@@ -335,9 +351,10 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
             lab2lin(Ln, a2, b2, (x0 + i) >= wbody, K, lr, lg, lb);
             int ir, ig, ib;
             const float xr = spline_index(lr, ir), xg = spline_index(lg, ig), xb = spline_index(lb, ib);
-            const float4 sr = spl[ir], sg = spl[ig], sb = spl[ib];
-            const float er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w), eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w),
-                        eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
+            const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
+            const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
+            const float er = spline_eval(xr, r01.x, r01.y, r23.x, r23.y), eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y),
+                        eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
             if (on.fast) {
                 o[0][i] = normalize_px_fast(er, on.mean[0], on.std[0], on.rstd[0]);
                 o[1][i] = normalize_px_fast(eg, on.mean[1], on.std[1], on.rstd[1]);
@@ -403,7 +420,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
     Workspace W(ws, ws_bytes);
     uint8_t* L8 = W.take<uint8_t>((size_t)n * h * w);
-    uint8_t* luts = W.take<uint8_t>((size_t)n * grid * 256 * kLutRow);
+    uint8_t* luts = W.take<uint8_t>(((size_t)n * grid * 256) << lut_row_shift(grid));
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
     const bool aligned = (((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0;
@@ -424,11 +441,11 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
     int span = (rows + g.th - 1) / g.th + 2;
     if (span > grid) span = grid;
-    const size_t smem = 1024 * 16 + (size_t)span * 256 * kLutRow;
+    const size_t smem = 1024 * 16 + (((size_t)span * 256) << lut_row_shift(grid));
     static bool attr_set[2] = {false, false};
     if (smem > 48 * 1024 && !attr_set[U8 ? 1 : 0]) {
         GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      1024 * 16 + 16 * 256 * kLutRow));
+                                      1024 * 16 + 16 * 256 * 16));
         attr_set[U8 ? 1 : 0] = true;
     }
     NormFast on;

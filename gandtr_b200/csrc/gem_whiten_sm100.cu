@@ -178,11 +178,12 @@ gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restr
 // Xpart[z][n][dim] = V[n][kz] . P[dim][kz]^T over the K-slice kz = [z*klen, (z+1)*klen)
 // (fp32 SIMT, 64x64 tile, BK = 16, 4x4 outputs per thread). Split-K fills the machine when n is small: the
 // slices are summed in a fixed order by whiten_reduce_l2n_kernel, so results are run-to-run deterministic.
+constexpr int kWBK = 32;   // K-step of the whitening GEMM
 __global__ void __launch_bounds__(256)
 whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int ldP, int n, int c, int dim, int klen,
                    float* __restrict__ Xpart) {
-    __shared__ float As[2][16][64 + 4];
-    __shared__ float Bs[2][16][64 + 4];
+    __shared__ float As[2][kWBK][64 + 4];
+    __shared__ float Bs[2][kWBK][64 + 4];
     const int tid = threadIdx.x;
     const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
     const int kbeg = blockIdx.z * klen, kend = min(c, kbeg + klen);
@@ -193,35 +194,41 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int lr = tid >> 2, lk = (tid & 3) << 2;  // each thread loads 4 consecutive k of one row
+    // each thread loads 4 consecutive k of rows lr and lr + 32 (8 threads cover the 32 k of a row: 128 contiguous bytes)
+    const int lr = tid >> 3, lk = (tid & 7) << 2;
     const bool vec = (c & 3) == 0 && (ldP & 3) == 0 && ((((uintptr_t)V) | ((uintptr_t)P)) & 15) == 0;
-    const int ar = row0 + lr, br = col0 + lr;
-    float a[4], b[4];
+    float a[2][4], b[2][4];
     auto fetch = [&](int k0) {
         const int k = k0 + lk;
-        if (vec && k + 3 < kend) {
-            const float4 av = ar < n ? __ldg((const float4*)(V + (size_t)ar * c + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 bv = br < dim ? __ldg((const float4*)(P + (size_t)br * ldP + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
-            b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-        } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                a[q] = (ar < n && k + q < kend) ? V[(size_t)ar * c + k + q] : 0.f;
-                b[q] = (br < dim && k + q < kend) ? P[(size_t)br * ldP + k + q] : 0.f;
+        for (int h = 0; h < 2; ++h) {
+            const int ar = row0 + lr + 32 * h, br = col0 + lr + 32 * h;
+            if (vec && k + 3 < kend) {
+                const float4 av = ar < n ? __ldg((const float4*)(V + (size_t)ar * c + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 bv = br < dim ? __ldg((const float4*)(P + (size_t)br * ldP + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a[h][0] = av.x; a[h][1] = av.y; a[h][2] = av.z; a[h][3] = av.w;
+                b[h][0] = bv.x; b[h][1] = bv.y; b[h][2] = bv.z; b[h][3] = bv.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a[h][q] = (ar < n && k + q < kend) ? V[(size_t)ar * c + k + q] : 0.f;
+                    b[h][q] = (br < dim && k + q < kend) ? P[(size_t)br * ldP + k + q] : 0.f;
+                }
             }
         }
     };
     // double-buffered shared tiles, next K-step prefetched into registers while the current one is multiplied
     fetch(kbeg);
     int buf = 0;
-    for (int k0 = kbeg; k0 < kend; k0 += 16, buf ^= 1) {
+    for (int k0 = kbeg; k0 < kend; k0 += kWBK, buf ^= 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { As[buf][lk + q][lr] = a[q]; Bs[buf][lk + q][lr] = b[q]; }
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { As[buf][lk + q][lr + 32 * h] = a[h][q]; Bs[buf][lk + q][lr + 32 * h] = b[h][q]; }
         __syncthreads();
-        if (k0 + 16 < kend) fetch(k0 + 16);
+        if (k0 + kWBK < kend) fetch(k0 + kWBK);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < kWBK; ++k) {
             const float4 av = *(const float4*)&As[buf][k][tr];
             const float4 bv = *(const float4*)&Bs[buf][k][tc];
             const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -314,7 +321,7 @@ static int desc_tail(const DescScales& D, int n, int c, int scales, const float*
     GDT_LAUNCH_CHECK();
     if (P) {
         const int splitk = whiten_splitk(n, c, dim);
-        const int klen = ceil_div(ceil_div(c, splitk), 16) * 16;
+        const int klen = ceil_div(ceil_div(c, splitk), kWBK) * kWBK;
         dim3 grid(ceil_div(dim, 64), ceil_div(n, 64), ceil_div(c, klen));
         whiten_gemm_kernel<<<grid, 256, 0, stream>>>(V, P, ldP, n, c, dim, klen, Xpart);
         GDT_LAUNCH_CHECK();
