@@ -74,30 +74,91 @@ __device__ __forceinline__ float gem_row_sum(const float* __restrict__ row, int 
 }
 
 // one warp per row; rows are ordered [scale][image][channel]; g has the same order
-__global__ void __launch_bounds__(256)
-gem_pool_kernel(GemScales S, long long rows_per_scale, long long total_rows, const float* __restrict__ p_dev, float eps,
-                float* __restrict__ g) {
+// Two rows per warp when a row is a whole number of 512-byte warp sweeps (ResNet 24x32, VGG 48x64, ...): both rows'
+// loads are issued before either is reduced (up to 16 independent 16-byte loads per lane).
+template <int MODE>
+__device__ __forceinline__ void gem_row_pair(const float* __restrict__ rowA, const float* __restrict__ rowB, int sweeps,
+                                             float eps, float p, int lane, float& sumA, float& sumB) {
+    float4 va[8], vb[8];
+    const float4* a4 = (const float4*)rowA;
+    const float4* b4 = (const float4*)rowB;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < sweeps) va[j] = ld_stream_f4(a4 + j * 32 + lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < sweeps) vb[j] = ld_stream_f4(b4 + j * 32 + lane);
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < sweeps) {
+            a0 += gem_pow<MODE>(fmaxf(va[j].x, eps), p) + gem_pow<MODE>(fmaxf(va[j].y, eps), p);
+            a1 += gem_pow<MODE>(fmaxf(va[j].z, eps), p) + gem_pow<MODE>(fmaxf(va[j].w, eps), p);
+            b0 += gem_pow<MODE>(fmaxf(vb[j].x, eps), p) + gem_pow<MODE>(fmaxf(vb[j].y, eps), p);
+            b1 += gem_pow<MODE>(fmaxf(vb[j].z, eps), p) + gem_pow<MODE>(fmaxf(vb[j].w, eps), p);
+        }
+    }
+    sumA = a0 + a1;
+    sumB = b0 + b1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sumA += __shfl_xor_sync(0xffffffffu, sumA, o);
+        sumB += __shfl_xor_sync(0xffffffffu, sumB, o);
+    }
+}
+
+// All rows of one launch for a fixed exponent mode. Kept out of line so that each mode gets its own register
+// allocation instead of the union of all four.
+template <int MODE>
+__device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_per_scale, long long total_rows, float p,
+                                           float eps, int root, float* __restrict__ g) {
     const int lane = threadIdx.x & 31;
-    const float p = __ldg(p_dev);
     const float inv_p = 1.0f / p;
     const long long nwarps = (long long)gridDim.x * 8;
-    for (long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); warp < total_rows; warp += nwarps) {
+    const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    // fast path: single scale, rows of 1..8 whole warp sweeps, 16-byte aligned base
+    const int hw0 = S.hw[0];
+    if (S.nscales == 1 && (hw0 & 127) == 0 && hw0 <= 1024 && (((uintptr_t)S.ptr[0]) & 15) == 0) {
+        const int sweeps = hw0 >> 7;
+        for (long long r = wid * 2; r < total_rows; r += nwarps * 2) {
+            const float* rowA = S.ptr[0] + r * hw0;
+            const float* rowB = (r + 1 < total_rows) ? rowA + hw0 : rowA;
+            float sa, sb;
+            gem_row_pair<MODE>(rowA, rowB, sweeps, eps, p, lane, sa, sb);
+            if (lane < 2 && r + lane < total_rows) {
+                const float mean = (lane == 0 ? sa : sb) / (float)hw0;
+                g[r + lane] = root ? powf(mean, inv_p) : mean;
+            }
+        }
+        return;
+    }
+    for (long long warp = wid; warp < total_rows; warp += nwarps) {
         const int s = (int)(warp / rows_per_scale);
         const long long r = warp - (long long)s * rows_per_scale;
         const int hw = S.hw[s];
-        const float* row = S.ptr[s] + r * hw;
-        float sum;
-        if (p == 3.0f) sum = gem_row_sum<3>(row, hw, eps, p, lane);
-        else if (p == 2.0f) sum = gem_row_sum<2>(row, hw, eps, p, lane);
-        else if (p == 1.0f) sum = gem_row_sum<1>(row, hw, eps, p, lane);
-        else sum = gem_row_sum<0>(row, hw, eps, p, lane);
-        if (lane == 0) g[warp] = powf(sum / (float)hw, inv_p);
+        const float sum = gem_row_sum<MODE>(S.ptr[s] + r * hw, hw, eps, p, lane);
+        if (lane == 0) {
+            const float mean = sum / (float)hw;
+            g[warp] = root ? powf(mean, inv_p) : mean;
+        }
     }
+}
+
+// one warp per row (or row pair); rows are ordered [scale][image][channel]; g has the same order.
+// root != 0: g = mean^(1/p) (GeM proper); root == 0: g = mean, the caller applies the root (gem_finalize_kernel).
+__global__ void __launch_bounds__(256, 3)
+gem_pool_kernel(const __grid_constant__ GemScales S, long long rows_per_scale, long long total_rows,
+                const float* __restrict__ p_dev, float eps, int root, float* __restrict__ g) {
+    const float p = __ldg(p_dev);
+    if (p == 3.0f) gem_pool_rows<3>(S, rows_per_scale, total_rows, p, eps, root, g);
+    else if (p == 2.0f) gem_pool_rows<2>(S, rows_per_scale, total_rows, p, eps, root, g);
+    else if (p == 1.0f) gem_pool_rows<1>(S, rows_per_scale, total_rows, p, eps, root, g);
+    else gem_pool_rows<0>(S, rows_per_scale, total_rows, p, eps, root, g);
 }
 
 static unsigned gem_pool_grid(long long total_rows) {
     const long long want = ceil_div_ll(total_rows, 8);
-    const long long cap = (long long)sm_count_current_device() * 16;   // 8 resident CTAs/SM x 2 for load balance
+    const long long cap = (long long)sm_count_current_device() * 12;   // 3 resident CTAs/SM x 4 for load balance
     return (unsigned)(want < cap ? want : cap);
 }
 
@@ -127,14 +188,20 @@ gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restr
     __shared__ float inv_norm[GDT_MAX_SCALES];
     const int img = blockIdx.x, tid = threadIdx.x;
     const bool normalised = (flags & GDT_DESC_NORMALISED) != 0;
+    const bool raw_mean = (flags & GDT_POOLED_RAW_MEAN) != 0;   // pooled values still need the 1/p root
+    const float inv_p = raw_mean ? 1.0f / __ldg(p_dev) : 1.0f;
     for (int s = 0; s < scales; ++s) {
         if (normalised) {
             if (tid == 0) inv_norm[s] = 1.0f;
             continue;
         }
-        const float* gs = D.ptr[s] + (size_t)img * c;
+        float* gs = const_cast<float*>(D.ptr[s]) + (size_t)img * c;
         float ss = 0.f;
-        for (int i = tid; i < c; i += 256) { const float v = gs[i]; ss += v * v; }
+        for (int i = tid; i < c; i += 256) {
+            float v = gs[i];
+            if (raw_mean) { v = powf(v, inv_p); gs[i] = v; }   // same thread re-reads these elements below
+            ss += v * v;
+        }
         ss = block_sum_256(ss, red);
         if (tid == 0) inv_norm[s] = sqrtf(ss) + 1e-6f;
     }
@@ -371,11 +438,11 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
     }
     const long long rows_per_scale = (long long)n * c;
     const long long total_rows = rows_per_scale * scales;
-    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, g);
+    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, 0, g);
     GDT_LAUNCH_CHECK();
     DescScales D;
     for (int s = 0; s < GDT_MAX_SCALES; ++s) D.ptr[s] = s < scales ? g + (size_t)s * n * c : nullptr;
-    return desc_tail(D, n, c, scales, p_dev, 1.0f, flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P), P, ldP, m, dim, desc, V,
+    return desc_tail(D, n, c, scales, p_dev, 1.0f, (flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P)) | GDT_POOLED_RAW_MEAN, P, ldP, m, dim, desc, V,
                      Xpart, stream);
 }
 
@@ -392,7 +459,7 @@ extern "C" int gdt_gem_pool(const float* fmap, int n, int c, int h, int w, const
     S.ptr[0] = fmap;
     S.hw[0] = h * w;
     const long long rows = (long long)n * c;
-    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, pooled);
+    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, 1, pooled);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

@@ -1,0 +1,132 @@
+"""Batched descriptor extraction -- replaces `extract_vectors / extract_ss / extract_ms`
+(mdir/external/cirtorch/networks/imageretrievalnet.py:312-359) and the dataset half of it
+(`ImagesFromList.__getitem__`, genericdataset.py:66-102; `imresize`, datahelpers.py:75-82).
+
+The reference runs batch size 1 with a `.cpu()` sync per image. Here: images are decoded / cropped / resized on the
+host exactly as the reference does (PIL, LANCZOS thumbnail), consecutive images of equal size are stacked into one
+pinned uint8 batch, and each batch is ONE K1 launch pair (CLAHE transform) + stock backbone + ONE K2 call. Descriptors
+stay on the device as rows of the local database shard ([n_local, D]); `extract_vectors` is the reference-shaped
+wrapper (D x n tensor on the host).
+
+Data parallel: `rank` / `world_size` take a contiguous block of the image list (`retrieval.shard_bounds`), which is
+exactly the row sharding `ShardedIndex` expects -- no collective on this path.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .retrieval import shard_bounds
+
+__all__ = ["imresize", "load_image", "extract_descriptors", "extract_vectors", "extract_ss", "extract_ms"]
+
+
+def imresize(img, imsize):
+    """datahelpers.py:75-82: in-place LANCZOS thumbnail so that max(size) <= imsize; arrays pass through."""
+    if isinstance(img, np.ndarray):
+        return img
+    from PIL import Image
+    img.thumbnail((imsize, imsize), getattr(Image, "LANCZOS", Image.Resampling.LANCZOS))
+    return img
+
+
+def load_image(item, imsize=None, bbx=None):
+    """One element of the image list -> uint8 HWC RGB array. `item` is a path, a PIL image or a uint8 array.
+    Crop / resize order and the bounding-box scale rule follow genericdataset.py:88-97."""
+    from PIL import Image
+    if isinstance(item, np.ndarray):
+        if bbx:
+            x0, y0, x1, y1 = [int(v) for v in bbx]
+            item = item[y0:y1, x0:x1]
+        return np.ascontiguousarray(item)
+    if isinstance(item, Image.Image):
+        img = item.convert("RGB")
+    else:
+        with open(item, "rb") as f:
+            img = Image.open(f).convert("RGB")
+    imfullsize = max(img.size)
+    if bbx:
+        img = img.crop(tuple(bbx))
+    if imsize is not None:
+        img = imresize(img, imsize * max(img.size) / imfullsize if bbx else imsize)
+    return np.asarray(img)
+
+
+class _Decode(torch.utils.data.Dataset):
+    def __init__(self, images, imsize, bbxs):
+        self.images, self.imsize, self.bbxs = images, imsize, bbxs
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        return torch.from_numpy(load_image(self.images[i], self.imsize, self.bbxs[i] if self.bbxs is not None else None).copy())
+
+
+def _descriptors_for_batch(model, x, ms, msp):
+    """x: [b,3,h,w] normalised CUDA batch -> [b, D]. Mirrors extract_ss (ms == [1]) and extract_ms."""
+    if len(ms) == 1 and ms[0] == 1:
+        return model.descriptors([model.feature_map(x)])
+    per_scale = []
+    for s in ms:
+        xs = x if s == 1 else torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+        per_scale.append(model.descriptors([model.feature_map(xs)]))       # net(input_t): GeM + L2N per scale
+    # v = sum_s d^msp ; v /= len(ms) ; v = v^(1/msp) ; v /= ||v||        (imageretrievalnet.py:344-357)
+    return _lib.desc_post(per_scale, msp if isinstance(msp, torch.Tensor) else float(msp))
+
+
+def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), msp=1, batch_size=32, workers=4,
+                        rank=0, world_size=1, print_freq=0):
+    """-> [n_local, D] float32 CUDA tensor: rows lo..hi of the descriptor matrix, (lo, hi) = shard_bounds(len(images)).
+    `net` is a gandtr_b200 SingleNetwork or ImageRetrievalNet; `transform` a gandtr_b200.transforms.Compose."""
+    model = getattr(net, "model", net)
+    model.eval()
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise _lib.GdtError("extract_descriptors needs the network on a CUDA device")
+    lo, hi = shard_bounds(len(images), world_size, rank)
+    local = list(images[lo:hi])
+    local_bbxs = list(bbxs[lo:hi]) if bbxs is not None else None
+    out = torch.empty((len(local), model.meta["out_channels"]), dtype=torch.float32, device=dev)
+    loader = torch.utils.data.DataLoader(_Decode(local, image_size, local_bbxs), batch_size=None, shuffle=False,
+                                         num_workers=min(workers, max(len(local), 1)) if len(local) > 8 else 0)
+    pending, shape, start = [], None, 0
+
+    def flush():
+        nonlocal pending, start
+        if not pending:
+            return
+        batch = torch.stack(pending).pin_memory()
+        with torch.no_grad():
+            x = transform.batch(batch.to(dev, non_blocking=True))
+            out[start:start + len(pending)] = _descriptors_for_batch(model, x, list(ms), msp)
+        start += len(pending)
+        pending = []
+
+    for i, img in enumerate(loader):
+        if shape is not None and (tuple(img.shape) != shape or len(pending) >= batch_size):
+            flush()
+        shape = tuple(img.shape)
+        pending.append(img)
+        if print_freq and ((i + 1) % print_freq == 0 or (i + 1) == len(local)):
+            print("\r>>>> {}/{} done...".format(i + 1, len(local)), end="")
+    flush()
+    if print_freq:
+        print("")
+    return out
+
+
+def extract_vectors(net, images, image_size, transform, bbxs=None, ms=[1], msp=1, print_freq=10, device=None, **kw):
+    """Reference signature and return convention (imageretrievalnet.py:312-339): D x n float32 tensor on the host."""
+    vecs = extract_descriptors(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq, **kw)
+    return vecs.t().contiguous().cpu()
+
+
+def extract_ss(net, input):
+    """imageretrievalnet.py:341-342."""
+    return net(input).cpu().data.squeeze()
+
+
+def extract_ms(net, input, ms, msp):
+    """imageretrievalnet.py:344-359."""
+    model = getattr(net, "model", net)
+    return _descriptors_for_batch(model, input.to(next(model.parameters()).device), list(ms), msp).squeeze(0).cpu()

@@ -110,6 +110,7 @@ int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, i
 #define GDT_GEM_AGGREGATE 1
 #define GDT_GEM_MSP_IS_P 2
 #define GDT_DESC_NORMALISED 4 /* internal to gdt_desc_post: inputs are already L2-normalised descriptors */
+#define GDT_POOLED_RAW_MEAN 8 /* internal to gdt_gem_whiten: pooled values are means, the 1/p root is still due */
 size_t gdt_gem_whiten_workspace_bytes(int n, int c, int scales, int dim);
 int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h, const int* host_w,
                    int n, int c, int scales, const float* p_dev, float eps, int flags,

@@ -1,0 +1,125 @@
+"""Rows a16-a22 of SURVEY.md 8(a) on the GPU: batched extraction, whitening learning, the CirDatasetAp score object and
+the validate / infer stage functions, on a small synthetic dataset (random-init VGG16, BASELINE config 1 in miniature)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_np as R
+from oracle import whiten_np as WO
+from tests.util import golden, synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vgg():
+    from gandtr_b200 import hub
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    return hub.gem_vgg16_hedngan(pretrained=False)
+
+
+def _dataset(ndb=24, nq=5):
+    sizes = [(64, 80), (64, 80), (72, 64), (64, 80)]
+    images = [synth_image(1000 + i, *sizes[i % len(sizes)], "smooth" if i % 4 else "noise") for i in range(ndb)]
+    qimages, gnd = [], []
+    for j in range(nq):
+        img = np.clip(images[j].astype(np.int16) + (8 if j % 2 else -8), 0, 255).astype(np.uint8)   # brightness jitter
+        qimages.append(img)
+        gnd.append({"ok": np.array([j]), "junk": np.array([(j + 7) % ndb])})
+    return images, qimages, gnd
+
+
+def test_batched_extraction_equals_per_image_forward(vgg):
+    from gandtr_b200.extract import extract_descriptors, extract_vectors
+    images, _, _ = _dataset()
+    d = extract_descriptors(vgg, images, None, vgg.transform, batch_size=4)
+    assert tuple(d.shape) == (len(images), 512) and d.is_cuda
+    with torch.no_grad():
+        for i in (0, 2, 5, 23):
+            ref = vgg(vgg.transform(images[i]).unsqueeze(0)).reshape(-1)
+            torch.testing.assert_close(d[i], ref, rtol=2e-5, atol=2e-7)
+    v = extract_vectors(vgg, images[:6], None, vgg.transform, print_freq=0)
+    assert tuple(v.shape) == (512, 6) and not v.is_cuda                   # reference convention: D x n on the host
+    torch.testing.assert_close(v.t(), d[:6].cpu(), rtol=1e-6, atol=1e-8)
+    # sharded extraction: the two halves are exactly the rows of the full matrix
+    halves = [extract_descriptors(vgg, images, None, vgg.transform, rank=r, world_size=2) for r in range(2)]
+    torch.testing.assert_close(torch.cat(halves), d, rtol=1e-6, atol=1e-8)
+
+
+def test_extract_ms_matches_reference_formula(vgg):
+    from gandtr_b200.extract import extract_ms
+    img = synth_image(5, 96, 128, "smooth")
+    x = vgg.transform(img).unsqueeze(0)
+    ms, msp = [1, 1 / np.sqrt(2), 0.5], 3.0
+    with torch.no_grad():
+        got = extract_ms(vgg, x, ms, msp)
+        v = torch.zeros(512, dtype=torch.float64)
+        for s in ms:
+            xs = x if s == 1 else torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+            v += vgg.model(xs).double().cpu().reshape(-1).pow(msp)          # imageretrievalnet.py:348-353
+        v = (v / len(ms)).pow(1.0 / msp)
+        v /= v.norm()
+    np.testing.assert_allclose(got.numpy(), v.numpy(), rtol=2e-5, atol=2e-7)
+
+
+def test_whitenlearn_matches_reference_golden_up_to_sign():
+    from gandtr_b200 import whiten as W
+    g = golden("whiten.npz")
+    m, P = W.whitenlearn(g["X"], g["qidxs"], g["pidxs"])
+    m, P = m.cpu().numpy(), P.cpu().numpy()
+    np.testing.assert_allclose(m, g["m"], rtol=1e-12, atol=1e-14)
+    sign = np.sign((P * g["P"]).sum(1, keepdims=True))
+    np.testing.assert_allclose(P * sign, g["P"], rtol=1e-6, atol=1e-8)
+    Y = W.whitenapply(g["X"][:, :50], m, P, dimensions=16).cpu().numpy()
+    np.testing.assert_allclose(Y * sign[:16], g["Y"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(Y.T @ Y, g["Y"].T @ g["Y"], rtol=1e-6, atol=1e-9)     # every inner product is unchanged
+    # stage function with named vectors (stages/whiten.py:30-75)
+    names = ["v%d" % i for i in range(g["X"].shape[1])]
+    meta, whit = W.learn_lw_whitening({}, (names, g["X"].T.copy(), [names[i] for i in g["qidxs"]], [names[i] for i in g["pidxs"]]))
+    assert meta["stats"]["failed_times"] == 0 and whit["P"].shape == g["P"].shape
+    mo, Po = WO.whitenlearn(g["X"], g["qidxs"], g["pidxs"])
+    np.testing.assert_allclose(np.abs(whit["P"]), np.abs(Po), rtol=1e-6, atol=1e-8)
+
+
+def test_cirdatasetap_and_validate_stage(vgg):
+    from gandtr_b200.extract import extract_descriptors
+    from gandtr_b200.score import SCORES, validate
+    images, qimages, gnd = _dataset()
+    ds = {"name": "synthetic", "images": images, "qimages": qimages, "bbxs": [None] * len(qimages), "gnd": gnd}
+    data = vgg.network_params.runtime["data"]
+    score = SCORES["cirdatasetap"]({"image_size": None, "dataset": ds, "transforms": data.get("transforms", data.get("augmentations")),
+                                    "mean_std": data["mean_std"]})
+    logged = []
+    avg = score(vgg, "cuda", lambda it, size, label, value, dtype: logged.append((it, size, label, value, dtype)))
+    # oracle: descriptors -> exact scores -> full ranking -> compute_map
+    db = extract_descriptors(vgg, images, None, vgg.transform).cpu().numpy()
+    q = extract_descriptors(vgg, qimages, None, vgg.transform).cpu().numpy()
+    m, aps, _, _ = R.compute_map(R.full_ranks(R.scores_exact(q, db)), gnd)
+    assert abs(avg["map"] - m) < 1e-12
+    assert avg["map"] > 0.9                                     # brightness-jittered copies must be found
+    labels = [x[2] for x in logged]
+    assert labels[0] == "dataset" and labels[1] == "score_avg" and labels.count("score") == len(qimages)
+    assert logged[1][4] == "scalar/score" and score.decisive_criterion == "val/learning/score_avg:map_medium"
+    out, = validate({"network": vgg, "data": {},
+                     "validation": {"type": "MultiCriterialValidation", "decisive_criterion": None,
+                                    "synthetic": {"type": "SingleValidation", "frequency": None, "network_overlay": None,
+                                                  "data": None, "criterion": {"type": "cirdatasetap", "image_size": None,
+                                                                              "dataset": ds}}}})
+    assert abs(out["eval"]["synthetic/validation/score_avg:map"] - m) < 1e-12
+
+
+def test_infer_stage_and_whitening_learning_chain(vgg, tmp_path):
+    from gandtr_b200.score import infer, infer_and_learn_whitening
+    images, _, _ = _dataset(12, 2)
+    meta, names, vecs = infer({"network": vgg}, (images,))
+    assert vecs.dtype == np.float64 and vecs.shape == (12, 512) and len(names) == 12
+    np.testing.assert_allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-5)
+    cids = ["%06d" % i for i in range(12)]
+    pkl = {"cids": cids, "images": images, "qidxs": [0, 1, 2, 3], "pidxs": [4, 5, 6, 7]}
+    meta, whit = infer_and_learn_whitening({"network": vgg, "whitening": {"type": "pca", "dataset_pkl": pkl, "directory": str(tmp_path)}})
+    assert whit["P"].shape == (512, 512) and whit["m"].shape == (512, 1)
+    assert meta["whitening_path"].endswith("whitening/pca-memory.pkl")
+    meta2, whit2 = infer_and_learn_whitening({"network": vgg, "whitening": {"type": "pca", "dataset_pkl": pkl, "directory": str(tmp_path)}})
+    assert meta2["status"] == "skipped" and whit2 is None
