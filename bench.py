@@ -203,7 +203,7 @@ def run_reference(args):
     if not args.no_retrieval:
         qps, what = cpu_retrieval_sample(args.db_rows)
         line["retrieval"] = {"metric": "1M-db top-100 queries/sec", "value": qps, "unit": "queries/s", "sample": what}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, batch):
@@ -218,8 +218,23 @@ def workload_config(args, batch):
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract goes to the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # stdout carries exactly one JSON line: library banners (e.g. "NCCL version ...") are sent to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -405,7 +420,7 @@ def main():
                 qps, what = cpu_retrieval_sample(args.db_rows)
                 line["retrieval"]["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(),
                                                      "kind": "port", "sample": what}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

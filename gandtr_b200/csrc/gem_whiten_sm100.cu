@@ -10,6 +10,8 @@
 // per row. It is HBM-bound: algorithmic bytes = 4*c*sum_s(h_s*w_s) per image. The remaining kernels
 // work on [n][c] vectors (KBs per image): per-image L2N / aggregation, a SIMT fp32 GEMM for the
 // whitening projection (P is read once per 64-image tile instead of once per image) and the final L2N.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gdt {
@@ -118,7 +120,7 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     // fast path: single scale, rows of 1..8 whole warp sweeps, 16-byte aligned base
     const int hw0 = S.hw[0];
-    if (S.nscales == 1 && (hw0 & 127) == 0 && hw0 <= 1024 && (((uintptr_t)S.ptr[0]) & 15) == 0) {
+    if (S.nscales == 1 && (hw0 & 127) == 0 && hw0 <= 1024 && (((uintptr_t)S.ptr[0]) & 15) == 0 && !(root & 2)) {
         const int sweeps = hw0 >> 7;
         for (long long r = wid * 2; r < total_rows; r += nwarps * 2) {
             const float* rowA = S.ptr[0] + r * hw0;
@@ -127,7 +129,7 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
             gem_row_pair<MODE>(rowA, rowB, sweeps, eps, p, lane, sa, sb);
             if (lane < 2 && r + lane < total_rows) {
                 const float mean = (lane == 0 ? sa : sb) / (float)hw0;
-                g[r + lane] = root ? powf(mean, inv_p) : mean;
+                g[r + lane] = (root & 1) ? powf(mean, inv_p) : mean;
             }
         }
         return;
@@ -139,7 +141,7 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
         const float sum = gem_row_sum<MODE>(S.ptr[s] + r * hw, hw, eps, p, lane);
         if (lane == 0) {
             const float mean = sum / (float)hw;
-            g[warp] = root ? powf(mean, inv_p) : mean;
+            g[warp] = (root & 1) ? powf(mean, inv_p) : mean;
         }
     }
 }
@@ -154,6 +156,13 @@ gem_pool_kernel(const __grid_constant__ GemScales S, long long rows_per_scale, l
     else if (p == 2.0f) gem_pool_rows<2>(S, rows_per_scale, total_rows, p, eps, root, g);
     else if (p == 1.0f) gem_pool_rows<1>(S, rows_per_scale, total_rows, p, eps, root, g);
     else gem_pool_rows<0>(S, rows_per_scale, total_rows, p, eps, root, g);
+}
+
+// debug switch (GDT_DEBUG_POOL_SINGLE=1): force the one-row-per-warp path, for A/B timing of the row-pair path
+static int pool_debug_flag() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GDT_DEBUG_POOL_SINGLE"); v = (e && e[0] == '1') ? 2 : 0; }
+    return v;
 }
 
 static unsigned gem_pool_grid(long long total_rows) {
@@ -438,7 +447,7 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
     }
     const long long rows_per_scale = (long long)n * c;
     const long long total_rows = rows_per_scale * scales;
-    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, 0, g);
+    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, 0 | pool_debug_flag(), g);
     GDT_LAUNCH_CHECK();
     DescScales D;
     for (int s = 0; s < GDT_MAX_SCALES; ++s) D.ptr[s] = s < scales ? g + (size_t)s * n * c : nullptr;
@@ -459,7 +468,7 @@ extern "C" int gdt_gem_pool(const float* fmap, int n, int c, int h, int w, const
     S.ptr[0] = fmap;
     S.hw[0] = h * w;
     const long long rows = (long long)n * c;
-    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, 1, pooled);
+    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, 1 | pool_debug_flag(), pooled);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

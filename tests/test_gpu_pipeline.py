@@ -39,7 +39,7 @@ def test_batched_extraction_equals_per_image_forward(vgg):
     with torch.no_grad():
         for i in (0, 2, 5, 23):
             ref = vgg(vgg.transform(images[i]).unsqueeze(0)).reshape(-1)
-            torch.testing.assert_close(d[i], ref, rtol=2e-5, atol=2e-7)
+            torch.testing.assert_close(d[i], ref, rtol=2e-5, atol=5e-6)   # cuDNN picks other conv algorithms for other batch sizes
     v = extract_vectors(vgg, images[:6], None, vgg.transform, print_freq=0)
     assert tuple(v.shape) == (512, 6) and not v.is_cuda                   # reference convention: D x n on the host
     torch.testing.assert_close(v.t(), d[:6].cpu(), rtol=1e-6, atol=1e-8)

@@ -15,7 +15,7 @@ if "clahe" in which:
         _lib.clahe_u8(x, MEAN, STD, out=out)
 if "gem" in which:
     c = 2048
-    fm = [torch.rand((32, c, h, w), device=dev) for h, w in ((24, 32), (17, 23), (12, 16))]
+    fm = [torch.rand((128, c, h, w), device=dev) for h, w in ((24, 32), (17, 23), (12, 16))]
     p = torch.tensor([3.0], device=dev)
     P = torch.randn((c, c), device=dev) / c ** 0.5
     m = torch.rand(c, device=dev) * 0.05
