@@ -42,10 +42,10 @@ def test_batched_extraction_equals_per_image_forward(vgg):
             torch.testing.assert_close(d[i], ref, rtol=2e-5, atol=5e-6)   # cuDNN picks other conv algorithms for other batch sizes
     v = extract_vectors(vgg, images[:6], None, vgg.transform, print_freq=0)
     assert tuple(v.shape) == (512, 6) and not v.is_cuda                   # reference convention: D x n on the host
-    torch.testing.assert_close(v.t(), d[:6].cpu(), rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(v.t(), d[:6].cpu(), rtol=2e-5, atol=5e-6)
     # sharded extraction: the two halves are exactly the rows of the full matrix
     halves = [extract_descriptors(vgg, images, None, vgg.transform, rank=r, world_size=2) for r in range(2)]
-    torch.testing.assert_close(torch.cat(halves), d, rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(torch.cat(halves), d, rtol=2e-5, atol=5e-6)   # batch boundaries move -> other cuDNN algorithms
 
 
 def test_extract_ms_matches_reference_formula(vgg):
