@@ -196,6 +196,66 @@ gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restr
     __shared__ float red[8];
     __shared__ float inv_norm[GDT_MAX_SCALES];
     const int img = blockIdx.x, tid = threadIdx.x;
+    if (c <= 2048) {
+        // register-resident path: every global load of a phase is issued before the first dependent operation
+        const bool normalised_ = (flags & GDT_DESC_NORMALISED) != 0;
+        const bool raw_mean_ = (flags & GDT_POOLED_RAW_MEAN) != 0;
+        const bool aggregate_ = (flags & GDT_GEM_AGGREGATE) != 0;
+        const float p_ = p_dev ? __ldg(p_dev) : msp_host;
+        const float inv_p_ = raw_mean_ ? 1.0f / p_ : 1.0f;
+        const float msp_ = (flags & GDT_GEM_MSP_IS_P) ? p_ : msp_host;
+        const float inv_msp_ = (float)(1.0 / (double)msp_);
+        float mv[8], acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = tid + j * 256;
+            mv[j] = (m && i < c) ? __ldg(m + i) : 0.f;
+            acc[j] = 0.f;
+        }
+        for (int s = 0; s < scales; ++s) {
+            const float* gs = D.ptr[s] + (size_t)img * c;
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int i = tid + j * 256; r[j] = i < c ? gs[i] : 0.f; }
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (tid + j * 256 < c) {
+                    if (raw_mean_) r[j] = powf(r[j], inv_p_);
+                    ss += r[j] * r[j];
+                }
+            }
+            float den = 1.0f;
+            if (!normalised_) den = sqrtf(block_sum_256(ss, red)) + 1e-6f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = normalised_ ? r[j] : r[j] / den;
+                if (!aggregate_) acc[j] = d;
+                else acc[j] += (msp_ == 1.0f) ? d : powf(d, msp_);
+            }
+        }
+        float* o = out + (size_t)img * c;
+        if (aggregate_) {
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = acc[j] / (float)scales;
+                if (msp_ != 1.0f) v = powf(v, inv_msp_);
+                if (tid + j * 256 >= c) v = 0.f;
+                acc[j] = v;
+                ss += v * v;
+            }
+            const float nrm = sqrtf(block_sum_256(ss, red));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = acc[j] / nrm;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = tid + j * 256;
+            if (i < c) o[i] = m ? acc[j] - mv[j] : acc[j];
+        }
+        return;
+    }
     const bool normalised = (flags & GDT_DESC_NORMALISED) != 0;
     const bool raw_mean = (flags & GDT_POOLED_RAW_MEAN) != 0;   // pooled values still need the 1/p root
     const float inv_p = raw_mean ? 1.0f / __ldg(p_dev) : 1.0f;
@@ -415,7 +475,7 @@ whiten_reduce_l2n_kernel(const float* __restrict__ Xpart, int n, int dim, int sp
 
 static int whiten_splitk(int n, int c, int dim) {
     const int tiles = ceil_div(dim, 64) * ceil_div(n, 64);
-    int z = ceil_div(2 * sm_count_current_device(), tiles);
+    int z = ceil_div(4 * sm_count_current_device(), tiles);
     const int zmax = c / 128 > 1 ? c / 128 : 1;          // at least 128 of K per slice
     if (z > zmax) z = zmax;
     if (z > 32) z = 32;

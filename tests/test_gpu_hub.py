@@ -114,7 +114,7 @@ def test_fused_eval_stack_equals_wrapper_by_wrapper_path(vgg):
     with torch.no_grad():
         both = net(torch.cat([x, x.flip(-1)]))
     assert tuple(both.shape) == (128, 2)
-    np.testing.assert_allclose(both[:, 0].cpu().numpy(), fused.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(both[:, 0].cpu().numpy(), fused.cpu().numpy(), rtol=2e-5, atol=5e-6)   # cuDNN algorithm depends on batch size
 
 
 def test_clahepost_wrapper_matches_reference_golden():
