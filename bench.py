@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=128, help="images per step per GPU")
     ap.add_argument("--db-rows", type=int, default=DB_ROWS)
     ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--db-dim", type=int, default=DB_DIM, help="descriptor dimension of the retrieval database (2048 | 512)")
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=48, help="images in the bounded CPU sample")
@@ -166,19 +167,19 @@ def cpu_extract_sample(n_images, seed=7):
     return n_images / (t_k1 + t_k2), max(threads, cv_threads), desc
 
 
-def cpu_retrieval_sample(db_rows, nq=32):
+def cpu_retrieval_sample(db_rows, nq=32, dim=DB_DIM):
     import numpy as np
     from oracle import reference_cpu as RC
     rg = np.random.default_rng(3)
     rows = min(db_rows, 250_000)
-    db = rg.standard_normal((rows, DB_DIM), dtype=np.float32)
+    db = rg.standard_normal((rows, dim), dtype=np.float32)
     db /= np.linalg.norm(db, axis=1, keepdims=True)
-    q = rg.standard_normal((nq, DB_DIM), dtype=np.float32)
+    q = rg.standard_normal((nq, dim), dtype=np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)
     t0 = time.perf_counter()
     RC.rank_numpy(db.T, q.T, TOPK)
     dt = (time.perf_counter() - t0) * (db_rows / rows)                      # linear in rows (argsort: n log n, ~+10%)
-    return nq / dt, "np.dot + np.argsort, %d queries x %d rows x %d (scaled linearly to %d rows)" % (nq, rows, DB_DIM, db_rows)
+    return nq / dt, "np.dot + np.argsort, %d queries x %d rows x %d (scaled linearly to %d rows)" % (nq, rows, dim, db_rows)
 
 
 def run_reference(args):
@@ -201,7 +202,7 @@ def run_reference(args):
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if not args.no_retrieval:
-        qps, what = cpu_retrieval_sample(args.db_rows)
+        qps, what = cpu_retrieval_sample(args.db_rows, dim=args.db_dim)
         line["retrieval"] = {"metric": "1M-db top-100 queries/sec", "value": qps, "unit": "queries/s", "sample": what}
     emit(line)
 
@@ -212,7 +213,7 @@ def workload_config(args, batch):
                         "(stock conv backbone between them excluded)",
             "batch_per_gpu": batch, "image": "1024x768", "feature_map": [C_FEAT, FH, FW], "whiten_dim": C_FEAT,
             "l2_policy": "inputs larger than L2 (u8 batch + feature maps + f32 output > 1 GB per step)",
-            "retrieval": {"db_rows": args.db_rows, "dim": DB_DIM, "queries": args.queries, "k": TOPK,
+            "retrieval": {"db_rows": args.db_rows, "dim": args.db_dim, "queries": args.queries, "k": TOPK,
                           "sharding": "row-wise over ranks, all_gather + merge"}}
 
 
@@ -378,9 +379,9 @@ def main():
         del out, fmaps_ms
         torch.cuda.empty_cache()
         lo, hi = shard_bounds(args.db_rows, world, rank)
-        index = ShardedIndex(synth_db_rows(lo, hi, DB_DIM, dev), n_total=args.db_rows, index_base=lo)
+        index = ShardedIndex(synth_db_rows(lo, hi, args.db_dim, dev), n_total=args.db_rows, index_base=lo)
         gq = torch.Generator(device="cpu").manual_seed(3)
-        q_host = torch.randn((args.queries, DB_DIM), generator=gq)
+        q_host = torch.randn((args.queries, args.db_dim), generator=gq)
         q_host = (q_host / q_host.norm(dim=1, keepdim=True)).pin_memory()
         q = q_host.to(dev)
         res_s = torch.empty((args.queries, TOPK), dtype=torch.float32).pin_memory()
@@ -397,13 +398,13 @@ def main():
             res_i.copy_(i, non_blocking=True)
         re_ms, w = timed(search_e2e, rK, rW)
         windows.append(w)
-        flops = 2.0 * args.queries * args.db_rows * DB_DIM
+        flops = 2.0 * args.queries * args.db_rows * args.db_dim
         line["retrieval"] = {
             "metric": "1M-db top-100 queries/sec", "value": args.queries * rK / (r_ms * 1e-3), "unit": "queries/s",
             "scaling": "strong (fixed database, row-sharded over the ranks)",
             "ms_per_search": r_ms / rK, "steps": rK, "warmup": rW, "gpu_launches": r_launches,
             "e2e": {"value": args.queries * rK / (re_ms * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": args.queries * DB_DIM * 4, "d2h_bytes_per_step": args.queries * TOPK * 12},
+                    "h2d_bytes_per_step": args.queries * args.db_dim * 4, "d2h_bytes_per_step": args.queries * TOPK * 12},
             "status": index.shard.last_status,
             "roofline": {"kernel": "K3 score_filter_kernel (tcgen05 fp16 coarse pass) + exact re-score/finalise",
                          "bound": "tensor", "achieved": flops / world / (r_ms / rK * 1e-3) / 1e12, "peak": tc_peak,
@@ -417,7 +418,7 @@ def main():
             ips, cores, what = cpu_extract_sample(args.cpu_images)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": what}
             if not args.no_retrieval:
-                qps, what = cpu_retrieval_sample(args.db_rows)
+                qps, what = cpu_retrieval_sample(args.db_rows, dim=args.db_dim)
                 line["retrieval"]["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(),
                                                      "kind": "port", "sample": what}
         emit(line)

@@ -118,9 +118,10 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
     const float inv_p = 1.0f / p;
     const long long nwarps = (long long)gridDim.x * 8;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    // fast path: single scale, rows of 1..8 whole warp sweeps, 16-byte aligned base
+    // row pairs (single scale, rows of 1..8 whole warp sweeps, 16-byte aligned base) pay off only when the per-row
+    // epilogue is the expensive root (gdt_gem_pool): measured on B200, one row per warp is faster otherwise
     const int hw0 = S.hw[0];
-    if (S.nscales == 1 && (hw0 & 127) == 0 && hw0 <= 1024 && (((uintptr_t)S.ptr[0]) & 15) == 0 && !(root & 2)) {
+    if (root && S.nscales == 1 && (hw0 & 127) == 0 && hw0 <= 1024 && (((uintptr_t)S.ptr[0]) & 15) == 0) {
         const int sweeps = hw0 >> 7;
         for (long long r = wid * 2; r < total_rows; r += nwarps * 2) {
             const float* rowA = S.ptr[0] + r * hw0;
@@ -129,7 +130,7 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
             gem_row_pair<MODE>(rowA, rowB, sweeps, eps, p, lane, sa, sb);
             if (lane < 2 && r + lane < total_rows) {
                 const float mean = (lane == 0 ? sa : sb) / (float)hw0;
-                g[r + lane] = (root & 1) ? powf(mean, inv_p) : mean;
+                g[r + lane] = root ? powf(mean, inv_p) : mean;
             }
         }
         return;
@@ -141,7 +142,7 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
         const float sum = gem_row_sum<MODE>(S.ptr[s] + r * hw, hw, eps, p, lane);
         if (lane == 0) {
             const float mean = sum / (float)hw;
-            g[warp] = (root & 1) ? powf(mean, inv_p) : mean;
+            g[warp] = root ? powf(mean, inv_p) : mean;
         }
     }
 }
@@ -156,13 +157,6 @@ gem_pool_kernel(const __grid_constant__ GemScales S, long long rows_per_scale, l
     else if (p == 2.0f) gem_pool_rows<2>(S, rows_per_scale, total_rows, p, eps, root, g);
     else if (p == 1.0f) gem_pool_rows<1>(S, rows_per_scale, total_rows, p, eps, root, g);
     else gem_pool_rows<0>(S, rows_per_scale, total_rows, p, eps, root, g);
-}
-
-// debug switch (GDT_DEBUG_POOL_SINGLE=1): force the one-row-per-warp path, for A/B timing of the row-pair path
-static int pool_debug_flag() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GDT_DEBUG_POOL_SINGLE"); v = (e && e[0] == '1') ? 2 : 0; }
-    return v;
 }
 
 static unsigned gem_pool_grid(long long total_rows) {
@@ -553,7 +547,7 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
     }
     const long long rows_per_scale = (long long)n * c;
     const long long total_rows = rows_per_scale * scales;
-    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, 0 | pool_debug_flag(), g);
+    gem_pool_kernel<<<gem_pool_grid(total_rows), 256, 0, stream>>>(S, rows_per_scale, total_rows, p_dev, eps, 0, g);
     GDT_LAUNCH_CHECK();
     DescScales D;
     for (int s = 0; s < GDT_MAX_SCALES; ++s) D.ptr[s] = s < scales ? g + (size_t)s * n * c : nullptr;
@@ -574,7 +568,7 @@ extern "C" int gdt_gem_pool(const float* fmap, int n, int c, int h, int w, const
     S.ptr[0] = fmap;
     S.hw[0] = h * w;
     const long long rows = (long long)n * c;
-    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, 1 | pool_debug_flag(), pooled);
+    gem_pool_kernel<<<gem_pool_grid(rows), 256, 0, stream>>>(S, rows, rows, p_dev, eps, 1, pooled);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
