@@ -48,6 +48,12 @@ SYMBOLS = [
                                  _P, _P, _c.c_size_t, _P]),
     ("gdt_db_prepare_workspace_bytes", _c.c_size_t, [_c.c_longlong, _c.c_int]),
     ("gdt_db_prepare", _c.c_int, [_P, _c.c_longlong, _c.c_int, _P, _P, _P, _c.c_size_t, _P]),
+    ("gdt_db_prepare_norm", _c.c_int, [_P, _c.c_longlong, _c.c_int, _P, _P]),
+    ("gdt_db_prepare_convert", _c.c_int, [_P, _c.c_longlong, _c.c_int, _P, _P, _P]),
+    ("gdt_score_topk_exchange_layout", _c.c_int, [_c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _P, _P]),
+    ("gdt_score_topk_filter", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _P, _P, _c.c_size_t, _P]),
+    ("gdt_score_topk_finalize", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P, _P,
+                                           _P, _c.c_size_t, _P]),
     ("gdt_score_topk_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_longlong, _c.c_int, _c.c_int]),
     ("gdt_score_topk", _c.c_int, [_P, _P, _P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P,
                                   _P, _P, _c.c_size_t, _P]),
@@ -317,6 +323,55 @@ def db_prepare(db):
               "gdt_db_prepare")
     _count("db_prepare")
     return shadow, norm_max
+
+
+def db_prepare_sharded(db, allreduce_max):
+    """gdt_db_prepare for one shard of a row-sharded database: `allreduce_max(tensor)` must reduce (MAX, in place)
+    over the ranks, so that every shard is converted with the same scale and filtered with the same error bound."""
+    _require(db, torch.float32, "db")
+    ndb, d = db.shape
+    lib = load()
+    shadow = torch.empty((ndb, d), dtype=torch.float16, device=db.device)
+    stats = torch.zeros(4, dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        if ndb:
+            check(lib.gdt_db_prepare_norm(_ptr(db), ndb, d, _ptr(stats), _stream()), "gdt_db_prepare_norm")
+        allreduce_max(stats[0:1])
+        if ndb:
+            check(lib.gdt_db_prepare_convert(_ptr(db), ndb, d, _ptr(shadow), _ptr(stats), _stream()), "gdt_db_prepare_convert")
+        allreduce_max(stats[1:4])     # an empty shard learns scale and bounds from its peers
+    _count("db_prepare")
+    return shadow, stats
+
+
+def score_topk_two_phase(q, db, shadow, stats, k, index_base=0, exchange=None):
+    """Filter -> `exchange(hist)` (an in-place SUM all-reduce of the int32 [nq, 256] histogram view) -> finalize."""
+    _require(q, torch.float32, "q")
+    _require(db, torch.float32, "db")
+    _require(shadow, torch.float16, "shadow")
+    _require(stats, torch.float32, "stats")
+    nq, d = q.shape
+    ndb = db.shape[0]
+    lib = load()
+    dev = q.device
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    status = torch.empty(4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_score_topk_workspace_bytes(nq, ndb, d, k), dev)
+        check(lib.gdt_score_topk_filter(_ptr(q), _ptr(shadow), _ptr(stats), nq, ndb, d, k, _ptr(status), _ptr(ws), ws.numel(),
+                                        _stream()), "gdt_score_topk_filter")
+        if exchange is not None:
+            off, nbytes = ctypes.c_size_t(), ctypes.c_size_t()
+            check(lib.gdt_score_topk_exchange_layout(nq, ndb, d, k, ctypes.byref(off), ctypes.byref(nbytes)),
+                  "gdt_score_topk_exchange_layout")
+            exchange(ws[off.value:off.value + nbytes.value].view(torch.int32).view(nq, 256))
+        check(lib.gdt_score_topk_finalize(_ptr(q), _ptr(db), nq, ndb, d, k, int(index_base), _ptr(scores), _ptr(idx),
+                                          _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_score_topk_finalize")
+    global launch_count
+    seed = max(32, (16 * k + 255) // 256)
+    launch_count += 3 + (1 if (ndb + 255) // 256 > seed else 0)
+    return scores, idx, status
 
 
 def score_topk_workspace_bytes(nq, ndb, d, k):

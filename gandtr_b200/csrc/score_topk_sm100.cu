@@ -725,22 +725,39 @@ extern "C" size_t gdt_db_prepare_workspace_bytes(long long ndb, int d) {
     return 256;
 }
 
-extern "C" int gdt_db_prepare(const float* db, long long ndb, int d, void* db_f16, float* db_stats, void* ws,
-                              size_t ws_bytes, void* stream_) {
-    (void)ws; (void)ws_bytes;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!db || !db_f16 || !db_stats || ndb <= 0 || d <= 0) return GDT_ERR_INVALID_ARGUMENT;
+static int db_prepare_impl(const float* db, long long ndb, int d, void* db_f16, float* db_stats, bool norm_phase,
+                           bool convert_phase, cudaStream_t stream) {
+    if (!db || !db_stats || ndb <= 0 || d <= 0 || (convert_phase && !db_f16)) return GDT_ERR_INVALID_ARGUMENT;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
-    GDT_CUDA(cudaMemsetAsync(db_stats, 0, 4 * sizeof(float), stream));
     const int sms = sm_count_current_device();
     long long blocks = ceil_div_ll(ndb, 8);
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-    db_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, db_stats);
-    GDT_LAUNCH_CHECK();
-    db_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, (__half*)db_f16, db_stats);
-    GDT_LAUNCH_CHECK();
+    if (norm_phase) {
+        GDT_CUDA(cudaMemsetAsync(db_stats, 0, 4 * sizeof(float), stream));
+        db_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, db_stats);
+        GDT_LAUNCH_CHECK();
+    }
+    if (convert_phase) {
+        GDT_CUDA(cudaMemsetAsync(db_stats + 1, 0, 3 * sizeof(float), stream));
+        db_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(db, ndb, d, (__half*)db_f16, db_stats);
+        GDT_LAUNCH_CHECK();
+    }
     return GDT_OK;
+}
+
+extern "C" int gdt_db_prepare(const float* db, long long ndb, int d, void* db_f16, float* db_stats, void* ws,
+                              size_t ws_bytes, void* stream_) {
+    (void)ws; (void)ws_bytes;
+    return db_prepare_impl(db, ndb, d, db_f16, db_stats, true, true, (cudaStream_t)stream_);
+}
+
+extern "C" int gdt_db_prepare_norm(const float* db, long long ndb, int d, float* db_stats, void* stream_) {
+    return db_prepare_impl(db, ndb, d, nullptr, db_stats, true, false, (cudaStream_t)stream_);
+}
+
+extern "C" int gdt_db_prepare_convert(const float* db, long long ndb, int d, void* db_f16, float* db_stats, void* stream_) {
+    return db_prepare_impl(db, ndb, d, db_f16, db_stats, false, true, (cudaStream_t)stream_);
 }
 
 extern "C" size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k) {
@@ -748,20 +765,34 @@ extern "C" size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, i
     return topk_plan(nq, ndb, d, k).total + 256;
 }
 
-extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_f16, const float* db_stats, int nq,
-                              long long ndb, int d, int k, long long index_base, float* top_scores, int64_t* top_idx,
-                              int32_t* status_dev, void* ws, size_t ws_bytes, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!q || !db || !db_f16 || !db_stats || !top_scores || !top_idx || !status_dev || !ws)
-        return GDT_ERR_INVALID_ARGUMENT;
+static int topk_check(const void* q, int nq, long long ndb, int d, int k, long long index_base, const void* ws,
+                      size_t ws_bytes) {
+    if (!q || !ws) return GDT_ERR_INVALID_ARGUMENT;
     if (nq <= 0 || ndb <= 0 || d <= 0 || k <= 0) return GDT_ERR_INVALID_ARGUMENT;
     if ((d & 7) != 0 || d > 8192 || k > 1024 || ndb > 0x7fffffffLL || index_base < 0 ||
         index_base + ndb > 0xffffffffLL)
         return GDT_ERR_UNSUPPORTED;
-    if ((((uintptr_t)db_f16) & 15) != 0) return GDT_ERR_INVALID_ARGUMENT;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
     if (ws_bytes < gdt_score_topk_workspace_bytes(nq, ndb, d, k) || (((uintptr_t)ws) & 255)) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    return GDT_OK;
+}
+
+extern "C" int gdt_score_topk_exchange_layout(int nq, long long ndb, int d, int k, size_t* hist_offset, size_t* hist_bytes) {
+    if (nq <= 0 || ndb <= 0 || d <= 0 || k <= 0 || !hist_offset || !hist_bytes) return GDT_ERR_INVALID_ARGUMENT;
+    const TopkPlan L = topk_plan(nq, ndb, d, k);
+    *hist_offset = L.hist;
+    *hist_bytes = (size_t)nq * kHistBins * 4;
+    return GDT_OK;
+}
+
+extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb,
+                                     int d, int k, int32_t* status_dev, void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!db_f16 || !db_stats || !status_dev) return GDT_ERR_INVALID_ARGUMENT;
+    if ((((uintptr_t)db_f16) & 15) != 0) return GDT_ERR_INVALID_ARGUMENT;
+    int rc = topk_check(q, nq, ndb, d, k, 0, ws, ws_bytes);
+    if (rc != GDT_OK) return rc;
 
     const TopkPlan L = topk_plan(nq, ndb, d, k);
     char* base = (char*)ws;
@@ -776,7 +807,7 @@ extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_f1
     GDT_LAUNCH_CHECK();
 
     CUtensorMap map_q, map_db;
-    int rc = make_f16_map(&map_q, qb, nq, d, kBlockM);
+    rc = make_f16_map(&map_q, qb, nq, d, kBlockM);
     if (rc != GDT_OK) return rc;
     rc = make_f16_map(&map_db, db_f16, ndb, d, kBlockN);
     if (rc != GDT_OK) return rc;
@@ -804,7 +835,18 @@ extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_f1
         score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
         GDT_LAUNCH_CHECK();
     }
+    return GDT_OK;
+}
 
+extern "C" int gdt_score_topk_finalize(const float* q, const float* db, int nq, long long ndb, int d, int k,
+                                       long long index_base, float* top_scores, int64_t* top_idx, int32_t* status_dev,
+                                       void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!db || !top_scores || !top_idx || !status_dev) return GDT_ERR_INVALID_ARGUMENT;
+    int rc = topk_check(q, nq, ndb, d, k, index_base, ws, ws_bytes);
+    if (rc != GDT_OK) return rc;
+    const TopkPlan L = topk_plan(nq, ndb, d, k);
+    char* base = (char*)ws;
     const int scap = survivor_capacity(k);
     const int dpad = (d + 3) & ~3;
     const size_t fsmem = (size_t)scap * 8 + (size_t)dpad * 4;
@@ -813,8 +855,18 @@ extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_f1
         GDT_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fattr = fsmem;
     }
-    topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.n_segs, L.cap0, L.cap1, scap, index_base, meta,
-                                                     cnt, hist, cand, top_scores, top_idx, status_dev);
+    topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.n_segs, L.cap0, L.cap1, scap, index_base,
+                                                     (const QMeta*)(base + L.meta), (const uint32_t*)(base + L.cnt),
+                                                     (const uint32_t*)(base + L.hist), (const uint64_t*)(base + L.cand),
+                                                     top_scores, top_idx, status_dev);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
+}
+
+extern "C" int gdt_score_topk(const float* q, const float* db, const void* db_f16, const float* db_stats, int nq,
+                              long long ndb, int d, int k, long long index_base, float* top_scores, int64_t* top_idx,
+                              int32_t* status_dev, void* ws, size_t ws_bytes, void* stream) {
+    int rc = gdt_score_topk_filter(q, db_f16, db_stats, nq, ndb, d, k, status_dev, ws, ws_bytes, stream);
+    if (rc != GDT_OK) return rc;
+    return gdt_score_topk_finalize(q, db, nq, ndb, d, k, index_base, top_scores, top_idx, status_dev, ws, ws_bytes, stream);
 }

@@ -42,16 +42,25 @@ def _world(group):
 class CudaOps:
     """The product's compute: every method is one or more launches of libgandtr_b200.so kernels."""
 
-    def prepare(self, db):
+    def prepare(self, db, group=None, world=1):
         from . import _lib
         d = db.shape[1]
-        if d % 8 == 0 and d <= 8192 and db.shape[0] > 0:
+        if d % 8 != 0 or d > 8192:
+            return {}
+        if world > 1:
+            # common scale / error bound on every rank, so that the per-query score histograms can be summed
+            shadow, stats = _lib.db_prepare_sharded(db, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group))
+            return {"shadow": shadow, "norm_max": stats, "group": group}
+        if db.shape[0] > 0:
             shadow, norm_max = _lib.db_prepare(db)
             return {"shadow": shadow, "norm_max": norm_max}
         return {}
 
     def local_topk(self, q, shard, k):
-        """(scores [nq,k], global idx [nq,k]) of one shard; exact ordering (score desc, index asc)."""
+        """(scores [nq,k], global idx [nq,k]) of one shard; exact ordering (score desc, index asc). On a sharded index
+        the lists hold this shard's members of the GLOBAL top k (fewer than k valid entries, (-inf, -1) padding)."""
+        if "group" in shard.aux:
+            return self._local_topk_exchanged(q, shard, k)
         from . import _lib
         db, aux, base = shard.db, shard.aux, shard.index_base
         nq, d = q.shape
@@ -67,6 +76,37 @@ class CudaOps:
         shard.last_status = status.tolist()
         if int(status[0]) != 0:
             # candidate overflow (massive ties / adversarial data): re-score exactly the flagged queries
+            bad = torch.nonzero(i[:, 0] == -2).flatten()
+            if bad.numel():
+                se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
+                s[bad] = se
+                i[bad] = ie
+        return s, i
+
+    def _local_topk_exchanged(self, q, shard, k):
+        """Row-sharded search with the histogram exchange (include/gandtr_b200.h, two-phase form). Every rank takes the
+        same code path (tcgen05 vs exact is decided from global quantities) so the collectives line up."""
+        from . import _lib
+        db, aux, base = shard.db, shard.aux, shard.index_base
+        nq, d = q.shape
+        group = aux["group"]
+        ndb = db.shape[0]
+        use_tc = k <= 1024 and nq * shard.n_total * d >= TC_MIN_WORK * dist.get_world_size(group) and shard.n_total <= 0xFFFFFFFF
+        if not use_tc:
+            if ndb == 0:
+                return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device),
+                        torch.full((nq, k), -1, dtype=torch.int64, device=q.device))
+            return self._exact_chunked(q, db, k, base)
+        if ndb == 0:
+            hist = torch.zeros((nq, 256), dtype=torch.int32, device=q.device)
+            dist.all_reduce(hist, group=group)          # take part in the histogram exchange with an empty contribution
+            return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device),
+                    torch.full((nq, k), -1, dtype=torch.int64, device=q.device))
+        s, i, st = _lib.score_topk_two_phase(q, db, aux["shadow"], aux["norm_max"], k, index_base=base,
+                                             exchange=lambda h: dist.all_reduce(h, group=group))
+        status = st.cpu()
+        shard.last_status = status.tolist()
+        if int(status[0]) != 0:
             bad = torch.nonzero(i[:, 0] == -2).flatten()
             if bad.numel():
                 se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
@@ -109,11 +149,15 @@ class DatabaseShard:
     """Rows [index_base, index_base + n) of the database, resident in HBM: fp32 rows + the fp16 shadow used by the
     tcgen05 coarse pass (6 bytes per element in total)."""
 
-    def __init__(self, db, index_base=0, ops=None):
+    def __init__(self, db, index_base=0, ops=None, group=None, world=1, n_total=None):
         self.ops = ops or CudaOps()
         self.db = db.contiguous()
         self.index_base = int(index_base)
-        self.aux = self.ops.prepare(self.db)
+        self.n_total = int(n_total if n_total is not None else db.shape[0])
+        try:
+            self.aux = self.ops.prepare(self.db, group=group, world=world)
+        except TypeError:          # injected ops with the single-argument signature (tests)
+            self.aux = self.ops.prepare(self.db)
         self.last_status = None
 
     @property
@@ -137,7 +181,7 @@ class ShardedIndex:
             if self.world > 1:
                 assert local_db.shape[0] == shard_bounds(self.n_total, self.world, self.rank)[1] - index_base, \
                     "local shard does not match shard_bounds(); pass index_base explicitly for custom partitions"
-        self.shard = DatabaseShard(local_db, index_base, self.ops)
+        self.shard = DatabaseShard(local_db, index_base, self.ops, group=group, world=self.world, n_total=self.n_total)
 
     @classmethod
     def from_full(cls, db, group=None, ops=None):

@@ -160,6 +160,23 @@ int gdt_desc_post(const float* const* host_descs, int n, int c, int scales, cons
 size_t gdt_db_prepare_workspace_bytes(long long ndb, int d);
 int gdt_db_prepare(const float* db, long long ndb, int d, void* db_f16, float* db_stats,
                    void* ws, size_t ws_bytes, void* stream);
+/* Two-phase form for row-sharded databases (the one real exchange step of the path). Every rank must
+ * filter in the same score units, so the shard statistics are made common first:
+ *     gdt_db_prepare_norm -> all-reduce(MAX) db_stats[0] -> gdt_db_prepare_convert -> all-reduce(MAX) db_stats[2..3]
+ * and per search
+ *     gdt_score_topk_filter -> all-reduce(SUM) of the per-query score histograms -> gdt_score_topk_finalize.
+ * With the summed histogram each rank keeps only candidates above the GLOBAL k-th-score threshold, so a shard
+ * re-scores ~k/G instead of ~k survivors per query and may return fewer than k valid entries (padding (-inf, -1));
+ * gdt_topk_merge over the gathered lists then yields exactly the global top k.
+ * gdt_score_topk_exchange_layout reports where the uint32 [nq][256] histograms live inside the workspace. */
+int gdt_db_prepare_norm(const float* db, long long ndb, int d, float* db_stats, void* stream);
+int gdt_db_prepare_convert(const float* db, long long ndb, int d, void* db_f16, float* db_stats, void* stream);
+int gdt_score_topk_exchange_layout(int nq, long long ndb, int d, int k, size_t* hist_offset, size_t* hist_bytes);
+int gdt_score_topk_filter(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb, int d, int k,
+                          int32_t* status_dev, void* ws, size_t ws_bytes, void* stream);
+int gdt_score_topk_finalize(const float* q, const float* db, int nq, long long ndb, int d, int k, long long index_base,
+                            float* top_scores, int64_t* top_idx, int32_t* status_dev,
+                            void* ws, size_t ws_bytes, void* stream);
 size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k);
 int gdt_score_topk(const float* q, const float* db, const void* db_f16, const float* db_stats,
                    int nq, long long ndb, int d, int k, long long index_base,
