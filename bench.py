@@ -32,6 +32,9 @@ DB_ROWS, DB_DIM, N_QUERIES, TOPK = 1_000_000, 2048, 10_000, 100
 MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 K1_BYTES_PER_IMG = 15 * H * W
 K2_BYTES_PER_IMG = 4 * C_FEAT * FH * FW + 4 * C_FEAT
+# measured DRAM traffic of K1 per image (dram__bytes_read.sum + dram__bytes_write.sum of clahe_hist + clahe_apply, ncu
+# --set full capture profiles/ncu_full_r1d.txt at 32 images: 76.0 + 7.9 + 102.4 + 246.6 MB) -- 1.15x the algorithmic bytes
+K1_TRAFFIC_PER_IMG = (76.037888e6 + 7.912192e6 + 102.354432e6 + 246.626560e6) / 32
 
 
 def parse():
@@ -364,7 +367,8 @@ def main():
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "K1 clahe_hist_kernel + clahe_apply_kernel (one gdt_clahe_u8 call)", "bound": "hbm",
                      "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "peak_source": hbm_src, "traffic": None, "ms_per_launch_pair": k1_ms,
+                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1d, per image x batch",
+                     "ms_per_launch_pair": k1_ms,
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + whiten (one gdt_gem_whiten call, single-scale)",
                         "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
