@@ -275,6 +275,7 @@ def main():
     gP = torch.Generator(device=dev).manual_seed(5)
     Pm = torch.randn((C_FEAT, C_FEAT), generator=gP, device=dev) / C_FEAT ** 0.5
     mm = torch.rand(C_FEAT, generator=gP, device=dev) * 0.05
+    Ps = _lib.whiten_prepare(Pm)          # once per learned whitening (like gdt_db_prepare for a database)
     out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
     desc_host = torch.empty((B, C_FEAT), dtype=torch.float32).pin_memory()
 
@@ -294,12 +295,12 @@ def main():
         transform.batch(imgs, out=out)
         if ev is not None:
             ev.record()
-        return _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm)
+        return _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm, P_split=Ps)
 
     def step_e2e():
         x = imgs_host.to(dev, non_blocking=True)
         transform.batch(x, out=out)
-        d = _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm)
+        d = _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm, P_split=Ps)
         desc_host.copy_(d, non_blocking=True)
 
     def timed(fn, steps, warm, mids=None):
@@ -354,7 +355,7 @@ def main():
 
     # ---- multi-scale variant of K2 (reported, not the headline) ----
     def step_ms():
-        return _lib.gem_whiten(fmaps_ms, p, aggregate=True, msp_is_p=True, P=Pm, m=mm)
+        return _lib.gem_whiten(fmaps_ms, p, aggregate=True, msp_is_p=True, P=Pm, m=mm, P_split=Ps)
     ms_ms, w = timed(step_ms, K, Wm)
     windows.append(w)
 
@@ -370,7 +371,7 @@ def main():
                      "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1d, per image x batch",
                      "ms_per_launch_pair": k1_ms,
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
-        "roofline_k2": {"kernel": "K2 gem_pool + finalize + whiten (one gdt_gem_whiten call, single-scale)",
+        "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
                         "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
                         "unit": "GB/s", "ms_per_call": k2_ms,
                         "multi_scale": {"ms_per_call": ms_ms / K, "achieved": B * (4 * C_FEAT * sum(h * w for h, w in MS_SIZES) + 4 * C_FEAT) / (ms_ms / K * 1e-3) / 1e9}},

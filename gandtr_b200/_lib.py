@@ -39,12 +39,13 @@ SYMBOLS = [
     ("gdt_clahe_f32", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P,
                                  _c.c_size_t, _P]),
     ("gdt_gem_whiten_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
-    ("gdt_gem_whiten", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P,
+    ("gdt_gem_whiten", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P, _P,
                                   _c.c_int, _P, _P, _c.c_size_t, _P]),
+    ("gdt_whiten_prepare", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     ("gdt_gem_pool", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _P, _P]),
     ("gdt_l2n_rows", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _P, _P]),
     ("gdt_desc_post_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int]),
-    ("gdt_desc_post", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P, _c.c_int,
+    ("gdt_desc_post", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P, _P, _c.c_int,
                                  _P, _P, _c.c_size_t, _P]),
     ("gdt_db_prepare_workspace_bytes", _c.c_size_t, [_c.c_longlong, _c.c_int]),
     ("gdt_db_prepare", _c.c_int, [_P, _c.c_longlong, _c.c_int, _P, _P, _P, _c.c_size_t, _P]),
@@ -200,9 +201,33 @@ def clahe_f32(x_chw, in_mean, in_std, out_mean, out_std, clip_limit=1.0, grid=8,
 
 # ---- K2 ----------------------------------------------------------------------------------------------
 
-def gem_whiten(fmaps, p, eps=1e-6, aggregate=False, msp_is_p=False, P=None, m=None, dim=None):
+def whiten_prepare(P):
+    """[dim, c] float32 CUDA projection -> [2, dim, c] TF32 hi / lo halves for the tcgen05 projection kernel (once per
+    learned whitening)."""
+    _require(P, torch.float32, "P")
+    if P.dim() != 2:
+        raise GdtError("P must be [dim, c]")
+    dim, c = P.shape
+    out = torch.empty((2, dim, c), dtype=torch.float32, device=P.device)
+    with torch.cuda.device(P.device):
+        check(load().gdt_whiten_prepare(_ptr(P), int(P.stride(0)), c, dim, _ptr(out), _stream()), "gdt_whiten_prepare")
+    _count("l2n_rows")
+    return out
+
+
+def _check_split(P_split, P, dim):
+    if P_split is None:
+        return None
+    _require(P_split, torch.float32, "P_split")
+    if tuple(P_split.shape) != (2, dim, P.shape[1]):
+        raise GdtError("P_split must be whiten_prepare(P[:dim]) with shape [2, dim, c]")
+    return P_split
+
+
+def gem_whiten(fmaps, p, eps=1e-6, aggregate=False, msp_is_p=False, P=None, m=None, dim=None, P_split=None):
     """fmaps: list (one per scale) of [n,c,h,w] float32 CUDA feature maps -> descriptors [n, dim] float32.
-    p: 1-element float32 CUDA tensor (GeM exponent, read on the device)."""
+    p: 1-element float32 CUDA tensor (GeM exponent, read on the device). P_split: whiten_prepare(P[:dim]) selects the
+    tcgen05 projection kernel."""
     if isinstance(fmaps, torch.Tensor):
         fmaps = [fmaps]
     scales = len(fmaps)
@@ -232,8 +257,10 @@ def gem_whiten(fmaps, p, eps=1e-6, aggregate=False, msp_is_p=False, P=None, m=No
     ws_ = (ctypes.c_int * scales)(*[int(f.shape[3]) for f in fmaps])
     with torch.cuda.device(dev):
         ws = _workspace(lib.gdt_gem_whiten_workspace_bytes(n, c, scales, dim), dev)
+        P_split = _check_split(P_split, P, dim) if P is not None else None
         check(lib.gdt_gem_whiten(ptrs, hs, ws_, n, c, scales, _ptr(p), float(eps), flags,
-                                 _ptr(P) if P is not None else None, int(ldP), _ptr(m) if m is not None else None,
+                                 _ptr(P) if P is not None else None, int(ldP),
+                                 _ptr(P_split) if P_split is not None else None, _ptr(m) if m is not None else None,
                                  dim, _ptr(desc), _ptr(ws), ws.numel(), _stream()), "gdt_gem_whiten")
     _count("gem_whiten" if P is not None else "gem")
     return desc
@@ -265,7 +292,7 @@ def l2n_rows(x, eps=1e-6):
     return out
 
 
-def desc_post(descs, msp, P=None, m=None, dim=None):
+def desc_post(descs, msp, P=None, m=None, dim=None, P_split=None):
     """Aggregation (msp: None = none, float, or 1-element CUDA tensor read on the device) and / or whitening of
     already L2-normalised per-scale descriptors, each [n, c] -> [n, dim]."""
     descs = [_require(d, torch.float32, "desc") for d in descs]
@@ -300,8 +327,10 @@ def desc_post(descs, msp, P=None, m=None, dim=None):
     lib = load()
     with torch.cuda.device(dev):
         ws = _workspace(lib.gdt_desc_post_workspace_bytes(n, c, dim), dev)
+        P_split = _check_split(P_split, P, dim) if P is not None else None
         check(lib.gdt_desc_post(ptrs, n, c, scales, _ptr(msp_dev) if msp_dev is not None else None, msp_host, flags,
-                                _ptr(P) if P is not None else None, int(ldP), _ptr(m) if m is not None else None, dim,
+                                _ptr(P) if P is not None else None, int(ldP),
+                                _ptr(P_split) if P_split is not None else None, _ptr(m) if m is not None else None, dim,
                                 _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_desc_post")
     _count("desc_post_whiten" if P is not None else "desc_post")
     return out

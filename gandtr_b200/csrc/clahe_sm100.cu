@@ -22,8 +22,6 @@ struct ClaheTables {
     uint4* lutL = nullptr;     // [32768]      packed lightness corners
     uint4* lutAB = nullptr;    // [32768][2]   packed chroma corners (a words, b words)
     float4* spline = nullptr;  // [1024]
-    uint16_t* q8 = nullptr;    // [256]  uint8 channel -> (t << 5) | f
-    float* lnew = nullptr;     // [256]  CLAHE byte -> L handed to LAB2RGB
     Lab2RgbConst K;
     float spline_host[4096];
     bool ready = false;
@@ -509,21 +507,6 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     pack_lab_lut(host_rgb2lab_lut, hL, hAB);
     build_inv_gamma_spline(T.spline_host);
     build_lab2rgb_const(T.K);
-    uint16_t q8[256];
-    float lnew[256];
-    for (int v = 0; v < 256; ++v) {
-        int t, f;
-        // Pil2Numpy: float32(u8) / 255.0 (core_transforms.py:83); already inside [0,1]
-        volatile float x = (float)v / 255.0f;
-        volatile float xs = x * 16384.0f;
-        int c = (int)lrintf(xs);
-        t = c >> 9; f = (c >> 5) & 15;
-        if (t >= 32) { t = 31; f = 16; }
-        q8[v] = (uint16_t)((t << 5) | f);
-        volatile float s = (float)v / 255.0f;
-        volatile float L = s * 100.0f;
-        lnew[v] = L;
-    }
     int rc = GDT_OK;
     auto up = [&](void** dptr, const void* src, size_t bytes) -> int {
         cudaError_t e = cudaMalloc(dptr, bytes);
@@ -535,8 +518,6 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     if (rc == GDT_OK) rc = up((void**)&T.lutL, hL, ncell * 16);
     if (rc == GDT_OK) rc = up((void**)&T.lutAB, hAB, ncell * 32);
     if (rc == GDT_OK) rc = up((void**)&T.spline, T.spline_host, 4096 * sizeof(float));
-    if (rc == GDT_OK) rc = up((void**)&T.q8, q8, sizeof(q8));
-    if (rc == GDT_OK) rc = up((void**)&T.lnew, lnew, sizeof(lnew));
     free(hL);
     free(hAB);
     if (rc == GDT_OK) T.ready = true;

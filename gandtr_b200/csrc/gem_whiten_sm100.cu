@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gdt {
 
@@ -30,6 +31,11 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     return r;
 }
 
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float rem = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
+}
 // x^p for x >= eps > 0. mode: 3 -> cube, 2 -> square, 1 -> identity, 0 -> generic exp2(p*log2 x)
 template <int MODE>
 __device__ __forceinline__ float gem_pow(float x, float p) {
@@ -243,10 +249,22 @@ gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restr
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = acc[j] / nrm;
         }
+        const bool split_ = (flags & GDT_SPLIT_OUT) != 0;     // tcgen05 whitening: write TF32 hi / lo halves
+        float* o_lo = out + (size_t)n * c + (size_t)img * c;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = tid + j * 256;
-            if (i < c) o[i] = m ? acc[j] - mv[j] : acc[j];
+            if (i < c) {
+                const float val = m ? acc[j] - mv[j] : acc[j];
+                if (split_) {
+                    uint32_t hi, lo;
+                    tf32_split(val, hi, lo);
+                    o[i] = __uint_as_float(hi);
+                    o_lo[i] = __uint_as_float(lo);
+                } else {
+                    o[i] = val;
+                }
+            }
         }
         return;
     }
@@ -318,11 +336,6 @@ gem_finalize_kernel(DescScales D, int n, int c, int scales, const float* __restr
 constexpr int kWBK = 32;    // K-step
 constexpr int kWLd = kWBK + 4;   // smem row stride (floats): fragment loads hit 32 distinct banks
 
-__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float rem = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
-}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -423,6 +436,146 @@ whiten_gemm_kernel(const float* __restrict__ V, const float* __restrict__ P, int
         }
 }
 
+// ---- whitening projection on tcgen05 (3xTF32) ----------------------------------------------------
+// Same contraction as whiten_gemm_kernel, for callers that prepared the projection once with gdt_whiten_prepare
+// (P split into TF32-exact hi / lo halves, [2][dim][c]). gem_finalize_kernel writes the centred descriptors already
+// split ([2][n][c]), so all four operands are plain TMA tiles and the kernel is a TMA -> tcgen05.mma(kind::tf32) ->
+// TMEM pipeline: per 32-wide K block three accumulating products lo*hi + hi*lo + hi*hi (12 MMAs of M=128, N=128, K=8).
+// One CTA per (128-row image tile, 128-column output tile, K slice); warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (TMEM -> partial sums in global memory).
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;           // fp32 elements; 32 * 4 B = one 128-byte swizzle span
+constexpr int kTcStages = 3;
+constexpr int kTcTile = kTcBM * kTcBK * 4;                      // 16 KB per operand tile
+constexpr int kTcStageBytes = 4 * kTcTile;                      // A_hi, A_lo, B_hi, B_lo
+constexpr int kTcSmem = kTcStages * kTcStageBytes + 1024 + 256;
+// kind::tf32 instruction descriptor: D = f32 (1 << 4), A = B = tf32 (format 2 at [7,10) and [10,13)), K-major both
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+whiten_tc_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
+                 const __grid_constant__ CUtensorMap map_ph, const __grid_constant__ CUtensorMap map_pl, int n, int dim,
+                 int klen, int c, float* __restrict__ Xpart) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = (uint64_t*)(smem_gen + kTcStages * kTcStageBytes);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kTcStages, bar_done = bar_empty + 8 * kTcStages;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kTcStages + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col0 = blockIdx.x * kTcBN, row0 = blockIdx.y * kTcBM;
+    const int kbeg = blockIdx.z * klen, kend = min(c, kbeg + klen);
+    const int nkb = (kend - kbeg + kTcBK - 1) / kTcBK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_vh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_vl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_ph) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_pl) : "memory");
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTcBN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t st = smem_base + stage * kTcStageBytes;
+                const int k = kbeg + kb * kTcBK;
+                mbar_arrive_expect_tx(bar_full + 8 * stage, kTcStageBytes);
+                tma_load_2d(st, &map_vh, bar_full + 8 * stage, k, row0);
+                tma_load_2d(st + kTcTile, &map_vl, bar_full + 8 * stage, k, row0);
+                tma_load_2d(st + 2 * kTcTile, &map_ph, bar_full + 8 * stage, k, col0);
+                tma_load_2d(st + 3 * kTcTile, &map_pl, bar_full + 8 * stage, k, col0);
+                if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t st = smem_base + stage * kTcStageBytes;
+                const uint64_t ah = umma_smem_desc(st), al = umma_smem_desc(st + kTcTile);
+                const uint64_t bh = umma_smem_desc(st + 2 * kTcTile), bl = umma_smem_desc(st + 3 * kTcTile);
+#pragma unroll
+                for (int kk = 0; kk < kTcBK / 8; ++kk) {
+                    const uint64_t o = (uint64_t)(kk * 2);      // +32 bytes along K inside the swizzle span
+                    umma_tf32(tmem_base, al + o, bh + o, kTcIdesc, (kb | kk) != 0 ? 1u : 0u);   // small terms first
+                    umma_tf32(tmem_base, ah + o, bl + o, kTcIdesc, 1u);
+                    umma_tf32(tmem_base, ah + o, bh + o, kTcIdesc, 1u);
+                }
+                umma_commit(bar_empty + 8 * stage);
+                if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(bar_done);
+        }
+    } else {
+        // epilogue: thread == output row (TMEM lane)
+        const int quarter = warp & 3;
+        const int r = row0 + quarter * 32 + lane;
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        float* xrow = Xpart + ((size_t)blockIdx.z * n + (r < n ? r : 0)) * dim + col0;
+#pragma unroll 1
+        for (int cc = 0; cc < kTcBN / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, v);
+            tmem_ld_wait();
+            if (r < n) {
+                if (col0 + cc * 32 + 32 <= dim && (dim & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *(float4*)(xrow + cc * 32 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + cc * 32 + j < dim) xrow[cc * 32 + j] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTcBN);
+    }
+}
+
+// split every element into TF32-exact hi and lo parts: out[0][i] = tf32(x), out[1][i] = tf32(x - tf32(x))
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ out) {
+    const size_t total = (size_t)rows * cols;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const size_t r = i / cols, k = i - r * cols;
+        uint32_t hi, lo;
+        tf32_split(src[r * ld + k], hi, lo);
+        out[i] = __uint_as_float(hi);
+        out[total + i] = __uint_as_float(lo);
+    }
+}
+
 // desc[r] = x / (||x||_2 + eps) with x = sum_z Xpart[z][r] (fixed order); one CTA per row, the row kept in registers
 constexpr int kReduceMaxPerThread = 8;   // rows up to 256 * 4 * 8 = 8192 wide stay in registers
 __global__ void __launch_bounds__(256)
@@ -488,22 +641,59 @@ __global__ void __launch_bounds__(256) l2n_rows_kernel(const float* X, float* Y,
     for (int i = threadIdx.x; i < dim; i += 256) y[i] = x[i] / den;
 }
 
-// finalize (+ whitening projection + final L2N) shared by gdt_gem_whiten and gdt_desc_post
+static int whiten_tc_slices(int n, int c, int dim) {
+    const int tiles = ceil_div(dim, kTcBN) * ceil_div(n, kTcBM);
+    int z = ceil_div(sm_count_current_device(), tiles);
+    const int zmax = c / 64 > 1 ? c / 64 : 1;              // at least two K blocks per slice
+    if (z > zmax) z = zmax;
+    if (z > 32) z = 32;
+    return z < 1 ? 1 : z;
+}
+static int whiten_ws_slices(int n, int c, int dim) {
+    const int a = whiten_splitk(n, c, dim), b = whiten_tc_slices(n, c, dim);
+    return a > b ? a : b;
+}
+
+// finalize (+ whitening projection + final L2N) shared by gdt_gem_whiten and gdt_desc_post.
+// V holds 2 * n * c floats (the second half is used by the tcgen05 path for the lo parts).
 static int desc_tail(const DescScales& D, int n, int c, int scales, const float* p_dev, float msp_host, int flags,
-                     const float* P, int ldP, const float* m, int dim, float* desc, float* V, float* Xpart,
-                     cudaStream_t stream) {
+                     const float* P, int ldP, const float* P_split, const float* m, int dim, float* desc, float* V,
+                     float* Xpart, cudaStream_t stream) {
+    const bool tc = P && P_split && (c & 3) == 0 && c <= 2048 && ((((uintptr_t)P_split) | ((uintptr_t)V)) & 15) == 0;
     float* fin_out = P ? V : desc;
-    gem_finalize_kernel<<<n, 256, 0, stream>>>(D, n, c, scales, p_dev, msp_host, flags, P ? m : nullptr, fin_out);
+    gem_finalize_kernel<<<n, 256, 0, stream>>>(D, n, c, scales, p_dev, msp_host, flags | (tc ? GDT_SPLIT_OUT : 0),
+                                               P ? m : nullptr, fin_out);
     GDT_LAUNCH_CHECK();
-    if (P) {
+    if (!P) return GDT_OK;
+    int slices;
+    if (tc) {
+        CUtensorMap mvh, mvl, mph, mpl;
+        int rc = make_tile_map(&mvh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, V, n, c, kTcBM);
+        if (rc == GDT_OK) rc = make_tile_map(&mvl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, V + (size_t)n * c, n, c, kTcBM);
+        if (rc == GDT_OK) rc = make_tile_map(&mph, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P_split, dim, c, kTcBN);
+        if (rc == GDT_OK) rc = make_tile_map(&mpl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P_split + (size_t)dim * c, dim, c, kTcBN);
+        if (rc != GDT_OK) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            GDT_CUDA(cudaFuncSetAttribute(whiten_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+            attr_set = true;
+        }
+        const int z = whiten_tc_slices(n, c, dim);
+        const int klen = ceil_div(ceil_div(c, z), kTcBK) * kTcBK;
+        dim3 grid(ceil_div(dim, kTcBN), ceil_div(n, kTcBM), ceil_div(c, klen));
+        whiten_tc_kernel<<<grid, 192, kTcSmem, stream>>>(mvh, mvl, mph, mpl, n, dim, klen, c, Xpart);
+        GDT_LAUNCH_CHECK();
+        slices = (int)grid.z;
+    } else {
         const int splitk = whiten_splitk(n, c, dim);
         const int klen = ceil_div(ceil_div(c, splitk), kWBK) * kWBK;
         dim3 grid(ceil_div(dim, 64), ceil_div(n, 64), ceil_div(c, klen));
         whiten_gemm_kernel<<<grid, 128, 0, stream>>>(V, P, ldP, n, c, dim, klen, Xpart);
         GDT_LAUNCH_CHECK();
-        whiten_reduce_l2n_kernel<<<n, 256, 0, stream>>>(Xpart, n, dim, (int)grid.z, 1e-6f, desc);
-        GDT_LAUNCH_CHECK();
+        slices = (int)grid.z;
     }
+    whiten_reduce_l2n_kernel<<<n, 256, 0, stream>>>(Xpart, n, dim, slices, 1e-6f, desc);
+    GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
 
@@ -513,13 +703,14 @@ using namespace gdt;
 
 extern "C" size_t gdt_gem_whiten_workspace_bytes(int n, int c, int scales, int dim) {
     if (n <= 0 || c <= 0 || scales <= 0) return 0;
-    return align_up((size_t)scales * n * c * sizeof(float), 256) + align_up((size_t)n * c * sizeof(float), 256) +
-           align_up((size_t)whiten_splitk(n, c, dim > 0 ? dim : c) * n * (dim > 0 ? dim : c) * sizeof(float), 256) + 256;
+    return align_up((size_t)scales * n * c * sizeof(float), 256) + align_up((size_t)2 * n * c * sizeof(float), 256) +
+           align_up((size_t)whiten_ws_slices(n, c, dim > 0 ? dim : c) * n * (dim > 0 ? dim : c) * sizeof(float), 256) + 256;
 }
 
 extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h, const int* host_w, int n, int c,
                               int scales, const float* p_dev, float eps, int flags, const float* P, int ldP,
-                              const float* m, int dim, float* desc, void* ws, size_t ws_bytes, void* stream_) {
+                              const float* P_split, const float* m, int dim, float* desc, void* ws, size_t ws_bytes,
+                              void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!host_fmaps || !host_h || !host_w || !p_dev || !desc || !ws) return GDT_ERR_INVALID_ARGUMENT;
     if (n <= 0 || c <= 0 || scales <= 0 || scales > GDT_MAX_SCALES) return GDT_ERR_INVALID_ARGUMENT;
@@ -532,8 +723,8 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
 
     Workspace W(ws, ws_bytes);
     float* g = W.take<float>((size_t)scales * n * c);
-    float* V = W.take<float>((size_t)n * c);
-    float* Xpart = W.take<float>((size_t)whiten_splitk(n, c, dim) * n * dim);
+    float* V = W.take<float>((size_t)2 * n * c);
+    float* Xpart = W.take<float>((size_t)whiten_ws_slices(n, c, dim) * n * dim);
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
     GemScales S;
@@ -551,7 +742,7 @@ extern "C" int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h,
     GDT_LAUNCH_CHECK();
     DescScales D;
     for (int s = 0; s < GDT_MAX_SCALES; ++s) D.ptr[s] = s < scales ? g + (size_t)s * n * c : nullptr;
-    return desc_tail(D, n, c, scales, p_dev, 1.0f, (flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P)) | GDT_POOLED_RAW_MEAN, P, ldP, m, dim, desc, V,
+    return desc_tail(D, n, c, scales, p_dev, 1.0f, (flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P)) | GDT_POOLED_RAW_MEAN, P, ldP, P_split, m, dim, desc, V,
                      Xpart, stream);
 }
 
@@ -585,12 +776,12 @@ extern "C" int gdt_l2n_rows(const float* x, int n, int dim, float eps, float* ou
 
 extern "C" size_t gdt_desc_post_workspace_bytes(int n, int c, int dim) {
     if (n <= 0 || c <= 0) return 0;
-    return align_up((size_t)n * c * sizeof(float), 256) + align_up((size_t)whiten_splitk(n, c, dim > 0 ? dim : c) * n * (dim > 0 ? dim : c) * sizeof(float), 256) + 256;
+    return align_up((size_t)2 * n * c * sizeof(float), 256) + align_up((size_t)whiten_ws_slices(n, c, dim > 0 ? dim : c) * n * (dim > 0 ? dim : c) * sizeof(float), 256) + 256;
 }
 
 extern "C" int gdt_desc_post(const float* const* host_descs, int n, int c, int scales, const float* msp_dev, float msp_host,
-                             int flags, const float* P, int ldP, const float* m, int dim, float* out, void* ws,
-                             size_t ws_bytes, void* stream_) {
+                             int flags, const float* P, int ldP, const float* P_split, const float* m, int dim, float* out,
+                             void* ws, size_t ws_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!host_descs || !out || !ws || n <= 0 || c <= 0 || scales <= 0 || scales > GDT_MAX_SCALES)
         return GDT_ERR_INVALID_ARGUMENT;
@@ -602,8 +793,8 @@ extern "C" int gdt_desc_post(const float* const* host_descs, int n, int c, int s
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
     Workspace W(ws, ws_bytes);
-    float* V = W.take<float>((size_t)n * c);
-    float* Xpart = W.take<float>((size_t)whiten_splitk(n, c, dim) * n * dim);
+    float* V = W.take<float>((size_t)2 * n * c);
+    float* Xpart = W.take<float>((size_t)whiten_ws_slices(n, c, dim) * n * dim);
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
     DescScales D;
     for (int s = 0; s < GDT_MAX_SCALES; ++s) {
@@ -611,6 +802,19 @@ extern "C" int gdt_desc_post(const float* const* host_descs, int n, int c, int s
         if (s < scales && !host_descs[s]) return GDT_ERR_INVALID_ARGUMENT;
     }
     return desc_tail(D, n, c, scales, msp_dev, msp_host,
-                     (flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P)) | GDT_DESC_NORMALISED, P, ldP, m, dim, out, V, Xpart,
+                     (flags & (GDT_GEM_AGGREGATE | GDT_GEM_MSP_IS_P)) | GDT_DESC_NORMALISED, P, ldP, P_split, m, dim, out, V, Xpart,
                      stream);
+}
+
+extern "C" int gdt_whiten_prepare(const float* P, int ldP, int c, int dim, float* P_split, void* stream_) {
+    if (!P || !P_split || c <= 0 || dim <= 0 || ldP < c) return GDT_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
+    const size_t total = (size_t)dim * c;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count_current_device() * 16;
+    if (blocks > cap) blocks = cap;
+    tf32_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(P, dim, c, ldP, P_split);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
 }

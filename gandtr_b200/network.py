@@ -92,10 +92,10 @@ class ImageRetrievalNet(nn.Module):
     def feature_map(self, x):
         return self.features(x).contiguous()
 
-    def descriptors(self, fmaps, aggregate=False, msp_is_p=False, P=None, m=None, dim=None):
+    def descriptors(self, fmaps, aggregate=False, msp_is_p=False, P=None, m=None, dim=None, P_split=None):
         """One K2 call on per-scale feature maps -> [N, dim]."""
         return _lib.gem_whiten(fmaps, self.pool.p.detach(), eps=self.pool.eps, aggregate=aggregate, msp_is_p=msp_is_p,
-                               P=P, m=m, dim=dim)
+                               P=P, m=m, dim=dim, P_split=P_split)
 
     def forward(self, x):
         o = self.descriptors([self.feature_map(x)])         # norm(pool(o)).squeeze(-1).squeeze(-1), imageretrievalnet.py:116
@@ -338,12 +338,14 @@ class CirtorchWhiten(Wrapper):
         self.P = torch.tensor(np.asarray(whitening["P"]), dtype=torch.float32, device=device).contiguous()
         self.m = torch.tensor(np.asarray(whitening["m"]), dtype=torch.float32, device=device).contiguous()
         self.dimensions = dimensions or self.P.shape[0]
+        # the projection is a learned constant: split it once into TF32 hi / lo halves for the tcgen05 kernel
+        self.P_split = _lib.whiten_prepare(self.P[:self.dimensions].contiguous()) if self.P.is_cuda else None
 
     def postprocess(self, tensor, _outputmodel, _meta):
         """[D] (one image) -> [dim];  [D, N] -> [dim, N]."""
         single = tensor.dim() == 1
         v = tensor.reshape(self.P.shape[1], -1).t().contiguous()
-        out = _lib.desc_post([v], None, P=self.P, m=self.m.reshape(-1), dim=self.dimensions)
+        out = _lib.desc_post([v], None, P=self.P, m=self.m.reshape(-1), dim=self.dimensions, P_split=self.P_split)
         return out.squeeze(0) if single else out.t()
 
     def __repr__(self):
@@ -483,7 +485,8 @@ class SingleNetwork(object):
         d = model.descriptors(fmaps, aggregate=True, msp_is_p=msp_is_p,
                               P=whiten.P if whiten is not None else None,
                               m=whiten.m.reshape(-1) if whiten is not None else None,
-                              dim=whiten.dimensions if whiten is not None else None)
+                              dim=whiten.dimensions if whiten is not None else None,
+                              P_split=whiten.P_split if whiten is not None else None)
         return d.squeeze(0) if d.shape[0] == 1 else d.t()
 
     def forward_batch(self, images, **params):

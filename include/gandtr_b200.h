@@ -104,6 +104,9 @@ int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, i
  *                                    (cirmultiscale wrapper present; also valid for scales == 1)
  *                 GDT_GEM_MSP_IS_P    exponent of that mean is p (wrapper.py:248-251), else 1
  * P, m          : whitening projection [dim][c] row-major (row stride ldP) and mean [c], or NULL
+ * P_split       : optional [2][dim][c] output of gdt_whiten_prepare(P) (TF32 hi / lo halves of the learned, constant
+ *                 projection, prepared once per whitening): selects the tcgen05 (kind::tf32, 3xTF32) projection
+ *                 kernel; NULL selects the mma.sync 3xTF32 kernel. Both are fp32-accurate (~1e-6 relative).
  * desc          : float32 [n][dim] row-major (dim == c when P == NULL)
  */
 #define GDT_MAX_SCALES 8
@@ -111,11 +114,13 @@ int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, i
 #define GDT_GEM_MSP_IS_P 2
 #define GDT_DESC_NORMALISED 4 /* internal to gdt_desc_post: inputs are already L2-normalised descriptors */
 #define GDT_POOLED_RAW_MEAN 8 /* internal to gdt_gem_whiten: pooled values are means, the 1/p root is still due */
+#define GDT_SPLIT_OUT 16      /* internal: centred descriptors are written as TF32 hi / lo halves */
 size_t gdt_gem_whiten_workspace_bytes(int n, int c, int scales, int dim);
 int gdt_gem_whiten(const float* const* host_fmaps, const int* host_h, const int* host_w,
                    int n, int c, int scales, const float* p_dev, float eps, int flags,
-                   const float* P, int ldP, const float* m, int dim,
+                   const float* P, int ldP, const float* P_split, const float* m, int dim,
                    float* desc, void* ws, size_t ws_bytes, void* stream);
+int gdt_whiten_prepare(const float* P, int ldP, int c, int dim, float* P_split, void* stream);
 
 /* The module-level pieces of the same path, for callers that drive the reference's objects one by one:
  *   gdt_gem_pool  `GeM.forward` / LF.gem (layers/pooling.py:36-47, layers/functional.py:21-22):
@@ -132,7 +137,7 @@ int gdt_gem_pool(const float* fmap, int n, int c, int h, int w, const float* p_d
 int gdt_l2n_rows(const float* x, int n, int dim, float eps, float* out, void* stream);
 size_t gdt_desc_post_workspace_bytes(int n, int c, int dim);
 int gdt_desc_post(const float* const* host_descs, int n, int c, int scales, const float* msp_dev, float msp_host,
-                  int flags, const float* P, int ldP, const float* m, int dim, float* out,
+                  int flags, const float* P, int ldP, const float* P_split, const float* m, int dim, float* out,
                   void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K3: query x database scoring fused with streaming top-k ----------------------------------------

@@ -15,11 +15,14 @@ def _run(fmaps, p, **kw):
     from gandtr_b200 import _lib
     fm = [torch.from_numpy(np.ascontiguousarray(f)).cuda() for f in fmaps]
     pt = torch.tensor([p], dtype=torch.float32, device="cuda")
-    P, m = kw.pop("P", None), kw.pop("m", None)
+    P, m, split = kw.pop("P", None), kw.pop("m", None), kw.pop("split", False)
+    P_split = None
     if P is not None:
         P = torch.tensor(P, dtype=torch.float32, device="cuda")
         m = torch.tensor(m, dtype=torch.float32, device="cuda").reshape(-1)
-    out = _lib.gem_whiten(fm, pt, 1e-6, P=P, m=m, **kw)
+        if split:
+            P_split = _lib.whiten_prepare(P[:kw.get("dim") or P.shape[0]].contiguous())
+    out = _lib.gem_whiten(fm, pt, 1e-6, P=P, m=m, P_split=P_split, **kw)
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -69,3 +72,20 @@ def test_unaligned_rows_and_offsets():
         _lib.gem_whiten([fm.permute(0, 1, 3, 2)], torch.tensor([3.0], device="cuda"))   # non-contiguous
     out = _lib.gem_whiten([fm], torch.tensor([3.0], device="cuda")).cpu().numpy()
     np.testing.assert_allclose(out, D.descriptor_pipeline([fm.cpu().numpy()], p=3.0), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n,c,hw,dim", [(128, 2048, (24, 32), 2048), (130, 512, (6, 8), 512), (5, 2048, (3, 4), 1000),
+                                        (64, 96, (4, 4), 96), (33, 512, (12, 16), 128), (1, 256, (2, 2), 256)])
+def test_whitening_tcgen05_path(n, c, hw, dim):
+    """The tcgen05 (kind::tf32, 3xTF32) projection selected by gdt_whiten_prepare against the float64 oracle and against
+    the mma.sync kernel: full / partial 128-row image tiles, partial 128-column output tiles, short K."""
+    rs = np.random.RandomState(n + c + dim)
+    fm = [(np.abs(rs.normal(0, 1, (n, c) + hw)) * (rs.rand(n, c, 1, 1) > 0.1)).astype(np.float32)]
+    P = rs.normal(0, 1, (c, c)) / np.sqrt(c)
+    m = 0.05 * rs.rand(c, 1)
+    ref = D.descriptor_pipeline(fm, p=3.0, aggregate=True, P=P, m=m, dimensions=dim)
+    tc = _run(fm, 3.0, aggregate=True, P=P, m=m, dim=dim, split=True)
+    simt = _run(fm, 3.0, aggregate=True, P=P, m=m, dim=dim)
+    np.testing.assert_allclose(tc, ref, rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(tc, simt, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(np.linalg.norm(tc, axis=1), 1.0, atol=1e-5)

@@ -156,3 +156,27 @@ def test_generators_build_in_stock_pytorch():
     assert tuple(y.shape) == (1, 3, 64, 64) and float(y.abs().max()) <= 1.0
     with pytest.raises(NotImplementedError):
         hub.gem_vgg16_cyclegan(pretrained=True, weights_dir=None)
+
+
+def test_inline_gan_clahe_embed_chain_stays_on_device(vgg):
+    """BASELINE config 5 in miniature: generator (stock PyTorch) -> ClahePost (K1', float input) -> VGG16 -> K2.
+    The CLAHE stage is checked bit-exactly against the oracle on the generator's own output."""
+    from gandtr_b200 import hub
+    from gandtr_b200.network import ClahePost
+    from oracle import clahe_np
+    torch.manual_seed(1)
+    gen = hub.cyclegan(pretrained=False)
+    x = gen.transform(synth_image(9, 64, 96, "smooth")).unsqueeze(0)
+    meanstd = [[0.5, 0.5, 0.5], [0.5, 0.5, 0.5]]
+    post = ClahePost(meanstd, 1.0, device="cuda")
+    with torch.no_grad():
+        fake = gen(x)                                            # [-1, 1] tanh output, normalised with mean = std = 0.5
+        eq = post.postprocess(fake, None, None)
+        assert eq.is_cuda and tuple(eq.shape) == tuple(fake.shape)
+        ref = clahe_np.clahe_post_f32(fake[0].cpu().numpy(), load_lut(), meanstd, clip_limit=1.0)
+        assert np.array_equal(eq[0].cpu().numpy().view(np.uint32), ref.view(np.uint32))
+        # re-normalise for the embedding network (ImageNet statistics) and extract
+        m0 = torch.tensor(MEAN, device="cuda").view(1, 3, 1, 1)
+        s0 = torch.tensor(STD, device="cuda").view(1, 3, 1, 1)
+        vec = vgg((eq * 0.5 + 0.5 - m0) / s0)
+    assert tuple(vec.shape) == (512, 1) and abs(float(vec.norm()) - 1.0) < 1e-5

@@ -18,7 +18,9 @@ for n, c, h, w in [(128, 2048, 24, 32), (128, 512, 48, 64)]:
     m = torch.rand(c, device="cuda") * 0.05
     t_pool = timeit(lambda: _lib.gem_pool(fm, p))
     t_gem = timeit(lambda: _lib.gem_whiten([fm], p, aggregate=True))
-    t_all = timeit(lambda: _lib.gem_whiten([fm], p, aggregate=True, P=P, m=m))
+    Ps = _lib.whiten_prepare(P)
+    t_simt = timeit(lambda: _lib.gem_whiten([fm], p, aggregate=True, P=P, m=m))
+    t_all = timeit(lambda: _lib.gem_whiten([fm], p, aggregate=True, P=P, m=m, P_split=Ps))
     gb = fm.numel() * 4 / 1e9
-    print("single=%s n=%d c=%d: pool %.1f us (%.0f GB/s)  pool+finalize %.1f us  +whiten %.1f us (%.0f GB/s)" % (
-        os.environ.get("GDT_DEBUG_POOL_SINGLE", "0"), n, c, t_pool * 1e3, gb / t_pool * 1e3, t_gem * 1e3, t_all * 1e3, gb / t_all * 1e3))
+    print("single=%s n=%d c=%d: pool %.1f us (%.0f GB/s)  pool+finalize %.1f us  +whiten(mma.sync) %.1f us  +whiten(tcgen05) %.1f us (%.0f GB/s)" % (
+        os.environ.get("GDT_DEBUG_POOL_SINGLE", "0"), n, c, t_pool * 1e3, gb / t_pool * 1e3, t_gem * 1e3, t_simt * 1e3, t_all * 1e3, gb / t_all * 1e3))

@@ -19,8 +19,9 @@ if "gem" in which:
     p = torch.tensor([3.0], device=dev)
     P = torch.randn((c, c), device=dev) / c ** 0.5
     m = torch.rand(c, device=dev) * 0.05
+    Ps = _lib.whiten_prepare(P)
     for _ in range(reps):
-        _lib.gem_whiten(fm[:1], p, aggregate=True, P=P, m=m)
+        _lib.gem_whiten(fm[:1], p, aggregate=True, P=P, m=m, P_split=Ps)
     _lib.gem_whiten(fm, p, aggregate=True, msp_is_p=True, P=P, m=m)
     fv = torch.rand((32, 512, 48, 64), device=dev)
     _lib.gem_whiten([fv], torch.tensor([2.92], device=dev), aggregate=True)
