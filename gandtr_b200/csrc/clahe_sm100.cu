@@ -265,8 +265,12 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
     const int wbody = (w >> 3) << 3;  // pixels >= wbody take OpenCV's scalar-tail op sequence
 
     ClaheAxis ax[4];
+    uint32_t sel[4];   // byte-permute selectors (tile columns i1, i2) of the 8-byte LUT rows
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ax[i] = clahe_axis(x0 + i, inv_tw, grid);
+    for (int i = 0; i < 4; ++i) {
+        ax[i] = clahe_axis(x0 + i, inv_tw, grid);
+        sel[i] = (uint32_t)(ax[i].i1 & 7) | ((uint32_t)(ax[i].i2 & 7) << 4);
+    }
 
     const size_t plane = (size_t)h * w;
     const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
@@ -339,10 +343,20 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
             const float a2 = lab_chroma_fast(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
             const float b2 = lab_chroma_fast(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
             // lightness through CLAHE: the two 16-byte rows hold the LUT value of every tile column at level v
-            const uint8_t* r1 = lrow1 + (v[i] << lsh);
-            const uint8_t* r2 = lrow2 + (v[i] << lsh);
-            const int l11 = r1[ax[i].i1], l12 = r1[ax[i].i2];
-            const int l21 = r2[ax[i].i1], l22 = r2[ax[i].i2];
+            int l11, l12, l21, l22;
+            if (lsh == 3) {
+                // 8-byte rows: one 64-bit load per tile row, the two tile-column bytes picked by one byte permute
+                const uint2 w1 = *(const uint2*)(lrow1 + (v[i] << 3));
+                const uint2 w2 = *(const uint2*)(lrow2 + (v[i] << 3));
+                const uint32_t p1 = __byte_perm(w1.x, w1.y, sel[i]), p2 = __byte_perm(w2.x, w2.y, sel[i]);
+                l11 = p1 & 255; l12 = (p1 >> 8) & 255;
+                l21 = p2 & 255; l22 = (p2 >> 8) & 255;
+            } else {
+                const uint8_t* r1 = lrow1 + (v[i] << lsh);
+                const uint8_t* r2 = lrow2 + (v[i] << lsh);
+                l11 = r1[ax[i].i1]; l12 = r1[ax[i].i2];
+                l21 = r2[ax[i].i1]; l22 = r2[ax[i].i2];
+            }
             const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
             const float Ln = lab_l_from_u8_fast(dst);
             float lr, lg, lb;

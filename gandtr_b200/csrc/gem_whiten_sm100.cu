@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256) l2n_rows_kernel(const float* X, float* Y,
 
 static int whiten_tc_slices(int n, int c, int dim) {
     const int tiles = ceil_div(dim, kTcBN) * ceil_div(n, kTcBM);
-    int z = ceil_div(sm_count_current_device(), tiles);
+    int z = sm_count_current_device() / tiles;              // one CTA per SM (198 KB of smem each): stay within one wave
     const int zmax = c / 64 > 1 ? c / 64 : 1;              // at least two K blocks per slice
     if (z > zmax) z = zmax;
     if (z > 32) z = 32;
@@ -678,8 +678,12 @@ static int desc_tail(const DescScales& D, int n, int c, int scales, const float*
             GDT_CUDA(cudaFuncSetAttribute(whiten_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
             attr_set = true;
         }
-        const int z = whiten_tc_slices(n, c, dim);
-        const int klen = ceil_div(ceil_div(c, z), kTcBK) * kTcBK;
+        int z = whiten_tc_slices(n, c, dim);
+        int klen = ceil_div(ceil_div(c, z), kTcBK) * kTcBK;
+        while (z > 1 && ceil_div(c, klen) * ceil_div(dim, kTcBN) * ceil_div(n, kTcBM) > sm_count_current_device()) {
+            --z;                                            // rounding klen up to whole K blocks must not add a wave
+            klen = ceil_div(ceil_div(c, z), kTcBK) * kTcBK;
+        }
         dim3 grid(ceil_div(dim, kTcBN), ceil_div(n, kTcBM), ceil_div(c, klen));
         whiten_tc_kernel<<<grid, 192, kTcSmem, stream>>>(mvh, mvl, mph, mpl, n, dim, klen, c, Xpart);
         GDT_LAUNCH_CHECK();

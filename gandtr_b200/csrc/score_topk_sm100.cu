@@ -240,12 +240,12 @@ struct FilterParams {
     int tile_begin, tile_end;          // database tile range of this launch
     int n_stripes, stripe_len, n_items;
     int seg_first;                     // candidate segment of stripe 0 of this launch
-    int n_segs, cap0, cap1;            // segments per query; capacity of segment 0 and of the others
+    int n_segs, n_seed, cap0, cap1;    // segments per query; the first n_seed (seed pass) hold cap0 entries, the rest cap1
     const QMeta* meta;
     uint32_t* tau;
     uint32_t* cnt;                     // [nq][n_segs]
     uint32_t* hist;
-    uint64_t* cand;                    // [nq][cap0 + (n_segs - 1) * cap1]
+    uint64_t* cand;                    // [nq][n_seed * cap0 + (n_segs - n_seed) * cap1]
 };
 
 // per-query threshold from the global histogram (scanned from the top, 128-bit loads through L2)
@@ -370,7 +370,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const int qrow = qt * kBlockM + quarter * 32 + lane;
             const bool valid = qrow < P.nq;
             const int seg = P.seg_first + stripe;
-            const uint32_t segcap = seg == 0 ? (uint32_t)P.cap0 : (uint32_t)P.cap1;
+            const uint32_t segcap = seg < P.n_seed ? (uint32_t)P.cap0 : (uint32_t)P.cap1;
             QMeta m;
             m.scale = 0.f; m.inv_scale = 0.f; m.margin = 0.f; m.pad = 0.f;
             float tau = pos_inf;
@@ -380,8 +380,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
             const size_t qv = valid ? (size_t)qrow : 0;
             uint32_t* hist_row = P.hist + qv * kHistBins;
-            uint64_t* seg_row = P.cand + qv * ((size_t)P.cap0 + (size_t)(P.n_segs - 1) * P.cap1) +
-                                (seg == 0 ? (size_t)0 : (size_t)P.cap0 + (size_t)(seg - 1) * P.cap1);
+            uint64_t* seg_row = P.cand + qv * ((size_t)P.n_seed * P.cap0 + (size_t)(P.n_segs - P.n_seed) * P.cap1) +
+                                (seg < P.n_seed ? (size_t)seg * P.cap0
+                                                : (size_t)P.n_seed * P.cap0 + (size_t)(seg - P.n_seed) * P.cap1);
             uint32_t slot = 0, inserted = 0;
             int tiles_done = 0;
             for (int t = t0; t < t1; ++t) {
@@ -461,8 +462,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // ---- finalisation -------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
-topk_finalize_kernel(const float* __restrict__ q, const float* __restrict__ db, int d, int dpad, int k, int n_segs, int cap0,
-                     int cap1, int scap, long long index_base, const QMeta* __restrict__ meta,
+topk_finalize_kernel(const float* __restrict__ q, const float* __restrict__ db, int d, int dpad, int k, int n_segs, int n_seed,
+                     int cap0, int cap1, int scap, long long index_base, const QMeta* __restrict__ meta,
                      const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ hist, const uint64_t* __restrict__ cand,
                      float* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t fsm[];
@@ -496,14 +497,14 @@ topk_finalize_kernel(const float* __restrict__ q, const float* __restrict__ db, 
     // gather the candidates that pass the final threshold from every segment of this query
     bool overflow = false;
     uint32_t total = 0;
-    const uint64_t* qcand = cand + (size_t)qi * ((size_t)cap0 + (size_t)(n_segs - 1) * cap1);
+    const uint64_t* qcand = cand + (size_t)qi * ((size_t)n_seed * cap0 + (size_t)(n_segs - n_seed) * cap1);
     for (int sgm = 0; sgm < n_segs; ++sgm) {
-        const uint32_t cap = sgm == 0 ? (uint32_t)cap0 : (uint32_t)cap1;
+        const uint32_t cap = sgm < n_seed ? (uint32_t)cap0 : (uint32_t)cap1;
         const uint32_t have = cnt[(size_t)qi * n_segs + sgm];
         total += have;
         if (have > cap) overflow = true;
         const uint32_t n = have > cap ? cap : have;
-        const uint64_t* crow = qcand + (sgm == 0 ? (size_t)0 : (size_t)cap0 + (size_t)(sgm - 1) * cap1);
+        const uint64_t* crow = qcand + (sgm < n_seed ? (size_t)sgm * cap0 : (size_t)n_seed * cap0 + (size_t)(sgm - n_seed) * cap1);
         for (uint32_t i = tid; i < n; i += 256) {
             const uint64_t c = __ldg(crow + i);
             if (__uint_as_float((uint32_t)(c >> 32)) >= thr) {
@@ -573,7 +574,7 @@ static void plan_items(int n_qtiles, int n_dtiles, int sms, int& n_stripes, int&
 }
 
 struct TopkPlan {
-    int n_qtiles, n_dtiles, seed_tiles, n_stripes, stripe_len, n_segs, cap0, cap1;
+    int n_qtiles, n_dtiles, seed_tiles, n_seed, seed_len, n_stripes, stripe_len, n_segs, cap0, cap1;
     size_t qb, meta, tau, cnt, hist, cand, total;
 };
 
@@ -582,9 +583,17 @@ static TopkPlan topk_plan(int nq, long long ndb, int d, int k) {
     L.n_qtiles = ceil_div(nq, kBlockM);
     L.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
     L.seed_tiles = seed_tiles_for(k) < L.n_dtiles ? seed_tiles_for(k) : L.n_dtiles;
-    plan_items(L.n_qtiles, L.n_dtiles - L.seed_tiles, sm_count_current_device(), L.n_stripes, L.stripe_len);
-    L.n_segs = 1 + L.n_stripes;
-    L.cap0 = L.seed_tiles * kBlockN;
+    const int sms = sm_count_current_device();
+    plan_items(L.n_qtiles, L.n_dtiles - L.seed_tiles, sms, L.n_stripes, L.stripe_len);
+    // the seed range itself is striped over idle SMs when there are few query tiles; a seed segment can hold every row of
+    // its stripe, so it cannot overflow however cold the threshold is
+    L.n_seed = sms / L.n_qtiles;
+    if (L.n_seed > L.seed_tiles / 8) L.n_seed = L.seed_tiles / 8;
+    if (L.n_seed < 1) L.n_seed = 1;
+    L.seed_len = ceil_div(L.seed_tiles, L.n_seed);
+    L.n_seed = ceil_div(L.seed_tiles, L.seed_len);
+    L.n_segs = L.n_seed + L.n_stripes;
+    L.cap0 = L.seed_len * kBlockN;
     L.cap1 = stripe_capacity(k);
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); const size_t r = off; off += bytes; return r; };
@@ -593,7 +602,7 @@ static TopkPlan topk_plan(int nq, long long ndb, int d, int k) {
     L.tau = take((size_t)nq * 4);
     L.cnt = take((size_t)nq * L.n_segs * 4);
     L.hist = take((size_t)nq * kHistBins * 4);
-    L.cand = take((size_t)nq * ((size_t)L.cap0 + (size_t)L.n_stripes * L.cap1) * 8);
+    L.cand = take((size_t)nq * ((size_t)L.n_seed * L.cap0 + (size_t)L.n_stripes * L.cap1) * 8);
     L.total = align_up(off, 256);
     return L;
 }
@@ -704,16 +713,16 @@ extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const f
     P.nq = nq; P.d = d; P.k = k; P.ndb = ndb;
     P.n_qtiles = L.n_qtiles;
     P.n_kblocks = ceil_div(d, kBlockK);
-    P.n_segs = L.n_segs; P.cap0 = L.cap0; P.cap1 = L.cap1;
+    P.n_segs = L.n_segs; P.n_seed = L.n_seed; P.cap0 = L.cap0; P.cap1 = L.cap1;
     P.meta = meta; P.tau = tau; P.cnt = cnt; P.hist = hist; P.cand = cand;
     // seed pass: the first tiles of the shard against every query tile establish the thresholds
     P.tile_begin = 0; P.tile_end = L.seed_tiles;
-    P.n_stripes = 1; P.stripe_len = L.seed_tiles; P.n_items = L.n_qtiles; P.seg_first = 0;
+    P.n_stripes = L.n_seed; P.stripe_len = L.seed_len; P.n_items = L.n_seed * L.n_qtiles; P.seg_first = 0;
     score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
     GDT_LAUNCH_CHECK();
     if (L.n_stripes > 0) {
         P.tile_begin = L.seed_tiles; P.tile_end = L.n_dtiles;
-        P.n_stripes = L.n_stripes; P.stripe_len = L.stripe_len; P.n_items = L.n_stripes * L.n_qtiles; P.seg_first = 1;
+        P.n_stripes = L.n_stripes; P.stripe_len = L.stripe_len; P.n_items = L.n_stripes * L.n_qtiles; P.seg_first = L.n_seed;
         score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
         GDT_LAUNCH_CHECK();
     }
@@ -737,7 +746,7 @@ extern "C" int gdt_score_topk_finalize(const float* q, const float* db, int nq, 
         GDT_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fattr = fsmem;
     }
-    topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.n_segs, L.cap0, L.cap1, scap, index_base,
+    topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.n_segs, L.n_seed, L.cap0, L.cap1, scap, index_base,
                                                      (const QMeta*)(base + L.meta), (const uint32_t*)(base + L.cnt),
                                                      (const uint32_t*)(base + L.hist), (const uint64_t*)(base + L.cand),
                                                      top_scores, top_idx, status_dev);
