@@ -13,6 +13,8 @@
 //           Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
 // Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 1 B/px
 // written by A and read by B (L2-resident for batches up to ~100 MB).
+#include <stdlib.h>
+
 #include "clahe_math.cuh"
 #include "common.cuh"
 
@@ -228,8 +230,8 @@ struct NormFast {
     int fast;   // div_by_const_ok() for all three std
 };
 
-template <bool U8>
-__global__ void __launch_bounds__(256, 4)
+template <bool U8, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
@@ -448,18 +450,12 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int sms = sm_count_current_device();
     int rows = 32;
     const int xchunks = ceil_div(w, 1024);
-    while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 4LL * sms) rows >>= 1;
+    while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 16LL * sms) rows >>= 1;   // >= ~3 waves
     dim3 gridB(xchunks, ceil_div(h, rows), n);
     // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
     int span = (rows + g.th - 1) / g.th + 2;
     if (span > grid) span = grid;
     const size_t smem = 1024 * 16 + (((size_t)span * 256) << lut_row_shift(grid));
-    static bool attr_set[2] = {false, false};
-    if (smem > 48 * 1024 && !attr_set[U8 ? 1 : 0]) {
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      1024 * 16 + 16 * 256 * 16));
-        attr_set[U8 ? 1 : 0] = true;
-    }
     NormFast on;
     on.fast = 1;
     for (int c = 0; c < 3; ++c) {
@@ -469,8 +465,20 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
         on.rstd[c] = r;
         if (!div_by_const_ok(out_norm.std[c])) on.fast = 0;
     }
-    clahe_apply_kernel<U8><<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
-                                                          vec_apply, T->lutAB, T->spline, T->K, in_norm, on);
+    // resident CTAs per SM the kernel is compiled for (register cap 64 / 40 / 32); debug override GDT_DEBUG_K1_OCC
+    static int occ = 0;
+    if (!occ) { const char* e = getenv("GDT_DEBUG_K1_OCC"); occ = e ? atoi(e) : 6; if (occ != 4 && occ != 8) occ = 6; }
+    auto launch = [&](auto kernel) -> int {
+        if (smem > 48 * 1024)
+            GDT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 + 16 * 256 * 16));
+        kernel<<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply, T->lutAB,
+                                            T->spline, T->K, in_norm, on);
+        return GDT_OK;
+    };
+    if (occ == 4) rc = launch(clahe_apply_kernel<U8, 4>);
+    else if (occ == 8) rc = launch(clahe_apply_kernel<U8, 8>);
+    else rc = launch(clahe_apply_kernel<U8, 6>);
+    if (rc != GDT_OK) return rc;
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
