@@ -13,8 +13,6 @@
 //           Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
 // Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 1 B/px
 // written by A and read by B (L2-resident for batches up to ~100 MB).
-#include <stdlib.h>
-
 #include "clahe_math.cuh"
 #include "common.cuh"
 
@@ -465,20 +463,13 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
         on.rstd[c] = r;
         if (!div_by_const_ok(out_norm.std[c])) on.fast = 0;
     }
-    // resident CTAs per SM the kernel is compiled for (register cap 64 / 40 / 32); debug override GDT_DEBUG_K1_OCC
-    static int occ = 0;
-    if (!occ) { const char* e = getenv("GDT_DEBUG_K1_OCC"); occ = e ? atoi(e) : 6; if (occ != 4 && occ != 8) occ = 6; }
-    auto launch = [&](auto kernel) -> int {
-        if (smem > 48 * 1024)
-            GDT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 + 16 * 256 * 16));
-        kernel<<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply, T->lutAB,
-                                            T->spline, T->K, in_norm, on);
-        return GDT_OK;
-    };
-    if (occ == 4) rc = launch(clahe_apply_kernel<U8, 4>);
-    else if (occ == 8) rc = launch(clahe_apply_kernel<U8, 8>);
-    else rc = launch(clahe_apply_kernel<U8, 6>);
-    if (rc != GDT_OK) return rc;
+    // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
+    // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
+    if (smem > 48 * 1024)
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      1024 * 16 + 16 * 256 * 16));
+    clahe_apply_kernel<U8, 4><<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
+                                                           T->lutAB, T->spline, T->K, in_norm, on);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
