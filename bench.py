@@ -297,9 +297,13 @@ def main():
             ev.record()
         return _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm, P_split=Ps)
 
+    from gandtr_b200.extract import HostBatchUploader
+    uploader = HostBatchUploader(dev)
+
     def step_e2e():
-        x = imgs_host.to(dev, non_blocking=True)
+        x = uploader.upload(imgs_host)                 # pinned host -> device on the copy stream (overlaps the previous step)
         transform.batch(x, out=out)
+        uploader.release(x)
         d = _lib.gem_whiten([fmap], p, aggregate=True, msp_is_p=False, P=Pm, m=mm, P_split=Ps)
         desc_host.copy_(d, non_blocking=True)
 

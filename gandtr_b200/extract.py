@@ -17,7 +17,44 @@ import torch
 from . import _lib
 from .retrieval import shard_bounds
 
-__all__ = ["imresize", "load_image", "extract_descriptors", "extract_vectors", "extract_ss", "extract_ms"]
+__all__ = ["imresize", "load_image", "extract_descriptors", "extract_vectors", "extract_ss", "extract_ms", "HostBatchUploader"]
+
+
+class HostBatchUploader:
+    """Double-buffered host -> device staging of uint8 image batches on a dedicated copy stream, so the PCIe transfer of
+    batch i+1 overlaps the kernels of batch i. `upload(host_batch)` returns a device tensor that is valid on the
+    caller's current stream; `release(device_batch)` (called after the last kernel that reads it was enqueued) lets
+    the slot be overwritten two uploads later."""
+
+    def __init__(self, device, slots=2):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [None] * slots
+        self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self.free = [None] * slots
+        self.i = 0
+
+    def upload(self, host_batch):
+        j = self.i % len(self.slots)
+        self.i += 1
+        if self.slots[j] is None or self.slots[j].shape != host_batch.shape or self.slots[j].dtype != host_batch.dtype:
+            self.slots[j] = torch.empty(host_batch.shape, dtype=host_batch.dtype, device=self.device)
+            self.free[j] = None
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[j] is not None:
+                self.copy_stream.wait_event(self.free[j])        # the consumer of the previous occupant has finished
+            self.slots[j].copy_(host_batch, non_blocking=True)
+            self.ready[j].record(self.copy_stream)
+        torch.cuda.current_stream(self.device).wait_event(self.ready[j])
+        return self.slots[j]
+
+    def release(self, device_batch):
+        for j, s in enumerate(self.slots):
+            if s is device_batch:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self.free[j] = ev
+
 
 
 def imresize(img, imsize):
@@ -90,6 +127,7 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
     loader = torch.utils.data.DataLoader(_Decode(local, image_size, local_bbxs), batch_size=None, shuffle=False,
                                          num_workers=min(workers, max(len(local), 1)) if len(local) > 8 else 0)
     pending, shape, start = [], None, 0
+    uploader = HostBatchUploader(dev)
 
     def flush():
         nonlocal pending, start
@@ -97,7 +135,9 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
             return
         batch = torch.stack(pending).pin_memory()
         with torch.no_grad():
-            x = transform.batch(batch.to(dev, non_blocking=True))
+            staged = uploader.upload(batch)
+            x = transform.batch(staged)
+            uploader.release(staged)                       # K1 was the only reader of the uint8 batch
             out[start:start + len(pending)] = _descriptors_for_batch(model, x, list(ms), msp)
         start += len(pending)
         pending = []
