@@ -75,3 +75,46 @@ def test_old_protocol_with_empty_query():
     np.testing.assert_allclose(ap, g["old_ap"], rtol=0, atol=1e-6, equal_nan=True)
     valid = ~np.isnan(ap)
     assert abs(ap[valid].sum() / valid.sum() - float(g["old_map"])) < 1e-6
+
+
+def _roxford_shaped(d=512, seed=1):
+    """4 993 'real' + 100 000 distractor unit vectors, 70 queries around planted positives, per-query
+    easy / hard / junk id lists (some queries without hard positives)."""
+    rs = np.random.RandomState(seed)
+    ndb, nq = 4993 + 100000, 70
+    db = rs.standard_normal((ndb, d)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    rs2 = np.random.RandomState(seed + 1)
+    gnd, q = [], []
+    for i in range(nq):
+        ids = rs2.permutation(4993)[:110]
+        ne, nh, nj = rs2.randint(10, 31), (0 if i % 9 == 8 else rs2.randint(10, 41)), rs2.randint(10, 41)
+        easy, hard, junk = ids[:ne], ids[ne:ne + nh], ids[ne + nh:ne + nh + nj]
+        centre = db[np.concatenate([easy, hard])].mean(0)
+        v = centre / np.linalg.norm(centre) + 0.35 * rs2.standard_normal(d) / np.sqrt(d)
+        # pull the positives towards the query so that they rank high among the distractors
+        db[easy] = db[easy] + rs2.uniform(-0.02, 0.14, (len(easy), 1)).astype(np.float32) * v / np.linalg.norm(v)
+        db[hard] = db[hard] + rs2.uniform(-0.06, 0.08, (len(hard), 1)).astype(np.float32) * v / np.linalg.norm(v)
+        q.append((v / np.linalg.norm(v)).astype(np.float32))
+        gnd.append({"bbx": None, "easy": easy, "hard": hard, "junk": junk})
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    return np.stack(q), db.astype(np.float32), gnd
+
+
+def test_roxford_shaped_eval_full_size_matches_oracle():
+    """BASELINE config 3 at full size: ranking + mAP (Easy / Medium / Hard) + mP@k on the GPU against the oracle's
+    compute_map_and_print restatement on the full 104 993 x 70 ranking."""
+    from gandtr_b200.retrieval import ShardedIndex, compute_map_and_print
+    q, db, gnd = _roxford_shaped()
+    index = ShardedIndex(torch.from_numpy(db).cuda())
+    qd = torch.from_numpy(q).cuda()
+    s, i = index.search(qd, 100)
+    os_, oi = R.topk(R.scores_exact(q, db), 100)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    avg, per = compute_map_and_print("roxford5k", index, qd, gnd, printer=lambda *_: None)
+    ranks = R.full_ranks(R.scores_exact(q, db))
+    oavg, oaps, _ = R.compute_map_protocols("roxford5k", ranks, gnd)
+    for name in ("easy", "medium", "hard"):
+        assert abs(avg["map_" + name] - oavg["map_" + name]) < 1e-12
+        np.testing.assert_array_equal(per["ap_" + name], oaps["ap_" + name])
+    assert np.isnan(per["ap_hard"][8]) and 0.2 < avg["map_medium"] <= 1.0
