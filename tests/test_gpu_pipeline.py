@@ -123,3 +123,33 @@ def test_infer_stage_and_whitening_learning_chain(vgg, tmp_path):
     assert meta["whitening_path"].endswith("whitening/pca-memory.pkl")
     meta2, whit2 = infer_and_learn_whitening({"network": vgg, "whitening": {"type": "pca", "dataset_pkl": pkl, "directory": str(tmp_path)}})
     assert meta2["status"] == "skipped" and whit2 is None
+
+
+def test_hard_negative_mining_equals_reference_walk():
+    """the K3-based search against the reference algorithm (full sort + per-query cluster walk,
+    traindataset.py:246-279) restated with the oracle's total order."""
+    from gandtr_b200.mining import search_hard_negatives
+    from tests.util import unit_rows
+    rs = np.random.RandomState(4)
+    d, nq, npool, nnum = 128, 40, 6000, 5
+    pool = unit_rows(rs, npool, d)
+    q = unit_rows(rs, nq, d)
+    poolclusters = rs.randint(0, 300, npool)
+    poolclusters[:200] = 7                                  # a big cluster: forces deep walks for cluster-7 neighbours
+    qclusters = rs.randint(0, 300, nq)
+    q[:5] = pool[:5] + 0.05 * rs.normal(0, 1, (5, d)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    nidxs, stats = search_hard_negatives(torch.from_numpy(q.T.copy()).cuda(), torch.from_numpy(pool.T.copy()).cuda(),
+                                         qclusters, poolclusters, nnum, depth=8)
+    ranks = R.full_ranks(R.scores_exact(q, pool))           # [npool, nq]
+    for qi in range(nq):
+        clusters, ref = {qclusters[qi]}, []
+        r = 0
+        while len(ref) < nnum:
+            cand = ranks[r, qi]
+            if poolclusters[cand] not in clusters:
+                ref.append(int(cand))
+                clusters.add(poolclusters[cand])
+            r += 1
+        assert nidxs[qi] == ref
+    assert len(stats["average_negative_distance"]) == nq * nnum
