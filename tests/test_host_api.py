@@ -91,3 +91,27 @@ def test_network_construction_matches_reference_layout():
     g = ResnetGenerator()
     assert sum(p.numel() for p in g.parameters()) == 11378179           # 9-block ResNet generator, instance norm
     assert list(g.state_dict().keys())[0] == "model.1.weight"
+
+
+def test_descriptor_store_roundtrip_and_resharding(tmp_path):
+    """blocks written by 3 'ranks', read back as 2 shards -- rows, ids and whitening survive."""
+    from gandtr_b200 import store
+    from gandtr_b200.retrieval import shard_bounds
+    rs = np.random.RandomState(0)
+    n, d = 1000, 16
+    x = rs.normal(0, 1, (n, d)).astype(np.float32)
+    whit = {"m": rs.rand(d, 1), "P": rs.normal(0, 1, (d, d))}
+    for r in range(3):
+        lo, hi = shard_bounds(n, 3, r)
+        store.save(str(tmp_path), x[lo:hi], ids=["img%d" % i for i in range(n)] if r == 0 else None,
+                   whitening=whit if r == 0 else None, rows_per_file=128, lo=lo, n_total=n)
+    man = store.load_manifest(str(tmp_path))
+    assert man["rows"] == n and man["dim"] == d and man["shards"][0]["lo"] == 0 and man["shards"][-1]["hi"] == n
+    parts = []
+    for r in range(2):
+        rows, lo, total = store.load_shard(str(tmp_path), r, 2, device="cpu")
+        assert lo == shard_bounds(n, 2, r)[0] and total == n
+        parts.append(rows.numpy())
+    np.testing.assert_array_equal(np.concatenate(parts), x)
+    w = store.load_whitening(str(tmp_path))
+    np.testing.assert_array_equal(w["P"], whit["P"])
