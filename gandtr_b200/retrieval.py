@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "CudaOps", "DatabaseShard", "ShardedIndex", "evaluate_map", "compute_map_and_print",
+__all__ = ["shard_bounds", "CudaOps", "DatabaseShard", "ShardedIndex", "evaluate_map", "evaluate_protocols", "compute_map_and_print",
            "TC_MIN_WORK"]
 
 # below this many multiply-adds the exact CUDA-core kernel is used instead of the tcgen05 pipeline
@@ -241,36 +241,59 @@ def _pad_ids(lists, device, fill=-1):
     return torch.from_numpy(arr).to(device)
 
 
-def evaluate_map(index, q, gnd, kappas=()):
-    """compute_map (evaluate.py:39-111) on the GPU. gnd: list of {'ok': ids, 'junk': ids}.
-    Returns (map, aps [nq] float64, mean P@k, P@k [nq, nk]) as NumPy, NaN rows for queries without positives."""
-    ops = index.ops
-    ok = [np.asarray(g["ok"], dtype=np.int64).reshape(-1) for g in gnd]
-    junk = [np.asarray(g.get("junk", []), dtype=np.int64).reshape(-1) for g in gnd]
-    probes = _pad_ids([np.concatenate([o, j]) for o, j in zip(ok, junk)], q.device)
-    before = index.positions(q, probes)
-    npos_h = [len(o) for o in ok]
-    njunk_h = [len(j) for j in junk]
-    pp, pj = max(1, max(npos_h)), max(1, max(njunk_h))
-    # split the [ok | junk] probe columns into the two padded matrices gdt_map_eval takes
-    cols = torch.arange(max(pp, pj), device=q.device)
-    npos = torch.tensor(npos_h, dtype=torch.int32, device=q.device)
-    njunk = torch.tensor(njunk_h, dtype=torch.int32, device=q.device)
-    pos_rank = before[:, :pp].contiguous()
-    jidx = (npos.long()[:, None] + cols[None, :pj]).clamp_(max=before.shape[1] - 1)
-    junk_rank = torch.gather(before, 1, jidx).contiguous()
+def _map_from_positions(ops, before, ok_cols, junk_cols, kappas, device):
+    """before: [nq, pu] positions of the probe ids; ok_cols / junk_cols: per query, the columns of `before` that hold its
+    positives / junk ids. Runs gdt_map_eval and averages like the reference loop."""
+    nq = len(ok_cols)
+    npos_h = [len(c) for c in ok_cols]
+    njunk_h = [len(c) for c in junk_cols]
+    pos_rank = torch.gather(before, 1, _pad_ids(ok_cols, device, fill=0)).contiguous()
+    junk_rank = torch.gather(before, 1, _pad_ids(junk_cols, device, fill=0)).contiguous()
+    npos = torch.tensor(npos_h, dtype=torch.int32, device=device)
+    njunk = torch.tensor(njunk_h, dtype=torch.int32, device=device)
     ap, prk = ops.map_eval(pos_rank, junk_rank, npos, njunk, list(kappas))
     ap, prk = ap.cpu().numpy(), prk.cpu().numpy()
     # same accumulation order as the reference loop (evaluate.py:98,106,108-109): sequential, empty queries skipped
     total, pr, nempty = 0.0, np.zeros(len(kappas)), 0
-    for i in range(len(gnd)):
+    for i in range(nq):
         if npos_h[i] == 0:
             nempty += 1
             continue
         total = total + ap[i]
         pr = pr + prk[i, :]
-    nvalid = len(gnd) - nempty
+    nvalid = nq - nempty
     return (total / nvalid if nvalid else float("nan")), ap, (pr / nvalid if nvalid else pr * np.nan), prk
+
+
+def evaluate_protocols(index, q, groups, protocols, kappas=()):
+    """Several (ok, junk) partitions of the same id groups with ONE pass over the database.
+    groups: per query {name: ids}; protocols: {protocol: (ok group names, junk group names)}.
+    Returns {protocol: (map, aps, mean P@k, P@k)}."""
+    names = sorted({n for ok, jk in protocols.values() for n in tuple(ok) + tuple(jk)})
+    ids, spans = [], []
+    for g in groups:
+        off, span, parts = 0, {}, []
+        for n in names:
+            a = np.asarray(g.get(n, []), dtype=np.int64).reshape(-1)
+            span[n] = (off, off + len(a))
+            off += len(a)
+            parts.append(a)
+        ids.append(np.concatenate(parts) if parts else np.zeros(0, np.int64))
+        spans.append(span)
+    before = index.positions(q, _pad_ids(ids, q.device))
+    out = {}
+    for prot, (ok_names, junk_names) in protocols.items():
+        ok_cols = [np.concatenate([np.arange(*sp[n]) for n in ok_names]) if ok_names else np.zeros(0, np.int64) for sp in spans]
+        junk_cols = [np.concatenate([np.arange(*sp[n]) for n in junk_names]) if junk_names else np.zeros(0, np.int64) for sp in spans]
+        out[prot] = _map_from_positions(index.ops, before, ok_cols, junk_cols, kappas, q.device)
+    return out
+
+
+def evaluate_map(index, q, gnd, kappas=()):
+    """compute_map (evaluate.py:39-111) on the GPU. gnd: list of {'ok': ids, 'junk': ids}.
+    Returns (map, aps [nq] float64, mean P@k, P@k [nq, nk]) as NumPy, NaN rows for queries without positives."""
+    groups = [{"ok": g["ok"], "junk": g.get("junk", [])} for g in gnd]
+    return evaluate_protocols(index, q, groups, {"map": (("ok",), ("junk",))}, kappas)["map"]
 
 
 def compute_map_and_print(dataset, index, q, gnd, kappas=(1, 5, 10), printer=print):
@@ -283,12 +306,11 @@ def compute_map_and_print(dataset, index, q, gnd, kappas=(1, 5, 10), printer=pri
     if not (dataset.startswith("roxford5k") or dataset.startswith("rparis6k")):
         raise ValueError("Unsupported ground-truth format for dataset %s" % dataset)
     out_avg, out_aps, mprs = {}, {}, {}
-    for name, ok_keys, junk_keys in (("easy", ("easy",), ("junk", "hard")),        # :125-131
-                                     ("medium", ("easy", "hard"), ("junk",)),       # :133-139
-                                     ("hard", ("hard",), ("junk", "easy"))):        # :141-147
-        g = [{"ok": np.concatenate([np.asarray(x[k_], dtype=np.int64).reshape(-1) for k_ in ok_keys]),
-              "junk": np.concatenate([np.asarray(x[k_], dtype=np.int64).reshape(-1) for k_ in junk_keys])} for x in gnd]
-        m, aps, mpr, _ = evaluate_map(index, q, g, kappas)
+    res = evaluate_protocols(index, q, gnd, {"easy": (("easy",), ("junk", "hard")),          # :125-131
+                                             "medium": (("easy", "hard"), ("junk",)),         # :133-139
+                                             "hard": (("hard",), ("junk", "easy"))}, kappas)  # :141-147
+    for name in ("easy", "medium", "hard"):
+        m, aps, mpr, _ = res[name]
         out_avg["map_" + name], out_aps["ap_" + name], mprs[name] = m, aps, mpr
     printer(">> {}: mAP E: {}, M: {}, H: {}".format(dataset, *[np.around(out_avg["map_" + n] * 100, decimals=2)
                                                                for n in ("easy", "medium", "hard")]))

@@ -98,3 +98,23 @@ def test_divider_free_normalisation_is_ieee_division_exhaustive(std):
     _lib.check(lib.gdt_debug_div_check(ctypes.c_float(std), int(lo), int(hi), ctypes.c_void_p(cnt.data_ptr()),
                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gdt_debug_div_check")
     assert int(cnt.item()) == 0
+
+
+@pytest.mark.parametrize("grid,h,w", [(4, 64, 96), (16, 128, 160), (16, 100, 130), (2, 33, 47), (1, 40, 40)])
+def test_other_tile_grids_bit_exact(grid, h, w):
+    """grid <= 8 uses the 8-byte LUT rows, 9..16 the 16-byte rows; non-divisible sizes take the reflect-padded path."""
+    lut = load_lut()
+    img = synth_image(400 + grid + h, h, w, "smooth")
+    out = _run_u8([img], clip=2.0, grid=grid)[0]
+    _assert_bits(out, O.transform_u8(img, lut, MEAN, STD, clip_limit=2.0, grid=grid), "grid %d %dx%d" % (grid, h, w))
+
+
+def test_normalisation_falls_back_to_hardware_division_for_awkward_std():
+    """A std whose significand is all ones is outside the proven range of the divider-free sequence: K1 must switch to
+    IEEE division and stay bit-exact."""
+    from gandtr_b200 import _lib
+    lut = load_lut()
+    img = synth_image(5, 48, 64, "smooth")
+    std = [float(np.float32(0.99999994)), 0.224, float(np.uint32(0x3E7FFFFF).view(np.float32))]
+    out = _lib.clahe_u8(torch.from_numpy(img[None]).cuda(), MEAN, std)[0].cpu().numpy()
+    _assert_bits(out, O.transform_u8(img, lut, MEAN, std), "awkward std")

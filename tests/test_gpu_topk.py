@@ -127,3 +127,44 @@ def test_golden_reference_ranks_top100():
     for qi in range(q.shape[0]):
         for pos in np.flatnonzero(i[qi] != ranks[:100, qi]):
             assert abs(float(ref_s[i[qi, pos], qi]) - float(ref_s[ranks[pos, qi], qi])) < 2e-7
+
+
+def test_tcgen05_edge_shapes():
+    """k larger than the shard (padding), k = 1, a single query against a long shard, and a ragged last tile."""
+    for nq, ndb, d, k in [(128, 600, 2048, 1000), (300, 70000, 64, 1), (1, 200001, 128, 100), (129, 257, 512, 257)]:
+        rs = np.random.RandomState(nq + ndb)
+        q, db = unit_rows(rs, nq, d), unit_rows(rs, ndb, d)
+        s, i, st = _tc(q, db, k)
+        assert st[0] == 0, st
+        os_, oi = R.topk(R.scores_exact(q, db), k)
+        _check_lists(s, i, os_, oi, q, db)
+        if k > ndb:
+            assert (i[:, ndb:].cpu().numpy() == -1).all() and np.isneginf(s[:, ndb:].cpu().numpy()).all()
+
+
+def test_index_repairs_overflowed_queries_exactly():
+    """Massive exact ties (duplicated rows) overflow the candidate segments of some queries; ShardedIndex must hand back
+    the exact ranking for them (index asc among equal scores)."""
+    from gandtr_b200.retrieval import ShardedIndex
+    rs = np.random.RandomState(8)
+    base = unit_rows(rs, 50, 64)
+    db = np.concatenate([np.repeat(base[:1], 30000, axis=0), unit_rows(rs, 40000, 64)])
+    q = unit_rows(rs, 6, 64)
+    q[0] = base[0]
+    index = ShardedIndex(torch.from_numpy(db).cuda())
+    s, i = index.search(torch.from_numpy(q).cuda(), 50)
+    os_, oi = R.topk(R.scores_exact(q, db), 50)
+    _check_lists(s, i, os_, oi, q, db)
+    assert index.shard.last_status[0] == -7 and (i[0].cpu().numpy() == np.arange(50)).all()
+
+
+def test_unnormalised_and_tiny_magnitude_vectors():
+    """Power-of-two scaling keeps the fp16 shadow in range: rows with norms ~1e4 and ~1e-4 rank exactly."""
+    rs = np.random.RandomState(12)
+    for scale in (1.0e4, 1.0e-4):
+        q = (unit_rows(rs, 40, 256) * np.float32(scale) * rs.uniform(0.5, 2.0, (40, 1)).astype(np.float32)).astype(np.float32)
+        db = (unit_rows(rs, 30000, 256) * np.float32(scale) * rs.uniform(0.2, 3.0, (30000, 1)).astype(np.float32)).astype(np.float32)
+        s, i, st = _tc(q, db, 100)
+        assert st[0] == 0
+        os_, oi = R.topk(R.scores_exact(q, db), 100)
+        _check_lists(s, i, os_, oi, q, db)
