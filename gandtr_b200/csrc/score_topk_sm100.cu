@@ -31,6 +31,7 @@
 // from the fp32 rows, so the returned scores and ranking are those of the exact kernel (score_exact_sm100.cu).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "select.cuh"
@@ -236,7 +237,7 @@ q_prepare_kernel(const float* __restrict__ q, int nq, int d, const float* __rest
 struct FilterParams {
     int nq, d, k;
     long long ndb;
-    int n_qtiles, n_kblocks;
+    int n_qtiles, n_qgroups, n_kblocks;   // n_qgroups = ceil(n_qtiles / CLUSTER): query tiles handled together by one cluster
     int tile_begin, tile_end;          // database tile range of this launch
     int n_stripes, stripe_len, n_items;
     int seg_first;                     // candidate segment of stripe 0 of this launch
@@ -275,6 +276,11 @@ __device__ __forceinline__ float scan_threshold(const uint32_t* hist_row, int k,
     return __int_as_float(0xff800000);
 }
 
+// CLUSTER > 1: CLUSTER CTAs of a thread-block cluster work on CLUSTER consecutive query tiles against the SAME stripe of
+// database tiles; each loads 1/CLUSTER of every database tile and multicasts it to all of them, so the L2 -> SM operand
+// traffic per CTA drops from 48 KB to 16 + 32/CLUSTER KB per K block (the operand feed, not the tensor pipe, limits the
+// single-CTA version). A stage is released to the producers only when the MMA warps of all CTAs have consumed it.
+template <int CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                     const FilterParams P) {
@@ -295,7 +301,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_db) : "memory");
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, CLUSTER);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -306,15 +312,20 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();      // peers' barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int crank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / CLUSTER, n_clusters = gridDim.x / CLUSTER;
+    constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
+    constexpr int kSliceRows = kBlockN / CLUSTER, kSliceBytes = kBBytes / CLUSTER;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-                const int stripe = item / P.n_qtiles, qt = item - stripe * P.n_qtiles;
+            for (int item = cluster_id; item < P.n_items; item += n_clusters) {
+                const int stripe = item / P.n_qgroups, qt = (item - stripe * P.n_qgroups) * CLUSTER + crank;
                 const int t0 = P.tile_begin + stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.tile_end);
                 for (int t = t0; t < t1; ++t) {
                     for (int kb = 0; kb < P.n_kblocks; ++kb) {
@@ -322,7 +333,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
                         mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
                         tma_load_2d(sa, &map_q, bar_full + 8 * stage, kb * kBlockK, qt * kBlockM);
-                        tma_load_2d(sb, &map_db, bar_full + 8 * stage, kb * kBlockK, t * kBlockN);
+                        if (CLUSTER == 1)
+                            tma_load_2d(sb, &map_db, bar_full + 8 * stage, kb * kBlockK, t * kBlockN);
+                        else        // my slice of the database tile, delivered to every CTA of the cluster
+                            tma_load_2d_mc(sb + crank * kSliceBytes, &map_db, bar_full + 8 * stage, kb * kBlockK,
+                                           t * kBlockN + crank * kSliceRows, kMask);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -332,8 +347,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-                const int stripe = item / P.n_qtiles;
+            for (int item = cluster_id; item < P.n_items; item += n_clusters) {
+                const int stripe = item / P.n_qgroups;
                 const int t0 = P.tile_begin + stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.tile_end);
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -350,7 +365,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                             umma_f16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), kInstrDesc,
                                      (kb | kk) != 0 ? 1u : 0u);
                         }
-                        umma_commit(bar_empty + 8 * stage);
+                        if (CLUSTER == 1) umma_commit(bar_empty + 8 * stage);
+                        else umma_commit_mc(bar_empty + 8 * stage, kMask);    // frees the stage in every CTA's producer
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(bar_tfull + 8 * acc);
@@ -364,8 +380,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const float neg_inf = __int_as_float(0xff800000), pos_inf = __int_as_float(0x7f800000);
         uint32_t acc = 0, acc_phase = 0;
-        for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-            const int stripe = item / P.n_qtiles, qt = item - stripe * P.n_qtiles;
+        for (int item = cluster_id; item < P.n_items; item += n_clusters) {
+            const int stripe = item / P.n_qgroups, qt = (item - stripe * P.n_qgroups) * CLUSTER + crank;
             const int t0 = P.tile_begin + stripe * P.stripe_len, t1 = min(t0 + P.stripe_len, P.tile_end);
             const int qrow = qt * kBlockM + quarter * 32 + lane;
             const bool valid = qrow < P.nq;
@@ -396,10 +412,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_addr + acc * kBlockN + c * 32, v);
                     tmem_ld_wait();
-                    if (c * 32 + 32 > ncols) {      // ragged last tile: rows past the end of the shard never qualify
-#pragma unroll
+                    if (c * 32 + 32 > ncols) {      // ragged last tile: rows past the end of the shard never qualify --
+#pragma unroll                                  // NaN fails every `>= tau` test, even while tau is still -inf
                         for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j >= ncols) v[j] = 0xff800000u;
+                            if (c * 32 + j >= ncols) v[j] = 0x7fc00000u;
                     }
                     float mg[4];
 #pragma unroll
@@ -453,6 +469,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -573,7 +590,54 @@ static void plan_items(int n_qtiles, int n_dtiles, int sms, int& n_stripes, int&
     n_stripes = ceil_div(n_dtiles, stripe_len);
 }
 
+// Cluster size of the filter kernel: 2 when there are at least two query tiles to pair (GDT_DEBUG_K3_CLUSTER = 1 | 2 | 4
+// overrides, for A/B timing). Decided from (nq) alone so that every entry point derives the same workspace layout.
+static int topk_cluster_size(int n_qtiles) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("GDT_DEBUG_K3_CLUSTER");
+        forced = e ? atoi(e) : 0;
+        if (forced != 1 && forced != 2 && forced != 4) forced = 0;
+    }
+    int c = forced ? forced : 2;
+    while (c > 1 && n_qtiles < c) c >>= 1;
+    return c;
+}
+
+template <int CLUSTER>
+static int max_active_clusters_t() {
+    static int cached = 0;
+    if (cached) return cached;
+    int n = 0;
+    if (cudaFuncSetAttribute(score_filter_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(sm_count_current_device() / CLUSTER * CLUSTER), 1, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, score_filter_kernel<CLUSTER>, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    if (n <= 0) n = sm_count_current_device() / CLUSTER - 2;   // conservative guess (odd-sized GPCs strand an SM each)
+    if (n < 1) n = 1;
+    cached = n;
+    return n;
+}
+// clusters of `cluster` CTAs (one CTA per SM) that can be resident at once
+static int max_active_clusters(int cluster) {
+    if (cluster == 4) return max_active_clusters_t<4>();
+    if (cluster == 2) return max_active_clusters_t<2>();
+    return sm_count_current_device();
+}
+
 struct TopkPlan {
+    int cluster, n_qgroups, n_units;   // CTAs per cluster, query-tile groups, clusters the grid can hold
     int n_qtiles, n_dtiles, seed_tiles, n_seed, seed_len, n_stripes, stripe_len, n_segs, cap0, cap1;
     size_t qb, meta, tau, cnt, hist, cand, total;
 };
@@ -584,10 +648,14 @@ static TopkPlan topk_plan(int nq, long long ndb, int d, int k) {
     L.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
     L.seed_tiles = seed_tiles_for(k) < L.n_dtiles ? seed_tiles_for(k) : L.n_dtiles;
     const int sms = sm_count_current_device();
-    plan_items(L.n_qtiles, L.n_dtiles - L.seed_tiles, sms, L.n_stripes, L.stripe_len);
+    L.cluster = topk_cluster_size(L.n_qtiles);
+    L.n_qgroups = ceil_div(L.n_qtiles, L.cluster);
+    L.n_units = max_active_clusters(L.cluster);
+    (void)sms;
+    plan_items(L.n_qgroups, L.n_dtiles - L.seed_tiles, L.n_units, L.n_stripes, L.stripe_len);
     // the seed range itself is striped over idle SMs when there are few query tiles; a seed segment can hold every row of
     // its stripe, so it cannot overflow however cold the threshold is
-    L.n_seed = sms / L.n_qtiles;
+    L.n_seed = L.n_units / L.n_qgroups;
     if (L.n_seed > L.seed_tiles / 8) L.n_seed = L.seed_tiles / 8;
     if (L.n_seed < 1) L.n_seed = 1;
     L.seed_len = ceil_div(L.seed_tiles, L.n_seed);
@@ -656,6 +724,40 @@ extern "C" size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, i
     return topk_plan(nq, ndb, d, k).total + 256;
 }
 
+template <int CLUSTER>
+static int launch_filter_t(int n_units, const CUtensorMap& map_q, const CUtensorMap& map_db, const FilterParams& P,
+                           cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GDT_CUDA(cudaFuncSetAttribute(score_filter_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        if (CLUSTER > 1)
+            GDT_CUDA(cudaFuncSetAttribute(score_filter_kernel<CLUSTER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+        attr_set = true;
+    }
+    const int units = P.n_items < n_units ? P.n_items : n_units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(units * CLUSTER), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CLUSTER > 1 ? 1 : 0;
+    GDT_CUDA(cudaLaunchKernelEx(&cfg, score_filter_kernel<CLUSTER>, map_q, map_db, P));
+    return GDT_OK;
+}
+
+static int launch_filter(int cluster, int n_units, const CUtensorMap& map_q, const CUtensorMap& map_db, const FilterParams& P,
+                         cudaStream_t stream) {
+    if (cluster == 4) return launch_filter_t<4>(n_units, map_q, map_db, P, stream);
+    if (cluster == 2) return launch_filter_t<2>(n_units, map_q, map_db, P, stream);
+    return launch_filter_t<1>(n_units, map_q, map_db, P, stream);
+}
+
 static int topk_check(const void* q, int nq, long long ndb, int d, int k, long long index_base, const void* ws,
                       size_t ws_bytes) {
     if (!q || !ws) return GDT_ERR_INVALID_ARGUMENT;
@@ -700,31 +802,27 @@ extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const f
     CUtensorMap map_q, map_db;
     rc = make_f16_map(&map_q, qb, nq, d, kBlockM);
     if (rc != GDT_OK) return rc;
-    rc = make_f16_map(&map_db, db_f16, ndb, d, kBlockN);
+    rc = make_f16_map(&map_db, db_f16, ndb, d, kBlockN / L.cluster);     // one multicast slice per CTA of a cluster
     if (rc != GDT_OK) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        GDT_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
-    }
     const int sms = sm_count_current_device();
     FilterParams P;
     P.nq = nq; P.d = d; P.k = k; P.ndb = ndb;
-    P.n_qtiles = L.n_qtiles;
+    P.n_qtiles = L.n_qtiles; P.n_qgroups = L.n_qgroups;
     P.n_kblocks = ceil_div(d, kBlockK);
     P.n_segs = L.n_segs; P.n_seed = L.n_seed; P.cap0 = L.cap0; P.cap1 = L.cap1;
     P.meta = meta; P.tau = tau; P.cnt = cnt; P.hist = hist; P.cand = cand;
+    (void)sms;
     // seed pass: the first tiles of the shard against every query tile establish the thresholds
     P.tile_begin = 0; P.tile_end = L.seed_tiles;
-    P.n_stripes = L.n_seed; P.stripe_len = L.seed_len; P.n_items = L.n_seed * L.n_qtiles; P.seg_first = 0;
-    score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
-    GDT_LAUNCH_CHECK();
+    P.n_stripes = L.n_seed; P.stripe_len = L.seed_len; P.n_items = L.n_seed * L.n_qgroups; P.seg_first = 0;
+    rc = launch_filter(L.cluster, L.n_units, map_q, map_db, P, stream);
+    if (rc != GDT_OK) return rc;
     if (L.n_stripes > 0) {
         P.tile_begin = L.seed_tiles; P.tile_end = L.n_dtiles;
-        P.n_stripes = L.n_stripes; P.stripe_len = L.stripe_len; P.n_items = L.n_stripes * L.n_qtiles; P.seg_first = L.n_seed;
-        score_filter_kernel<<<P.n_items < sms ? P.n_items : sms, kThreads, kSmemBytes, stream>>>(map_q, map_db, P);
-        GDT_LAUNCH_CHECK();
+        P.n_stripes = L.n_stripes; P.stripe_len = L.stripe_len; P.n_items = L.n_stripes * L.n_qgroups; P.seg_first = L.n_seed;
+        rc = launch_filter(L.cluster, L.n_units, map_q, map_db, P, stream);
+        if (rc != GDT_OK) return rc;
     }
     return GDT_OK;
 }

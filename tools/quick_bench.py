@@ -35,7 +35,7 @@ if "gem" in which:
         ms = timeit(lambda: _lib.gem_whiten(fm, p2, aggregate=True, msp_is_p=agg, P=P, m=m))
         print("   p=2.92: %.3f ms %.0f GB/s" % (ms, byts / ms / 1e6))
 if "topk" in which:
-    for (nq, ndb, d) in [(1024, 131072, 512), (10000, 125000, 2048), (10000, 1000000, 512)]:
+    for (nq, ndb, d) in [(1024, 131072, 512), (10000, 125000, 2048), (10000, 1000000, 512), (10000, 1000000, 2048)]:
         db = torch.randn((ndb, d), device="cuda"); db /= db.norm(dim=1, keepdim=True)
         q = torch.randn((nq, d), device="cuda"); q /= q.norm(dim=1, keepdim=True)
         shadow, nmax = _lib.db_prepare(db)
