@@ -6,6 +6,7 @@ KRE=${2:-'clahe|gem_pool|whiten_gemm|score_filter|topk_finalize'}
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?" >> gpurun_out/summary.txt
 timeout 1200 python -m pytest tests -q -m gpu --timeout 300 -x > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest_gpu exit $?" >> gpurun_out/summary.txt
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?" >> gpurun_out/summary.txt
 timeout 300 python tools/quick_bench.py topk > gpurun_out/quick_bench_topk_$TAG.log 2>&1; echo "quick_topk exit $?" >> gpurun_out/summary.txt
@@ -16,6 +17,7 @@ if [ $rc -eq 0 ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -c 30 -o gpurun_out/prof_$TAG -f python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu_full exit $?" >> gpurun_out/summary.txt
 fi
 cat gpurun_out/summary.txt
+tail -n 3 gpurun_out/smoke_$TAG.log
 tail -n 25 gpurun_out/pytest_gpu_$TAG.log
 cat gpurun_out/bench_$TAG.json
 tail -n 5 gpurun_out/bench_$TAG.err gpurun_out/quick_bench_topk_$TAG.log gpurun_out/prof_plain.log
