@@ -14,6 +14,7 @@ for N in 1 2 4 8; do
   fi
 done
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus $NMAX --steps 5 --warmup 3 --db-rows 10000000 --db-dim 512 > gpurun_out/scale_${TAG}_10M512_n$NMAX.json 2> gpurun_out/scale_${TAG}_10M512_n$NMAX.err; echo "bench 10M n=$NMAX exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --db-rows 10000000 --db-dim 512 > gpurun_out/scale_${TAG}_10M512_n1.json 2> gpurun_out/scale_${TAG}_10M512_n1.err; echo "bench 10M n=1 exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
 for f in gpurun_out/scale_${TAG}_*.json; do echo "== $f"; python - "$f" <<'PY'
 import json,sys
