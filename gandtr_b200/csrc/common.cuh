@@ -55,4 +55,12 @@ const ClaheTables* clahe_tables_for_current_device();
 
 int sm_count_current_device();
 
+// index of the calling thread's current device, clamped to [0, 32): function attributes and occupancy results are per
+// device, so the "already configured" flags of the launch helpers are arrays indexed by it
+inline int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) dev = 0;
+    return dev;
+}
+
 }  // namespace gdt

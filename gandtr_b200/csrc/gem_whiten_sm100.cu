@@ -673,10 +673,11 @@ static int desc_tail(const DescScales& D, int n, int c, int scales, const float*
         if (rc == GDT_OK) rc = make_tile_map(&mph, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P_split, dim, c, kTcBN);
         if (rc == GDT_OK) rc = make_tile_map(&mpl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P_split + (size_t)dim * c, dim, c, kTcBN);
         if (rc != GDT_OK) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[32] = {false};
+        const int slot = current_device_slot();
+        if (!attr_set[slot]) {
             GDT_CUDA(cudaFuncSetAttribute(whiten_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-            attr_set = true;
+            attr_set[slot] = true;
         }
         int z = whiten_tc_slices(n, c, dim);
         int klen = ceil_div(ceil_div(c, z), kTcBK) * kTcBK;

@@ -177,7 +177,8 @@ extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long lon
     const size_t smem = (size_t)kRankQB * dpad * 4 + (size_t)kRankQB * ((pmax + 1) & ~1) * 4 + (size_t)kRankQB * pmax * 8 +
                         (size_t)kRankQB * pmax * 4;
     if (smem > 200 * 1024) return GDT_ERR_UNSUPPORTED;
-    static size_t attr_bytes = 0;
+    static size_t attr_bytes_dev[32] = {0};
+    size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > attr_bytes) {
         GDT_CUDA(cudaFuncSetAttribute(rank_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;
@@ -206,7 +207,8 @@ extern "C" int gdt_map_eval(const int64_t* pos_rank, int pmax_pos, const int64_t
     const int np_pos = next_pow2(pmax_pos), np_junk = next_pow2(pmax_junk);
     const size_t smem = (size_t)(np_pos + np_junk) * 8;
     if (smem > 200 * 1024) return GDT_ERR_UNSUPPORTED;
-    static size_t attr_bytes = 0;
+    static size_t attr_bytes_dev[32] = {0};
+    size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > attr_bytes) {
         GDT_CUDA(cudaFuncSetAttribute(map_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;

@@ -182,7 +182,8 @@ int launch_exact_scores(const float* q, const float* db, int nq, long long ndb, 
     const int dpad = (d + 3) & ~3;
     const size_t smem = (size_t)kExactQB * dpad * sizeof(float);
     if (smem > 200 * 1024) return GDT_ERR_UNSUPPORTED;
-    static size_t attr_bytes = 0;
+    static size_t attr_bytes_dev[32] = {0};
+    size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > attr_bytes) {
         GDT_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;
@@ -253,7 +254,8 @@ extern "C" int gdt_topk_merge(const float* scores, const int64_t* idx, int g, in
     if (!have_device()) return GDT_ERR_NO_DEVICE;
     const int np = next_pow2((int)total);
     const size_t smem = (size_t)np * sizeof(uint64_t);
-    static size_t attr_bytes = 0;
+    static size_t attr_bytes_dev[32] = {0};
+    size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > attr_bytes) {
         GDT_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;

@@ -606,7 +606,8 @@ static int topk_cluster_size(int n_qtiles) {
 
 template <int CLUSTER>
 static int max_active_clusters_t() {
-    static int cached = 0;
+    static int cached_dev[32] = {0};
+    int& cached = cached_dev[current_device_slot()];
     if (cached) return cached;
     int n = 0;
     if (cudaFuncSetAttribute(score_filter_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess) {
@@ -727,12 +728,11 @@ extern "C" size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, i
 template <int CLUSTER>
 static int launch_filter_t(int n_units, const CUtensorMap& map_q, const CUtensorMap& map_db, const FilterParams& P,
                            cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[32] = {false};
+    const int slot = current_device_slot();
+    if (!attr_set[slot]) {
         GDT_CUDA(cudaFuncSetAttribute(score_filter_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        if (CLUSTER > 1)
-            GDT_CUDA(cudaFuncSetAttribute(score_filter_kernel<CLUSTER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
-        attr_set = true;
+        attr_set[slot] = true;
     }
     const int units = P.n_items < n_units ? P.n_items : n_units;
     cudaLaunchConfig_t cfg = {};
@@ -839,10 +839,11 @@ extern "C" int gdt_score_topk_finalize(const float* q, const float* db, int nq, 
     const int scap = survivor_capacity(k);
     const int dpad = (d + 3) & ~3;
     const size_t fsmem = (size_t)scap * 8 + (size_t)dpad * 4;
-    static size_t fattr = 0;
-    if (fsmem > 48 * 1024 && fsmem > fattr) {
+    static size_t fattr[32] = {0};
+    const int slot = current_device_slot();
+    if (fsmem > 48 * 1024 && fsmem > fattr[slot]) {
         GDT_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        fattr = fsmem;
+        fattr[slot] = fsmem;
     }
     topk_finalize_kernel<<<nq, 256, fsmem, stream>>>(q, db, d, dpad, k, L.n_segs, L.n_seed, L.cap0, L.cap1, scap, index_base,
                                                      (const QMeta*)(base + L.meta), (const uint32_t*)(base + L.cnt),
