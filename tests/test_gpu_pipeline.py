@@ -153,3 +153,44 @@ def test_hard_negative_mining_equals_reference_walk():
             r += 1
         assert nidxs[qi] == ref
     assert len(stats["average_negative_distance"]) == nq * nnum
+
+
+def test_file_formats_checkpoint_whitening_gnd_and_jpeg_paths(vgg, tmp_path, monkeypatch):
+    """SURVEY 8(b) 'File formats': a reference-layout checkpoint + whitening pickle load through the pretrained hub path,
+    gnd_<dataset>.pkl drives CirDatasetAp, and images come from JPEG files on disk (PIL decode, LANCZOS thumbnail)."""
+    import pickle
+    from PIL import Image
+    from gandtr_b200 import hub
+    from gandtr_b200.score import CirDatasetAp
+    # --- checkpoint in the reference layout (mdir/learning/network.py:212-220) + whitening pickle (stages/whiten.py:75)
+    wdir = tmp_path / "weights"
+    wdir.mkdir()
+    torch.save(vgg.state_dict(), str(wdir / "hedngan_embed_vgg16.pth"))
+    rs = np.random.RandomState(3)
+    whit = {"m": 0.05 * rs.rand(512, 1), "P": rs.normal(0, 1, (512, 512)) / np.sqrt(512)}
+    with open(str(wdir / "hedngan_embed_vgg16_lw.pkl"), "wb") as f:
+        pickle.dump(whit, f)
+    net = hub.gem_vgg16_hedngan(pretrained=True, weights_dir=str(wdir))
+    assert [type(w).__name__ for w in net.wrappers["eval"].wrappers] == ["CirtorchWhiten", "CirMultiscaleAggregation"]
+    for k, v in vgg.model.state_dict().items():
+        assert torch.equal(v, net.model.state_dict()[k])
+    img = synth_image(3, 96, 128, "smooth")
+    with torch.no_grad():
+        vec = net(net.transform(img).unsqueeze(0))
+    assert tuple(vec.shape) == (512,) and abs(float(vec.norm()) - 1.0) < 1e-5      # whitened multi-scale descriptor
+    # --- dataset on disk: JPEG files + gnd pickle (cirtorch/datasets/testdataset.py:6-38)
+    root = tmp_path / "data" / "test" / "roxford5k"
+    (root / "jpg").mkdir(parents=True)
+    names = ["im%03d" % i for i in range(10)]
+    for i, n in enumerate(names):
+        Image.fromarray(synth_image(50 + i, 120, 160, "smooth")).save(str(root / "jpg" / (n + ".jpg")), quality=95)
+    gnd = [{"bbx": [10, 10, 150, 110], "easy": [0], "hard": [5], "junk": [9]}, {"bbx": None, "easy": [1], "hard": [], "junk": []}]
+    with open(str(root / "gnd_roxford5k.pkl"), "wb") as f:
+        pickle.dump({"imlist": names, "qimlist": names[:2], "gnd": gnd}, f)
+    monkeypatch.setenv("GANDTR_DATA_ROOT", str(tmp_path / "data"))
+    data = vgg.network_params.runtime["data"]
+    score = CirDatasetAp({"image_size": 128, "dataset": "roxford5k", "transforms": data.get("transforms", data.get("augmentations")),
+                          "mean_std": data["mean_std"]})
+    assert score.bbxs == [(10, 10, 150, 110), None] and len(score.images) == 10
+    avg = score(vgg, "cuda", lambda *a: None)
+    assert set(avg) == {"map_easy", "map_medium", "map_hard"} and avg["map_easy"] == 1.0     # each query finds its own image
