@@ -193,4 +193,11 @@ def test_file_formats_checkpoint_whitening_gnd_and_jpeg_paths(vgg, tmp_path, mon
                           "mean_std": data["mean_std"]})
     assert score.bbxs == [(10, 10, 150, 110), None] and len(score.images) == 10
     avg = score(vgg, "cuda", lambda *a: None)
-    assert set(avg) == {"map_easy", "map_medium", "map_hard"} and avg["map_easy"] == 1.0     # each query finds its own image
+    assert set(avg) == {"map_easy", "map_medium", "map_hard"}
+    # oracle on the same descriptors (queries are cropped / resized by the same loader)
+    from gandtr_b200.extract import extract_descriptors
+    db = extract_descriptors(vgg, score.images, 128, vgg.transform).cpu().numpy()
+    q = extract_descriptors(vgg, score.qimages, 128, vgg.transform, bbxs=score.bbxs).cpu().numpy()
+    oavg, _, _ = R.compute_map_protocols("roxford5k", R.full_ranks(R.scores_exact(q, db)), gnd)
+    for k in avg:
+        assert abs(avg[k] - oavg[k]) < 1e-12
