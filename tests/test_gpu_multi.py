@@ -63,3 +63,44 @@ def test_sharded_search_two_gpus_nccl():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1)
+
+
+def _score_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from gandtr_b200 import hub
+        from gandtr_b200.extract import extract_descriptors
+        from gandtr_b200.score import CirDatasetAp
+        from tests.util import synth_image
+        torch.backends.cudnn.allow_tf32 = False
+        torch.manual_seed(0)
+        net = hub.gem_vgg16_hedngan(pretrained=False, device="cuda:%d" % rank)
+        images = [synth_image(1000 + i, 64, 80, "smooth" if i % 4 else "noise") for i in range(21)]
+        qimages = [np.clip(images[j].astype(np.int16) + 8, 0, 255).astype(np.uint8) for j in range(4)]
+        gnd = [{"ok": np.array([j]), "junk": np.array([(j + 5) % 21])} for j in range(4)]
+        data = net.network_params.runtime["data"]
+        score = CirDatasetAp({"image_size": None, "dataset": {"name": "syn", "images": images, "qimages": qimages,
+                                                              "bbxs": [None] * 4, "gnd": gnd},
+                              "transforms": data.get("transforms", data.get("augmentations")), "mean_std": data["mean_std"]})
+        avg = score(net, "cuda", lambda *a: None)                       # database extraction and index sharded over 2 ranks
+        db = extract_descriptors(net, images, None, net.transform).cpu().numpy()
+        q = extract_descriptors(net, qimages, None, net.transform).cpu().numpy()
+        m, _, _, _ = R.compute_map(R.full_ranks(R.scores_exact(q, db)), gnd)
+        assert abs(avg["map"] - m) < 1e-9, (avg, m)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_score_object_sharded_over_two_gpus():
+    """CirDatasetAp with the database extraction and the index sharded over 2 ranks equals the single-process oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_score_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
