@@ -115,6 +115,51 @@ __device__ __forceinline__ void gem_row_pair(const float* __restrict__ rowA, con
     }
 }
 
+// Rows of one scale with G lanes per row. Loads are predicated, the loop is warp-uniform (full-mask shuffles).
+template <int MODE, int G>
+__device__ __noinline__ void gem_pool_scale(const float* __restrict__ base, int hw, long long rows, float* __restrict__ g,
+                                               float p, float eps, int root, float inv_p, long long wid, long long nwarps) {
+    constexpr int RPW = 32 / G;                       // rows per warp
+    const int lane = threadIdx.x & 31, lg = lane & (G - 1), sub = lane / G;
+    for (long long rb = wid * RPW; rb < rows; rb += nwarps * RPW) {
+        const long long r = rb + sub;
+        const bool valid = r < rows;
+        const float* row = base + (valid ? r : 0) * hw;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        int head = (int)(((16u - ((uintptr_t)row & 15u)) & 15u) >> 2);     // peel to 16-byte alignment
+        if (head > hw) head = hw;
+        if (valid && lg < head) acc0 += gem_pow<MODE>(fmaxf(row[lg], eps), p);
+        const float4* body = (const float4*)(row + head);
+        const int nvec = (hw - head) >> 2;
+        for (int b0 = 0; b0 < nvec; b0 += G * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = b0 + j * G + lg;
+                v[j] = (valid && i < nvec) ? ld_stream_f4(body + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (valid && b0 + j * G + lg < nvec) {
+                    acc0 += gem_pow<MODE>(fmaxf(v[j].x, eps), p);
+                    acc1 += gem_pow<MODE>(fmaxf(v[j].y, eps), p);
+                    acc2 += gem_pow<MODE>(fmaxf(v[j].z, eps), p);
+                    acc3 += gem_pow<MODE>(fmaxf(v[j].w, eps), p);
+                }
+            }
+        }
+        const int tail0 = head + (nvec << 2);
+        if (valid && tail0 + lg < hw) acc2 += gem_pow<MODE>(fmaxf(row[tail0 + lg], eps), p);
+        float acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (valid && lg == 0) {
+            const float mean = acc / (float)hw;
+            g[r] = root ? powf(mean, inv_p) : mean;
+        }
+    }
+}
+
 // All rows of one launch for a fixed exponent mode. Kept out of line so that each mode gets its own register
 // allocation instead of the union of all four.
 template <int MODE>
@@ -141,15 +186,14 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
         }
         return;
     }
-    for (long long warp = wid; warp < total_rows; warp += nwarps) {
-        const int s = (int)(warp / rows_per_scale);
-        const long long r = warp - (long long)s * rows_per_scale;
+    // generic path, scale by scale: G lanes per row (32 for long rows, 16 / 8 for the short rows of the small scales, so a
+    // warp keeps 2 / 4 rows in flight), every warp takes part in every scale (grid-stride)
+    for (int s = 0; s < S.nscales; ++s) {
         const int hw = S.hw[s];
-        const float sum = gem_row_sum<MODE>(S.ptr[s] + r * hw, hw, eps, p, lane);
-        if (lane == 0) {
-            const float mean = sum / (float)hw;
-            g[warp] = root ? powf(mean, inv_p) : mean;
-        }
+        float* gs = g + (long long)s * rows_per_scale;
+        if (hw > 256) gem_pool_scale<MODE, 32>(S.ptr[s], hw, rows_per_scale, gs, p, eps, root, inv_p, wid, nwarps);
+        else if (hw > 96) gem_pool_scale<MODE, 16>(S.ptr[s], hw, rows_per_scale, gs, p, eps, root, inv_p, wid, nwarps);
+        else gem_pool_scale<MODE, 8>(S.ptr[s], hw, rows_per_scale, gs, p, eps, root, inv_p, wid, nwarps);
     }
 }
 
