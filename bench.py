@@ -443,6 +443,26 @@ def main():
         line["retrieval"]["roofline"]["frac"] = line["retrieval"]["roofline"]["achieved"] / tc_peak
         del index
 
+    # ---- context: the same path with the STOCK ResNet-101 backbone in the loop (hub model, random init, batch 8) ----
+    if world == 1:
+        try:
+            from gandtr_b200 import hub
+            net = hub.gem_resnet101_cyclegan(pretrained=False, device=dev)
+            sub = imgs[:8]
+            def step_full():
+                with torch.no_grad():
+                    return net.model.descriptors([net.model.feature_map(net.transform.batch(sub))])
+            f_ms, w = timed(step_full, 5, 3)
+            windows.append(w)
+            line["with_stock_backbone"] = {"images_per_s": 8 * 5 / (f_ms * 1e-3), "ms_per_image": f_ms / 5 / 8, "batch": 8,
+                                           "backbone": "torchvision resnet101 (random init), fp32, torch default cudnn flags",
+                                           "note": "K1 + backbone + K2 through hub model objects; the backbone is out of scope "
+                                                   "(north_star) and dominates"}
+            del net
+            torch.cuda.empty_cache()
+        except Exception as e:                      # torchvision missing etc.: context only, never fatal
+            line["with_stock_backbone"] = {"unavailable": str(e)[:200]}
+
     # ---- BASELINE config 3: revisited-Oxford-shaped ranking + mAP (latency-bound; reported in ms) ----
     if world == 1 and not args.no_retrieval:
         from gandtr_b200.retrieval import compute_map_and_print

@@ -82,39 +82,6 @@ __device__ __forceinline__ float gem_row_sum(const float* __restrict__ row, int 
 }
 
 // one warp per row; rows are ordered [scale][image][channel]; g has the same order
-// Two rows per warp when a row is a whole number of 512-byte warp sweeps (ResNet 24x32, VGG 48x64, ...): both rows'
-// loads are issued before either is reduced (up to 16 independent 16-byte loads per lane).
-template <int MODE>
-__device__ __forceinline__ void gem_row_pair(const float* __restrict__ rowA, const float* __restrict__ rowB, int sweeps,
-                                             float eps, float p, int lane, float& sumA, float& sumB) {
-    float4 va[8], vb[8];
-    const float4* a4 = (const float4*)rowA;
-    const float4* b4 = (const float4*)rowB;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (j < sweeps) va[j] = ld_stream_f4(a4 + j * 32 + lane);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (j < sweeps) vb[j] = ld_stream_f4(b4 + j * 32 + lane);
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (j < sweeps) {
-            a0 += gem_pow<MODE>(fmaxf(va[j].x, eps), p) + gem_pow<MODE>(fmaxf(va[j].y, eps), p);
-            a1 += gem_pow<MODE>(fmaxf(va[j].z, eps), p) + gem_pow<MODE>(fmaxf(va[j].w, eps), p);
-            b0 += gem_pow<MODE>(fmaxf(vb[j].x, eps), p) + gem_pow<MODE>(fmaxf(vb[j].y, eps), p);
-            b1 += gem_pow<MODE>(fmaxf(vb[j].z, eps), p) + gem_pow<MODE>(fmaxf(vb[j].w, eps), p);
-        }
-    }
-    sumA = a0 + a1;
-    sumB = b0 + b1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sumA += __shfl_xor_sync(0xffffffffu, sumA, o);
-        sumB += __shfl_xor_sync(0xffffffffu, sumB, o);
-    }
-}
-
 // Rows of one scale with G lanes per row. Loads are predicated, the loop is warp-uniform (full-mask shuffles).
 template <int MODE, int G>
 __device__ __noinline__ void gem_pool_scale(const float* __restrict__ base, int hw, long long rows, float* __restrict__ g,
@@ -165,28 +132,10 @@ __device__ __noinline__ void gem_pool_scale(const float* __restrict__ base, int 
 template <int MODE>
 __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_per_scale, long long total_rows, float p,
                                            float eps, int root, float* __restrict__ g) {
-    const int lane = threadIdx.x & 31;
     const float inv_p = 1.0f / p;
     const long long nwarps = (long long)gridDim.x * 8;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    // row pairs (single scale, rows of 1..8 whole warp sweeps, 16-byte aligned base) pay off only when the per-row
-    // epilogue is the expensive root (gdt_gem_pool): measured on B200, one row per warp is faster otherwise
-    const int hw0 = S.hw[0];
-    if (root && S.nscales == 1 && (hw0 & 127) == 0 && hw0 <= 1024 && (((uintptr_t)S.ptr[0]) & 15) == 0) {
-        const int sweeps = hw0 >> 7;
-        for (long long r = wid * 2; r < total_rows; r += nwarps * 2) {
-            const float* rowA = S.ptr[0] + r * hw0;
-            const float* rowB = (r + 1 < total_rows) ? rowA + hw0 : rowA;
-            float sa, sb;
-            gem_row_pair<MODE>(rowA, rowB, sweeps, eps, p, lane, sa, sb);
-            if (lane < 2 && r + lane < total_rows) {
-                const float mean = (lane == 0 ? sa : sb) / (float)hw0;
-                g[r + lane] = root ? powf(mean, inv_p) : mean;
-            }
-        }
-        return;
-    }
-    // generic path, scale by scale: G lanes per row (32 for long rows, 16 / 8 for the short rows of the small scales, so a
+    // scale by scale: G lanes per row (32 for long rows, 16 / 8 for the short rows of the small scales, so a
     // warp keeps 2 / 4 rows in flight), every warp takes part in every scale (grid-stride)
     for (int s = 0; s < S.nscales; ++s) {
         const int hw = S.hw[s];
@@ -197,7 +146,7 @@ __device__ __noinline__ void gem_pool_rows(const GemScales& S, long long rows_pe
     }
 }
 
-// one warp per row (or row pair); rows are ordered [scale][image][channel]; g has the same order.
+// G lanes per row; rows are ordered [scale][image][channel]; g has the same order.
 // root != 0: g = mean^(1/p) (GeM proper); root == 0: g = mean, the caller applies the root (gem_finalize_kernel).
 __global__ void __launch_bounds__(256, 3)
 gem_pool_kernel(const __grid_constant__ GemScales S, long long rows_per_scale, long long total_rows,
