@@ -220,7 +220,8 @@ q_prepare_kernel(const float* __restrict__ q, int nq, int d, const float* __rest
         const float dx_max = __ldg(db_stats + 2), hx_max = __ldg(db_stats + 3);
         const float dq = sqrtf(rr), hq = sqrtf(hh);
         // fp32 accumulation on the tensor cores: one rounding per K=16 MMA plus the alignment error inside it
-        const float acc = ((float)(d / 16 + 16)) * 4.76837158203125e-07f;    // * 2^-21
+        const float acc = ((float)(d / 16 + 16)) * 9.5367431640625e-07f;     // * 2^-20: 2x the bound, the accumulator's
+                                                                             // internal alignment width is undocumented
         const float eq = (dq * xs_max + hq * dx_max + acc * hq * hx_max) * 1.001f;
         QMeta m;
         m.scale = hq * hx_max * 1.0001f;                                     // |coarse score| <= scale
