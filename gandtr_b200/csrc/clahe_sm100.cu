@@ -3,16 +3,16 @@
 // functional.py:28-35,55-63,81-85,140-161}) and the ClahePost wrapper
 // (mdir/components/data/wrapper.py:325-348), bit-exact against the reference's OpenCV 4.13.0 path.
 //
-// Two launches per batch, both HBM-streaming with coalesced 16-byte accesses:
-//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> Q14 lightness (one 16 B gather from
-//           the L2-resident packed lattice table) -> uint8 L8 scratch + 256-bin shared-memory histogram
-//           (warp-aggregated atomics: __match_any_sync elects one lane per distinct bin) -> clip,
-//           redistribute, prefix sum -> 256-byte tile LUT.
-//   pass B  clahe_apply_kernel  one CTA per (image, row band, 1024-px column chunk): tile LUTs of the
-//           band staged in shared memory, per pixel: bilinear LUT blend -> chroma (32 B gather) ->
-//           Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
-// Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 1 B/px
-// written by A and read by B (L2-resident for batches up to ~100 MB).
+// Two launches per batch, both streaming with coalesced 16-byte accesses:
+//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> lattice cell + fractions (integer arithmetic) -> Q14
+//           lightness (one 16 B gather from the L2-resident packed lattice table, dp2a trilinear) -> uint8 L8 scratch
+//           + 4-byte cell code scratch + 256-bin shared-memory histogram (bank-skewed copies per warp) -> clip,
+//           redistribute, prefix sum -> tile LUT (transposed rows).
+//   pass B  clahe_apply_kernel  one CTA per (image, row band, 1024-px column chunk): LUT rows of the band and the
+//           inverse-gamma spline staged in shared memory, per pixel: bilinear LUT blend -> chroma (one 256-bit gather
+//           addressed by the cell code) -> Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
+// Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 5 B/px written by A and
+// read by B (the input itself is read once).
 #include "clahe_math.cuh"
 #include "common.cuh"
 
@@ -61,6 +61,18 @@ __device__ __forceinline__ void cell_from_f32(float r, float g, float b, const N
     cell = (tr << 10) | (tg << 5) | tb;
 }
 
+// Per-pixel "cell code" written by pass A and consumed by pass B (so the quantisation of the input pixel happens once):
+// bits [0,15) lattice cell, [15,20) fr, [20,25) fg, [25,30) fb  (fractions are 0..16)
+__device__ __forceinline__ uint32_t pack_code(int cell, int fr, int fg, int fb) {
+    return (uint32_t)cell | ((uint32_t)fr << 15) | ((uint32_t)fg << 20) | ((uint32_t)fb << 25);
+}
+__device__ __forceinline__ void unpack_code(uint32_t c, int& cell, int& fr, int& fg, int& fb) {
+    cell = (int)(c & 0x7fffu);
+    fr = (int)((c >> 15) & 31u);
+    fg = (int)((c >> 20) & 31u);
+    fb = (int)(c >> 25);
+}
+
 __device__ __forceinline__ int l8_from_cell(const uint4* __restrict__ lutL, int cell, int fr, int fg, int fb) {
     const uint4 w = __ldg(lutL + cell);
     return lab_l8_fast(lab_trilinear(w.x, w.y, w.z, w.w, fr, fg, fb));
@@ -96,7 +108,8 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
 
 template <bool U8>
 __global__ void __launch_bounds__(256)
-clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_t* __restrict__ lutT, int h, int w,
+clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ codes,
+                  uint8_t* __restrict__ lutT, int h, int w,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, const uint4* __restrict__ lutL,
                   Norm3 in_norm) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
@@ -112,6 +125,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
     const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
     const float* inf = (const float*)in_ + (size_t)img * plane * 3;
     uint8_t* l8img = L8 + (size_t)img * plane;
+    uint32_t* codeimg = codes + (size_t)img * plane;
 
     if (vec_ok) {
         // tile fully inside the image, 4 consecutive pixels per thread
@@ -137,6 +151,8 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
                     for (int i = 0; i < 4; ++i) cell_from_u8(rr[i], gg[i], bb[i], cell[i], fr[i], fg[i], fb[i]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) wv[i] = __ldg(lutL + cell[i]);      // four gathers in flight
+                    *(uint4*)(codeimg + p) = make_uint4(pack_code(cell[0], fr[0], fg[0], fb[0]), pack_code(cell[1], fr[1], fg[1], fb[1]),
+                                                        pack_code(cell[2], fr[2], fg[2], fb[2]), pack_code(cell[3], fr[3], fg[3], fb[3]));
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         v[i] = lab_l8_fast(lab_trilinear(wv[i].x, wv[i].y, wv[i].z, wv[i].w, fr[i], fg[i], fb[i]));
@@ -146,12 +162,15 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
                     const float4 b4 = __ldg((const float4*)(inf + 2 * plane + p));
                     const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w},
                                 bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    uint32_t cd[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         int cell, fr, fg, fb;
                         cell_from_f32(rr[i], gg[i], bb[i], in_norm, cell, fr, fg, fb);
+                        cd[i] = pack_code(cell, fr, fg, fb);
                         v[i] = l8_from_cell(lutL, cell, fr, fg, fb);
                     }
+                    *(uint4*)(codeimg + p) = make_uint4(cd[0], cd[1], cd[2], cd[3]);
                 }
                 *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
             }
@@ -176,7 +195,10 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint8_
                     cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
                 }
                 v = l8_from_cell(lutL, cell, fr, fg, fb);
-                if (ey < h && ex < w) l8img[p] = (uint8_t)v;
+                if (ey < h && ex < w) {
+                    l8img[p] = (uint8_t)v;
+                    codeimg[p] = pack_code(cell, fr, fg, fb);
+                }
             }
             hist_add(hist, v);
         }
@@ -228,12 +250,12 @@ struct NormFast {
     int fast;   // div_by_const_ok() for all three std
 };
 
-template <bool U8, int MINB>
+template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
-clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
+clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
-                   Norm3 in_norm, NormFast on) {
+                   NormFast on) {
     extern __shared__ __align__(16) uint8_t smem[];
     // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
     // less than 16-byte ones
@@ -273,18 +295,17 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
     }
 
     const size_t plane = (size_t)h * w;
-    const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
-    const float* inf = (const float*)in_ + (size_t)img * plane * 3;
+    const uint32_t* codeimg = codes + (size_t)img * plane;
     const uint8_t* l8img = L8 + (size_t)img * plane;
     float* outimg = out + (size_t)img * plane * 3;
     const uint8_t* lut_bytes = (const uint8_t*)luts;
 
-    // software prefetch (vectorised u8 path): the next row's pixel words are requested before this row's arithmetic
-    uint32_t nx0 = 0, nx1 = 0, nx2 = 0, nxl = 0;
-    if (U8 && vec_ok) {
+    // software prefetch (vectorised path): the next row's codes and lightness bytes are requested before this row's arithmetic
+    uint4 nxc = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t nxl = 0;
+    if (vec_ok) {
         const size_t p = (size_t)y0 * w + x0;
-        const uint32_t* src = (const uint32_t*)(in8 + p * 3);
-        nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2);
+        nxc = __ldg((const uint4*)(codeimg + p));
         nxl = __ldg((const uint32_t*)(l8img + p));
     }
     for (int y = y0; y < y1; ++y) {
@@ -295,39 +316,23 @@ clahe_apply_kernel(const void* __restrict__ in_, const uint8_t* __restrict__ L8,
 
         int cell[4], fr[4], fg[4], fb[4], v[4];
         if (vec_ok) {
-            const uint32_t lw = U8 ? nxl : __ldg((const uint32_t*)(l8img + p));
-            v[0] = lw & 255; v[1] = (lw >> 8) & 255; v[2] = (lw >> 16) & 255; v[3] = lw >> 24;
-            if (U8) {
-                const uint32_t a0 = nx0, a1 = nx1, a2 = nx2;
-                if (y + 1 < y1) {
-                    const uint32_t* nsrc = (const uint32_t*)(in8 + (p + w) * 3);
-                    nx0 = __ldg(nsrc); nx1 = __ldg(nsrc + 1); nx2 = __ldg(nsrc + 2);
-                    nxl = __ldg((const uint32_t*)(l8img + p + w));
-                }
-                cell_from_u8(a0 & 255, (a0 >> 8) & 255, (a0 >> 16) & 255, cell[0], fr[0], fg[0], fb[0]);
-                cell_from_u8(a0 >> 24, a1 & 255, (a1 >> 8) & 255, cell[1], fr[1], fg[1], fb[1]);
-                cell_from_u8((a1 >> 16) & 255, a1 >> 24, a2 & 255, cell[2], fr[2], fg[2], fb[2]);
-                cell_from_u8((a2 >> 8) & 255, (a2 >> 16) & 255, a2 >> 24, cell[3], fr[3], fg[3], fb[3]);
-            } else {
-                const float4 r4 = __ldg((const float4*)(inf + p));
-                const float4 g4 = __ldg((const float4*)(inf + plane + p));
-                const float4 b4 = __ldg((const float4*)(inf + 2 * plane + p));
-                cell_from_f32(r4.x, g4.x, b4.x, in_norm, cell[0], fr[0], fg[0], fb[0]);
-                cell_from_f32(r4.y, g4.y, b4.y, in_norm, cell[1], fr[1], fg[1], fb[1]);
-                cell_from_f32(r4.z, g4.z, b4.z, in_norm, cell[2], fr[2], fg[2], fb[2]);
-                cell_from_f32(r4.w, g4.w, b4.w, in_norm, cell[3], fr[3], fg[3], fb[3]);
+            const uint32_t lw = nxl;
+            const uint4 cw = nxc;
+            if (y + 1 < y1) {
+                nxc = __ldg((const uint4*)(codeimg + p + w));
+                nxl = __ldg((const uint32_t*)(l8img + p + w));
             }
+            v[0] = lw & 255; v[1] = (lw >> 8) & 255; v[2] = (lw >> 16) & 255; v[3] = lw >> 24;
+            unpack_code(cw.x, cell[0], fr[0], fg[0], fb[0]);
+            unpack_code(cw.y, cell[1], fr[1], fg[1], fb[1]);
+            unpack_code(cw.z, cell[2], fr[2], fg[2], fb[2]);
+            unpack_code(cw.w, cell[3], fr[3], fg[3], fb[3]);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (i < npx) {
                     v[i] = l8img[p + i];
-                    if (U8) {
-                        cell_from_u8(in8[(p + i) * 3], in8[(p + i) * 3 + 1], in8[(p + i) * 3 + 2], cell[i], fr[i], fg[i], fb[i]);
-                    } else {
-                        cell_from_f32(inf[p + i], inf[plane + p + i], inf[2 * plane + p + i], in_norm, cell[i], fr[i],
-                                      fg[i], fb[i]);
-                    }
+                    unpack_code(codeimg[p + i], cell[i], fr[i], fg[i], fb[i]);
                 } else {
                     v[i] = 0; cell[i] = 0; fr[i] = fg[i] = fb[i] = 0;
                 }
@@ -432,6 +437,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
     Workspace W(ws, ws_bytes);
     uint8_t* L8 = W.take<uint8_t>((size_t)n * h * w);
+    uint32_t* codes = W.take<uint32_t>((size_t)n * h * w);
     uint8_t* luts = W.take<uint8_t>(((size_t)n * grid * 256) << lut_row_shift(grid));
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
@@ -440,7 +446,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
 
     dim3 gridA(grid * grid, n);
-    clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
+    clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, codes, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
                                                       vec_hist, T->lutL, in_norm);
     GDT_LAUNCH_CHECK();
 
@@ -466,10 +472,10 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
     // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
     if (smem > 48 * 1024)
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<U8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-    clahe_apply_kernel<U8, 4><<<gridB, 256, smem, stream>>>(in, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
-                                                           T->lutAB, T->spline, T->K, in_norm, on);
+    clahe_apply_kernel<4><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
+                                                       T->lutAB, T->spline, T->K, on);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
@@ -550,7 +556,7 @@ extern "C" int gdt_debug_get_spline_table(float* host_out_4096) {
 
 extern "C" size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid) {
     if (n <= 0 || h <= 0 || w <= 0 || grid < 1) return 0;
-    return align_up((size_t)n * h * w, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 256;
+    return align_up((size_t)n * h * w, 256) + align_up((size_t)n * h * w * 4, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 512;
 }
 
 extern "C" int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,
