@@ -13,6 +13,8 @@
 //           addressed by the cell code) -> Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
 // Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 5 B/px written by A and
 // read by B (the input itself is read once).
+#include <stdlib.h>
+
 #include "clahe_math.cuh"
 #include "common.cuh"
 
@@ -22,6 +24,7 @@ struct ClaheTables {
     uint4* lutL = nullptr;     // [32768]      packed lightness corners
     uint4* lutAB = nullptr;    // [32768][2]   packed chroma corners (a words, b words)
     float4* spline = nullptr;  // [1024]
+    cudaTextureObject_t texL = 0, texAB = 0, texSpline = 0;   // the same tables behind the texture path (point fetch)
     Lab2RgbConst K;
     float spline_host[4096];
     bool ready = false;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ codes,
                   uint8_t* __restrict__ lutT, int h, int w,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, const uint4* __restrict__ lutL,
-                  Norm3 in_norm) {
+                  Norm3 in_norm, cudaTextureObject_t texL, int texmode) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
@@ -150,7 +153,8 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
 #pragma unroll
                     for (int i = 0; i < 4; ++i) cell_from_u8(rr[i], gg[i], bb[i], cell[i], fr[i], fg[i], fb[i]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) wv[i] = __ldg(lutL + cell[i]);      // four gathers in flight
+                    for (int i = 0; i < 4; ++i)                                     // four gathers in flight
+                        wv[i] = (texmode & 4) ? tex1Dfetch<uint4>(texL, cell[i]) : __ldg(lutL + cell[i]);
                     *(uint4*)(codeimg + p) = make_uint4(pack_code(cell[0], fr[0], fg[0], fb[0]), pack_code(cell[1], fr[1], fg[1], fb[1]),
                                                         pack_code(cell[2], fr[2], fg[2], fb[2]), pack_code(cell[3], fr[3], fg[3], fb[3]));
 #pragma unroll
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
-                   NormFast on) {
+                   NormFast on, cudaTextureObject_t texAB, cudaTextureObject_t texSpline, int texmode) {
     extern __shared__ __align__(16) uint8_t smem[];
     // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
     // less than 16-byte ones
@@ -344,7 +348,12 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
         for (int i = 0; i < 4; ++i) {
             // chroma
             uint4 wa, wb;
-            ld_cell_ab(lutAB, cell[i], wa, wb);
+            if (texmode & 2) {          // texture pipe instead of the LSU pipe
+                wa = tex1Dfetch<uint4>(texAB, cell[i] * 2);
+                wb = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
+            } else {
+                ld_cell_ab(lutAB, cell[i], wa, wb);
+            }
             const float a2 = lab_chroma_fast(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
             const float b2 = lab_chroma_fast(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
             // lightness through CLAHE: the two 16-byte rows hold the LUT value of every tile column at level v
@@ -368,10 +377,20 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
             lab2lin(Ln, a2, b2, (x0 + i) >= wbody, K, lr, lg, lb);
             int ir, ig, ib;
             const float xr = spline_index(lr, ir), xg = spline_index(lg, ig), xb = spline_index(lb, ib);
-            const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
-            const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
-            const float er = spline_eval(xr, r01.x, r01.y, r23.x, r23.y), eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y),
-                        eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
+            float er, eg, eb;
+            if (texmode & 1) {          // spline segments through the texture pipe: no shared-memory bank conflicts
+                const float4 sr = tex1Dfetch<float4>(texSpline, ir), sg = tex1Dfetch<float4>(texSpline, ig),
+                             sb = tex1Dfetch<float4>(texSpline, ib);
+                er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
+                eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w);
+                eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
+            } else {
+                const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
+                const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
+                er = spline_eval(xr, r01.x, r01.y, r23.x, r23.y);
+                eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y);
+                eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
+            }
             if (on.fast) {
                 o[0][i] = normalize_px_fast(er, on.mean[0], on.std[0], on.rstd[0]);
                 o[1][i] = normalize_px_fast(eg, on.mean[1], on.std[1], on.rstd[1]);
@@ -445,9 +464,12 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
     const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
 
+    // which table gathers take the texture pipe (bit 0 spline, 1 chroma lattice, 2 lightness lattice); debug override
+    static int texmode = -1;
+    if (texmode < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texmode = e ? atoi(e) : 0; }
     dim3 gridA(grid * grid, n);
     clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, codes, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
-                                                      vec_hist, T->lutL, in_norm);
+                                                      vec_hist, T->lutL, in_norm, T->texL, texmode);
     GDT_LAUNCH_CHECK();
 
     // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
@@ -475,7 +497,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
         GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
     clahe_apply_kernel<4><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
-                                                       T->lutAB, T->spline, T->K, on);
+                                                       T->lutAB, T->spline, T->K, on, T->texAB, T->texSpline, texmode);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
@@ -539,6 +561,26 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     if (rc == GDT_OK) rc = up((void**)&T.spline, T.spline_host, 4096 * sizeof(float));
     free(hL);
     free(hAB);
+    auto make_tex = [&](cudaTextureObject_t* tex, void* ptr, size_t bytes, bool is_float) -> int {
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = ptr;
+        rd.res.linear.desc = is_float ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uint4>();
+        rd.res.linear.sizeInBytes = bytes;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaError_t e = cudaCreateTextureObject(tex, &rd, &td, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaCreateTextureObject(tables)", __FILE__, __LINE__);
+        return GDT_OK;
+    };
+    if (rc == GDT_OK) rc = make_tex(&T.texL, T.lutL, ncell * 16, false);
+    if (rc == GDT_OK) rc = make_tex(&T.texAB, T.lutAB, ncell * 32, false);
+    if (rc == GDT_OK) rc = make_tex(&T.texSpline, T.spline, 4096 * sizeof(float), true);
     if (rc == GDT_OK) T.ready = true;
     return rc;
 }
