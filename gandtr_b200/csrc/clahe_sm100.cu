@@ -351,6 +351,9 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
             if (texmode & 2) {          // texture pipe instead of the LSU pipe
                 wa = tex1Dfetch<uint4>(texAB, cell[i] * 2);
                 wb = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
+            } else if (texmode & 8) {   // one half each
+                wa = tex1Dfetch<uint4>(texAB, cell[i] * 2);
+                wb = __ldg(lutAB + cell[i] * 2 + 1);
             } else {
                 ld_cell_ab(lutAB, cell[i], wa, wb);
             }
@@ -384,6 +387,13 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
                 er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
                 eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w);
                 eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
+            } else if (texmode & 16) {  // one channel through the texture pipe, two through shared memory
+                const float4 sr = tex1Dfetch<float4>(texSpline, ir);
+                const float2 g01 = spl_fb[ig], b01 = spl_fb[ib];
+                const float2 g23 = spl_cd[ig], b23 = spl_cd[ib];
+                er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
+                eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y);
+                eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
             } else {
                 const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
                 const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
