@@ -351,9 +351,6 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
             if (texmode & 2) {          // texture pipe instead of the LSU pipe
                 wa = tex1Dfetch<uint4>(texAB, cell[i] * 2);
                 wb = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
-            } else if (texmode & 8) {   // one half each
-                wa = tex1Dfetch<uint4>(texAB, cell[i] * 2);
-                wb = __ldg(lutAB + cell[i] * 2 + 1);
             } else {
                 ld_cell_ab(lutAB, cell[i], wa, wb);
             }
@@ -387,13 +384,6 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
                 er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
                 eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w);
                 eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
-            } else if (texmode & 16) {  // one channel through the texture pipe, two through shared memory
-                const float4 sr = tex1Dfetch<float4>(texSpline, ir);
-                const float2 g01 = spl_fb[ig], b01 = spl_fb[ib];
-                const float2 g23 = spl_cd[ig], b23 = spl_cd[ib];
-                er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
-                eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y);
-                eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
             } else {
                 const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
                 const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
@@ -474,9 +464,12 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
     const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
 
-    // which table gathers take the texture pipe (bit 0 spline, 1 chroma lattice, 2 lightness lattice); debug override
+    // Which table gathers take the texture pipe instead of the LSU pipe (bit 0 spline, 1 chroma lattice, 2 lightness
+    // lattice). Pass B is bound by LSU wavefronts (shared-memory spline / LUT lookups + the scattered lattice gather):
+    // moving the chroma gather to the otherwise idle texture pipe measured -6 % on B200, the other two cost time
+    // (profiles/k1_texpipe_ab_r1m.log). GDT_DEBUG_K1_TEX overrides for A/B runs.
     static int texmode = -1;
-    if (texmode < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texmode = e ? atoi(e) : 0; }
+    if (texmode < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texmode = e ? atoi(e) : 2; }
     dim3 gridA(grid * grid, n);
     clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, codes, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
                                                       vec_hist, T->lutL, in_norm, T->texL, texmode);
