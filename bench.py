@@ -33,8 +33,9 @@ MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 K1_BYTES_PER_IMG = 15 * H * W
 K2_BYTES_PER_IMG = 4 * C_FEAT * FH * FW + 4 * C_FEAT
 # measured DRAM traffic of K1 per image (dram__bytes_read.sum + dram__bytes_write.sum of clahe_hist + clahe_apply, ncu
-# --set full capture profiles/ncu_full_r1d.txt at 32 images: 76.0 + 7.9 + 102.4 + 246.6 MB) -- 1.15x the algorithmic bytes
-K1_TRAFFIC_PER_IMG = (76.037888e6 + 7.912192e6 + 102.354432e6 + 246.626560e6) / 32
+# --set full capture profiles/ncu_full_r1m.txt at 32 images: 76.0 + 74.6 + 127.5 + 244.0 MB) -- 1.38x the algorithmic
+# bytes: the 5 B/px scratch (lightness byte + cell code) is written by pass A and read by pass B
+K1_TRAFFIC_PER_IMG = (76.039424e6 + 74.577664e6 + 127.460864e6 + 243.959040e6) / 32
 
 
 def parse():
@@ -394,7 +395,7 @@ def main():
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "K1 clahe_hist_kernel + clahe_apply_kernel (one gdt_clahe_u8 call)", "bound": "hbm",
                      "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1d, per image x batch",
+                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1m, per image x batch",
                      "ms_per_launch_pair": k1_ms,
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
