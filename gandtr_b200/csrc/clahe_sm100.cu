@@ -254,9 +254,7 @@ struct NormFast {
     int fast;   // div_by_const_ok() for all three std
 };
 
-// SPL selects the shared-memory layout of the inverse-gamma spline: 0 = two 8-byte halves, 1 = 16-byte segments,
-// 2 = the 8-byte halves replicated four times, copy (lane & 3) living in its own quarter of the banks
-template <int MINB, int SPL>
+template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
@@ -265,11 +263,9 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
     extern __shared__ __align__(16) uint8_t smem[];
     // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
     // less than 16-byte ones
-    constexpr int kSplBytes = SPL == 2 ? 1024 * 16 * 4 : 1024 * 16;
-    float2* spl_fb = (float2*)smem;                      // [1024 (x4)] (f, b)
-    float2* spl_cd = (float2*)(smem + kSplBytes / 2);    // [1024 (x4)] (c, d)
-    float4* spl4 = (float4*)smem;                        // SPL == 1: [1024] (f, b, c, d)
-    uint2* luts = (uint2*)(smem + kSplBytes);            // [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
+    float2* spl_fb = (float2*)smem;              // [1024] (f, b)
+    float2* spl_cd = (float2*)(smem + 1024 * 8); // [1024] (c, d)
+    uint2* luts = (uint2*)(smem + 1024 * 16);    // [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
     const int lsh = lut_row_shift(grid);
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
@@ -283,18 +279,8 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
         for (int i = tid; i < nwords; i += 256) luts[i] = __ldg(src + i);
         for (int i = tid; i < 1024; i += 256) {
             const float4 sgm = __ldg(spline + i);
-            if (SPL == 1) {
-                spl4[i] = sgm;
-            } else if (SPL == 2) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {      // entry i of copy c -> bank pair 4 * (i & 3) + c of row i >> 2
-                    spl_fb[((i >> 2) << 4) | ((i & 3) << 2) | c] = make_float2(sgm.x, sgm.y);
-                    spl_cd[((i >> 2) << 4) | ((i & 3) << 2) | c] = make_float2(sgm.z, sgm.w);
-                }
-            } else {
-                spl_fb[i] = make_float2(sgm.x, sgm.y);
-                spl_cd[i] = make_float2(sgm.z, sgm.w);
-            }
+            spl_fb[i] = make_float2(sgm.x, sgm.y);
+            spl_cd[i] = make_float2(sgm.z, sgm.w);
         }
     }
     __syncthreads();
@@ -399,22 +385,11 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
                 eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w);
                 eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
             } else {
-                if (SPL == 1) {
-                    const float4 sr = spl4[ir], sg = spl4[ig], sb = spl4[ib];
-                    er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
-                    eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w);
-                    eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
-                } else {
-                    const int cp = SPL == 2 ? (tid & 3) : 0;
-                    const int jr = SPL == 2 ? (((ir >> 2) << 4) | ((ir & 3) << 2) | cp) : ir;
-                    const int jg = SPL == 2 ? (((ig >> 2) << 4) | ((ig & 3) << 2) | cp) : ig;
-                    const int jb = SPL == 2 ? (((ib >> 2) << 4) | ((ib & 3) << 2) | cp) : ib;
-                    const float2 r01 = spl_fb[jr], g01 = spl_fb[jg], b01 = spl_fb[jb];
-                    const float2 r23 = spl_cd[jr], g23 = spl_cd[jg], b23 = spl_cd[jb];
-                    er = spline_eval(xr, r01.x, r01.y, r23.x, r23.y);
-                    eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y);
-                    eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
-                }
+                const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
+                const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
+                er = spline_eval(xr, r01.x, r01.y, r23.x, r23.y);
+                eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y);
+                eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
             }
             if (on.fast) {
                 o[0][i] = normalize_px_fast(er, on.mean[0], on.std[0], on.rstd[0]);
@@ -509,10 +484,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
     int span = (rows + g.th - 1) / g.th + 2;
     if (span > grid) span = grid;
-    static int splmode = -1;     // spline layout in shared memory (see clahe_apply_kernel); GDT_DEBUG_K1_SPL overrides
-    if (splmode < 0) { const char* e = getenv("GDT_DEBUG_K1_SPL"); splmode = e ? atoi(e) : 0; if (splmode < 0 || splmode > 2) splmode = 0; }
-    const size_t lut_bytes = ((size_t)span * 256) << lut_row_shift(grid);
-    const size_t smem = (splmode == 2 ? 1024 * 16 * 4 : 1024 * 16) + lut_bytes;
+    const size_t smem = 1024 * 16 + (((size_t)span * 256) << lut_row_shift(grid));
     NormFast on;
     on.fast = 1;
     for (int c = 0; c < 3; ++c) {
@@ -524,17 +496,11 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     }
     // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
     // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
-    auto launch = [&](auto kernel) -> int {
-        if (smem > 48 * 1024)
-            GDT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 * 4 + 16 * 256 * 16));
-        kernel<<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply, T->lutAB,
-                                            T->spline, T->K, on, T->texAB, T->texSpline, texmode);
-        return GDT_OK;
-    };
-    if (splmode == 1) rc = launch(clahe_apply_kernel<4, 1>);
-    else if (splmode == 2) rc = launch(clahe_apply_kernel<3, 2>);
-    else rc = launch(clahe_apply_kernel<4, 0>);
-    if (rc != GDT_OK) return rc;
+    if (smem > 48 * 1024)
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      1024 * 16 + 16 * 256 * 16));
+    clahe_apply_kernel<4><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
+                                                       T->lutAB, T->spline, T->K, on, T->texAB, T->texSpline, texmode);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
