@@ -75,13 +75,29 @@ class CudaOps:
         status = st.cpu()  # one small sync per search: the status word decides whether a repair pass is needed
         shard.last_status = status.tolist()
         if int(status[0]) != 0:
-            # candidate overflow (massive ties / adversarial data): re-score exactly the flagged queries
-            bad = torch.nonzero(i[:, 0] == -2).flatten()
-            if bad.numel():
-                se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
-                s[bad] = se
-                i[bad] = ie
+            self._repair(q, shard, k, s, i)
         return s, i
+
+    def _repair(self, q, shard, k, s, i):
+        """Candidate overflow (dense near-ties, duplicated rows): first retry the flagged queries alone with a much larger
+        k -- that multiplies the candidate and survivor capacities and spreads the shard over more stripes -- and only
+        what still overflows goes to the exact CUDA-core scan."""
+        from . import _lib
+        db, aux, base = shard.db, shard.aux, shard.index_base
+        bad = torch.nonzero(i[:, 0] == -2).flatten()
+        if not bad.numel():
+            return
+        kk = min(1024, max(8 * k, 512))
+        if kk > k:
+            s2, i2, st2 = _lib.score_topk(q[bad].contiguous(), db, aux["shadow"], aux["norm_max"], kk, index_base=base)
+            ok = i2[:, 0] != -2
+            s[bad[ok]] = s2[ok, :k]
+            i[bad[ok]] = i2[ok, :k]
+            bad = bad[~ok]
+        if bad.numel():
+            se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
+            s[bad] = se
+            i[bad] = ie
 
     def _local_topk_exchanged(self, q, shard, k):
         """Row-sharded search with the histogram exchange (include/gandtr_b200.h, two-phase form). Every rank takes the
@@ -107,11 +123,7 @@ class CudaOps:
         status = st.cpu()
         shard.last_status = status.tolist()
         if int(status[0]) != 0:
-            bad = torch.nonzero(i[:, 0] == -2).flatten()
-            if bad.numel():
-                se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
-                s[bad] = se
-                i[bad] = ie
+            self._repair(q, shard, k, s, i)      # local, no collective: the repaired lists are supersets of what is needed
         return s, i
 
     @staticmethod

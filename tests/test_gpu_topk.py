@@ -158,6 +158,26 @@ def test_index_repairs_overflowed_queries_exactly():
     assert index.shard.last_status[0] == -7 and (i[0].cpu().numpy() == np.arange(50)).all()
 
 
+def test_index_repairs_duplicate_clusters_on_the_tensor_path(monkeypatch):
+    """A few thousand exact duplicates overflow the per-stripe candidate segments at k = 50; the retry with a larger k has
+    room for them, so the exact CUDA-core scan is never needed."""
+    from gandtr_b200 import retrieval
+    rs = np.random.RandomState(9)
+    base = unit_rows(rs, 3, 128)
+    db = np.concatenate([unit_rows(rs, 60000, 128), np.repeat(base[:1], 2500, axis=0), unit_rows(rs, 60000, 128)])
+    q = unit_rows(rs, 5, 128)
+    q[2] = base[0]
+    calls = []
+    orig = retrieval.CudaOps._exact_chunked
+    monkeypatch.setattr(retrieval.CudaOps, "_exact_chunked", staticmethod(lambda *a, **k: calls.append(1) or orig(*a, **k)))
+    monkeypatch.setattr(retrieval, "TC_MIN_WORK", 1)
+    index = retrieval.ShardedIndex(torch.from_numpy(db).cuda())
+    s, i = index.search(torch.from_numpy(q).cuda(), 50)
+    os_, oi = R.topk(R.scores_exact(q, db), 50)
+    _check_lists(s, i, os_, oi, q, db)
+    assert index.shard.last_status[0] == -7 and not calls and (i[2].cpu().numpy() == 60000 + np.arange(50)).all()
+
+
 def test_unnormalised_and_tiny_magnitude_vectors():
     """Power-of-two scaling keeps the fp16 shadow in range: rows with norms ~1e4 and ~1e-4 rank exactly."""
     rs = np.random.RandomState(12)
