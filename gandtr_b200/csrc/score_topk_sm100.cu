@@ -72,9 +72,9 @@ __host__ __device__ inline int stripe_capacity(int k) {
     return next_pow2(c);
 }
 __host__ __device__ inline int survivor_capacity(int k) {
-    int c = 4 * k;
+    int c = 8 * k;
     if (c < 2048) c = 2048;
-    return next_pow2(c);
+    return next_pow2(c);       // <= 8192 keys (64 KB of shared memory) at k = 1024
 }
 
 // histogram bin of a coarse score relative to the query's scale: 32 bins per octave over [2^-8, 1)

@@ -87,7 +87,7 @@ class CudaOps:
         bad = torch.nonzero(i[:, 0] == -2).flatten()
         if not bad.numel():
             return
-        kk = min(1024, max(8 * k, 512))
+        kk = 1024              # 8192-entry candidate segments per stripe, 8192 survivors
         if kk > k:
             s2, i2, st2 = _lib.score_topk(q[bad].contiguous(), db, aux["shadow"], aux["norm_max"], kk, index_base=base)
             ok = i2[:, 0] != -2
