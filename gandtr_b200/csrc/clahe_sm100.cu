@@ -15,8 +15,6 @@
 // read by B (the input itself is read once).
 #include <stdlib.h>
 
-#include <mutex>
-
 #include "clahe_math.cuh"
 #include "common.cuh"
 
@@ -446,27 +444,6 @@ static int clahe_geometry(int n, int h, int w, double clip_limit, int grid, Clah
     return GDT_OK;
 }
 
-// two internal non-blocking streams per device for the chunk overlap of clahe_launch
-struct ClaheSideStreams {
-    std::mutex lock;             // fork / launch / join of one call must not interleave with another host thread's
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-    bool ready = false;
-};
-static ClaheSideStreams* side_streams_for_current_device() {
-    static ClaheSideStreams all[32];
-    ClaheSideStreams& S = all[current_device_slot()];
-    if (!S.ready) {
-        bool ok = cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int k = 0; k < 2 && ok; ++k)
-            ok = cudaStreamCreateWithFlags(&S.st[k], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&S.join[k], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); return nullptr; }
-        S.ready = true;
-    }
-    return &S;
-}
-
 template <bool U8>
 static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, int grid, const Norm3& in_norm,
                         const Norm3& out_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -493,6 +470,21 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // (profiles/k1_texpipe_ab_r1m.log). GDT_DEBUG_K1_TEX overrides for A/B runs.
     static int texmode = -1;
     if (texmode < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texmode = e ? atoi(e) : 2; }
+    dim3 gridA(grid * grid, n);
+    clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, codes, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
+                                                      vec_hist, T->lutL, in_norm, T->texL, texmode);
+    GDT_LAUNCH_CHECK();
+
+    // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
+    const int sms = sm_count_current_device();
+    int rows = 32;
+    const int xchunks = ceil_div(w, 1024);
+    while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 16LL * sms) rows >>= 1;   // >= ~3 waves
+    dim3 gridB(xchunks, ceil_div(h, rows), n);
+    // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
+    int span = (rows + g.th - 1) / g.th + 2;
+    if (span > grid) span = grid;
+    const size_t smem = 1024 * 16 + (((size_t)span * 256) << lut_row_shift(grid));
     NormFast on;
     on.fast = 1;
     for (int c = 0; c < 3; ++c) {
@@ -502,61 +494,14 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
         on.rstd[c] = r;
         if (!div_by_const_ok(out_norm.std[c])) on.fast = 0;
     }
-    const int sms = sm_count_current_device();
-    const int xchunks = ceil_div(w, 1024);
-    const size_t plane = (size_t)h * w;
-    const size_t in_stride = plane * 3 * (U8 ? 1 : 4);
-    const size_t lut_stride = ((size_t)grid * 256) << lut_row_shift(grid);
-
-    // one chunk of images: pass A then pass B on stream `st`
-    auto run_chunk = [&](int i0, int cn, cudaStream_t st) -> int {
-        const void* cin = (const char*)in + (size_t)i0 * in_stride;
-        dim3 gridA(grid * grid, cn);
-        clahe_hist_kernel<U8><<<gridA, 256, 0, st>>>(cin, L8 + (size_t)i0 * plane, codes + (size_t)i0 * plane,
-                                                     luts + (size_t)i0 * lut_stride, h, w, grid, g.th, g.tw, g.clip,
-                                                     g.lut_scale, vec_hist, T->lutL, in_norm, T->texL, texmode);
-        GDT_LAUNCH_CHECK();
-        // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
-        int rows = 32;
-        while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * cn < 16LL * sms) rows >>= 1;   // >= ~3 waves
-        dim3 gridB(xchunks, ceil_div(h, rows), cn);
-        // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
-        int span = (rows + g.th - 1) / g.th + 2;
-        if (span > grid) span = grid;
-        const size_t smem = 1024 * 16 + (((size_t)span * 256) << lut_row_shift(grid));
-        // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster
-        if (smem > 48 * 1024)
-            GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          1024 * 16 + 16 * 256 * 16));
-        clahe_apply_kernel<4><<<gridB, 256, smem, st>>>(codes + (size_t)i0 * plane, L8 + (size_t)i0 * plane,
-                                                       luts + (size_t)i0 * lut_stride, out + (size_t)i0 * plane * 3, h, w, grid,
-                                                       g.inv_th, g.inv_tw, rows, vec_apply, T->lutAB, T->spline, T->K, on,
-                                                       T->texAB, T->texSpline, texmode);
-        GDT_LAUNCH_CHECK();
-        return GDT_OK;
-    };
-
-    // Large batches are cut into chunks that alternate between two internal streams (forked from and joined back into the
-    // caller's stream), so pass A of one chunk runs next to pass B of the previous one: A leaves LSU-pipe and issue slots
-    // free that B is starved of, and vice versa. GDT_DEBUG_K1_CHUNKS overrides the chunk count (1 = no overlap).
-    static int forced_chunks = -1;
-    if (forced_chunks < 0) { const char* e = getenv("GDT_DEBUG_K1_CHUNKS"); forced_chunks = e ? atoi(e) : 0; }
-    int nchunks = forced_chunks > 0 ? forced_chunks : (n * plane >= (size_t)32 * 768 * 1024 ? 4 : 1);
-    if (nchunks > n) nchunks = n;
-    ClaheSideStreams* S = nchunks > 1 ? side_streams_for_current_device() : nullptr;
-    if (!S) return run_chunk(0, n, stream);
-    std::lock_guard<std::mutex> guard(S->lock);
-    GDT_CUDA(cudaEventRecord(S->fork, stream));
-    for (int k = 0; k < 2; ++k) GDT_CUDA(cudaStreamWaitEvent(S->st[k], S->fork, 0));
-    for (int c = 0; c < nchunks; ++c) {
-        const int i0 = (int)((long long)n * c / nchunks), i1 = (int)((long long)n * (c + 1) / nchunks);
-        rc = run_chunk(i0, i1 - i0, S->st[c & 1]);
-        if (rc != GDT_OK) return rc;
-    }
-    for (int k = 0; k < 2; ++k) {
-        GDT_CUDA(cudaEventRecord(S->join[k], S->st[k]));
-        GDT_CUDA(cudaStreamWaitEvent(stream, S->join[k], 0));
-    }
+    // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
+    // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
+    if (smem > 48 * 1024)
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      1024 * 16 + 16 * 256 * 16));
+    clahe_apply_kernel<4><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
+                                                       T->lutAB, T->spline, T->K, on, T->texAB, T->texSpline, texmode);
+    GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
 
