@@ -397,6 +397,8 @@ def main():
                      "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1m, per image x batch",
                      "ms_per_launch_pair": k1_ms,
+                     "note": "nominal bound; ncu shows the LSU pipe (89 % in pass B) and instruction issue (69 %) as the actual "
+                             "limiters of the bit-exact pipeline, DRAM at ~15 % (profiles/ncu_full_r1n.txt)",
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
                         "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
