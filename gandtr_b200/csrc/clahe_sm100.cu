@@ -254,12 +254,16 @@ struct NormFast {
     int fast;   // div_by_const_ok() for all three std
 };
 
-template <int MINB>
+// FAST = the common configuration compiled without per-pixel mode tests: width a multiple of 8 (no OpenCV scalar-tail
+// pixels), chroma lattice through the texture pipe, spline through shared memory, divider-free normalisation.
+template <int MINB, bool FAST>
 __global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
-                   NormFast on, cudaTextureObject_t texAB, cudaTextureObject_t texSpline, int texmode) {
+                   NormFast on, cudaTextureObject_t texAB, cudaTextureObject_t texSpline, int texmode_) {
+    const int texmode = FAST ? 2 : texmode_;
+    if (FAST) on.fast = 1;
     extern __shared__ __align__(16) uint8_t smem[];
     // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
     // less than 16-byte ones
@@ -374,7 +378,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
             const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
             const float Ln = lab_l_from_u8_fast(dst);
             float lr, lg, lb;
-            lab2lin(Ln, a2, b2, (x0 + i) >= wbody, K, lr, lg, lb);
+            lab2lin(Ln, a2, b2, FAST ? false : (x0 + i) >= wbody, K, lr, lg, lb);
             int ir, ig, ib;
             const float xr = spline_index(lr, ir), xg = spline_index(lg, ig), xb = spline_index(lb, ib);
             float er, eg, eb;
@@ -497,10 +501,16 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
     // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
     if (smem > 48 * 1024)
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-    clahe_apply_kernel<4><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows, vec_apply,
-                                                       T->lutAB, T->spline, T->K, on, T->texAB, T->texSpline, texmode);
+    if ((w & 7) == 0 && texmode == 2 && on.fast && smem <= 48 * 1024)
+        clahe_apply_kernel<4, true><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
+                                                                 vec_apply, T->lutAB, T->spline, T->K, on, T->texAB,
+                                                                 T->texSpline, texmode);
+    else
+        clahe_apply_kernel<4, false><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
+                                                                  vec_apply, T->lutAB, T->spline, T->K, on, T->texAB,
+                                                                  T->texSpline, texmode);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
