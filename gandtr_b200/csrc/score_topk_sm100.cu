@@ -402,8 +402,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                                 : (size_t)P.n_seed * P.cap0 + (size_t)(seg - P.n_seed) * P.cap1);
             uint32_t slot = 0, inserted = 0;
             int tiles_done = 0;
-            for (int t = t0; t < t1; ++t) {
-                if (valid && t != t0) tau = fmaxf(tau, from_ordered_bits(__ldcg(P.tau + qrow)));
+            uint32_t tau_pub = ordered_bits(tau);     // threshold published by all stripes of this query, one tile stale:
+            for (int t = t0; t < t1; ++t) {           // the load is issued a tile ahead so its latency is never exposed
+                tau = fmaxf(tau, from_ordered_bits(tau_pub));
+                if (valid) tau_pub = __ldcg(P.tau + qrow);
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
                 const long long col0 = (long long)t * kBlockN;
