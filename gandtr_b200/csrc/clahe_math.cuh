@@ -109,27 +109,29 @@ inline bool div_by_const_ok(float b) {
 
 // ---- RGB -> Lab (Q14 integer LUT path) ----------------------------------------------------------
 
-// Quantise a [0,1] float channel to the LUT cell `t` (0..31) and 4-bit fraction `f` (0..16).
-// OpenCV: c = cvRound(x * 16384); t = c >> 9; f = (c >> 5) & 15, neighbour index clamped to 32.
-// c == 16384 (t == 32, f == 0) is folded into (t = 31, f = 16): identical weights on identical
-// lattice points, and keeps every cell inside a 32^3 packed table.
+// Quantise a [0,1] float channel to the lattice index `t` (0..32) and the 4-bit fraction `f` (0..15).
+// OpenCV: c = cvRound(x * 16384); t = c >> 9; f = (c >> 5) & 15, neighbour index clamped to 32. c == 16384 gives
+// (t = 32, f = 0): the packed tables below have 33 cells per axis, the "+1" neighbours of the last cell are the clamped
+// ones and carry weight 0.
 GDT_HD void lab_cell(float x01, int& t, int& f) {
-    int c = f_rint(f_mul(x01, 16384.0f));
+    const int c = f_rint(f_mul(x01, 16384.0f));
     t = c >> 9;
     f = (c >> 5) & 15;
-    if (t >= 32) { t = 31; f = 16; }
 }
 
 // 8-bit input channel: c = cvRound((float(v) / 255.0f) * 16384) == (v * 32768 + 255) / 510 for every v in [0, 255]
-// (v * 16384 / 255 is never within 1/510 of a half-integer, far outside the float rounding error; all 256 values are
-// checked in tests/test_clahe_fastmath.py).
+// (v * 16384 / 255 is never within 1/510 of a half-integer, far outside the float rounding error), and
+// t << 4 | f == c >> 5 == (v * 514 + 4) >> 8  (one multiply-add and one shift; all 256 values are checked in
+// tests/test_clahe_fastmath.py). v == 255 gives t = 32, f = 0.
 GDT_HD void lab_cell_u8(int v, int& t, int& f) {
-    // (c >> 5) with c = (v*32768 + 255) / 510 is one division: floor(floor(X / 510) / 32) == floor(X / 16320)
-    const unsigned tf = ((unsigned)v * 32768u + 255u) / 16320u;   // t << 4 | f, 512 only for v == 255
+    const unsigned tf = ((unsigned)v * 514u + 4u) >> 8;
     t = (int)(tf >> 4);
     f = (int)(tf & 15u);
-    if (tf == 512u) { t = 31; f = 16; }
 }
+
+// index of a lattice cell in the packed 33^3 tables
+GDT_HD int lab_cell_index(int tr, int tg, int tb) { return (tr * 33 + tg) * 33 + tb; }
+constexpr int kLabCells = 33 * 33 * 33;
 
 // One channel of the trilinear interpolation. `w` holds the four (dx,dy) corner pairs of the cell,
 // each 32-bit word = value(dz=0) | value(dz=1) << 16 (values in [0,16384]).
@@ -168,6 +170,11 @@ GDT_HD int lab_l8_fast(int o0) {
     const float spc = div_by_const<1>(L, 100.0f, 1.0f / 100.0f);
     return f_trunc(f_mul(spc, 255.0f));
 }
+
+// lab_l8 in integer arithmetic: trunc(((o * 2^-14) * 100 / 100) * 255) == (o * 255) >> 14 for every o in [0, 16384]
+// (o * 255 / 16384 is an integer only at o = 0 and 16384, and is otherwise at least 2^-14 away from one -- four float
+// ulps at 255; exhaustively tested).
+GDT_HD int lab_l8_int(int o0) { return (o0 * 255) >> 14; }
 
 // Q14 chroma -> the a (or b) value handed to LAB2RGB after the reference's normalise/denormalise
 // round trip:  a = o*2^-14*256 - 128 ; spc = (a + 128) / 255 ; a' = spc*255 - 128.
@@ -222,6 +229,34 @@ struct Lab2RgbConst {
     float C[9];        // float32(XYZ2sRGB_D65[k][j] * whitePt[j]), row-major
 };
 
+// SIMD-body sequence, lightness half: L -> (y, fy). Depends only on the CLAHE output byte, see build_fy_table.
+GDT_HD void lab_fy_body(float L, float& y, float& fy) {
+    const float c16 = 16.0f / 116.0f;
+    const float r903 = 1.0f / 903.3f, r116 = 1.0f / 116.0f;
+    if (L <= 8.0f) {
+        y = f_mul(L, r903);
+        fy = f_add(f_mul(y, 7.787f), c16);
+    } else {
+        fy = f_mul(f_add(L, 16.0f), r116);
+        y = f_mul(f_mul(fy, fy), fy);
+    }
+}
+
+// SIMD-body sequence, chroma half: `y1`, `y4`, `y7` are the products C[1]*y, C[4]*y, C[7]*y.
+GDT_HD void lab2lin_body_from_fy(float fy, float y1, float y4, float y7, float a, float b, const Lab2RgbConst& K,
+                                 float& r, float& g, float& bl) {
+    const float c16 = 16.0f / 116.0f;
+    const float fth = 6.0f / 29.0f;
+    const float r500 = 1.0f / 500.0f, r200 = 1.0f / 200.0f, r7787 = 1.0f / 7.787f;
+    const float fx = f_add(f_mul(a, r500), fy);
+    const float fz = f_sub(fy, f_mul(b, r200));
+    const float X = fx <= fth ? f_mul(f_sub(fx, c16), r7787) : f_mul(f_mul(fx, fx), fx);
+    const float Z = fz <= fth ? f_mul(f_sub(fz, c16), r7787) : f_mul(f_mul(fz, fz), fz);
+    r = f_add(f_mul(K.C[0], X), f_add(y1, f_mul(K.C[2], Z)));
+    g = f_add(f_mul(K.C[3], X), f_add(y4, f_mul(K.C[5], Z)));
+    bl = f_add(f_mul(K.C[6], X), f_add(y7, f_mul(K.C[8], Z)));
+}
+
 // `tail` selects OpenCV's scalar-tail sequence (last W % 8 pixels of every row): true divisions and
 // ((C0*X + C1*y) + C2*Z); the SIMD body multiplies by f32 reciprocals and uses C0*X + (C1*y + C2*Z).
 // Returns the three *linear* channels, unclipped.
@@ -230,22 +265,8 @@ GDT_HD void lab2lin(float L, float a, float b, bool tail, const Lab2RgbConst& K,
     const float fth = 6.0f / 29.0f;
     float y, fy, fx, fz, X, Z;
     if (!tail) {
-        const float r903 = 1.0f / 903.3f, r116 = 1.0f / 116.0f, r500 = 1.0f / 500.0f, r200 = 1.0f / 200.0f,
-                    r7787 = 1.0f / 7.787f;
-        if (L <= 8.0f) {
-            y = f_mul(L, r903);
-            fy = f_add(f_mul(y, 7.787f), c16);
-        } else {
-            fy = f_mul(f_add(L, 16.0f), r116);
-            y = f_mul(f_mul(fy, fy), fy);
-        }
-        fx = f_add(f_mul(a, r500), fy);
-        fz = f_sub(fy, f_mul(b, r200));
-        X = fx <= fth ? f_mul(f_sub(fx, c16), r7787) : f_mul(f_mul(fx, fx), fx);
-        Z = fz <= fth ? f_mul(f_sub(fz, c16), r7787) : f_mul(f_mul(fz, fz), fz);
-        r = f_add(f_mul(K.C[0], X), f_add(f_mul(K.C[1], y), f_mul(K.C[2], Z)));
-        g = f_add(f_mul(K.C[3], X), f_add(f_mul(K.C[4], y), f_mul(K.C[5], Z)));
-        bl = f_add(f_mul(K.C[6], X), f_add(f_mul(K.C[7], y), f_mul(K.C[8], Z)));
+        lab_fy_body(L, y, fy);
+        lab2lin_body_from_fy(fy, f_mul(K.C[1], y), f_mul(K.C[4], y), f_mul(K.C[7], y), a, b, K, r, g, bl);
     } else {
         if (L <= 8.0f) {
             y = f_div(L, 903.3f);
@@ -335,19 +356,34 @@ inline void build_lab2rgb_const(Lab2RgbConst& K) {
         for (int j = 0; j < 3; ++j) K.C[k * 3 + j] = (float)(M[k * 3 + j] * wp[j]);
 }
 
+// Lightness half of Lab->RGB per CLAHE output byte v (SIMD-body sequence): {fy, C[1]*y, C[4]*y, C[7]*y} of
+// L = (float(v) / 255) * 100. tab: 256 * 4 floats. Built with the same functions the kernels inline.
+inline void build_fy_table(const Lab2RgbConst& K, float* tab) {
+    for (int v = 0; v < 256; ++v) {
+        float y, fy;
+        lab_fy_body(lab_l_from_u8(v), y, fy);
+        tab[v * 4 + 0] = fy;
+        tab[v * 4 + 1] = f_mul(K.C[1], y);
+        tab[v * 4 + 2] = f_mul(K.C[4], y);
+        tab[v * 4 + 3] = f_mul(K.C[7], y);
+    }
+}
+
 // Re-pack the 33^3 x 3 lattice table into per-cell words (see lab_trilinear):
-//   lutL [cell][dxdy]        4 words  = 16 B per cell   (pass A: lightness only)
-//   lutAB[cell][ch(a,b)][dxdy] 8 words = 32 B per cell  (pass B: chroma)
-// cell = (tr*32 + tg)*32 + tb, tr/tg/tb in 0..31.
+//   lutL [cell][dxdy]          4 words = 16 B per cell   (lightness)
+//   lutAB[cell][ch(a,b)][dxdy] 8 words = 32 B per cell   (chroma)
+// cell = lab_cell_index(tr, tg, tb), tr/tg/tb in 0..32; neighbour indices are clamped to 32 (weight 0 there).
 inline void pack_lab_lut(const int16_t* lut33, uint32_t* lutL, uint32_t* lutAB) {
-    for (int tr = 0; tr < 32; ++tr)
-        for (int tg = 0; tg < 32; ++tg)
-            for (int tb = 0; tb < 32; ++tb) {
-                const int cell = (tr * 32 + tg) * 32 + tb;
+    for (int tr = 0; tr < 33; ++tr)
+        for (int tg = 0; tg < 33; ++tg)
+            for (int tb = 0; tb < 33; ++tb) {
+                const int cell = lab_cell_index(tr, tg, tb);
+                const int tb1 = tb < 32 ? tb + 1 : 32;
                 for (int dx = 0; dx < 2; ++dx)
                     for (int dy = 0; dy < 2; ++dy) {
-                        const int16_t* p0 = lut33 + (((tr + dx) * 33 + (tg + dy)) * 33 + tb) * 3;
-                        const int16_t* p1 = p0 + 3;
+                        const int r1 = tr + dx < 32 ? tr + dx : 32, g1 = tg + dy < 32 ? tg + dy : 32;
+                        const int16_t* p0 = lut33 + ((r1 * 33 + g1) * 33 + tb) * 3;
+                        const int16_t* p1 = lut33 + ((r1 * 33 + g1) * 33 + tb1) * 3;
                         const int q = dx * 2 + dy;
                         lutL[cell * 4 + q] = (uint32_t)(uint16_t)p0[0] | ((uint32_t)(uint16_t)p1[0] << 16);
                         lutAB[cell * 8 + q] = (uint32_t)(uint16_t)p0[1] | ((uint32_t)(uint16_t)p1[1] << 16);

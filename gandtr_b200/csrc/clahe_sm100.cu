@@ -4,15 +4,16 @@
 // (mdir/components/data/wrapper.py:325-348), bit-exact against the reference's OpenCV 4.13.0 path.
 //
 // Two launches per batch, both streaming with coalesced 16-byte accesses:
-//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> lattice cell + fractions (integer arithmetic) -> Q14
-//           lightness (one 16 B gather from the L2-resident packed lattice table, dp2a trilinear) -> uint8 L8 scratch
-//           + 4-byte cell code scratch + 256-bin shared-memory histogram (bank-skewed copies per warp) -> clip,
-//           redistribute, prefix sum -> tile LUT (transposed rows).
+//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> lattice cell + fractions (integer arithmetic, one
+//           multiply-shift per channel) -> the three Q14 Lab channels by ONE integer trilinear interpolation with shared
+//           weights (lightness record through the LSU pipe, chroma records through the texture pipe; dp2a) -> uint8 L8
+//           scratch (integer formula) + packed 2 x 16-bit chroma scratch + 256-bin shared-memory histogram
+//           (bank-skewed copies per warp) -> clip, redistribute, prefix sum -> tile LUT (transposed rows).
 //   pass B  clahe_apply_kernel  one CTA per (image, row band, 1024-px column chunk): LUT rows of the band and the
-//           inverse-gamma spline staged in shared memory, per pixel: bilinear LUT blend -> chroma (one 256-bit gather
-//           addressed by the cell code) -> Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores.
+//           inverse-gamma spline staged in shared memory, per pixel: bilinear LUT blend -> Lab->RGB (lightness half from
+//           a 256-entry table) -> spline inverse gamma -> normalise -> planar float4 stores. No lattice access.
 // Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 5 B/px written by A and
-// read by B (the input itself is read once).
+// read by B (the input itself is read once, and quantised / interpolated once).
 #include <stdlib.h>
 
 #include "clahe_math.cuh"
@@ -21,16 +22,22 @@
 namespace gdt {
 
 struct ClaheTables {
-    uint4* lutL = nullptr;     // [32768]      packed lightness corners
-    uint4* lutAB = nullptr;    // [32768][2]   packed chroma corners (a words, b words)
+    uint4* lutL = nullptr;     // [33^3]      packed lightness corners
+    uint4* lutAB = nullptr;    // [33^3][2]   packed chroma corners (a words, b words)
     float4* spline = nullptr;  // [1024]
-    cudaTextureObject_t texL = 0, texAB = 0, texSpline = 0;   // the same tables behind the texture path (point fetch)
+    float4* fytab = nullptr;   // [256]       {fy, C1*y, C4*y, C7*y} per CLAHE output byte (build_fy_table)
+    cudaTextureObject_t texL = 0, texAB = 0, texSpline = 0, texFy = 0;   // the same tables behind the texture path
     Lab2RgbConst K;
     float spline_host[4096];
+    float fy_host[1024];
     bool ready = false;
 };
 
 static ClaheTables g_tables[32];
+
+// defaults of the pass-B A/B switches (see clahe_launch)
+constexpr int kDefaultSplTex = 0;
+constexpr int kDefaultFyTex = 1;
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -51,7 +58,7 @@ __device__ __forceinline__ void cell_from_u8(int r, int g, int b, int& cell, int
     lab_cell_u8(r, tr, fr);
     lab_cell_u8(g, tg, fg);
     lab_cell_u8(b, tb, fb);
-    cell = (tr << 10) | (tg << 5) | tb;
+    cell = lab_cell_index(tr, tg, tb);
 }
 
 __device__ __forceinline__ void cell_from_f32(float r, float g, float b, const Norm3& in, int& cell, int& fr, int& fg,
@@ -61,24 +68,17 @@ __device__ __forceinline__ void cell_from_f32(float r, float g, float b, const N
     lab_cell(clamp01(f_add(f_mul(r, in.std[0]), in.mean[0])), tr, fr);
     lab_cell(clamp01(f_add(f_mul(g, in.std[1]), in.mean[1])), tg, fg);
     lab_cell(clamp01(f_add(f_mul(b, in.std[2]), in.mean[2])), tb, fb);
-    cell = (tr << 10) | (tg << 5) | tb;
+    cell = lab_cell_index(tr, tg, tb);
 }
 
-// Per-pixel "cell code" written by pass A and consumed by pass B (so the quantisation of the input pixel happens once):
-// bits [0,15) lattice cell, [15,20) fr, [20,25) fg, [25,30) fb  (fractions are 0..16)
-__device__ __forceinline__ uint32_t pack_code(int cell, int fr, int fg, int fb) {
-    return (uint32_t)cell | ((uint32_t)fr << 15) | ((uint32_t)fg << 20) | ((uint32_t)fb << 25);
-}
-__device__ __forceinline__ void unpack_code(uint32_t c, int& cell, int& fr, int& fg, int& fb) {
-    cell = (int)(c & 0x7fffu);
-    fr = (int)((c >> 15) & 31u);
-    fg = (int)((c >> 20) & 31u);
-    fb = (int)(c >> 25);
-}
-
-__device__ __forceinline__ int l8_from_cell(const uint4* __restrict__ lutL, int cell, int fr, int fg, int fb) {
-    const uint4 w = __ldg(lutL + cell);
-    return lab_l8_fast(lab_trilinear(w.x, w.y, w.z, w.w, fr, fg, fb));
+// Per-pixel scratch written by pass A and consumed by pass B: the CLAHE input byte and the two Q14 chroma channels
+// packed as a | b << 16 (each in [0, 16384]). The input pixel is quantised and interpolated exactly once.
+__device__ __forceinline__ void lab_from_records(const uint4& wl, const uint4& wa, const uint4& wb, int fr, int fg, int fb,
+                                                 int& l8, uint32_t& ab) {
+    l8 = lab_l8_int(lab_trilinear(wl.x, wl.y, wl.z, wl.w, fr, fg, fb));
+    const int oa = lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr, fg, fb);
+    const int ob = lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr, fg, fb);
+    ab = (uint32_t)oa | ((uint32_t)ob << 16);
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -109,12 +109,15 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
                  : "l"(lutAB + cell * 2));
 }
 
-template <bool U8>
+// `gq`, `gr` = 256 / gw, 256 % gw (gw = 4-pixel groups per tile row): the vectorised loop walks (row, group) incrementally,
+// no division per step. TEXAB: chroma records through the texture pipe (idle otherwise), lightness through the LSU pipe.
+template <bool U8, bool TEXAB>
 __global__ void __launch_bounds__(256)
-clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ codes,
+clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w,
-                  int grid, int th, int tw, int clip, float lut_scale, int vec_ok, const uint4* __restrict__ lutL,
-                  Norm3 in_norm, cudaTextureObject_t texL, int texmode) {
+                  int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
+                  const uint4* __restrict__ lutL, const uint4* __restrict__ lutAB, Norm3 in_norm,
+                  cudaTextureObject_t texAB) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
@@ -128,58 +131,56 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
     const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
     const float* inf = (const float*)in_ + (size_t)img * plane * 3;
     uint8_t* l8img = L8 + (size_t)img * plane;
-    uint32_t* codeimg = codes + (size_t)img * plane;
+    uint32_t* abimg = AB + (size_t)img * plane;
 
     if (vec_ok) {
         // tile fully inside the image, 4 consecutive pixels per thread
         const int gw = tw >> 2;
-        const int ngroups = th * gw;
-        for (int base = 0; base < ngroups; base += 256) {
-            const int gidx = base + tid;
-            const bool valid = gidx < ngroups;
-            int v[4] = {256, 256, 256, 256};
-            if (valid) {
-                const int row = gidx / gw, c4 = gidx - row * gw;
-                const int y = ty * th + row, x0 = tx * tw + (c4 << 2);
-                const size_t p = (size_t)y * w + x0;
-                if (U8) {
-                    const uint32_t* src = (const uint32_t*)(in8 + p * 3);
-                    const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
-                    const int rr[4] = {(int)(a0 & 255), (int)(a0 >> 24), (int)((a1 >> 16) & 255), (int)((a2 >> 8) & 255)};
-                    const int gg[4] = {(int)((a0 >> 8) & 255), (int)(a1 & 255), (int)(a1 >> 24), (int)((a2 >> 16) & 255)};
-                    const int bb[4] = {(int)((a0 >> 16) & 255), (int)((a1 >> 8) & 255), (int)(a2 & 255), (int)(a2 >> 24)};
-                    int cell[4], fr[4], fg[4], fb[4];
-                    uint4 wv[4];
+        int row = tid / gw, c4 = tid - row * gw;
+        for (; row < th; ) {
+            const int y = ty * th + row, x0 = tx * tw + (c4 << 2);
+            const size_t p = (size_t)y * w + x0;
+            int cell[4], fr[4], fg[4], fb[4];
+            if (U8) {
+                const uint32_t* src = (const uint32_t*)(in8 + p * 3);
+                const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+                const int rr[4] = {(int)(a0 & 255), (int)(a0 >> 24), (int)((a1 >> 16) & 255), (int)((a2 >> 8) & 255)};
+                const int gg[4] = {(int)((a0 >> 8) & 255), (int)(a1 & 255), (int)(a1 >> 24), (int)((a2 >> 16) & 255)};
+                const int bb[4] = {(int)((a0 >> 16) & 255), (int)((a1 >> 8) & 255), (int)(a2 & 255), (int)(a2 >> 24)};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) cell_from_u8(rr[i], gg[i], bb[i], cell[i], fr[i], fg[i], fb[i]);
+                for (int i = 0; i < 4; ++i) cell_from_u8(rr[i], gg[i], bb[i], cell[i], fr[i], fg[i], fb[i]);
+            } else {
+                const float4 r4 = __ldg((const float4*)(inf + p));
+                const float4 g4 = __ldg((const float4*)(inf + plane + p));
+                const float4 b4 = __ldg((const float4*)(inf + 2 * plane + p));
+                const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w},
+                            bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)                                     // four gathers in flight
-                        wv[i] = (texmode & 4) ? tex1Dfetch<uint4>(texL, cell[i]) : __ldg(lutL + cell[i]);
-                    *(uint4*)(codeimg + p) = make_uint4(pack_code(cell[0], fr[0], fg[0], fb[0]), pack_code(cell[1], fr[1], fg[1], fb[1]),
-                                                        pack_code(cell[2], fr[2], fg[2], fb[2]), pack_code(cell[3], fr[3], fg[3], fb[3]));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        v[i] = lab_l8_fast(lab_trilinear(wv[i].x, wv[i].y, wv[i].z, wv[i].w, fr[i], fg[i], fb[i]));
-                } else {
-                    const float4 r4 = __ldg((const float4*)(inf + p));
-                    const float4 g4 = __ldg((const float4*)(inf + plane + p));
-                    const float4 b4 = __ldg((const float4*)(inf + 2 * plane + p));
-                    const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w},
-                                bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                    uint32_t cd[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        int cell, fr, fg, fb;
-                        cell_from_f32(rr[i], gg[i], bb[i], in_norm, cell, fr, fg, fb);
-                        cd[i] = pack_code(cell, fr, fg, fb);
-                        v[i] = l8_from_cell(lutL, cell, fr, fg, fb);
-                    }
-                    *(uint4*)(codeimg + p) = make_uint4(cd[0], cd[1], cd[2], cd[3]);
-                }
-                *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+                for (int i = 0; i < 4; ++i) cell_from_f32(rr[i], gg[i], bb[i], in_norm, cell[i], fr[i], fg[i], fb[i]);
             }
+            uint4 wl[4], wa[4], wb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                                   // twelve gathers in flight
+                wl[i] = __ldg(lutL + cell[i]);
+                if (TEXAB) {
+                    wa[i] = tex1Dfetch<uint4>(texAB, cell[i] * 2);
+                    wb[i] = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
+                } else {
+                    ld_cell_ab(lutAB, cell[i], wa[i], wb[i]);
+                }
+            }
+            int v[4];
+            uint32_t ab[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lab_from_records(wl[i], wa[i], wb[i], fr[i], fg[i], fb[i], v[i], ab[i]);
+            *(uint4*)(abimg + p) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
+            *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
 #pragma unroll
             for (int i = 0; i < 4; ++i) hist_add(hist, v[i]);
+            // next (row, group) of this thread: + 256 groups
+            row += gq;
+            c4 += gr;
+            if (c4 >= gw) { c4 -= gw; ++row; }
         }
     } else {
         // generic: extended (REFLECT_101-padded) tile, one pixel per thread per step
@@ -198,10 +199,14 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                 } else {
                     cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
                 }
-                v = l8_from_cell(lutL, cell, fr, fg, fb);
+                const uint4 wl = __ldg(lutL + cell);
+                uint4 wa, wb;
+                ld_cell_ab(lutAB, cell, wa, wb);
+                uint32_t ab;
+                lab_from_records(wl, wa, wb, fr, fg, fb, v, ab);
                 if (ey < h && ex < w) {
                     l8img[p] = (uint8_t)v;
-                    codeimg[p] = pack_code(cell, fr, fg, fb);
+                    abimg[p] = ab;
                 }
             }
             hist_add(hist, v);
@@ -255,14 +260,18 @@ struct NormFast {
 };
 
 // FAST = the common configuration compiled without per-pixel mode tests: width a multiple of 8 (no OpenCV scalar-tail
-// pixels), chroma lattice through the texture pipe, spline through shared memory, divider-free normalisation.
-template <int MINB, bool FAST>
+// pixels), 8-byte LUT rows, divider-free normalisation, 16-byte aligned rows.
+// SPLTEX = how many of the three inverse-gamma spline lookups go through the texture pipe instead of shared memory
+// (pass B is bound by shared-memory wavefronts + issue; the texture pipe is idle since pass A took over the lattice).
+// FYTEX  = lightness half of Lab->RGB ({fy, C1*y, C4*y, C7*y}, a function of the CLAHE output byte) fetched from the
+// 256-entry table through the texture pipe instead of being recomputed (FAST only).
+template <int MINB, bool FAST, int SPLTEX, bool FYTEX>
 __global__ void __launch_bounds__(256, MINB)
-clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
+clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
-                   int vec_ok, const uint4* __restrict__ lutAB, const float4* __restrict__ spline, Lab2RgbConst K,
-                   NormFast on, cudaTextureObject_t texAB, cudaTextureObject_t texSpline, int texmode_) {
-    const int texmode = FAST ? 2 : texmode_;
+                   int vec_ok_, const float4* __restrict__ spline, Lab2RgbConst K,
+                   NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy) {
+    const int vec_ok = FAST ? 1 : vec_ok_;
     if (FAST) on.fast = 1;
     extern __shared__ __align__(16) uint8_t smem[];
     // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
@@ -270,7 +279,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
     float2* spl_fb = (float2*)smem;              // [1024] (f, b)
     float2* spl_cd = (float2*)(smem + 1024 * 8); // [1024] (c, d)
     uint2* luts = (uint2*)(smem + 1024 * 16);    // [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
-    const int lsh = lut_row_shift(grid);
+    const int lsh = FAST ? 3 : lut_row_shift(grid);
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const int y0 = blockIdx.y * rows_per_cta;
@@ -281,10 +290,12 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
         const int nwords = ((ty_hi - ty_lo + 1) * 256) << (lsh - 3);
         const uint2* src = (const uint2*)(lutT + ((((size_t)img * grid + ty_lo) * 256) << lsh));
         for (int i = tid; i < nwords; i += 256) luts[i] = __ldg(src + i);
-        for (int i = tid; i < 1024; i += 256) {
-            const float4 sgm = __ldg(spline + i);
-            spl_fb[i] = make_float2(sgm.x, sgm.y);
-            spl_cd[i] = make_float2(sgm.z, sgm.w);
+        if (SPLTEX < 3) {
+            for (int i = tid; i < 1024; i += 256) {
+                const float4 sgm = __ldg(spline + i);
+                spl_fb[i] = make_float2(sgm.x, sgm.y);
+                spl_cd[i] = make_float2(sgm.z, sgm.w);
+            }
         }
     }
     __syncthreads();
@@ -303,17 +314,18 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
     }
 
     const size_t plane = (size_t)h * w;
-    const uint32_t* codeimg = codes + (size_t)img * plane;
+    const uint32_t* abimg = AB + (size_t)img * plane;
     const uint8_t* l8img = L8 + (size_t)img * plane;
     float* outimg = out + (size_t)img * plane * 3;
     const uint8_t* lut_bytes = (const uint8_t*)luts;
 
-    // software prefetch (vectorised path): the next row's codes and lightness bytes are requested before this row's arithmetic
+    // software prefetch (vectorised path): the next row's chroma words and lightness bytes are requested before this
+    // row's arithmetic
     uint4 nxc = make_uint4(0u, 0u, 0u, 0u);
     uint32_t nxl = 0;
     if (vec_ok) {
         const size_t p = (size_t)y0 * w + x0;
-        nxc = __ldg((const uint4*)(codeimg + p));
+        nxc = __ldg((const uint4*)(abimg + p));
         nxl = __ldg((const uint32_t*)(l8img + p));
     }
     for (int y = y0; y < y1; ++y) {
@@ -322,27 +334,25 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
         const uint8_t* lrow2 = lut_bytes + (((size_t)(ay.i2 - ty_lo) * 256) << lsh);
         const size_t p = (size_t)y * w + x0;
 
-        int cell[4], fr[4], fg[4], fb[4], v[4];
+        int v[4];
+        uint32_t ab[4];
         if (vec_ok) {
             const uint32_t lw = nxl;
             const uint4 cw = nxc;
             if (y + 1 < y1) {
-                nxc = __ldg((const uint4*)(codeimg + p + w));
+                nxc = __ldg((const uint4*)(abimg + p + w));
                 nxl = __ldg((const uint32_t*)(l8img + p + w));
             }
             v[0] = lw & 255; v[1] = (lw >> 8) & 255; v[2] = (lw >> 16) & 255; v[3] = lw >> 24;
-            unpack_code(cw.x, cell[0], fr[0], fg[0], fb[0]);
-            unpack_code(cw.y, cell[1], fr[1], fg[1], fb[1]);
-            unpack_code(cw.z, cell[2], fr[2], fg[2], fb[2]);
-            unpack_code(cw.w, cell[3], fr[3], fg[3], fb[3]);
+            ab[0] = cw.x; ab[1] = cw.y; ab[2] = cw.z; ab[3] = cw.w;
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (i < npx) {
                     v[i] = l8img[p + i];
-                    unpack_code(codeimg[p + i], cell[i], fr[i], fg[i], fb[i]);
+                    ab[i] = abimg[p + i];
                 } else {
-                    v[i] = 0; cell[i] = 0; fr[i] = fg[i] = fb[i] = 0;
+                    v[i] = 0; ab[i] = 0;
                 }
             }
         }
@@ -350,17 +360,10 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
         float o[3][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            // chroma
-            uint4 wa, wb;
-            if (texmode & 2) {          // texture pipe instead of the LSU pipe
-                wa = tex1Dfetch<uint4>(texAB, cell[i] * 2);
-                wb = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
-            } else {
-                ld_cell_ab(lutAB, cell[i], wa, wb);
-            }
-            const float a2 = lab_chroma_fast(lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr[i], fg[i], fb[i]));
-            const float b2 = lab_chroma_fast(lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr[i], fg[i], fb[i]));
-            // lightness through CLAHE: the two 16-byte rows hold the LUT value of every tile column at level v
+            // chroma: Q14 -> the a / b handed to LAB2RGB
+            const float a2 = lab_chroma_fast((int)(ab[i] & 0xffffu));
+            const float b2 = lab_chroma_fast((int)(ab[i] >> 16));
+            // lightness through CLAHE: the two LUT rows hold the LUT value of every tile column at level v
             int l11, l12, l21, l22;
             if (lsh == 3) {
                 // 8-byte rows: one 64-bit load per tile row, the two tile-column bytes picked by one byte permute
@@ -376,34 +379,30 @@ clahe_apply_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict
                 l21 = r2[ax[i].i1]; l22 = r2[ax[i].i2];
             }
             const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
-            const float Ln = lab_l_from_u8_fast(dst);
             float lr, lg, lb;
-            lab2lin(Ln, a2, b2, FAST ? false : (x0 + i) >= wbody, K, lr, lg, lb);
-            int ir, ig, ib;
-            const float xr = spline_index(lr, ir), xg = spline_index(lg, ig), xb = spline_index(lb, ib);
-            float er, eg, eb;
-            if (texmode & 1) {          // spline segments through the texture pipe: no shared-memory bank conflicts
-                const float4 sr = tex1Dfetch<float4>(texSpline, ir), sg = tex1Dfetch<float4>(texSpline, ig),
-                             sb = tex1Dfetch<float4>(texSpline, ib);
-                er = spline_eval(xr, sr.x, sr.y, sr.z, sr.w);
-                eg = spline_eval(xg, sg.x, sg.y, sg.z, sg.w);
-                eb = spline_eval(xb, sb.x, sb.y, sb.z, sb.w);
+            if (FAST && FYTEX) {
+                const float4 fy = tex1Dfetch<float4>(texFy, dst);
+                lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
             } else {
-                const float2 r01 = spl_fb[ir], g01 = spl_fb[ig], b01 = spl_fb[ib];
-                const float2 r23 = spl_cd[ir], g23 = spl_cd[ig], b23 = spl_cd[ib];
-                er = spline_eval(xr, r01.x, r01.y, r23.x, r23.y);
-                eg = spline_eval(xg, g01.x, g01.y, g23.x, g23.y);
-                eb = spline_eval(xb, b01.x, b01.y, b23.x, b23.y);
+                lab2lin(lab_l_from_u8_fast(dst), a2, b2, FAST ? false : (x0 + i) >= wbody, K, lr, lg, lb);
             }
-            if (on.fast) {
-                o[0][i] = normalize_px_fast(er, on.mean[0], on.std[0], on.rstd[0]);
-                o[1][i] = normalize_px_fast(eg, on.mean[1], on.std[1], on.rstd[1]);
-                o[2][i] = normalize_px_fast(eb, on.mean[2], on.std[2], on.rstd[2]);
-            } else {
-                o[0][i] = normalize_px(er, on.mean[0], on.std[0]);
-                o[1][i] = normalize_px(eg, on.mean[1], on.std[1]);
-                o[2][i] = normalize_px(eb, on.mean[2], on.std[2]);
+            int ix[3];
+            const float xs[3] = {spline_index(lr, ix[0]), spline_index(lg, ix[1]), spline_index(lb, ix[2])};
+            float e[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c < SPLTEX) {       // texture pipe: no shared-memory bank conflicts
+                    const float4 sg = tex1Dfetch<float4>(texSpline, ix[c]);
+                    e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
+                } else {
+                    const float2 s01 = spl_fb[ix[c]], s23 = spl_cd[ix[c]];
+                    e[c] = spline_eval(xs[c], s01.x, s01.y, s23.x, s23.y);
+                }
             }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                o[c][i] = on.fast ? normalize_px_fast(e[c], on.mean[c], on.std[c], on.rstd[c])
+                                  : normalize_px(e[c], on.mean[c], on.std[c]);
         }
         if (vec_ok) {
 #pragma unroll
@@ -460,7 +459,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
     Workspace W(ws, ws_bytes);
     uint8_t* L8 = W.take<uint8_t>((size_t)n * h * w);
-    uint32_t* codes = W.take<uint32_t>((size_t)n * h * w);
+    uint32_t* AB = W.take<uint32_t>((size_t)n * h * w);
     uint8_t* luts = W.take<uint8_t>(((size_t)n * grid * 256) << lut_row_shift(grid));
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
@@ -468,15 +467,22 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
     const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
 
-    // Which table gathers take the texture pipe instead of the LSU pipe (bit 0 spline, 1 chroma lattice, 2 lightness
-    // lattice). Pass B is bound by LSU wavefronts (shared-memory spline / LUT lookups + the scattered lattice gather):
-    // moving the chroma gather to the otherwise idle texture pipe measured -6 % on B200, the other two cost time
-    // (profiles/k1_texpipe_ab_r1m.log). GDT_DEBUG_K1_TEX overrides for A/B runs.
-    static int texmode = -1;
-    if (texmode < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texmode = e ? atoi(e) : 2; }
+    // A/B switches (profiles/k1_v2_ab_r1q.log): GDT_DEBUG_K1_TEX bit 0 = pass A fetches the chroma lattice records through
+    // the texture pipe; GDT_DEBUG_K1_SPLTEX = 0..3 spline lookups of pass B through the texture pipe; GDT_DEBUG_K1_FYTEX =
+    // lightness half of Lab->RGB from the 256-entry table (texture pipe) instead of recomputing it.
+    static int texab = -1, spltex = -1, fytex = -1;
+    if (texab < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texab = e ? (atoi(e) & 1) : 1; }
+    if (spltex < 0) { const char* e = getenv("GDT_DEBUG_K1_SPLTEX"); spltex = e ? atoi(e) : kDefaultSplTex; if (spltex < 0 || spltex > 3) spltex = kDefaultSplTex; }
+    if (fytex < 0) { const char* e = getenv("GDT_DEBUG_K1_FYTEX"); fytex = e ? (atoi(e) & 1) : kDefaultFyTex; }
     dim3 gridA(grid * grid, n);
-    clahe_hist_kernel<U8><<<gridA, 256, 0, stream>>>(in, L8, codes, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
-                                                      vec_hist, T->lutL, in_norm, T->texL, texmode);
+    const int gw = vec_hist ? (g.tw >> 2) : 1;
+    const int gq = 256 / gw, gr = 256 % gw;
+    if (texab)
+        clahe_hist_kernel<U8, true><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
+                                                                vec_hist, gq, gr, T->lutL, T->lutAB, in_norm, T->texAB);
+    else
+        clahe_hist_kernel<U8, false><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
+                                                                 vec_hist, gq, gr, T->lutL, T->lutAB, in_norm, T->texAB);
     GDT_LAUNCH_CHECK();
 
     // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
@@ -501,16 +507,26 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
     // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
     if (smem > 48 * 1024)
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-    if ((w & 7) == 0 && texmode == 2 && on.fast && smem <= 48 * 1024)
-        clahe_apply_kernel<4, true><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
-                                                                 vec_apply, T->lutAB, T->spline, T->K, on, T->texAB,
-                                                                 T->texSpline, texmode);
-    else
-        clahe_apply_kernel<4, false><<<gridB, 256, smem, stream>>>(codes, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, rows,
-                                                                  vec_apply, T->lutAB, T->spline, T->K, on, T->texAB,
-                                                                  T->texSpline, texmode);
+#define GDT_APPLY(FAST_, S_, F_)                                                                                         \
+    clahe_apply_kernel<4, FAST_, S_, F_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, \
+                                                                        rows, vec_apply, T->spline, T->K, on, T->texSpline, T->texFy)
+    if ((w & 7) == 0 && vec_apply && grid <= 8 && on.fast && smem <= 48 * 1024) {
+        switch (spltex * 2 + fytex) {
+            case 0: GDT_APPLY(true, 0, false); break;
+            case 1: GDT_APPLY(true, 0, true); break;
+            case 2: GDT_APPLY(true, 1, false); break;
+            case 3: GDT_APPLY(true, 1, true); break;
+            case 4: GDT_APPLY(true, 2, false); break;
+            case 5: GDT_APPLY(true, 2, true); break;
+            case 6: GDT_APPLY(true, 3, false); break;
+            default: GDT_APPLY(true, 3, true); break;
+        }
+    } else {
+        GDT_APPLY(false, 0, false);
+    }
+#undef GDT_APPLY
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
@@ -554,13 +570,14 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     ClaheTables& T = g_tables[dev];
     if (T.ready) return GDT_OK;
 
-    const size_t ncell = 32 * 32 * 32;
+    const size_t ncell = kLabCells;
     uint32_t* hL = (uint32_t*)malloc(ncell * 4 * sizeof(uint32_t));
     uint32_t* hAB = (uint32_t*)malloc(ncell * 8 * sizeof(uint32_t));
     if (!hL || !hAB) { free(hL); free(hAB); return GDT_ERR_INVALID_ARGUMENT; }
     pack_lab_lut(host_rgb2lab_lut, hL, hAB);
     build_inv_gamma_spline(T.spline_host);
     build_lab2rgb_const(T.K);
+    build_fy_table(T.K, T.fy_host);
     int rc = GDT_OK;
     auto up = [&](void** dptr, const void* src, size_t bytes) -> int {
         cudaError_t e = cudaMalloc(dptr, bytes);
@@ -572,6 +589,7 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     if (rc == GDT_OK) rc = up((void**)&T.lutL, hL, ncell * 16);
     if (rc == GDT_OK) rc = up((void**)&T.lutAB, hAB, ncell * 32);
     if (rc == GDT_OK) rc = up((void**)&T.spline, T.spline_host, 4096 * sizeof(float));
+    if (rc == GDT_OK) rc = up((void**)&T.fytab, T.fy_host, 1024 * sizeof(float));
     free(hL);
     free(hAB);
     auto make_tex = [&](cudaTextureObject_t* tex, void* ptr, size_t bytes, bool is_float) -> int {
@@ -594,6 +612,7 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     if (rc == GDT_OK) rc = make_tex(&T.texL, T.lutL, ncell * 16, false);
     if (rc == GDT_OK) rc = make_tex(&T.texAB, T.lutAB, ncell * 32, false);
     if (rc == GDT_OK) rc = make_tex(&T.texSpline, T.spline, 4096 * sizeof(float), true);
+    if (rc == GDT_OK) rc = make_tex(&T.texFy, T.fytab, 1024 * sizeof(float), true);
     if (rc == GDT_OK) T.ready = true;
     return rc;
 }

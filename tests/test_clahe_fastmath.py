@@ -1,6 +1,8 @@
 """The divider-free / table-free formulas of gandtr_b200/csrc/clahe_math.cuh restated with exact rational arithmetic and
 checked against the reference's float32 expressions over their WHOLE domains:
   lab_cell_u8      (v*32768 + 255) // 510          == cvRound(float32(v)/255 * 16384)            v in [0, 255]
+                   (v*514 + 4) >> 8                == cvRound(...) >> 5   (t << 4 | f)            v in [0, 255]
+  lab_l8_int       (o*255) >> 14                   == trunc(((o*2^-14*100)/100) * 255)            o in [0, 16384]
   lab_l8_fast      div_by_const<1>(L, 100)         == L / 100                                     o in [0, 16384]
   lab_chroma_fast  div_by_const<1>(o/64, 255)      == (a + 128) / 255                             o in [0, 16384]
   lab_l_from_u8    div_by_const<1>(v, 255)         == float32(v) / 255                            v in [0, 255]
@@ -38,6 +40,13 @@ def test_u8_cell_quantisation_integer_formula():
     for v in range(256):
         ref = int(np.rint((f32(v) / f32(255)) * f32(16384)))
         assert (v * 32768 + 255) // 510 == ref
+        assert (v * 514 + 4) >> 8 == ref >> 5          # lattice index t = ref >> 9 (0..32), fraction f = (ref >> 5) & 15
+
+
+def test_lightness_byte_integer_formula():
+    for o in range(0, 16385):
+        L = (f32(o) * f32(1.0 / 16384.0)) * f32(100)
+        assert int((L / f32(100)) * f32(255)) == (o * 255) >> 14
 
 
 def test_lightness_and_chroma_divisions_exact_on_their_domains():
