@@ -35,9 +35,10 @@ struct ClaheTables {
 
 static ClaheTables g_tables[32];
 
-// defaults of the pass-B A/B switches (see clahe_launch)
-constexpr int kDefaultSplTex = 0;
-constexpr int kDefaultFyTex = 1;
+// A/B switches (gdt_debug_k1_config): texab = pass A fetches the chroma lattice records through the texture pipe;
+// spltex = 0..3 spline lookups of pass B through the texture pipe; fytex = lightness half of Lab->RGB from the 256-entry
+// table (texture pipe) instead of recomputing it. Every combination is bit-identical; only the pipe balance differs.
+static int g_k1_texab = 1, g_k1_spltex = 0, g_k1_fytex = 1;
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -467,13 +468,8 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
     const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
 
-    // A/B switches (profiles/k1_v2_ab_r1q.log): GDT_DEBUG_K1_TEX bit 0 = pass A fetches the chroma lattice records through
-    // the texture pipe; GDT_DEBUG_K1_SPLTEX = 0..3 spline lookups of pass B through the texture pipe; GDT_DEBUG_K1_FYTEX =
-    // lightness half of Lab->RGB from the 256-entry table (texture pipe) instead of recomputing it.
-    static int texab = -1, spltex = -1, fytex = -1;
-    if (texab < 0) { const char* e = getenv("GDT_DEBUG_K1_TEX"); texab = e ? (atoi(e) & 1) : 1; }
-    if (spltex < 0) { const char* e = getenv("GDT_DEBUG_K1_SPLTEX"); spltex = e ? atoi(e) : kDefaultSplTex; if (spltex < 0 || spltex > 3) spltex = kDefaultSplTex; }
-    if (fytex < 0) { const char* e = getenv("GDT_DEBUG_K1_FYTEX"); fytex = e ? (atoi(e) & 1) : kDefaultFyTex; }
+    // A/B switches, see gdt_debug_k1_config (profiles/k1_v2_ab_r1q.log)
+    const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex;
     dim3 gridA(grid * grid, n);
     const int gw = vec_hist ? (g.tw >> 2) : 1;
     const int gq = 256 / gw, gr = 256 % gw;
@@ -554,6 +550,14 @@ extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, 
     volatile float r = 1.0f / b;
     div_check_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(b, r, lo_bits, hi_bits, mismatches_dev);
     GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex) {
+    if (spltex < 0 || spltex > 3) return GDT_ERR_INVALID_ARGUMENT;
+    g_k1_texab = texab ? 1 : 0;
+    g_k1_spltex = spltex;
+    g_k1_fytex = fytex ? 1 : 0;
     return GDT_OK;
 }
 

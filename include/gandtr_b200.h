@@ -69,6 +69,12 @@ int gdt_debug_get_spline_table(float* host_out_4096);
  * that sequence differs from IEEE a / b. Expected: 0. */
 int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches_dev, void* stream);
 
+/* debug/test hook: which pipe K1's table lookups take (every combination computes bit-identical results).
+ *   texab  : pass A fetches the chroma lattice records through the texture pipe (default 1)
+ *   spltex : 0..3 of pass B's inverse-gamma spline lookups go through the texture pipe (default 0)
+ *   fytex  : pass B takes the lightness half of Lab->RGB from a 256-entry table through the texture pipe (default 1) */
+int gdt_debug_k1_config(int texab, int spltex, int fytex);
+
 /* ---- K1: CLAHE preprocessing ------------------------------------------------------------------
  * Fused `pil2np | apply_clahe:clip:grid:lab | totensor | normalize`
  * (mdir/components/data/transform/core_transforms.py:35-100,

@@ -118,3 +118,20 @@ def test_normalisation_falls_back_to_hardware_division_for_awkward_std():
     std = [float(np.float32(0.99999994)), 0.224, float(np.uint32(0x3E7FFFFF).view(np.float32))]
     out = _lib.clahe_u8(torch.from_numpy(img[None]).cuda(), MEAN, std)[0].cpu().numpy()
     _assert_bits(out, O.transform_u8(img, lut, MEAN, std), "awkward std")
+
+
+def test_every_pipe_variant_is_bit_identical():
+    """K1's A/B switches (texture pipe vs LSU / shared memory, table vs recomputed lightness half) never change a bit."""
+    from gandtr_b200 import _lib
+    lib = _lib.load()
+    lut = load_lut()
+    img = synth_image(11, 96, 128, "smooth")
+    ref = O.transform_u8(img, lut, MEAN, STD)
+    try:
+        for texab in (0, 1):
+            for spltex in (0, 1, 2, 3):
+                for fytex in (0, 1):
+                    _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex), "gdt_debug_k1_config")
+                    _assert_bits(_run_u8([img])[0], ref, "variant %d %d %d" % (texab, spltex, fytex))
+    finally:
+        lib.gdt_debug_k1_config(1, 0, 1)

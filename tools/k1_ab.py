@@ -1,4 +1,4 @@
-"""Timing of K1 (run with GDT_DEBUG_K1_OCC=4/6/8 to compare pass-B occupancy variants)."""
+"""A/B timing of K1's pipe variants in one process (gdt_debug_k1_config): texab x spltex x fytex at 128 images."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
@@ -12,8 +12,17 @@ def timeit(fn, iters=10, warm=3):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
-for n in (32, 128):
-    x = synth_images_torch(n, 1, "cuda")
-    out = torch.empty((n, 3, 768, 1024), dtype=torch.float32, device="cuda")
-    ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=out))
-    print("occ=%s n=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic" % (os.environ.get("GDT_DEBUG_K1_OCC", "6"), n, ms, n / ms * 1e3, n * 15 * 768 * 1024 / ms / 1e6))
+lib = _lib.load()
+n = 128
+x = synth_images_torch(n, 1, "cuda")
+out = torch.empty((n, 3, 768, 1024), dtype=torch.float32, device="cuda")
+best = None
+for texab in (1, 0):
+    for fytex in (1, 0):
+        for spltex in (0, 1, 2, 3):
+            _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex), "cfg")
+            ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=out))
+            print("texab=%d fytex=%d spltex=%d n=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic" % (texab, fytex, spltex, n, ms, n / ms * 1e3, n * 15 * 768 * 1024 / ms / 1e6), flush=True)
+            if best is None or ms < best[0]: best = (ms, texab, spltex, fytex)
+print("best: %.3f ms texab=%d spltex=%d fytex=%d" % best)
+lib.gdt_debug_k1_config(1, 0, 1)
