@@ -34,7 +34,7 @@ SYMBOLS = [
     ("gdt_is_initialised", _c.c_int, []),
     ("gdt_debug_get_spline_table", _c.c_int, [_P]),
     ("gdt_debug_div_check", _c.c_int, [_c.c_float, _c.c_uint32, _c.c_uint32, _P, _P]),
-    ("gdt_debug_k1_config", _c.c_int, [_c.c_int, _c.c_int, _c.c_int]),
+    ("gdt_debug_k1_config", _c.c_int, [_c.c_int] * 5),
     ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_clahe_u8", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _c.c_size_t, _P]),
     ("gdt_clahe_f32", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P,
@@ -66,6 +66,13 @@ SYMBOLS = [
     ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
     ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P]),
     ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
+    ("gdt_thumbnail_geometry", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P, _P, _P, _P]),
+    ("gdt_resize_plan_create", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P]),
+    ("gdt_resize_plan_destroy", None, [_P]),
+    ("gdt_resize_plan_info", _c.c_int, [_P, _P, _P, _P, _P]),
+    ("gdt_resize_workspace_bytes", _c.c_size_t, [_P]),
+    ("gdt_resize_u8", _c.c_int, [_P, _P, _c.c_size_t, _P, _P, _c.c_size_t, _P]),
+    ("gdt_debug_resize_coeffs", _c.c_int, [_c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P, _P, _c.c_size_t]),
 ]
 
 _lib = None
@@ -75,7 +82,7 @@ launch_count = 0  # number of library compute calls made by this process (bench.
 
 # kernels launched by each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"clahe": 2, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
-                    "topk_merge": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1}
+                    "topk_merge": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1, "resize": 2}
 
 
 class GdtError(RuntimeError):
@@ -148,6 +155,14 @@ def ensure_init(device):
         torch.cuda.current_stream().synchronize()
         check(lib.gdt_init(lut.ctypes.data_as(ctypes.c_void_p)), "gdt_init")
     _initialised_devices.add(idx)
+
+
+K1_DEFAULT_CONFIG = (1, 0, 1, 1, 4)     # texab, spltex, fytex, chroma_a, occ_a -- must match clahe_sm100.cu's statics
+
+
+def k1_config_default():
+    """Restore K1's built-in work split / pipe choice after an A/B run (debug hook)."""
+    check(load().gdt_debug_k1_config(*K1_DEFAULT_CONFIG), "gdt_debug_k1_config")
 
 
 def _f3(v):
@@ -520,3 +535,56 @@ def map_eval(pos_rank, junk_rank, npos, njunk, kappas):
                                   _ptr(njunk), nq, _ptr(kap), nk, _ptr(ap), _ptr(prk), _stream()), "gdt_map_eval")
     _count("map_eval")
     return ap, prk[:, :nk]
+
+
+# ---- K5: dataset image geometry ------------------------------------------------------------------
+
+def thumbnail_geometry(w, h, imsize):
+    """Host only: (out_w, out_h, fx, fy, resized) Pillow picks for `Image.thumbnail((imsize, imsize), LANCZOS)`."""
+    ow, oh, fx, fy = (_c.c_int(), _c.c_int(), _c.c_int(), _c.c_int())
+    rc = load().gdt_thumbnail_geometry(int(w), int(h), float(imsize), _c.byref(ow), _c.byref(oh), _c.byref(fx), _c.byref(fy))
+    if rc < 0:
+        check(rc, "gdt_thumbnail_geometry")
+    return ow.value, oh.value, fx.value, fy.value, bool(rc)
+
+
+class ResizePlan:
+    """Filter coefficients of one (w, h, imsize) geometry on the current device (gdt_resize_plan_create)."""
+
+    def __init__(self, w, h, imsize, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise GdtError("gandtr_b200 kernels need a CUDA device, got %s" % self.device)
+        self._h = _c.c_void_p()
+        with torch.cuda.device(self.device):
+            check(load().gdt_resize_plan_create(int(w), int(h), float(imsize), _c.byref(self._h)), "gdt_resize_plan_create")
+        ow, oh = _c.c_int(), _c.c_int()
+        check(load().gdt_resize_plan_info(self._h, _c.byref(ow), _c.byref(oh), None, None), "gdt_resize_plan_info")
+        self.in_size, self.out_size = (int(w), int(h)), (ow.value, oh.value)
+        self.ws_bytes = load().gdt_resize_workspace_bytes(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                load().gdt_resize_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def resize_u8(plan, src, out=None):
+    """src: uint8 CUDA tensor [h, w, 3] (any row stride: a crop view is fine) -> [out_h, out_w, 3] contiguous."""
+    if not isinstance(src, torch.Tensor) or not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 3 or src.shape[2] != 3:
+        raise GdtError("resize_u8 needs a uint8 CUDA tensor [h, w, 3] (gandtr_b200 has no CPU path)")
+    if src.stride(2) != 1 or src.stride(1) != 3:
+        raise GdtError("resize_u8: pixels must be packed RGB (strides (*, 3, 1)), got %s" % (src.stride(),))
+    if (src.shape[1], src.shape[0]) != plan.in_size:
+        raise GdtError("resize_u8: plan is for %s, image is %s" % (plan.in_size, (src.shape[1], src.shape[0])))
+    ow, oh = plan.out_size
+    if out is None:
+        out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        ws = _workspace(plan.ws_bytes, src.device)
+        check(load().gdt_resize_u8(plan._h, _ptr(src), src.stride(0), _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_resize_u8")
+    _count("resize")
+    return out

@@ -38,7 +38,9 @@ static ClaheTables g_tables[32];
 // A/B switches (gdt_debug_k1_config): texab = pass A fetches the chroma lattice records through the texture pipe;
 // spltex = 0..3 spline lookups of pass B through the texture pipe; fytex = lightness half of Lab->RGB from the 256-entry
 // table (texture pipe) instead of recomputing it. Every combination is bit-identical; only the pipe balance differs.
-static int g_k1_texab = 1, g_k1_spltex = 0, g_k1_fytex = 1;
+//   chroma_a = interpolate the chroma in pass A (one lattice visit per pixel) instead of pass B (gather hidden under
+//   pass B's arithmetic); occ_a = resident CTAs per SM pass A is compiled for (4 or 6).
+static int g_k1_texab = 1, g_k1_spltex = 0, g_k1_fytex = 1, g_k1_chroma_a = 1, g_k1_occ_a = 4;
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -72,8 +74,20 @@ __device__ __forceinline__ void cell_from_f32(float r, float g, float b, const N
     cell = lab_cell_index(tr, tg, tb);
 }
 
-// Per-pixel scratch written by pass A and consumed by pass B: the CLAHE input byte and the two Q14 chroma channels
-// packed as a | b << 16 (each in [0, 16384]). The input pixel is quantised and interpolated exactly once.
+// Per-pixel "cell code" (chroma interpolated in pass B): bits [0,16) lattice cell, [16,20) fr, [20,24) fg, [24,28) fb
+__device__ __forceinline__ uint32_t pack_code(int cell, int fr, int fg, int fb) {
+    return (uint32_t)cell | ((uint32_t)fr << 16) | ((uint32_t)fg << 20) | ((uint32_t)fb << 24);
+}
+__device__ __forceinline__ void unpack_code(uint32_t c, int& cell, int& fr, int& fg, int& fb) {
+    cell = (int)(c & 0xffffu);
+    fr = (int)((c >> 16) & 15u);
+    fg = (int)((c >> 20) & 15u);
+    fb = (int)(c >> 24);
+}
+
+// Per-pixel scratch written by pass A and consumed by pass B: the CLAHE input byte and EITHER the two Q14 chroma channels
+// packed as a | b << 16 (each in [0, 16384]; CHROMA_A: the lattice is interpolated once, in pass A) OR the cell code
+// (pass B fetches the chroma records itself, overlapping the gather with its arithmetic).
 __device__ __forceinline__ void lab_from_records(const uint4& wl, const uint4& wa, const uint4& wb, int fr, int fg, int fb,
                                                  int& l8, uint32_t& ab) {
     l8 = lab_l8_int(lab_trilinear(wl.x, wl.y, wl.z, wl.w, fr, fg, fb));
@@ -112,8 +126,8 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
 
 // `gq`, `gr` = 256 / gw, 256 % gw (gw = 4-pixel groups per tile row): the vectorised loop walks (row, group) incrementally,
 // no division per step. TEXAB: chroma records through the texture pipe (idle otherwise), lightness through the LSU pipe.
-template <bool U8, bool TEXAB>
-__global__ void __launch_bounds__(256)
+template <bool U8, bool TEXAB, bool CHROMA_A, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
@@ -159,21 +173,32 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
 #pragma unroll
                 for (int i = 0; i < 4; ++i) cell_from_f32(rr[i], gg[i], bb[i], in_norm, cell[i], fr[i], fg[i], fb[i]);
             }
-            uint4 wl[4], wa[4], wb[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {                                   // twelve gathers in flight
-                wl[i] = __ldg(lutL + cell[i]);
-                if (TEXAB) {
-                    wa[i] = tex1Dfetch<uint4>(texAB, cell[i] * 2);
-                    wb[i] = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
-                } else {
-                    ld_cell_ab(lutAB, cell[i], wa[i], wb[i]);
-                }
-            }
             int v[4];
             uint32_t ab[4];
+            if (CHROMA_A) {
+                uint4 wl[4], wa[4], wb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) lab_from_records(wl[i], wa[i], wb[i], fr[i], fg[i], fb[i], v[i], ab[i]);
+                for (int i = 0; i < 4; ++i) {                                   // twelve gathers in flight
+                    wl[i] = __ldg(lutL + cell[i]);
+                    if (TEXAB) {
+                        wa[i] = tex1Dfetch<uint4>(texAB, cell[i] * 2);
+                        wb[i] = tex1Dfetch<uint4>(texAB, cell[i] * 2 + 1);
+                    } else {
+                        ld_cell_ab(lutAB, cell[i], wa[i], wb[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) lab_from_records(wl[i], wa[i], wb[i], fr[i], fg[i], fb[i], v[i], ab[i]);
+            } else {
+                uint4 wl[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wl[i] = __ldg(lutL + cell[i]);      // four gathers in flight
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[i] = lab_l8_int(lab_trilinear(wl[i].x, wl[i].y, wl[i].z, wl[i].w, fr[i], fg[i], fb[i]));
+                    ab[i] = pack_code(cell[i], fr[i], fg[i], fb[i]);
+                }
+            }
             *(uint4*)(abimg + p) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
             *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
 #pragma unroll
@@ -201,10 +226,15 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                     cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
                 }
                 const uint4 wl = __ldg(lutL + cell);
-                uint4 wa, wb;
-                ld_cell_ab(lutAB, cell, wa, wb);
                 uint32_t ab;
-                lab_from_records(wl, wa, wb, fr, fg, fb, v, ab);
+                if (CHROMA_A) {
+                    uint4 wa, wb;
+                    ld_cell_ab(lutAB, cell, wa, wb);
+                    lab_from_records(wl, wa, wb, fr, fg, fb, v, ab);
+                } else {
+                    v = lab_l8_int(lab_trilinear(wl.x, wl.y, wl.z, wl.w, fr, fg, fb));
+                    ab = pack_code(cell, fr, fg, fb);
+                }
                 if (ey < h && ex < w) {
                     l8img[p] = (uint8_t)v;
                     abimg[p] = ab;
@@ -266,12 +296,14 @@ struct NormFast {
 // (pass B is bound by shared-memory wavefronts + issue; the texture pipe is idle since pass A took over the lattice).
 // FYTEX  = lightness half of Lab->RGB ({fy, C1*y, C4*y, C7*y}, a function of the CLAHE output byte) fetched from the
 // 256-entry table through the texture pipe instead of being recomputed (FAST only).
-template <int MINB, bool FAST, int SPLTEX, bool FYTEX>
+// CHROMA_A = pass A already interpolated the chroma (AB holds a | b << 16); otherwise AB holds the cell code and the
+// chroma records are fetched here through the texture pipe.
+template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A>
 __global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    int vec_ok_, const float4* __restrict__ spline, Lab2RgbConst K,
-                   NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy) {
+                   NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy, cudaTextureObject_t texAB) {
     const int vec_ok = FAST ? 1 : vec_ok_;
     if (FAST) on.fast = 1;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -362,8 +394,18 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             // chroma: Q14 -> the a / b handed to LAB2RGB
-            const float a2 = lab_chroma_fast((int)(ab[i] & 0xffffu));
-            const float b2 = lab_chroma_fast((int)(ab[i] >> 16));
+            int oa, ob;
+            if (CHROMA_A) {
+                oa = (int)(ab[i] & 0xffffu);
+                ob = (int)(ab[i] >> 16);
+            } else {
+                int cell, fr, fg, fb;
+                unpack_code(ab[i], cell, fr, fg, fb);
+                const uint4 wa = tex1Dfetch<uint4>(texAB, cell * 2), wb = tex1Dfetch<uint4>(texAB, cell * 2 + 1);
+                oa = lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr, fg, fb);
+                ob = lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr, fg, fb);
+            }
+            const float a2 = lab_chroma_fast(oa), b2 = lab_chroma_fast(ob);
             // lightness through CLAHE: the two LUT rows hold the LUT value of every tile column at level v
             int l11, l12, l21, l22;
             if (lsh == 3) {
@@ -469,16 +511,18 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
 
     // A/B switches, see gdt_debug_k1_config (profiles/k1_v2_ab_r1q.log)
-    const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex;
+    const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, chroma_a = g_k1_chroma_a, occ_a = g_k1_occ_a;
     dim3 gridA(grid * grid, n);
     const int gw = vec_hist ? (g.tw >> 2) : 1;
     const int gq = 256 / gw, gr = 256 % gw;
-    if (texab)
-        clahe_hist_kernel<U8, true><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
-                                                                vec_hist, gq, gr, T->lutL, T->lutAB, in_norm, T->texAB);
-    else
-        clahe_hist_kernel<U8, false><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip, g.lut_scale,
-                                                                 vec_hist, gq, gr, T->lutL, T->lutAB, in_norm, T->texAB);
+#define GDT_HIST(T_, C_, O_)                                                                                           \
+    clahe_hist_kernel<U8, T_, C_, O_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip,      \
+                                                                  g.lut_scale, vec_hist, gq, gr, T->lutL, T->lutAB,     \
+                                                                  in_norm, T->texAB)
+    if (!chroma_a) { if (occ_a >= 6) GDT_HIST(false, false, 6); else GDT_HIST(false, false, 4); }
+    else if (texab) { if (occ_a >= 6) GDT_HIST(true, true, 6); else GDT_HIST(true, true, 4); }
+    else GDT_HIST(false, true, 4);
+#undef GDT_HIST
     GDT_LAUNCH_CHECK();
 
     // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
@@ -503,24 +547,31 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
     // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
     if (smem > 48 * 1024)
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    {
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-#define GDT_APPLY(FAST_, S_, F_)                                                                                         \
-    clahe_apply_kernel<4, FAST_, S_, F_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, grid, g.inv_th, g.inv_tw, \
-                                                                        rows, vec_apply, T->spline, T->K, on, T->texSpline, T->texFy)
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      1024 * 16 + 16 * 256 * 16));
+    }
+#define GDT_APPLY(FAST_, S_, F_, C_)                                                                                     \
+    clahe_apply_kernel<4, FAST_, S_, F_, C_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, grid, g.inv_th,         \
+                                                                            g.inv_tw, rows, vec_apply, T->spline, T->K, on, \
+                                                                            T->texSpline, T->texFy, T->texAB)
     if ((w & 7) == 0 && vec_apply && grid <= 8 && on.fast && smem <= 48 * 1024) {
-        switch (spltex * 2 + fytex) {
-            case 0: GDT_APPLY(true, 0, false); break;
-            case 1: GDT_APPLY(true, 0, true); break;
-            case 2: GDT_APPLY(true, 1, false); break;
-            case 3: GDT_APPLY(true, 1, true); break;
-            case 4: GDT_APPLY(true, 2, false); break;
-            case 5: GDT_APPLY(true, 2, true); break;
-            case 6: GDT_APPLY(true, 3, false); break;
-            default: GDT_APPLY(true, 3, true); break;
+        switch ((spltex > 1 ? 1 : spltex) * 4 + fytex * 2 + chroma_a) {
+            case 0: GDT_APPLY(true, 0, false, false); break;
+            case 1: GDT_APPLY(true, 0, false, true); break;
+            case 2: GDT_APPLY(true, 0, true, false); break;
+            case 3: GDT_APPLY(true, 0, true, true); break;
+            case 4: GDT_APPLY(true, 1, false, false); break;
+            case 5: GDT_APPLY(true, 1, false, true); break;
+            case 6: GDT_APPLY(true, 1, true, false); break;
+            default: GDT_APPLY(true, 1, true, true); break;
         }
+    } else if (chroma_a) {
+        GDT_APPLY(false, 0, false, true);
     } else {
-        GDT_APPLY(false, 0, false);
+        GDT_APPLY(false, 0, false, false);
     }
 #undef GDT_APPLY
     GDT_LAUNCH_CHECK();
@@ -553,11 +604,13 @@ extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, 
     return GDT_OK;
 }
 
-extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex) {
-    if (spltex < 0 || spltex > 3) return GDT_ERR_INVALID_ARGUMENT;
+extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a) {
+    if (spltex < 0 || spltex > 1 || (occ_a != 4 && occ_a != 6)) return GDT_ERR_INVALID_ARGUMENT;
     g_k1_texab = texab ? 1 : 0;
     g_k1_spltex = spltex;
     g_k1_fytex = fytex ? 1 : 0;
+    g_k1_chroma_a = chroma_a ? 1 : 0;
+    g_k1_occ_a = occ_a;
     return GDT_OK;
 }
 

@@ -1,0 +1,83 @@
+"""Device-side image geometry of the dataset loader -- SURVEY 8(f) N1. Replaces, on the GPU, what the reference's
+DataLoader workers do per image on the host (`ImagesFromList.__getitem__`, mdir/external/cirtorch/datasets/
+genericdataset.py:66-102; `imresize`, datahelpers.py:75-82): bounding-box crop and the LANCZOS `thumbnail` to `imsize`,
+bit-identical to Pillow (K5, csrc/resize_sm100.cu). Decoding stays with the reference's own decoder (PIL) by default, so
+the pixels entering K5 -- and therefore K1's output -- are exactly the reference's; `decode="nvjpeg"` hands JPEG bytes to
+the GPU decoder instead (torchvision.io.decode_jpeg on the device; library plumbing, NOT bit-identical to libjpeg).
+
+    loader = DeviceImageLoader(imsize=1024, device="cuda")
+    img = loader.load(path_or_pil_or_array, bbx=None)      # uint8 CUDA tensor [h, w, 3], what load_image returns on the host
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["DeviceImageLoader", "thumbnail_size"]
+
+
+def thumbnail_size(w, h, imsize):
+    """(out_w, out_h) of `Image.thumbnail((imsize, imsize))` on a w x h image."""
+    ow, oh, _, _, _ = _lib.thumbnail_geometry(w, h, imsize)
+    return ow, oh
+
+
+class DeviceImageLoader:
+    def __init__(self, imsize=None, device=None, decode="pil", max_plans=256):
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise _lib.GdtError("DeviceImageLoader needs a CUDA device (gandtr_b200 has no CPU path)")
+        if decode not in ("pil", "nvjpeg"):
+            raise ValueError("decode must be 'pil' or 'nvjpeg'")
+        self.imsize = imsize
+        self.decode = decode
+        self.max_plans = max_plans
+        self._plans = {}
+
+    # -- decoding -----------------------------------------------------------------------------------
+    def _decode(self, item):
+        """-> uint8 [h, w, 3] tensor, on the device for nvjpeg, pinned host memory otherwise."""
+        from PIL import Image
+        if isinstance(item, torch.Tensor):
+            return item
+        if isinstance(item, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(item))
+        if isinstance(item, Image.Image):
+            return torch.from_numpy(np.asarray(item.convert("RGB")).copy())
+        if self.decode == "nvjpeg" and str(item).lower().endswith((".jpg", ".jpeg")):
+            from torchvision.io import decode_jpeg, read_file, ImageReadMode
+            chw = decode_jpeg(read_file(str(item)), device=self.device, mode=ImageReadMode.RGB)
+            return chw.permute(1, 2, 0).contiguous()
+        with open(item, "rb") as f:                       # pil_loader (datahelpers.py:20-27): open + convert('RGB')
+            return torch.from_numpy(np.asarray(Image.open(f).convert("RGB")).copy())
+
+    def _plan(self, w, h, imsize):
+        key = (w, h, float(imsize))
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= self.max_plans:
+                self._plans.pop(next(iter(self._plans)))
+            plan = self._plans[key] = _lib.ResizePlan(w, h, imsize, self.device)
+        return plan
+
+    # -- geometry -----------------------------------------------------------------------------------
+    def resize(self, img, imsize=None, bbx=None):
+        """img: decoded uint8 [h, w, 3] tensor (host or device) -> uint8 CUDA [h', w', 3]: crop to `bbx`
+        (x0, y0, x1, y1), then thumbnail; the bounding-box scale rule is genericdataset.py:93-97."""
+        imsize = self.imsize if imsize is None else imsize
+        if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3:
+            raise _lib.GdtError("DeviceImageLoader: expected a uint8 [h, w, 3] image, got %s %s" % (img.dtype, tuple(img.shape)))
+        if not img.is_cuda:
+            img = (img if img.is_pinned() else img.pin_memory()).to(self.device, non_blocking=True)
+        full = max(img.shape[0], img.shape[1])
+        if bbx:
+            x0, y0, x1, y1 = [int(v) for v in bbx]
+            img = img[y0:y1, x0:x1]                       # a view: K5 reads it through the parent's row stride
+        if imsize is None:
+            return img.contiguous()
+        h, w = int(img.shape[0]), int(img.shape[1])
+        size = imsize * max(w, h) / full if bbx else imsize
+        return _lib.resize_u8(self._plan(w, h, size), img)
+
+    def load(self, item, bbx=None, imsize=None):
+        return self.resize(self._decode(item), imsize=imsize, bbx=bbx)

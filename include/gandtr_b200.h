@@ -69,11 +69,43 @@ int gdt_debug_get_spline_table(float* host_out_4096);
  * that sequence differs from IEEE a / b. Expected: 0. */
 int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches_dev, void* stream);
 
-/* debug/test hook: which pipe K1's table lookups take (every combination computes bit-identical results).
- *   texab  : pass A fetches the chroma lattice records through the texture pipe (default 1)
- *   spltex : 0..3 of pass B's inverse-gamma spline lookups go through the texture pipe (default 0)
- *   fytex  : pass B takes the lightness half of Lab->RGB from a 256-entry table through the texture pipe (default 1) */
-int gdt_debug_k1_config(int texab, int spltex, int fytex);
+/* debug/test hook: work split and pipe choice of K1's table lookups (every combination computes bit-identical results).
+ *   texab    : pass A fetches the chroma lattice records through the texture pipe (when chroma_a)
+ *   spltex   : 0..1 of pass B's inverse-gamma spline lookups go through the texture pipe
+ *   fytex    : pass B takes the lightness half of Lab->RGB from a 256-entry table through the texture pipe
+ *   chroma_a : the chroma is interpolated in pass A (one lattice visit per pixel) instead of pass B
+ *   occ_a    : resident CTAs per SM pass A is compiled for (4 or 6) */
+int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a);
+
+/* ---- K5: dataset image geometry (crop + LANCZOS thumbnail) ---------------------------------------
+ * The image-size half of the reference's dataset loader on the device:
+ *   ImagesFromList.__getitem__ crop + imresize   (mdir/external/cirtorch/datasets/genericdataset.py:86-97)
+ *   imresize = img.thumbnail((imsize, imsize), Image.LANCZOS)   (mdir/external/cirtorch/datasets/datahelpers.py:75-82)
+ * Bit-exact against Pillow's 8-bit resampler (aspect-preserving target size, reducing_gap = 2.0 integer box reduction,
+ * two-pass 22-bit fixed-point LANCZOS with uint8 rounding between the passes). A crop is a sub-rectangle of the source:
+ * pass the pointer of its first pixel and the full image's row stride.
+ *
+ * gdt_thumbnail_geometry : host only. Target size and pre-reduction factors Pillow picks for a w x h image and the request
+ *                          (imsize, imsize); returns 1 when the image is resized, 0 when it is left alone (out = in),
+ *                          negative gdt_status on bad arguments.
+ * gdt_resize_plan_create : per (w, h, imsize) geometry: filter coefficients computed on the host in double precision
+ *                          (the libm calls Pillow makes) and uploaded to the current device. Synchronous; setup, not
+ *                          hot path. Destroy with gdt_resize_plan_destroy.
+ * gdt_resize_u8          : src uint8 [h][w][3] with row stride src_stride bytes (device) -> dst uint8
+ *                          [out_h][out_w][3] contiguous (device). Asynchronous on `stream`; scratch from `ws`
+ *                          (gdt_resize_workspace_bytes(plan), 256-byte aligned). 1 - 3 launches. */
+typedef struct gdt_resize_plan gdt_resize_plan;
+int gdt_thumbnail_geometry(int w, int h, double imsize, int* out_w, int* out_h, int* fx, int* fy);
+int gdt_resize_plan_create(int in_w, int in_h, double imsize, gdt_resize_plan** plan_out);
+void gdt_resize_plan_destroy(gdt_resize_plan* plan);
+int gdt_resize_plan_info(const gdt_resize_plan* plan, int* out_w, int* out_h, int* fx, int* fy);
+size_t gdt_resize_workspace_bytes(const gdt_resize_plan* plan);
+int gdt_resize_u8(const gdt_resize_plan* plan, const uint8_t* src, size_t src_stride, uint8_t* dst, void* ws,
+                  size_t ws_bytes, void* stream);
+/* debug/test hook (host only): Pillow's precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter.
+ * bounds: out_size x (first input index, tap count); kk: out_size x ksize int32 (capacity in elements). */
+int gdt_debug_resize_coeffs(int in_size, float in0, float in1, int out_size, int* ksize, int* bounds, int32_t* kk,
+                            size_t kk_capacity);
 
 /* ---- K1: CLAHE preprocessing ------------------------------------------------------------------
  * Fused `pil2np | apply_clahe:clip:grid:lab | totensor | normalize`

@@ -1,4 +1,4 @@
-"""A/B timing of K1's pipe variants in one process (gdt_debug_k1_config): texab x spltex x fytex at 128 images."""
+"""A/B timing of K1's work-split / pipe variants in one process (gdt_debug_k1_config) at 128 images."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
@@ -17,12 +17,12 @@ n = 128
 x = synth_images_torch(n, 1, "cuda")
 out = torch.empty((n, 3, 768, 1024), dtype=torch.float32, device="cuda")
 best = None
-for texab in (1, 0):
+for chroma_a, texab, occ_a in ((1, 1, 4), (1, 1, 6), (0, 0, 4), (0, 0, 6)):
     for fytex in (1, 0):
-        for spltex in (0, 1, 2, 3):
-            _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex), "cfg")
+        for spltex in (0, 1):
+            _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex, chroma_a, occ_a), "cfg")
             ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=out))
-            print("texab=%d fytex=%d spltex=%d n=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic" % (texab, fytex, spltex, n, ms, n / ms * 1e3, n * 15 * 768 * 1024 / ms / 1e6), flush=True)
-            if best is None or ms < best[0]: best = (ms, texab, spltex, fytex)
-print("best: %.3f ms texab=%d spltex=%d fytex=%d" % best)
-lib.gdt_debug_k1_config(1, 0, 1)
+            print("chroma_a=%d texab=%d occ_a=%d fytex=%d spltex=%d n=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic" % (chroma_a, texab, occ_a, fytex, spltex, n, ms, n / ms * 1e3, n * 15 * 768 * 1024 / ms / 1e6), flush=True)
+            if best is None or ms < best[0]: best = (ms, chroma_a, texab, occ_a, fytex, spltex)
+print("best: %.3f ms chroma_a=%d texab=%d occ_a=%d fytex=%d spltex=%d" % best)
+_lib.k1_config_default()
