@@ -157,7 +157,7 @@ def ensure_init(device):
     _initialised_devices.add(idx)
 
 
-K1_DEFAULT_CONFIG = (1, 0, 1, 1, 4)     # texab, spltex, fytex, chroma_a, occ_a -- must match clahe_sm100.cu's statics
+K1_DEFAULT_CONFIG = (0, 0, 0, 0, 4)     # texab, spltex, fytex, chroma_a, occ_a -- must match clahe_sm100.cu's statics
 
 
 def k1_config_default():

@@ -35,12 +35,15 @@ struct ClaheTables {
 
 static ClaheTables g_tables[32];
 
-// A/B switches (gdt_debug_k1_config): texab = pass A fetches the chroma lattice records through the texture pipe;
+// A/B switches (gdt_debug_k1_config): texab bit 0 = pass A fetches the chroma lattice records through the texture pipe
+// (when chroma_a), bit 1 = pass A fetches the lightness records through the texture pipe (when !chroma_a);
 // spltex = 0..3 spline lookups of pass B through the texture pipe; fytex = lightness half of Lab->RGB from the 256-entry
 // table (texture pipe) instead of recomputing it. Every combination is bit-identical; only the pipe balance differs.
 //   chroma_a = interpolate the chroma in pass A (one lattice visit per pixel) instead of pass B (gather hidden under
 //   pass B's arithmetic); occ_a = resident CTAs per SM pass A is compiled for (4 or 6).
-static int g_k1_texab = 1, g_k1_spltex = 0, g_k1_fytex = 1, g_k1_chroma_a = 1, g_k1_occ_a = 4;
+// Defaults = the fastest combination measured on B200 (profiles/k1_v2_ab_r1q.log): chroma in pass B (its gather hides
+// under pass B's arithmetic; in pass A it is exposed: 1.03 vs 1.20 ms per 128 images), everything else recomputed.
+static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_chroma_a = 0, g_k1_occ_a = 4;
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -126,13 +129,14 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
 
 // `gq`, `gr` = 256 / gw, 256 % gw (gw = 4-pixel groups per tile row): the vectorised loop walks (row, group) incrementally,
 // no division per step. TEXAB: chroma records through the texture pipe (idle otherwise), lightness through the LSU pipe.
-template <bool U8, bool TEXAB, bool CHROMA_A, int MINB>
+// TEXL: the lightness records take the texture pipe too (pass A is bound by the LSU pipe's scattered 16-byte gathers).
+template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, bool TEXL>
 __global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
                   const uint4* __restrict__ lutL, const uint4* __restrict__ lutAB, Norm3 in_norm,
-                  cudaTextureObject_t texAB) {
+                  cudaTextureObject_t texAB, cudaTextureObject_t texL) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
@@ -192,7 +196,8 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
             } else {
                 uint4 wl[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) wl[i] = __ldg(lutL + cell[i]);      // four gathers in flight
+                for (int i = 0; i < 4; ++i)                                      // four gathers in flight
+                    wl[i] = TEXL ? tex1Dfetch<uint4>(texL, cell[i]) : __ldg(lutL + cell[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v[i] = lab_l8_int(lab_trilinear(wl[i].x, wl[i].y, wl[i].z, wl[i].w, fr[i], fg[i], fb[i]));
@@ -515,13 +520,19 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     dim3 gridA(grid * grid, n);
     const int gw = vec_hist ? (g.tw >> 2) : 1;
     const int gq = 256 / gw, gr = 256 % gw;
-#define GDT_HIST(T_, C_, O_)                                                                                           \
-    clahe_hist_kernel<U8, T_, C_, O_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip,      \
-                                                                  g.lut_scale, vec_hist, gq, gr, T->lutL, T->lutAB,     \
-                                                                  in_norm, T->texAB)
-    if (!chroma_a) { if (occ_a >= 6) GDT_HIST(false, false, 6); else GDT_HIST(false, false, 4); }
-    else if (texab) { if (occ_a >= 6) GDT_HIST(true, true, 6); else GDT_HIST(true, true, 4); }
-    else GDT_HIST(false, true, 4);
+#define GDT_HIST(T_, C_, O_, L_)                                                                                       \
+    clahe_hist_kernel<U8, T_, C_, O_, L_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip,  \
+                                                                      g.lut_scale, vec_hist, gq, gr, T->lutL, T->lutAB, \
+                                                                      in_norm, T->texAB, T->texL)
+    if (!chroma_a) {
+        if (texab & 2) GDT_HIST(false, false, 4, true);
+        else if (occ_a >= 6) GDT_HIST(false, false, 6, false);
+        else GDT_HIST(false, false, 4, false);
+    } else if (texab & 1) {
+        if (occ_a >= 6) GDT_HIST(true, true, 6, false); else GDT_HIST(true, true, 4, false);
+    } else {
+        GDT_HIST(false, true, 4, false);
+    }
 #undef GDT_HIST
     GDT_LAUNCH_CHECK();
 
@@ -606,7 +617,7 @@ extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, 
 
 extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a) {
     if (spltex < 0 || spltex > 1 || (occ_a != 4 && occ_a != 6)) return GDT_ERR_INVALID_ARGUMENT;
-    g_k1_texab = texab ? 1 : 0;
+    g_k1_texab = texab & 3;
     g_k1_spltex = spltex;
     g_k1_fytex = fytex ? 1 : 0;
     g_k1_chroma_a = chroma_a ? 1 : 0;

@@ -89,13 +89,18 @@ def load_image(item, imsize=None, bbx=None):
 
 
 class _Decode(torch.utils.data.Dataset):
-    def __init__(self, images, imsize, bbxs):
-        self.images, self.imsize, self.bbxs = images, imsize, bbxs
+    """Worker side: decode (+ crop / LANCZOS thumbnail on the host unless `device_resize`)."""
+
+    def __init__(self, images, imsize, bbxs, device_resize=False):
+        self.images, self.imsize, self.bbxs, self.device_resize = images, imsize, bbxs, device_resize
 
     def __len__(self):
         return len(self.images)
 
     def __getitem__(self, i):
+        if self.device_resize:      # decode only: crop and thumbnail run on the GPU (K5, gandtr_b200/loader.py)
+            # arrays are never resized by the reference (imresize passes them through): flag them
+            return torch.from_numpy(load_image(self.images[i], None, None).copy()), isinstance(self.images[i], np.ndarray)
         return torch.from_numpy(load_image(self.images[i], self.imsize, self.bbxs[i] if self.bbxs is not None else None).copy())
 
 
@@ -112,9 +117,11 @@ def _descriptors_for_batch(model, x, ms, msp):
 
 
 def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), msp=1, batch_size=32, workers=4,
-                        rank=0, world_size=1, print_freq=0):
+                        rank=0, world_size=1, print_freq=0, device_resize=False):
     """-> [n_local, D] float32 CUDA tensor: rows lo..hi of the descriptor matrix, (lo, hi) = shard_bounds(len(images)).
-    `net` is a gandtr_b200 SingleNetwork or ImageRetrievalNet; `transform` a gandtr_b200.transforms.Compose."""
+    `net` is a gandtr_b200 SingleNetwork or ImageRetrievalNet; `transform` a gandtr_b200.transforms.Compose.
+    `device_resize`: the workers only decode; bounding-box crop and the LANCZOS thumbnail run on the GPU (K5,
+    bit-identical to the host path), so the host cores are left to the JPEG decoder."""
     model = getattr(net, "model", net)
     model.eval()
     dev = next(model.parameters()).device
@@ -124,25 +131,35 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
     local = list(images[lo:hi])
     local_bbxs = list(bbxs[lo:hi]) if bbxs is not None else None
     out = torch.empty((len(local), model.meta["out_channels"]), dtype=torch.float32, device=dev)
-    loader = torch.utils.data.DataLoader(_Decode(local, image_size, local_bbxs), batch_size=None, shuffle=False,
+    loader = torch.utils.data.DataLoader(_Decode(local, image_size, local_bbxs, device_resize), batch_size=None, shuffle=False,
                                          num_workers=min(workers, max(len(local), 1)) if len(local) > 8 else 0)
     pending, shape, start = [], None, 0
     uploader = HostBatchUploader(dev)
+    geometry = None
+    if device_resize:
+        from .loader import DeviceImageLoader
+        geometry = DeviceImageLoader(imsize=image_size, device=dev)
 
     def flush():
         nonlocal pending, start
         if not pending:
             return
-        batch = torch.stack(pending).pin_memory()
         with torch.no_grad():
-            staged = uploader.upload(batch)
-            x = transform.batch(staged)
-            uploader.release(staged)                       # K1 was the only reader of the uint8 batch
+            if device_resize:
+                x = transform.batch(torch.stack(pending))      # already on the device
+            else:
+                staged = uploader.upload(torch.stack(pending).pin_memory())
+                x = transform.batch(staged)
+                uploader.release(staged)                       # K1 was the only reader of the uint8 batch
             out[start:start + len(pending)] = _descriptors_for_batch(model, x, list(ms), msp)
         start += len(pending)
         pending = []
 
     for i, img in enumerate(loader):
+        if device_resize:
+            img, is_array = img
+            bbx = local_bbxs[i] if local_bbxs is not None else None
+            img = geometry.resize(img, bbx=bbx) if not is_array else geometry.crop_only(img, bbx)
         if shape is not None and (tuple(img.shape) != shape or len(pending) >= batch_size):
             flush()
         shape = tuple(img.shape)

@@ -79,5 +79,16 @@ class DeviceImageLoader:
         size = imsize * max(w, h) / full if bbx else imsize
         return _lib.resize_u8(self._plan(w, h, size), img)
 
+    def crop_only(self, img, bbx=None):
+        """Arrays are cropped but never resized by the reference (datahelpers.py:76-79)."""
+        if not img.is_cuda:
+            img = (img if img.is_pinned() else img.pin_memory()).to(self.device, non_blocking=True)
+        if bbx:
+            x0, y0, x1, y1 = [int(v) for v in bbx]
+            img = img[y0:y1, x0:x1]
+        return img.contiguous()
+
     def load(self, item, bbx=None, imsize=None):
+        if isinstance(item, np.ndarray):
+            return self.crop_only(self._decode(item), bbx)
         return self.resize(self._decode(item), imsize=imsize, bbx=bbx)

@@ -48,6 +48,26 @@ def test_batched_extraction_equals_per_image_forward(vgg):
     torch.testing.assert_close(torch.cat(halves), d, rtol=2e-5, atol=5e-6)   # batch boundaries move -> other cuDNN algorithms
 
 
+def test_device_resize_extraction_equals_host_resize(vgg):
+    """with `device_resize` the workers only decode; crop + LANCZOS thumbnail run on the GPU (K5) and feed K1
+    the very same pixels, so the descriptors are those of the host-resize path."""
+    from gandtr_b200.extract import extract_descriptors, load_image
+    from gandtr_b200.loader import DeviceImageLoader
+    images = [synth_image(1200 + i, *[(150, 200), (200, 150), (96, 128)][i % 3], "smooth" if i % 3 else "noise") for i in range(9)]
+    bbxs = [None, (10, 20, 190, 140), None, None, (5, 5, 120, 190), None, None, None, (0, 0, 100, 90)]
+    ld = DeviceImageLoader(imsize=96, device="cuda")
+    from PIL import Image
+    pil = [Image.fromarray(a) for a in images]
+    for img, bbx in zip(pil, bbxs):
+        assert np.array_equal(ld.load(img, bbx=bbx).cpu().numpy(), load_image(img.copy(), 96, bbx))
+        assert ld.load(img, bbx=bbx).shape[0] <= 96
+    host = extract_descriptors(vgg, pil, 96, vgg.transform, bbxs=bbxs, batch_size=4)
+    dev = extract_descriptors(vgg, pil, 96, vgg.transform, bbxs=bbxs, batch_size=4, device_resize=True)
+    assert torch.equal(host, dev)
+    # arrays pass through unresized on both paths (datahelpers.py:76-79)
+    assert torch.equal(extract_descriptors(vgg, images[:3], 96, vgg.transform), extract_descriptors(vgg, images[:3], 96, vgg.transform, device_resize=True))
+
+
 def test_extract_ms_matches_reference_formula(vgg):
     from gandtr_b200.extract import extract_ms
     img = synth_image(5, 96, 128, "smooth")
