@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from .retrieval import shard_bounds
 
-__all__ = ["imresize", "load_image", "extract_descriptors", "extract_vectors", "extract_ss", "extract_ms", "HostBatchUploader"]
+__all__ = ["imresize", "load_image", "crop_box", "crop_like_pil", "extract_descriptors", "extract_vectors", "extract_ss", "extract_ms", "HostBatchUploader"]
 
 
 class HostBatchUploader:
@@ -66,14 +66,32 @@ def imresize(img, imsize):
     return img
 
 
+def crop_box(bbx):
+    """Image.crop's box arithmetic: every coordinate is rounded (half to even), not truncated."""
+    return tuple(int(round(v)) for v in bbx)
+
+
+def crop_like_pil(arr, bbx):
+    """img.crop(bbx) on an [h, w, c] array / tensor: rounded box, pixels outside the image are black."""
+    x0, y0, x1, y1 = crop_box(bbx)
+    h, w = arr.shape[0], arr.shape[1]
+    if 0 <= x0 <= x1 <= w and 0 <= y0 <= y1 <= h:
+        return arr[y0:y1, x0:x1]
+    out = (torch.zeros if isinstance(arr, torch.Tensor) else np.zeros)((max(y1 - y0, 0), max(x1 - x0, 0)) + tuple(arr.shape[2:]),
+                                                                      **({"dtype": arr.dtype, "device": arr.device} if isinstance(arr, torch.Tensor) else {"dtype": arr.dtype}))
+    sx0, sy0, sx1, sy1 = max(x0, 0), max(y0, 0), min(x1, w), min(y1, h)
+    if sx1 > sx0 and sy1 > sy0:
+        out[sy0 - y0:sy1 - y0, sx0 - x0:sx1 - x0] = arr[sy0:sy1, sx0:sx1]
+    return out
+
+
 def load_image(item, imsize=None, bbx=None):
     """One element of the image list -> uint8 HWC RGB array. `item` is a path, a PIL image or a uint8 array.
     Crop / resize order and the bounding-box scale rule follow genericdataset.py:88-97."""
     from PIL import Image
     if isinstance(item, np.ndarray):
         if bbx:
-            x0, y0, x1, y1 = [int(v) for v in bbx]
-            item = item[y0:y1, x0:x1]
+            item = crop_like_pil(item, bbx)
         return np.ascontiguousarray(item)
     if isinstance(item, Image.Image):
         img = item.convert("RGB")
@@ -144,11 +162,14 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
         nonlocal pending, start
         if not pending:
             return
+        batch = torch.stack(pending)                           # device_resize: already on the device
+        if not device_resize:
+            batch = batch.pin_memory()                         # stays referenced until the descriptors are enqueued
         with torch.no_grad():
             if device_resize:
-                x = transform.batch(torch.stack(pending))      # already on the device
+                x = transform.batch(batch)
             else:
-                staged = uploader.upload(torch.stack(pending).pin_memory())
+                staged = uploader.upload(batch)
                 x = transform.batch(staged)
                 uploader.release(staged)                       # K1 was the only reader of the uint8 batch
             out[start:start + len(pending)] = _descriptors_for_batch(model, x, list(ms), msp)

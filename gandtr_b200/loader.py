@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .extract import crop_like_pil
 
 __all__ = ["DeviceImageLoader", "thumbnail_size"]
 
@@ -71,8 +72,7 @@ class DeviceImageLoader:
             img = (img if img.is_pinned() else img.pin_memory()).to(self.device, non_blocking=True)
         full = max(img.shape[0], img.shape[1])
         if bbx:
-            x0, y0, x1, y1 = [int(v) for v in bbx]
-            img = img[y0:y1, x0:x1]                       # a view: K5 reads it through the parent's row stride
+            img = crop_like_pil(img, bbx)                 # inside the image: a view, K5 reads it through the parent's row stride
         if imsize is None:
             return img.contiguous()
         h, w = int(img.shape[0]), int(img.shape[1])
@@ -84,8 +84,7 @@ class DeviceImageLoader:
         if not img.is_cuda:
             img = (img if img.is_pinned() else img.pin_memory()).to(self.device, non_blocking=True)
         if bbx:
-            x0, y0, x1, y1 = [int(v) for v in bbx]
-            img = img[y0:y1, x0:x1]
+            img = crop_like_pil(img, bbx)
         return img.contiguous()
 
     def load(self, item, bbx=None, imsize=None):

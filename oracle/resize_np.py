@@ -182,8 +182,13 @@ def load_resized_u8(img, imsize=None, bbx=None):
     img = np.asarray(img, dtype=np.uint8)
     full = max(img.shape[0], img.shape[1])
     if bbx:
-        x0, y0, x1, y1 = [int(v) for v in bbx]
-        img = img[y0:y1, x0:x1]
+        x0, y0, x1, y1 = [int(round(v)) for v in bbx]     # Image.crop rounds the box; outside pixels are black
+        h, w = img.shape[:2]
+        out = np.zeros((max(y1 - y0, 0), max(x1 - x0, 0)) + img.shape[2:], dtype=np.uint8)
+        sx0, sy0, sx1, sy1 = max(x0, 0), max(y0, 0), min(x1, w), min(y1, h)
+        if sx1 > sx0 and sy1 > sy0:
+            out[sy0 - y0:sy1 - y0, sx0 - x0:sx1 - x0] = img[sy0:sy1, sx0:sx1]
+        img = out
     if imsize is not None:
         img = thumbnail_u8(img, imsize * max(img.shape[0], img.shape[1]) / full if bbx else imsize)
     return np.ascontiguousarray(img)

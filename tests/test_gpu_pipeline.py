@@ -48,13 +48,31 @@ def test_batched_extraction_equals_per_image_forward(vgg):
     torch.testing.assert_close(torch.cat(halves), d, rtol=2e-5, atol=5e-6)   # batch boundaries move -> other cuDNN algorithms
 
 
+def test_extraction_is_deterministic_across_repeats_and_batchings(vgg):
+    """Race detector for the double-buffered upload / K1 / K2 chain: the same images give the same bits, run after run, and
+    rows do not depend on which other images shared their launch (uint8 -> CLAHE is per image; cuDNN picks algorithms per
+    batch size, hence the tolerance on the second half)."""
+    from gandtr_b200.extract import extract_descriptors
+    images, qimages, _ = _dataset()
+    first = extract_descriptors(vgg, images, None, vgg.transform)
+    for _ in range(4):
+        assert torch.equal(extract_descriptors(vgg, images, None, vgg.transform), first)
+    q = extract_descriptors(vgg, qimages, None, vgg.transform)
+    for _ in range(4):
+        assert torch.equal(extract_descriptors(vgg, qimages, None, vgg.transform), q)
+    torch.testing.assert_close(extract_descriptors(vgg, images, None, vgg.transform, batch_size=1), first, rtol=2e-5, atol=5e-6)
+    x = vgg.transform.batch(torch.from_numpy(np.stack([images[0], images[1]])).cuda())
+    for _ in range(4):
+        assert torch.equal(vgg.transform.batch(torch.from_numpy(np.stack([images[0], images[1]])).cuda()), x)
+
+
 def test_device_resize_extraction_equals_host_resize(vgg):
     """with `device_resize` the workers only decode; crop + LANCZOS thumbnail run on the GPU (K5) and feed K1
     the very same pixels, so the descriptors are those of the host-resize path."""
     from gandtr_b200.extract import extract_descriptors, load_image
     from gandtr_b200.loader import DeviceImageLoader
     images = [synth_image(1200 + i, *[(150, 200), (200, 150), (96, 128)][i % 3], "smooth" if i % 3 else "noise") for i in range(9)]
-    bbxs = [None, (10, 20, 190, 140), None, None, (5, 5, 120, 190), None, None, None, (0, 0, 100, 90)]
+    bbxs = [None, (10, 20, 140, 190), None, None, (5.5, 4.5, 120.2, 190.7), None, None, None, (0, 0, 100, 90)]
     ld = DeviceImageLoader(imsize=96, device="cuda")
     from PIL import Image
     pil = [Image.fromarray(a) for a in images]

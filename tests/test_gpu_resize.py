@@ -43,7 +43,7 @@ def test_extremes_and_crop():
     assert np.array_equal(_dev(a, 64), R.thumbnail_u8(a, 64))
     assert np.array_equal(_dev(255 - a, 64), R.thumbnail_u8(255 - a, 64))
     img = synth_image(77, 300, 400, "smooth")
-    for bbx in [(30, 40, 330, 250), (1, 1, 399, 299), (100, 0, 103, 300)]:
+    for bbx in [(30, 40, 330, 250), (1, 1, 399, 299), (100, 0, 103, 300), (136.5, 34.1, 348.5, 255.7), (-10, -5, 200, 310)]:
         assert np.array_equal(_dev(img, 256, bbx), R.load_resized_u8(img, 256, bbx)), bbx
     assert np.array_equal(_dev(img, None, (10, 20, 200, 220)), img[20:220, 10:200])      # crop only
 
