@@ -40,6 +40,9 @@ class HostBatchUploader:
         if self.slots[j] is None or self.slots[j].shape != host_batch.shape or self.slots[j].dtype != host_batch.dtype:
             self.slots[j] = torch.empty(host_batch.shape, dtype=host_batch.dtype, device=self.device)
             self.free[j] = None
+            # The block comes from the compute stream's pool: kernels already queued there may still be using its previous
+            # contents (a workspace, an older slot). The copy stream must not write into it before they are done.
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             if self.free[j] is not None:
                 self.copy_stream.wait_event(self.free[j])        # the consumer of the previous occupant has finished
