@@ -33,9 +33,9 @@ MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 K1_BYTES_PER_IMG = 15 * H * W
 K2_BYTES_PER_IMG = 4 * C_FEAT * FH * FW + 4 * C_FEAT
 # measured DRAM traffic of K1 per image (dram__bytes_read.sum + dram__bytes_write.sum of clahe_hist + clahe_apply, ncu
-# --set full capture profiles/ncu_full_r1m.txt at 32 images: 76.0 + 74.6 + 127.5 + 244.0 MB) -- 1.38x the algorithmic
+# --set full capture profiles/ncu_k1_r1q.txt at 32 images: 76.1 + 75.0 + 127.7 + 243.9 MB) -- 1.38x the algorithmic
 # bytes: the 5 B/px scratch (lightness byte + cell code) is written by pass A and read by pass B
-K1_TRAFFIC_PER_IMG = (76.039424e6 + 74.577664e6 + 127.460864e6 + 243.959040e6) / 32
+K1_TRAFFIC_PER_IMG = (76.089600e6 + 74.962944e6 + 127.656448e6 + 243.922176e6) / 32
 
 
 def parse():
@@ -56,9 +56,10 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------- inputs
 
-def synth_images_torch(n, seed, device):
+def synth_images_torch(n, seed, device, h=None, w=None):
     """Smooth sinusoid + noise family of SURVEY 8(d), generated with torch (host or device)."""
     import torch
+    H, W = (h or globals()["H"]), (w or globals()["W"])
     g = torch.Generator(device=device).manual_seed(seed)
     yy = torch.arange(H, device=device, dtype=torch.float32).view(1, H, 1, 1)
     xx = torch.arange(W, device=device, dtype=torch.float32).view(1, 1, W, 1)
@@ -395,10 +396,11 @@ def main():
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "K1 clahe_hist_kernel + clahe_apply_kernel (one gdt_clahe_u8 call)", "bound": "hbm",
                      "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1m, per image x batch",
+                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1q, per image x batch",
                      "ms_per_launch_pair": k1_ms,
-                     "note": "nominal bound; ncu shows the LSU pipe (89 % in pass B) and instruction issue (69 %) as the actual "
-                             "limiters of the bit-exact pipeline, DRAM at ~15 % (profiles/ncu_full_r1n.txt)",
+                     "note": "nominal bound; ncu shows issue (74 %), the LSU pipe (73 %: shared-memory spline / LUT lookups) and the "
+                             "texture pipe (65 %: scattered lattice records) as the limiters of pass B and the LSU pipe (79 %: "
+                             "scattered lattice records) of pass A; DRAM at ~22 % (profiles/ncu_k1_r1q.txt)",
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
                         "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -483,6 +485,39 @@ def main():
                                        "map_easy_medium_hard_ms": m_ms / 5,
                                        "map": {k: round(float(v), 6) for k, v in res["avg"].items()}}
         del rindex
+
+    # ---- dataset image geometry on the device (K5): 3072x2304 "photo" -> LANCZOS thumbnail 1024 ----
+    if world == 1:
+        try:
+            from gandtr_b200.loader import DeviceImageLoader
+            gh, gw = 2304, 3072
+            photos = [synth_images_torch(1, 900 + i, dev, h=gh, w=gw)[0] for i in range(8)]     # 170 MB > L2
+            ld = DeviceImageLoader(imsize=1024, device=dev)
+            def step_geom():
+                for ph in photos:
+                    ld.resize(ph)
+            g_ms, w = timed(step_geom, 5, 3)
+            windows.append(w)
+            per = g_ms / 5 / len(photos)
+            oh, ow = ld.resize(photos[0]).shape[:2]
+            alg = 3.0 * gh * gw + 3.0 * oh * ow
+            line["image_geometry"] = {"kernel": "K5 resize_h_kernel + resize_v_kernel (Pillow LANCZOS thumbnail, bit-exact)",
+                                      "workload": "%dx%d uint8 RGB -> %dx%d" % (gw, gh, ow, oh), "ms_per_image": per,
+                                      "images_per_s": 1e3 / per, "bound": "hbm", "achieved": alg / per / 1e6, "peak": hbm_peak,
+                                      "unit": "GB/s", "frac": alg / per / 1e6 / hbm_peak,
+                                      "algorithmic_bytes_per_image": alg}
+            if rank == 0 and not args.no_cpu_baseline:
+                from PIL import Image
+                arr = photos[0].cpu().numpy()
+                t0 = time.time()
+                for _ in range(3):
+                    im = Image.fromarray(arr)
+                    im.thumbnail((1024, 1024), getattr(Image, "LANCZOS", Image.Resampling.LANCZOS))
+                line["image_geometry"]["cpu_baseline"] = {"value": 3 / (time.time() - t0), "unit": "images/s", "cores": 1, "kind": "reference",
+                                                          "sample": "Pillow Image.thumbnail on the same image, 3 repeats (one DataLoader worker's share)"}
+            del photos
+        except Exception as e:                      # context only, never fatal
+            line["image_geometry"] = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         line["clocks"] = sampler.stop(windows)

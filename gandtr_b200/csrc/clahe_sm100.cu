@@ -36,7 +36,8 @@ struct ClaheTables {
 static ClaheTables g_tables[32];
 
 // A/B switches (gdt_debug_k1_config): texab bit 0 = pass A fetches the chroma lattice records through the texture pipe
-// (when chroma_a), bit 1 = pass A fetches the lightness records through the texture pipe (when !chroma_a);
+// (when chroma_a), bit 1 / bit 2 = pass A fetches all / every other lightness record through the texture pipe (when
+// !chroma_a);
 // spltex = 0..3 spline lookups of pass B through the texture pipe; fytex = lightness half of Lab->RGB from the 256-entry
 // table (texture pipe) instead of recomputing it. Every combination is bit-identical; only the pipe balance differs.
 //   chroma_a = interpolate the chroma in pass A (one lattice visit per pixel) instead of pass B (gather hidden under
@@ -129,8 +130,9 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
 
 // `gq`, `gr` = 256 / gw, 256 % gw (gw = 4-pixel groups per tile row): the vectorised loop walks (row, group) incrementally,
 // no division per step. TEXAB: chroma records through the texture pipe (idle otherwise), lightness through the LSU pipe.
-// TEXL: the lightness records take the texture pipe too (pass A is bound by the LSU pipe's scattered 16-byte gathers).
-template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, bool TEXL>
+// TEXL: which lightness-record gathers take the texture pipe instead of the LSU pipe (pass A is bound by the LSU pipe's
+// scattered 16-byte gathers): 0 none, 1 all, 2 every other pixel (both pipes gather in parallel).
+template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL>
 __global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w,
@@ -197,7 +199,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                 uint4 wl[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)                                      // four gathers in flight
-                    wl[i] = TEXL ? tex1Dfetch<uint4>(texL, cell[i]) : __ldg(lutL + cell[i]);
+                    wl[i] = (TEXL == 1 || (TEXL == 2 && (i & 1))) ? tex1Dfetch<uint4>(texL, cell[i]) : __ldg(lutL + cell[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v[i] = lab_l8_int(lab_trilinear(wl[i].x, wl[i].y, wl[i].z, wl[i].w, fr[i], fg[i], fb[i]));
@@ -525,13 +527,14 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
                                                                       g.lut_scale, vec_hist, gq, gr, T->lutL, T->lutAB, \
                                                                       in_norm, T->texAB, T->texL)
     if (!chroma_a) {
-        if (texab & 2) GDT_HIST(false, false, 4, true);
-        else if (occ_a >= 6) GDT_HIST(false, false, 6, false);
-        else GDT_HIST(false, false, 4, false);
+        if (texab & 4) GDT_HIST(false, false, 4, 2);
+        else if (texab & 2) GDT_HIST(false, false, 4, 1);
+        else if (occ_a >= 6) GDT_HIST(false, false, 6, 0);
+        else GDT_HIST(false, false, 4, 0);
     } else if (texab & 1) {
-        if (occ_a >= 6) GDT_HIST(true, true, 6, false); else GDT_HIST(true, true, 4, false);
+        if (occ_a >= 6) GDT_HIST(true, true, 6, 0); else GDT_HIST(true, true, 4, 0);
     } else {
-        GDT_HIST(false, true, 4, false);
+        GDT_HIST(false, true, 4, 0);
     }
 #undef GDT_HIST
     GDT_LAUNCH_CHECK();
@@ -617,7 +620,7 @@ extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, 
 
 extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a) {
     if (spltex < 0 || spltex > 1 || (occ_a != 4 && occ_a != 6)) return GDT_ERR_INVALID_ARGUMENT;
-    g_k1_texab = texab & 3;
+    g_k1_texab = texab & 7;
     g_k1_spltex = spltex;
     g_k1_fytex = fytex ? 1 : 0;
     g_k1_chroma_a = chroma_a ? 1 : 0;

@@ -68,7 +68,7 @@ reduce_kernel(const uint8_t* __restrict__ src, size_t src_stride, int w, int h, 
 __global__ void __launch_bounds__(kHCols)
 resize_h_kernel(const uint8_t* __restrict__ src, size_t src_stride, int row0, int nrows, uint8_t* __restrict__ dst,
                 size_t dst_stride, int out_w, const int* __restrict__ bounds, const int32_t* __restrict__ kkT) {
-    extern __shared__ uint8_t span[];
+    extern __shared__ __align__(16) uint8_t span[];
     const int tid = threadIdx.x;
     const int xx0 = blockIdx.x * kHCols;
     const int xx = xx0 + tid;
@@ -82,14 +82,26 @@ resize_h_kernel(const uint8_t* __restrict__ src, size_t src_stride, int row0, in
         cnt = __ldg(bounds + xx * 2 + 1);
     }
     const int r0 = blockIdx.y * kHRows, r1 = min(r0 + kHRows, nrows);
+    uint32_t* span32 = (uint32_t*)span;
     for (int r = r0; r < r1; ++r) {
         const uint8_t* row = src + (size_t)(row0 + r) * src_stride + (size_t)first * 3;
+        // staged as aligned 32-bit words: the span starts `mis` bytes into the first word (rows of 3-byte pixels and
+        // crop views start anywhere); the words lie inside the source row's allocation except possibly the last one,
+        // which is read bytewise
+        const int mis = (int)((uintptr_t)row & 3);
+        const uint32_t* row32 = (const uint32_t*)(row - mis);
+        const int nwords = (mis + nbytes + 3) >> 2;
         __syncthreads();                                  // the previous row's readers are done
-        for (int i = tid; i < nbytes; i += kHCols) span[i] = __ldg(row + i);
+        for (int i = tid; i < nwords - 1; i += kHCols) span32[i] = __ldg(row32 + i);
+        if (tid == 0) {
+            uint32_t wv = 0;
+            for (int b = (nwords - 1) * 4; b < mis + nbytes; ++b) wv |= (uint32_t)__ldg(row - mis + b) << (8 * (b & 3));
+            span32[nwords - 1] = wv;
+        }
         __syncthreads();
         if (xx < out_w) {
             int a0 = 1 << (kResizePrecisionBits - 1), a1 = a0, a2 = a0;
-            const uint8_t* p = span + xmin * 3;
+            const uint8_t* p = span + mis + xmin * 3;
             for (int k = 0; k < cnt; ++k) {
                 const int c = __ldg(kkT + (size_t)k * out_w + xx);
                 a0 += (int)p[k * 3] * c;
@@ -226,7 +238,7 @@ extern "C" int gdt_resize_plan_create(int in_w, int in_h, double imsize, gdt_res
             const int s = bh[(size_t)xl * 2] + bh[(size_t)xl * 2 + 1] - bh[(size_t)xx0 * 2];
             if (s > span) span = s;
         }
-        p->h_smem_bytes = span * 3;
+        p->h_smem_bytes = (int)align_up((size_t)span * 3 + 8, 16);      // + up to 3 bytes of misalignment, whole words
         auto up = [&](void** d, const void* hsrc, size_t bytes) -> int {
             cudaError_t e = cudaMalloc(d, bytes);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(resize plan)", __FILE__, __LINE__);

@@ -71,7 +71,7 @@ int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned lo
 
 /* debug/test hook: work split and pipe choice of K1's table lookups (every combination computes bit-identical results).
  *   texab    : bit 0: pass A fetches the chroma lattice records through the texture pipe (when chroma_a);
- *              bit 1: pass A fetches the lightness records through the texture pipe (when !chroma_a)
+ *              bit 1 / bit 2: pass A fetches all / every other lightness record through the texture pipe (when !chroma_a)
  *   spltex   : 0..1 of pass B's inverse-gamma spline lookups go through the texture pipe
  *   fytex    : pass B takes the lightness half of Lab->RGB from a 256-entry table through the texture pipe
  *   chroma_a : the chroma is interpolated in pass A (one lattice visit per pixel) instead of pass B

@@ -128,7 +128,7 @@ def test_every_pipe_variant_is_bit_identical():
     img = synth_image(11, 96, 128, "smooth")
     ref = O.transform_u8(img, lut, MEAN, STD)
     try:
-        for chroma_a, texab, occ_a in ((1, 1, 4), (1, 0, 4), (1, 1, 6), (0, 0, 4), (0, 0, 6), (0, 2, 4)):
+        for chroma_a, texab, occ_a in ((1, 1, 4), (1, 0, 4), (1, 1, 6), (0, 0, 4), (0, 0, 6), (0, 2, 4), (0, 4, 4)):
             for spltex in (0, 1):
                 for fytex in (0, 1):
                     _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex, chroma_a, occ_a), "gdt_debug_k1_config")

@@ -1,7 +1,6 @@
 #!/bin/bash
-# race hunt: the pipeline suite four times
-mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
-for i in 1 2 3 4; do
-timeout 600 python -m pytest tests/test_gpu_pipeline.py -q -m gpu --timeout 300 > gpurun_out/pytest_k1_$i.log 2>&1; echo "pytest $i exit $?" >> gpurun_out/summary.txt
-done
-cat gpurun_out/summary.txt; grep -h "^E  \|passed\|failed" gpurun_out/pytest_k1_*.log | cut -c1-300
+# K1 / K5 visit: bit-exactness suites + K1 variant timing at 128 images
+mkdir -p gpurun_out; rm -f gpurun_out/summary.txt gpurun_out/k1_ab.log
+timeout 600 python -m pytest tests/test_gpu_clahe.py tests/test_gpu_resize.py -q -m gpu --timeout 300 > gpurun_out/pytest_k1.log 2>&1; echo "pytest exit $?" >> gpurun_out/summary.txt
+timeout 300 python tools/k1_ab.py >> gpurun_out/k1_ab.log 2>&1
+cat gpurun_out/summary.txt; tail -5 gpurun_out/pytest_k1.log; cat gpurun_out/k1_ab.log
