@@ -2,7 +2,7 @@
 # One GPU visit: parity suite, contract bench, launch list and full ncu captures of the hot kernels.
 # usage: bash tools/gpu_round.sh <tag> [ncu-kernel-regex]
 TAG=${1:-rX}
-KRE=${2:-'clahe|gem_pool|whiten_gemm|score_filter|topk_finalize'}
+KRE=${2:-'clahe|resize_|reduce_kernel|gem_pool|whiten_tc|score_filter|topk_finalize'}
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
@@ -14,7 +14,7 @@ timeout 300 python tools/prof_target.py > gpurun_out/prof_plain.log 2>&1
 rc=$?; echo "prof_plain exit $rc" >> gpurun_out/summary.txt
 if [ $rc -eq 0 ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/prof_target.py > gpurun_out/ncu_launches.log 2>&1; echo "ncu_launches exit $?" >> gpurun_out/summary.txt
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -c 30 -o gpurun_out/prof_$TAG -f python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu_full exit $?" >> gpurun_out/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -c 40 -o gpurun_out/prof_$TAG -f python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu_full exit $?" >> gpurun_out/summary.txt
 fi
 cat gpurun_out/summary.txt
 tail -n 3 gpurun_out/smoke_$TAG.log

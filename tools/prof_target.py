@@ -5,7 +5,7 @@ import torch
 from gandtr_b200 import _lib
 from bench import synth_images_torch, MEAN, STD
 
-which = sys.argv[1:] or ["clahe", "gem", "topk"]
+which = sys.argv[1:] or ["clahe", "resize", "gem", "topk"]
 dev = torch.device("cuda", 0)
 reps = 3
 if "clahe" in which:
@@ -13,6 +13,14 @@ if "clahe" in which:
     out = torch.empty((32, 3, 768, 1024), dtype=torch.float32, device=dev)
     for _ in range(reps):
         _lib.clahe_u8(x, MEAN, STD, out=out)
+if "resize" in which:
+    from gandtr_b200.loader import DeviceImageLoader
+    ph = synth_images_torch(1, 900, dev, h=2304, w=3072)[0]
+    ld = DeviceImageLoader(imsize=1024, device=dev)
+    for _ in range(reps):
+        ld.resize(ph)
+    big = synth_images_torch(1, 901, dev, h=3456, w=4608)[0]      # pre-reduction by 2, then LANCZOS
+    ld.resize(big)
 if "gem" in which:
     c = 2048
     fm = [torch.rand((128, c, h, w), device=dev) for h, w in ((24, 32), (17, 23), (12, 16))]
