@@ -217,12 +217,11 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
         }
     } else {
         // generic: extended (REFLECT_101-padded) tile, one pixel per thread per step
-        const int npx = th * tw;
-        for (int base = 0; base < npx; base += 256) {
-            const int pidx = base + tid;
+        // (row, col) walk incrementally: + 256 pixels per step, gq / gr = 256 / tw, 256 % tw
+        int row = tid / tw, col = tid - row * tw;
+        for (; row < th; ) {
             int v = 256;
-            if (pidx < npx) {
-                const int row = pidx / tw, col = pidx - row * tw;
+            {
                 const int ey = ty * th + row, ex = tx * tw + col;
                 const int sy = reflect101(ey, h), sx = reflect101(ex, w);
                 const size_t p = (size_t)sy * w + sx;
@@ -248,6 +247,9 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                 }
             }
             hist_add(hist, v);
+            row += gq;
+            col += gr;
+            if (col >= tw) { col -= tw; ++row; }
         }
     }
     __syncthreads();
@@ -520,7 +522,7 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     // A/B switches, see gdt_debug_k1_config (profiles/k1_v2_ab_r1q.log)
     const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, chroma_a = g_k1_chroma_a, occ_a = g_k1_occ_a;
     dim3 gridA(grid * grid, n);
-    const int gw = vec_hist ? (g.tw >> 2) : 1;
+    const int gw = vec_hist ? (g.tw >> 2) : g.tw;      // walk unit per tile row: 4-pixel groups or single pixels
     const int gq = 256 / gw, gr = 256 % gw;
 #define GDT_HIST(T_, C_, O_, L_)                                                                                       \
     clahe_hist_kernel<U8, T_, C_, O_, L_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip,  \
