@@ -155,11 +155,17 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
     uint32_t* abimg = AB + (size_t)img * plane;
 
     if (vec_ok) {
-        // tile fully inside the image, 4 consecutive pixels per thread
-        const int gw = tw >> 2;
-        int row = tid / gw, c4 = tid - row * gw;
-        for (; row < th; ) {
-            const int y = ty * th + row, x0 = tx * tw + (c4 << 2);
+        // 4 consecutive pixels per thread, groups aligned to 4 pixels of the image row. vec_ok == 1: the tile is a whole
+        // number of groups inside the image. vec_ok == 2 (image padded by OpenCV and / or tile width not a multiple of
+        // 4): the groups cover the tile's REAL pixels [xa, xb) x [ya, yb); pixels of a straddling group that belong to
+        // the neighbouring tile are computed (the scratch vector both CTAs store is identical) but not counted; the
+        // reflected padding is counted by the scalar loop below.
+        const int xa = tx * tw, xb = min(xa + tw, w), ya = ty * th, yb = min(ya + th, h);
+        const int g0 = xa >> 2, ngx = ((xb + 3) >> 2) - g0, nry = yb - ya;
+        const int vq = ngx > 0 ? 256 / ngx : 0, vr = ngx > 0 ? 256 - vq * ngx : 0;
+        int row = ngx > 0 ? tid / ngx : nry, c4 = ngx > 0 ? tid - row * ngx : 0;
+        for (; row < nry; ) {
+            const int y = ya + row, x0 = (g0 + c4) << 2;
             const size_t p = (size_t)y * w + x0;
             int cell[4], fr[4], fg[4], fb[4];
             if (U8) {
@@ -209,11 +215,29 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
             *(uint4*)(abimg + p) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
             *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hist_add(hist, v[i]);
+            for (int i = 0; i < 4; ++i) hist_add(hist, (vec_ok == 1 || (x0 + i >= xa && x0 + i < xb)) ? v[i] : 256);
             // next (row, group) of this thread: + 256 groups
-            row += gq;
-            c4 += gr;
-            if (c4 >= gw) { c4 -= gw; ++row; }
+            row += vq;
+            c4 += vr;
+            if (c4 >= ngx) { c4 -= ngx; ++row; }
+        }
+        if (vec_ok == 2) {
+            // reflected padding of this tile: right strip (all tile rows) then bottom strip (columns left of the right strip)
+            const int xe = xa + tw, ye = ya + th;
+            const int rx0 = max(xa, w), rw = xe - rx0;                 // right strip: cols [rx0, xe), rows [ya, ye)
+            const int by0 = max(ya, h), bw = min(xe, w) - xa;          // bottom strip: rows [by0, ye), cols [xa, xa + bw)
+            const int nright = rw > 0 ? rw * th : 0, nbottom = (ye > by0 && bw > 0) ? (ye - by0) * bw : 0;
+            for (int i = tid; i < nright + nbottom; i += 256) {
+                int ey, ex;
+                if (i < nright) { ey = ya + i / rw; ex = rx0 + i % rw; }
+                else { const int j = i - nright; ey = by0 + j / bw; ex = xa + j % bw; }
+                const size_t p = (size_t)reflect101(ey, h) * w + reflect101(ex, w);
+                int cell, fr, fg, fb;
+                if (U8) cell_from_u8(in8[p * 3], in8[p * 3 + 1], in8[p * 3 + 2], cell, fr, fg, fb);
+                else cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
+                const uint4 wl = __ldg(lutL + cell);
+                hist_add(hist, lab_l8_int(lab_trilinear(wl.x, wl.y, wl.z, wl.w, fr, fg, fb)));
+            }
         }
     } else {
         // generic: extended (REFLECT_101-padded) tile, one pixel per thread per step
@@ -517,12 +541,13 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
 
     const bool aligned = (((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0;
     const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
-    const int vec_hist = (vec_apply && g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 0;
+    // 1: whole 4-pixel groups per tile row; 2: aligned groups over ragged / padded tiles (needs whole groups per image row)
+    const int vec_hist = !vec_apply ? 0 : ((g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 2);
 
     // A/B switches, see gdt_debug_k1_config (profiles/k1_v2_ab_r1q.log)
     const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, chroma_a = g_k1_chroma_a, occ_a = g_k1_occ_a;
     dim3 gridA(grid * grid, n);
-    const int gw = vec_hist ? (g.tw >> 2) : g.tw;      // walk unit per tile row: 4-pixel groups or single pixels
+    const int gw = g.tw;                               // scalar path: walk unit = one pixel of a tile row
     const int gq = 256 / gw, gr = 256 % gw;
 #define GDT_HIST(T_, C_, O_, L_)                                                                                       \
     clahe_hist_kernel<U8, T_, C_, O_, L_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip,  \

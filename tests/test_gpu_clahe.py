@@ -33,7 +33,8 @@ def test_reference_golden_bit_exact():
 
 @pytest.mark.parametrize("kind,h,w", [("smooth", 96, 128), ("noise", 64, 64), ("dark", 120, 160), ("smooth", 61, 77),
                                       ("noise", 37, 53), ("smooth", 100, 130), ("smooth", 8, 8), ("smooth", 72, 100),
-                                      ("dark", 50, 1100)])
+                                      ("dark", 50, 1100), ("smooth", 683, 1024), ("noise", 9, 64), ("smooth", 20, 12),
+                                      ("noise", 75, 36), ("smooth", 41, 2044)])
 def test_oracle_bit_exact_shapes(kind, h, w):
     lut = load_lut()
     img = synth_image(100 + h + w, h, w, kind)
