@@ -35,6 +35,7 @@ SYMBOLS = [
     ("gdt_debug_get_spline_table", _c.c_int, [_P]),
     ("gdt_debug_div_check", _c.c_int, [_c.c_float, _c.c_uint32, _c.c_uint32, _P, _P]),
     ("gdt_debug_k1_config", _c.c_int, [_c.c_int] * 5),
+    ("gdt_debug_k1_rows", _c.c_int, [_c.c_int]),
     ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_clahe_u8", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _c.c_size_t, _P]),
     ("gdt_clahe_f32", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P,

@@ -45,6 +45,7 @@ static ClaheTables g_tables[32];
 // Defaults = the fastest combination measured on B200 (profiles/k1_v2_ab_r1q.log): chroma in pass B (its gather hides
 // under pass B's arithmetic; in pass A it is exposed: 1.03 vs 1.20 ms per 128 images), everything else recomputed.
 static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_chroma_a = 0, g_k1_occ_a = 4;
+static int g_k1_rows = 0;     // > 0: rows per pass-B CTA forced (gdt_debug_k1_rows), 0: pass_b_rows()
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -523,6 +524,22 @@ static int clahe_geometry(int n, int h, int w, double clip_limit, int grid, Clah
     return GDT_OK;
 }
 
+// rows per pass-B CTA: the largest candidate whose grid wastes < 3 % of its last wave, else the most efficient one
+static int pass_b_rows(int h, long long ctas_per_band, long long slots) {
+    static const int cand[] = {48, 40, 32, 28, 24, 20, 16, 12, 8, 6, 4, 2};
+    int best = 2;
+    double best_eff = -1.0;
+    for (int r : cand) {
+        const long long ctas = (long long)ceil_div(h, r) * ctas_per_band;
+        const long long waves = ceil_div_ll(ctas, slots);
+        // rows that do not divide h leave a short last band: count it as full work (conservative)
+        const double eff = (double)ctas / (double)(waves * slots);
+        if (ctas >= slots && eff >= 0.97) return r;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = r; }
+    }
+    return best;
+}
+
 template <bool U8>
 static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, int grid, const Norm3& in_norm,
                         const Norm3& out_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -566,11 +583,13 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
 #undef GDT_HIST
     GDT_LAUNCH_CHECK();
 
-    // enough CTAs to fill the machine, as many rows per CTA as that allows (amortises the LUT staging)
+    // Rows per CTA: as many as possible (amortises the LUT / spline staging) while the grid still fills whole waves of
+    // the machine: 4 resident CTAs per SM, and a last wave that is mostly empty costs up to a wave of time (32 rows on
+    // 128 images of 768 rows = 5.2 waves; 24 rows = 6.9).
     const int sms = sm_count_current_device();
-    int rows = 32;
     const int xchunks = ceil_div(w, 1024);
-    while (rows > 2 && (long long)ceil_div(h, rows) * xchunks * n < 16LL * sms) rows >>= 1;   // >= ~3 waves
+    int rows = pass_b_rows(h, (long long)xchunks * n, 4LL * sms);
+    if (g_k1_rows > 0) rows = g_k1_rows;
     dim3 gridB(xchunks, ceil_div(h, rows), n);
     // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
     int span = (rows + g.th - 1) / g.th + 2;
@@ -652,6 +671,12 @@ extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_
     g_k1_fytex = fytex ? 1 : 0;
     g_k1_chroma_a = chroma_a ? 1 : 0;
     g_k1_occ_a = occ_a;
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_rows(int rows_per_cta) {
+    if (rows_per_cta < 0 || rows_per_cta > 64) return GDT_ERR_INVALID_ARGUMENT;
+    g_k1_rows = rows_per_cta;
     return GDT_OK;
 }
 

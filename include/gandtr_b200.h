@@ -77,6 +77,8 @@ int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned lo
  *   chroma_a : the chroma is interpolated in pass A (one lattice visit per pixel) instead of pass B
  *   occ_a    : resident CTAs per SM pass A is compiled for (4 or 6) */
 int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a);
+/* debug/test hook: force the image rows per pass-B CTA of K1 (1..64; 0 = the built-in wave-quantisation rule) */
+int gdt_debug_k1_rows(int rows_per_cta);
 
 /* ---- K5: dataset image geometry (crop + LANCZOS thumbnail) ---------------------------------------
  * The image-size half of the reference's dataset loader on the device:

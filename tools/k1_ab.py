@@ -25,6 +25,11 @@ for chroma_a, texab, occ_a in ((0, 0, 4),):
             print("chroma_a=%d texab=%d occ_a=%d fytex=%d spltex=%d n=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic" % (chroma_a, texab, occ_a, fytex, spltex, n, ms, n / ms * 1e3, n * 15 * 768 * 1024 / ms / 1e6), flush=True)
             if best is None or ms < best[0]: best = (ms, chroma_a, texab, occ_a, fytex, spltex)
 _lib.k1_config_default()
+for rows in (32, 48, 24, 16, 12, 8, 0):
+    _lib.check(lib.gdt_debug_k1_rows(rows), "rows")
+    for nn in (128, 32):
+        ms = timeit(lambda: _lib.clahe_u8(x[:nn], MEAN, STD, out=out[:nn]))
+        print("rows_per_cta=%d n=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic" % (rows, nn, ms, nn / ms * 1e3, nn * 15 * 768 * 1024 / ms / 1e6), flush=True)
 for hh, ww in ((683, 1024), (768, 1020), (681, 1023)):      # sizes that take the reflect-padded pass A / non-FAST pass B paths
     xo = synth_images_torch(n, 2, "cuda", h=hh, w=ww)
     oo = torch.empty((n, 3, hh, ww), dtype=torch.float32, device="cuda")
