@@ -4,16 +4,19 @@
 // (mdir/components/data/wrapper.py:325-348), bit-exact against the reference's OpenCV 4.13.0 path.
 //
 // Two launches per batch, both streaming with coalesced 16-byte accesses:
-//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> lattice cell + fractions (integer arithmetic, one
-//           multiply-shift per channel) -> the three Q14 Lab channels by ONE integer trilinear interpolation with shared
-//           weights (lightness record through the LSU pipe, chroma records through the texture pipe; dp2a) -> uint8 L8
-//           scratch (integer formula) + packed 2 x 16-bit chroma scratch + 256-bin shared-memory histogram
+//   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> lattice cell + 4-bit fractions (integer arithmetic, one
+//           multiply-shift per channel) -> Q14 lightness (one 16 B gather of the packed lattice record, dp2a trilinear)
+//           -> uint8 L8 scratch (integer formula) + 4-byte cell-code scratch + 256-bin shared-memory histogram
 //           (bank-skewed copies per warp) -> clip, redistribute, prefix sum -> tile LUT (transposed rows).
 //   pass B  clahe_apply_kernel  one CTA per (image, row band, 1024-px column chunk): LUT rows of the band and the
-//           inverse-gamma spline staged in shared memory, per pixel: bilinear LUT blend -> Lab->RGB (lightness half from
-//           a 256-entry table) -> spline inverse gamma -> normalise -> planar float4 stores. No lattice access.
+//           inverse-gamma spline staged in shared memory, per pixel: bilinear LUT blend -> chroma (32 B lattice record
+//           addressed by the cell code, texture pipe) -> Lab->RGB -> spline inverse gamma -> normalise -> planar float4
+//           stores.
 // Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 5 B/px written by A and
-// read by B (the input itself is read once, and quantised / interpolated once).
+// read by B (the input itself is read and quantised once).
+// The alternative work split (CHROMA_A: pass A interpolates all three channels with shared weights, pass B never
+// touches the lattice) is compiled in and bit-identical; it issues 31 % fewer instructions but is slower on B200
+// because the gathers are exposed in pass A (see g_k1_* below and profiles/README.md).
 #include <stdlib.h>
 
 #include "clahe_math.cuh"
@@ -38,7 +41,7 @@ static ClaheTables g_tables[32];
 // A/B switches (gdt_debug_k1_config): texab bit 0 = pass A fetches the chroma lattice records through the texture pipe
 // (when chroma_a), bit 1 / bit 2 = pass A fetches all / every other lightness record through the texture pipe (when
 // !chroma_a);
-// spltex = 0..3 spline lookups of pass B through the texture pipe; fytex = lightness half of Lab->RGB from the 256-entry
+// spltex = 0..1 spline lookups of pass B through the texture pipe; fytex = lightness half of Lab->RGB from the 256-entry
 // table (texture pipe) instead of recomputing it. Every combination is bit-identical; only the pipe balance differs.
 //   chroma_a = interpolate the chroma in pass A (one lattice visit per pixel) instead of pass B (gather hidden under
 //   pass B's arithmetic); occ_a = resident CTAs per SM pass A is compiled for (4 or 6).
