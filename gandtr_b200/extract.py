@@ -138,11 +138,15 @@ def _descriptors_for_batch(model, x, ms, msp):
 
 
 def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), msp=1, batch_size=32, workers=4,
-                        rank=0, world_size=1, print_freq=0, device_resize=False):
+                        rank=0, world_size=1, print_freq=0, device_resize=None):
     """-> [n_local, D] float32 CUDA tensor: rows lo..hi of the descriptor matrix, (lo, hi) = shard_bounds(len(images)).
     `net` is a gandtr_b200 SingleNetwork or ImageRetrievalNet; `transform` a gandtr_b200.transforms.Compose.
     `device_resize`: the workers only decode; bounding-box crop and the LANCZOS thumbnail run on the GPU (K5,
-    bit-identical to the host path), so the host cores are left to the JPEG decoder."""
+    bit-identical to the host path), so the host cores are left to the JPEG decoder. Default (None): on whenever there
+    is geometry work to do (an `image_size` or bounding boxes); without any, whole batches are uploaded as they are.
+    False keeps Pillow's crop / thumbnail in the workers (the reference's arrangement)."""
+    if device_resize is None:
+        device_resize = image_size is not None or (bbxs is not None and any(b for b in bbxs))
     model = getattr(net, "model", net)
     model.eval()
     dev = next(model.parameters()).device
