@@ -1,6 +1,8 @@
 #!/bin/bash
 # One GPU visit: parity suite, contract bench, launch list and full ncu captures of the hot kernels.
 # usage: bash tools/gpu_round.sh <tag> [ncu-kernel-regex]
+# NOTE: gpurun returns at most 64 MiB of gpurun_out/: keep the full capture to ~24 launches (a 40-launch capture with
+# sources was 70+ MiB and the whole visit's output was dropped in r1q).
 TAG=${1:-rX}
 KRE=${2:-'clahe|resize_|reduce_kernel|gem_pool|whiten_tc|score_filter|topk_finalize'}
 mkdir -p gpurun_out
@@ -14,7 +16,7 @@ timeout 300 python tools/prof_target.py > gpurun_out/prof_plain.log 2>&1
 rc=$?; echo "prof_plain exit $rc" >> gpurun_out/summary.txt
 if [ $rc -eq 0 ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/prof_target.py > gpurun_out/ncu_launches.log 2>&1; echo "ncu_launches exit $?" >> gpurun_out/summary.txt
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -c 40 -o gpurun_out/prof_$TAG -f python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu_full exit $?" >> gpurun_out/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -c 24 -o gpurun_out/prof_$TAG -f python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu_full exit $?" >> gpurun_out/summary.txt
 fi
 cat gpurun_out/summary.txt
 tail -n 3 gpurun_out/smoke_$TAG.log
