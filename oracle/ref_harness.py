@@ -25,6 +25,8 @@ def load_reference():
         if m not in sys.modules:
             sys.modules[m] = MagicMock(name=m)
     sys.modules["matplotlib"].rcParams = {"font.size": 10}
+    if isinstance(sys.modules["h5py"], MagicMock):      # default_loader does isinstance(path, h5py.Dataset)
+        sys.modules["h5py"].Dataset = type("Dataset", (), {})
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import hubconf  # noqa: side effect: torch.set_num_threads(3) (mdir/stages/validate.py:10)

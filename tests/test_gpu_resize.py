@@ -21,7 +21,7 @@ def test_pillow_golden_bit_exact():
     g = golden("resize.npz")
     n = len([k for k in g.files if k.startswith("img")])
     for i in range(n):
-        bbx = tuple(int(v) for v in g["bbx%d" % i]) or None
+        bbx = tuple(float(v) for v in g["bbx%d" % i]) or None
         out = _dev(g["img%d" % i], int(g["imsize%d" % i]), bbx)
         ref = g["out%d" % i]
         assert out.shape == ref.shape and np.array_equal(out, ref), "golden case %d" % i

@@ -15,7 +15,7 @@ def _cases():
     n = len([k for k in g.files if k.startswith("img")])
     assert n >= 9
     for i in range(n):
-        bbx = tuple(int(v) for v in g["bbx%d" % i]) or None
+        bbx = tuple(float(v) for v in g["bbx%d" % i]) or None
         yield g["img%d" % i], int(g["imsize%d" % i]), bbx, g["out%d" % i]
 
 
