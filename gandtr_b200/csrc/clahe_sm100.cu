@@ -139,7 +139,7 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
 template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL>
 __global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
-                  uint8_t* __restrict__ lutT, int h, int w,
+                  uint8_t* __restrict__ lutT, int h, int w, int pitch,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
                   const uint4* __restrict__ lutL, const uint4* __restrict__ lutAB, Norm3 in_norm,
                   cudaTextureObject_t texAB, cudaTextureObject_t texL) {
@@ -155,8 +155,9 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
     const size_t plane = (size_t)h * w;
     const uint8_t* in8 = (const uint8_t*)in_ + (size_t)img * plane * 3;
     const float* inf = (const float*)in_ + (size_t)img * plane * 3;
-    uint8_t* l8img = L8 + (size_t)img * plane;
-    uint32_t* abimg = AB + (size_t)img * plane;
+    // scratch rows are `pitch` = align4(w) elements apart: 4-pixel groups are 16-byte aligned for every width
+    uint8_t* l8img = L8 + (size_t)img * h * pitch;
+    uint32_t* abimg = AB + (size_t)img * h * pitch;
 
     if (vec_ok) {
         // 4 consecutive pixels per thread, groups aligned to 4 pixels of the image row. vec_ok == 1: the tile is a whole
@@ -170,11 +171,28 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
         int row = ngx > 0 ? tid / ngx : nry, c4 = ngx > 0 ? tid - row * ngx : 0;
         for (; row < nry; ) {
             const int y = ya + row, x0 = (g0 + c4) << 2;
-            const size_t p = (size_t)y * w + x0;
+            const size_t p = (size_t)y * w + x0, ps = (size_t)y * pitch + x0;
             int cell[4], fr[4], fg[4], fb[4];
             if (U8) {
-                const uint32_t* src = (const uint32_t*)(in8 + p * 3);
-                const uint32_t a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+                // 12 bytes of 4 packed RGB pixels. Rows of odd widths start at any byte: read the aligned words that
+                // cover them and realign by a funnel shift. A group cut by the row end (width not a multiple of 4) is
+                // read bytewise; its missing pixels are zeros (their scratch slots are padding, never counted).
+                uint32_t a0, a1, a2;
+                const uint8_t* src8 = in8 + p * 3;
+                if (x0 + 4 <= w) {
+                    const unsigned mis = (unsigned)((uintptr_t)src8 & 3);
+                    const uint32_t* src = (const uint32_t*)(src8 - mis);
+                    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+                    const uint32_t w3 = mis ? __ldg(src + 3) : 0u;      // mis == 0: the 12 bytes end with w2
+                    a0 = __funnelshift_r(w0, w1, mis * 8);
+                    a1 = __funnelshift_r(w1, w2, mis * 8);
+                    a2 = __funnelshift_r(w2, w3, mis * 8);
+                } else {
+                    uint32_t b[3] = {0u, 0u, 0u};
+                    const int nb = (w - x0) * 3;
+                    for (int k = 0; k < nb; ++k) b[k >> 2] |= (uint32_t)__ldg(src8 + k) << (8 * (k & 3));
+                    a0 = b[0]; a1 = b[1]; a2 = b[2];
+                }
                 const int rr[4] = {(int)(a0 & 255), (int)(a0 >> 24), (int)((a1 >> 16) & 255), (int)((a2 >> 8) & 255)};
                 const int gg[4] = {(int)((a0 >> 8) & 255), (int)(a1 & 255), (int)(a1 >> 24), (int)((a2 >> 16) & 255)};
                 const int bb[4] = {(int)((a0 >> 16) & 255), (int)((a1 >> 8) & 255), (int)(a2 & 255), (int)(a2 >> 24)};
@@ -216,8 +234,8 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                     ab[i] = pack_code(cell[i], fr[i], fg[i], fb[i]);
                 }
             }
-            *(uint4*)(abimg + p) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
-            *(uint32_t*)(l8img + p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+            *(uint4*)(abimg + ps) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
+            *(uint32_t*)(l8img + ps) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
 #pragma unroll
             for (int i = 0; i < 4; ++i) hist_add(hist, (vec_ok == 1 || (x0 + i >= xa && x0 + i < xb)) ? v[i] : 256);
             // next (row, group) of this thread: + 256 groups
@@ -270,8 +288,8 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                     ab = pack_code(cell, fr, fg, fb);
                 }
                 if (ey < h && ex < w) {
-                    l8img[p] = (uint8_t)v;
-                    abimg[p] = ab;
+                    l8img[(size_t)sy * pitch + sx] = (uint8_t)v;
+                    abimg[(size_t)sy * pitch + sx] = ab;
                 }
             }
             hist_add(hist, v);
@@ -327,10 +345,11 @@ struct NormFast {
     int fast;   // div_by_const_ok() for all three std
 };
 
-// FAST = the common configuration compiled without per-pixel mode tests: width a multiple of 8 (no OpenCV scalar-tail
-// pixels), 8-byte LUT rows, divider-free normalisation, 16-byte aligned rows.
-// SPLTEX = how many of the three inverse-gamma spline lookups go through the texture pipe instead of shared memory
-// (pass B is bound by shared-memory wavefronts + issue; the texture pipe is idle since pass A took over the lattice).
+// FAST = the common configuration compiled without per-pixel mode tests: 8-byte LUT rows (grid <= 8) and divider-free
+// normalisation. Any width: OpenCV's scalar-tail pixels (the last w % 8 of a row) are handled by a warp-uniform split --
+// warps without tail pixels run the SIMD-body sequence only -- and the planar float4 stores fall back to scalar stores
+// on the (row, channel) combinations that are not 16-byte aligned (widths that are not a multiple of 4).
+// SPLTEX = how many of the three inverse-gamma spline lookups go through the texture pipe instead of shared memory.
 // FYTEX  = lightness half of Lab->RGB ({fy, C1*y, C4*y, C7*y}, a function of the CLAHE output byte) fetched from the
 // 256-entry table through the texture pipe instead of being recomputed (FAST only).
 // CHROMA_A = pass A already interpolated the chroma (AB holds a | b << 16); otherwise AB holds the cell code and the
@@ -338,10 +357,9 @@ struct NormFast {
 template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A>
 __global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
-                   float* __restrict__ out, int h, int w, int grid, float inv_th, float inv_tw, int rows_per_cta,
-                   int vec_ok_, const float4* __restrict__ spline, Lab2RgbConst K,
+                   float* __restrict__ out, int h, int w, int pitch, int grid, float inv_th, float inv_tw, int rows_per_cta,
+                   const float4* __restrict__ spline, Lab2RgbConst K,
                    NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy, cudaTextureObject_t texAB) {
-    const int vec_ok = FAST ? 1 : vec_ok_;
     if (FAST) on.fast = 1;
     extern __shared__ __align__(16) uint8_t smem[];
     // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
@@ -371,9 +389,11 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
     __syncthreads();
 
     const int x0 = (blockIdx.x * 256 + tid) * 4;
+    const int wbody = (w >> 3) << 3;  // pixels >= wbody take OpenCV's scalar-tail op sequence
+    // does this warp own any scalar-tail pixel? (uniform per warp and constant over the rows)
+    const bool tail_warp = __any_sync(0xffffffffu, x0 < w && x0 + 4 > wbody);
     if (x0 >= w) return;
     const int npx = min(4, w - x0);
-    const int wbody = (w >> 3) << 3;  // pixels >= wbody take OpenCV's scalar-tail op sequence
 
     ClaheAxis ax[4];
     uint32_t sel[4];   // byte-permute selectors (tile columns i1, i2) of the 8-byte LUT rows
@@ -384,116 +404,114 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
     }
 
     const size_t plane = (size_t)h * w;
-    const uint32_t* abimg = AB + (size_t)img * plane;
-    const uint8_t* l8img = L8 + (size_t)img * plane;
+    const uint32_t* abimg = AB + (size_t)img * h * pitch;     // scratch rows are `pitch` = align4(w) elements apart
+    const uint8_t* l8img = L8 + (size_t)img * h * pitch;
     float* outimg = out + (size_t)img * plane * 3;
     const uint8_t* lut_bytes = (const uint8_t*)luts;
 
-    // software prefetch (vectorised path): the next row's chroma words and lightness bytes are requested before this
-    // row's arithmetic
-    uint4 nxc = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t nxl = 0;
-    if (vec_ok) {
-        const size_t p = (size_t)y0 * w + x0;
-        nxc = __ldg((const uint4*)(abimg + p));
-        nxl = __ldg((const uint32_t*)(l8img + p));
+    // one pixel: CLAHE blend of the lightness, chroma, Lab -> RGB, inverse gamma, normalisation
+    auto pixel = [&](int i, int v, uint32_t abw, const ClaheAxis& ay, const uint8_t* lrow1, const uint8_t* lrow2,
+                     bool tail, float& o0, float& o1, float& o2) {
+        // chroma: Q14 -> the a / b handed to LAB2RGB
+        int oa, ob;
+        if (CHROMA_A) {
+            oa = (int)(abw & 0xffffu);
+            ob = (int)(abw >> 16);
+        } else {
+            int cell, fr, fg, fb;
+            unpack_code(abw, cell, fr, fg, fb);
+            const uint4 wa = tex1Dfetch<uint4>(texAB, cell * 2), wb = tex1Dfetch<uint4>(texAB, cell * 2 + 1);
+            oa = lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr, fg, fb);
+            ob = lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr, fg, fb);
+        }
+        const float a2 = lab_chroma_fast(oa), b2 = lab_chroma_fast(ob);
+        // lightness through CLAHE: the two LUT rows hold the LUT value of every tile column at level v
+        int l11, l12, l21, l22;
+        if (lsh == 3) {
+            // 8-byte rows: one 64-bit load per tile row, the two tile-column bytes picked by one byte permute
+            const uint2 w1 = *(const uint2*)(lrow1 + (v << 3));
+            const uint2 w2 = *(const uint2*)(lrow2 + (v << 3));
+            const uint32_t p1 = __byte_perm(w1.x, w1.y, sel[i]), p2 = __byte_perm(w2.x, w2.y, sel[i]);
+            l11 = p1 & 255; l12 = (p1 >> 8) & 255;
+            l21 = p2 & 255; l22 = (p2 >> 8) & 255;
+        } else {
+            const uint8_t* r1 = lrow1 + (v << lsh);
+            const uint8_t* r2 = lrow2 + (v << lsh);
+            l11 = r1[ax[i].i1]; l12 = r1[ax[i].i2];
+            l21 = r2[ax[i].i1]; l22 = r2[ax[i].i2];
+        }
+        const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
+        float lr, lg, lb;
+        if (FAST && FYTEX && !tail) {
+            const float4 fy = tex1Dfetch<float4>(texFy, dst);
+            lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
+        } else {
+            lab2lin(lab_l_from_u8_fast(dst), a2, b2, tail, K, lr, lg, lb);
+        }
+        int ix[3];
+        const float xs[3] = {spline_index(lr, ix[0]), spline_index(lg, ix[1]), spline_index(lb, ix[2])};
+        float e[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c < SPLTEX) {       // texture pipe: no shared-memory bank conflicts
+                const float4 sg = tex1Dfetch<float4>(texSpline, ix[c]);
+                e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
+            } else {
+                const float2 s01 = spl_fb[ix[c]], s23 = spl_cd[ix[c]];
+                e[c] = spline_eval(xs[c], s01.x, s01.y, s23.x, s23.y);
+            }
+        }
+        o0 = on.fast ? normalize_px_fast(e[0], on.mean[0], on.std[0], on.rstd[0]) : normalize_px(e[0], on.mean[0], on.std[0]);
+        o1 = on.fast ? normalize_px_fast(e[1], on.mean[1], on.std[1], on.rstd[1]) : normalize_px(e[1], on.mean[1], on.std[1]);
+        o2 = on.fast ? normalize_px_fast(e[2], on.mean[2], on.std[2], on.rstd[2]) : normalize_px(e[2], on.mean[2], on.std[2]);
+    };
+
+    // software prefetch: the next row's scratch words are requested before this row's arithmetic
+    uint4 nxc;
+    uint32_t nxl;
+    {
+        const size_t ps = (size_t)y0 * pitch + x0;
+        nxc = __ldg((const uint4*)(abimg + ps));
+        nxl = __ldg((const uint32_t*)(l8img + ps));
     }
     for (int y = y0; y < y1; ++y) {
         const ClaheAxis ay = clahe_axis(y, inv_th, grid);
         const uint8_t* lrow1 = lut_bytes + (((size_t)(ay.i1 - ty_lo) * 256) << lsh);
         const uint8_t* lrow2 = lut_bytes + (((size_t)(ay.i2 - ty_lo) * 256) << lsh);
-        const size_t p = (size_t)y * w + x0;
+        const size_t p = (size_t)y * w + x0, ps = (size_t)y * pitch + x0;
 
-        int v[4];
-        uint32_t ab[4];
-        if (vec_ok) {
-            const uint32_t lw = nxl;
-            const uint4 cw = nxc;
-            if (y + 1 < y1) {
-                nxc = __ldg((const uint4*)(abimg + p + w));
-                nxl = __ldg((const uint32_t*)(l8img + p + w));
-            }
-            v[0] = lw & 255; v[1] = (lw >> 8) & 255; v[2] = (lw >> 16) & 255; v[3] = lw >> 24;
-            ab[0] = cw.x; ab[1] = cw.y; ab[2] = cw.z; ab[3] = cw.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < npx) {
-                    v[i] = l8img[p + i];
-                    ab[i] = abimg[p + i];
-                } else {
-                    v[i] = 0; ab[i] = 0;
-                }
-            }
+        uint32_t lw = nxl;
+        uint4 cw = nxc;
+        if (y + 1 < y1) {
+            nxc = __ldg((const uint4*)(abimg + ps + pitch));
+            nxl = __ldg((const uint32_t*)(l8img + ps + pitch));
         }
+        if (npx < 4) {          // slots past the row end are padding (possibly never written): neutral values
+            if (npx < 2) { cw.y = 0u; lw &= 0xffu; }
+            if (npx < 3) { cw.z = 0u; lw &= 0xffffu; }
+            cw.w = 0u; lw &= 0xffffffu;
+        }
+        const int v[4] = {(int)(lw & 255), (int)((lw >> 8) & 255), (int)((lw >> 16) & 255), (int)(lw >> 24)};
+        const uint32_t ab[4] = {cw.x, cw.y, cw.z, cw.w};
 
         float o[3][4];
+        if (tail_warp) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // chroma: Q14 -> the a / b handed to LAB2RGB
-            int oa, ob;
-            if (CHROMA_A) {
-                oa = (int)(ab[i] & 0xffffu);
-                ob = (int)(ab[i] >> 16);
-            } else {
-                int cell, fr, fg, fb;
-                unpack_code(ab[i], cell, fr, fg, fb);
-                const uint4 wa = tex1Dfetch<uint4>(texAB, cell * 2), wb = tex1Dfetch<uint4>(texAB, cell * 2 + 1);
-                oa = lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr, fg, fb);
-                ob = lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr, fg, fb);
-            }
-            const float a2 = lab_chroma_fast(oa), b2 = lab_chroma_fast(ob);
-            // lightness through CLAHE: the two LUT rows hold the LUT value of every tile column at level v
-            int l11, l12, l21, l22;
-            if (lsh == 3) {
-                // 8-byte rows: one 64-bit load per tile row, the two tile-column bytes picked by one byte permute
-                const uint2 w1 = *(const uint2*)(lrow1 + (v[i] << 3));
-                const uint2 w2 = *(const uint2*)(lrow2 + (v[i] << 3));
-                const uint32_t p1 = __byte_perm(w1.x, w1.y, sel[i]), p2 = __byte_perm(w2.x, w2.y, sel[i]);
-                l11 = p1 & 255; l12 = (p1 >> 8) & 255;
-                l21 = p2 & 255; l22 = (p2 >> 8) & 255;
-            } else {
-                const uint8_t* r1 = lrow1 + (v[i] << lsh);
-                const uint8_t* r2 = lrow2 + (v[i] << lsh);
-                l11 = r1[ax[i].i1]; l12 = r1[ax[i].i2];
-                l21 = r2[ax[i].i1]; l22 = r2[ax[i].i2];
-            }
-            const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
-            float lr, lg, lb;
-            if (FAST && FYTEX) {
-                const float4 fy = tex1Dfetch<float4>(texFy, dst);
-                lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
-            } else {
-                lab2lin(lab_l_from_u8_fast(dst), a2, b2, FAST ? false : (x0 + i) >= wbody, K, lr, lg, lb);
-            }
-            int ix[3];
-            const float xs[3] = {spline_index(lr, ix[0]), spline_index(lg, ix[1]), spline_index(lb, ix[2])};
-            float e[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (c < SPLTEX) {       // texture pipe: no shared-memory bank conflicts
-                    const float4 sg = tex1Dfetch<float4>(texSpline, ix[c]);
-                    e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
-                } else {
-                    const float2 s01 = spl_fb[ix[c]], s23 = spl_cd[ix[c]];
-                    e[c] = spline_eval(xs[c], s01.x, s01.y, s23.x, s23.y);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                o[c][i] = on.fast ? normalize_px_fast(e[c], on.mean[c], on.std[c], on.rstd[c])
-                                  : normalize_px(e[c], on.mean[c], on.std[c]);
-        }
-        if (vec_ok) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                __stcs((float4*)(outimg + c * plane + p), make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
+            for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ay, lrow1, lrow2, (x0 + i) >= wbody, o[0][i], o[1][i], o[2][i]);
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+            for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ay, lrow1, lrow2, false, o[0][i], o[1][i], o[2][i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float* dst = outimg + c * plane + p;
+            if (npx == 4 && (((uintptr_t)dst) & 15) == 0) {
+                __stcs((float4*)dst, make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
+            } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (i < npx) outimg[c * plane + p + i] = o[c][i];
+                    if (i < npx) __stcs(dst + i, o[c][i]);
+            }
         }
     }
 }
@@ -554,15 +572,20 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     if (rc != GDT_OK) return rc;
     if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
     Workspace W(ws, ws_bytes);
-    uint8_t* L8 = W.take<uint8_t>((size_t)n * h * w);
-    uint32_t* AB = W.take<uint32_t>((size_t)n * h * w);
+    const int pitch = (w + 3) & ~3;          // scratch row pitch in elements: every 4-pixel group is 16-byte aligned
+    uint8_t* L8 = W.take<uint8_t>((size_t)n * h * pitch);
+    uint32_t* AB = W.take<uint32_t>((size_t)n * h * pitch);
     uint8_t* luts = W.take<uint8_t>(((size_t)n * grid * 256) << lut_row_shift(grid));
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
-    const bool aligned = (((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0;
-    const int vec_apply = (aligned && (w % 4) == 0) ? 1 : 0;
-    // 1: whole 4-pixel groups per tile row; 2: aligned groups over ragged / padded tiles (needs whole groups per image row)
-    const int vec_hist = !vec_apply ? 0 : ((g.eh == h && g.ew == w && (g.tw % 4) == 0) ? 1 : 2);
+    // Pass A, 4-pixel groups: 1 = every tile is a whole number of aligned groups inside the image; 2 = aligned groups
+    // over ragged / padded tiles (uint8 input: any width, rows are realigned by funnel shifts; float input: planar
+    // float4 loads need a width that is a multiple of 4 and an aligned base); 0 = one pixel per thread.
+    const bool in_aligned = (((uintptr_t)in) & 15) == 0;
+    int vec_hist;
+    if (in_aligned && (w % 4) == 0 && g.eh == h && g.ew == w && (g.tw % 4) == 0) vec_hist = 1;
+    else if (U8 ? (((uintptr_t)in) & 3) == 0 : (in_aligned && (w % 4) == 0)) vec_hist = 2;
+    else vec_hist = 0;
 
     // A/B switches, see gdt_debug_k1_config (profiles/k1_v2_ab_r1q.log)
     const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, chroma_a = g_k1_chroma_a, occ_a = g_k1_occ_a;
@@ -570,9 +593,9 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     const int gw = g.tw;                               // scalar path: walk unit = one pixel of a tile row
     const int gq = 256 / gw, gr = 256 % gw;
 #define GDT_HIST(T_, C_, O_, L_)                                                                                       \
-    clahe_hist_kernel<U8, T_, C_, O_, L_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, grid, g.th, g.tw, g.clip,  \
-                                                                      g.lut_scale, vec_hist, gq, gr, T->lutL, T->lutAB, \
-                                                                      in_norm, T->texAB, T->texL)
+    clahe_hist_kernel<U8, T_, C_, O_, L_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw,   \
+                                                                      g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL,  \
+                                                                      T->lutAB, in_norm, T->texAB, T->texL)
     if (!chroma_a) {
         if (texab & 4) GDT_HIST(false, false, 4, 2);
         else if (texab & 2) GDT_HIST(false, false, 4, 1);
@@ -617,10 +640,10 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
                                       1024 * 16 + 16 * 256 * 16));
     }
 #define GDT_APPLY(FAST_, S_, F_, C_)                                                                                     \
-    clahe_apply_kernel<4, FAST_, S_, F_, C_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, grid, g.inv_th,         \
-                                                                            g.inv_tw, rows, vec_apply, T->spline, T->K, on, \
+    clahe_apply_kernel<4, FAST_, S_, F_, C_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, pitch, grid, g.inv_th,  \
+                                                                            g.inv_tw, rows, T->spline, T->K, on,            \
                                                                             T->texSpline, T->texFy, T->texAB)
-    if ((w & 7) == 0 && vec_apply && grid <= 8 && on.fast && smem <= 48 * 1024) {
+    if (grid <= 8 && on.fast && smem <= 48 * 1024) {
         switch ((spltex > 1 ? 1 : spltex) * 4 + fytex * 2 + chroma_a) {
             case 0: GDT_APPLY(true, 0, false, false); break;
             case 1: GDT_APPLY(true, 0, false, true); break;
@@ -756,7 +779,8 @@ extern "C" int gdt_debug_get_spline_table(float* host_out_4096) {
 
 extern "C" size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid) {
     if (n <= 0 || h <= 0 || w <= 0 || grid < 1) return 0;
-    return align_up((size_t)n * h * w, 256) + align_up((size_t)n * h * w * 4, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 512;
+    const size_t pitch = ((size_t)w + 3) & ~(size_t)3;
+    return align_up((size_t)n * h * pitch, 256) + align_up((size_t)n * h * pitch * 4, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 512;
 }
 
 extern "C" int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,

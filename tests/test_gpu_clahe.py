@@ -51,6 +51,30 @@ def test_batch_and_clip_limits():
             _assert_bits(out[i], O.transform_u8(img, lut, MEAN, STD, clip_limit=clip), "clip %g img %d" % (clip, i))
 
 
+@pytest.mark.parametrize("h,w", [(37, 53), (45, 81), (64, 130), (33, 1027)])
+def test_batches_of_odd_widths_bit_exact(h, w):
+    """Widths that are not a multiple of 4: image k of a batch starts at an arbitrary byte (uint8 input) and at a float
+    that is not 16-byte aligned (planar output); rows are realigned by funnel shifts, stores fall back per row/channel."""
+    lut = load_lut()
+    imgs = [synth_image(700 + i + w, h, w, "noise" if i == 1 else "smooth") for i in range(5)]
+    out = _run_u8(imgs)
+    for i, img in enumerate(imgs):
+        _assert_bits(out[i], O.transform_u8(img, lut, MEAN, STD), "odd batch %dx%d img %d" % (h, w, i))
+
+
+def test_clahe_post_float_variant_odd_width_bit_exact():
+    from gandtr_b200 import _lib
+    lut = load_lut()
+    rs = np.random.RandomState(12)
+    x = rs.rand(2, 3, 41, 67).astype(np.float32) * 2 - 1          # normalised with mean = std = 0.5
+    y = _lib.clahe_f32(torch.from_numpy(x).cuda(), [0.5] * 3, [0.5] * 3, MEAN, STD, 1.0, 8).cpu().numpy()
+    for i in range(2):
+        t = (x[i] * np.float32(0.5) + np.float32(0.5)).transpose(1, 2, 0)
+        ref = O.apply_clahe_rgb_f32(t, lut)
+        m, s = np.asarray(MEAN, np.float32)[:, None, None], np.asarray(STD, np.float32)[:, None, None]
+        _assert_bits(y[i], (np.ascontiguousarray(ref.transpose(2, 0, 1)) - m) / s, "clahepost odd width %d" % i)
+
+
 def test_full_size_image_bit_exact():
     """BASELINE config size (1024x768)."""
     lut = load_lut()
