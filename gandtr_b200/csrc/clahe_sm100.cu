@@ -179,7 +179,10 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                 // read bytewise; its missing pixels are zeros (their scratch slots are padding, never counted).
                 uint32_t a0, a1, a2;
                 const uint8_t* src8 = in8 + p * 3;
-                if (x0 + 4 <= w) {
+                if (vec_ok == 1) {                               // aligned rows: the 12 bytes are three aligned words
+                    const uint32_t* src = (const uint32_t*)src8;
+                    a0 = __ldg(src); a1 = __ldg(src + 1); a2 = __ldg(src + 2);
+                } else if (x0 + 4 <= w) {
                     const unsigned mis = (unsigned)((uintptr_t)src8 & 3);
                     const uint32_t* src = (const uint32_t*)(src8 - mis);
                     const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
@@ -354,7 +357,9 @@ struct NormFast {
 // 256-entry table through the texture pipe instead of being recomputed (FAST only).
 // CHROMA_A = pass A already interpolated the chroma (AB holds a | b << 16); otherwise AB holds the cell code and the
 // chroma records are fetched here through the texture pipe.
-template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A>
+// ANYW = widths with scalar-tail pixels (w % 8 != 0) or unaligned planar rows; without it (the common case, chosen by the
+// host) the tail split and the store alignment test are compiled out.
+template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A, bool ANYW>
 __global__ void __launch_bounds__(256, MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int pitch, int grid, float inv_th, float inv_tw, int rows_per_cta,
@@ -391,7 +396,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
     const int x0 = (blockIdx.x * 256 + tid) * 4;
     const int wbody = (w >> 3) << 3;  // pixels >= wbody take OpenCV's scalar-tail op sequence
     // does this warp own any scalar-tail pixel? (uniform per warp and constant over the rows)
-    const bool tail_warp = __any_sync(0xffffffffu, x0 < w && x0 + 4 > wbody);
+    const bool tail_warp = ANYW && __any_sync(0xffffffffu, x0 < w && x0 + 4 > wbody);
     if (x0 >= w) return;
     const int npx = min(4, w - x0);
 
@@ -486,7 +491,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
             nxc = __ldg((const uint4*)(abimg + ps + pitch));
             nxl = __ldg((const uint32_t*)(l8img + ps + pitch));
         }
-        if (npx < 4) {          // slots past the row end are padding (possibly never written): neutral values
+        if (ANYW && npx < 4) {  // slots past the row end are padding (possibly never written): neutral values
             if (npx < 2) { cw.y = 0u; lw &= 0xffu; }
             if (npx < 3) { cw.z = 0u; lw &= 0xffffu; }
             cw.w = 0u; lw &= 0xffffffu;
@@ -505,7 +510,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float* dst = outimg + c * plane + p;
-            if (npx == 4 && (((uintptr_t)dst) & 15) == 0) {
+            if (!ANYW || (npx == 4 && (((uintptr_t)dst) & 15) == 0)) {
                 __stcs((float4*)dst, make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
             } else {
 #pragma unroll
@@ -632,32 +637,35 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     }
     // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
     // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
-    if (smem > 48 * 1024)
-    {
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // widths with OpenCV scalar-tail pixels or rows of the planar output that are not 16-byte aligned
+    const bool anyw = (w & 7) != 0 || (((uintptr_t)out) & 15) != 0;
+    if (smem > 48 * 1024) {
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
     }
-#define GDT_APPLY(FAST_, S_, F_, C_)                                                                                     \
-    clahe_apply_kernel<4, FAST_, S_, F_, C_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, pitch, grid, g.inv_th,  \
-                                                                            g.inv_tw, rows, T->spline, T->K, on,            \
-                                                                            T->texSpline, T->texFy, T->texAB)
+#define GDT_APPLY(FAST_, S_, F_, C_, A_)                                                                                 \
+    clahe_apply_kernel<4, FAST_, S_, F_, C_, A_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, pitch, grid,        \
+                                                                                g.inv_th, g.inv_tw, rows, T->spline, T->K,  \
+                                                                                on, T->texSpline, T->texFy, T->texAB)
     if (grid <= 8 && on.fast && smem <= 48 * 1024) {
-        switch ((spltex > 1 ? 1 : spltex) * 4 + fytex * 2 + chroma_a) {
-            case 0: GDT_APPLY(true, 0, false, false); break;
-            case 1: GDT_APPLY(true, 0, false, true); break;
-            case 2: GDT_APPLY(true, 0, true, false); break;
-            case 3: GDT_APPLY(true, 0, true, true); break;
-            case 4: GDT_APPLY(true, 1, false, false); break;
-            case 5: GDT_APPLY(true, 1, false, true); break;
-            case 6: GDT_APPLY(true, 1, true, false); break;
-            default: GDT_APPLY(true, 1, true, true); break;
+        if (anyw) {     // the pipe variants are A/B material for the common case only
+            if (chroma_a) GDT_APPLY(true, 0, false, true, true); else GDT_APPLY(true, 0, false, false, true);
+        } else switch ((spltex > 1 ? 1 : spltex) * 4 + fytex * 2 + chroma_a) {
+            case 0: GDT_APPLY(true, 0, false, false, false); break;
+            case 1: GDT_APPLY(true, 0, false, true, false); break;
+            case 2: GDT_APPLY(true, 0, true, false, false); break;
+            case 3: GDT_APPLY(true, 0, true, true, false); break;
+            case 4: GDT_APPLY(true, 1, false, false, false); break;
+            case 5: GDT_APPLY(true, 1, false, true, false); break;
+            case 6: GDT_APPLY(true, 1, true, false, false); break;
+            default: GDT_APPLY(true, 1, true, true, false); break;
         }
     } else if (chroma_a) {
-        GDT_APPLY(false, 0, false, true);
+        GDT_APPLY(false, 0, false, true, true);
     } else {
-        GDT_APPLY(false, 0, false, false);
+        GDT_APPLY(false, 0, false, false, true);
     }
 #undef GDT_APPLY
     GDT_LAUNCH_CHECK();
