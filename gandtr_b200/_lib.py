@@ -36,10 +36,12 @@ SYMBOLS = [
     ("gdt_debug_div_check", _c.c_int, [_c.c_float, _c.c_uint32, _c.c_uint32, _P, _P]),
     ("gdt_debug_k1_config", _c.c_int, [_c.c_int] * 5),
     ("gdt_debug_k1_rows", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_chunk", _c.c_int, [_c.c_int]),
     ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_clahe_u8", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _c.c_size_t, _P]),
     ("gdt_clahe_f32", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P,
                                  _c.c_size_t, _P]),
+    ("gdt_meanstd_adapt", _c.c_int, [_P, _c.c_longlong, _c.c_longlong, _P, _P, _P, _P, _P, _P]),
     ("gdt_gem_whiten_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_gem_whiten", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_float, _c.c_int, _P, _c.c_int, _P, _P,
                                   _c.c_int, _P, _P, _c.c_size_t, _P]),
@@ -82,7 +84,7 @@ _initialised_devices = set()
 launch_count = 0  # number of library compute calls made by this process (bench.py reports kernel launches from it)
 
 # kernels launched by each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"clahe": 2, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
+KERNELS_PER_CALL = {"clahe": 2, "meanstd_adapt": 1, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
                     "topk_merge": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1, "resize": 2}
 
 
@@ -213,6 +215,24 @@ def clahe_f32(x_chw, in_mean, in_std, out_mean, out_std, clip_limit=1.0, grid=8,
         check(lib.gdt_clahe_f32(_ptr(x_chw), n, h, w, float(clip_limit), int(grid), _f3(in_mean), _f3(in_std),
                                 _f3(out_mean), _f3(out_std), _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_clahe_f32")
     _count("clahe")
+    return out
+
+
+def meanstd_adapt(x, in_mean, in_std, out_mean, out_std, out=None):
+    """[n,3,h,w] or [3,h,w] float32 CUDA -> ((x * in_std + in_mean) - out_mean) / out_std, same shape (MeanStdPost)."""
+    _require(x, torch.float32, "x")
+    if x.dim() not in (3, 4) or x.shape[-3] != 3:
+        raise GdtError("x must be [n, 3, h, w] or [3, h, w]")
+    n = x.shape[0] if x.dim() == 4 else 1
+    plane = x.shape[-1] * x.shape[-2]
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _require(out, torch.float32, "out")
+    with torch.cuda.device(x.device):
+        check(load().gdt_meanstd_adapt(_ptr(x), n, plane, _f3(in_mean), _f3(in_std), _f3(out_mean), _f3(out_std), _ptr(out),
+                                       _stream()), "gdt_meanstd_adapt")
+    _count("meanstd_adapt")
     return out
 
 

@@ -49,6 +49,8 @@ static ClaheTables g_tables[32];
 // under pass B's arithmetic; in pass A it is exposed: 1.03 vs 1.20 ms per 128 images), everything else recomputed.
 static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_chroma_a = 0, g_k1_occ_a = 4;
 static int g_k1_rows = 0;     // > 0: rows per pass-B CTA forced (gdt_debug_k1_rows), 0: pass_b_rows()
+static int g_k1_chunk = -1;   // images per (pass A, pass B) launch pair: -1 automatic (scratch of a chunk stays in L2),
+                              // 0 whole batch at once, > 0 forced (gdt_debug_k1_chunk)
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -567,8 +569,8 @@ static int pass_b_rows(int h, long long ctas_per_band, long long slots) {
 }
 
 template <bool U8>
-static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, int grid, const Norm3& in_norm,
-                        const Norm3& out_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_limit, int grid, const Norm3& in_norm,
+                              const Norm3& out_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const ClaheTables* T = clahe_tables_for_current_device();
     if (!T) return GDT_ERR_NOT_INITIALISED;
     if (!in || !out || !ws) return GDT_ERR_INVALID_ARGUMENT;
@@ -672,6 +674,76 @@ static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, 
     return GDT_OK;
 }
 
+
+// Images per launch pair. Pass A writes 5 B/px of scratch that pass B reads back: when the whole batch goes through pass
+// A first, the scratch of a large batch (128 images of 1024x768: 503 MB) has left the 126 MB L2 long before pass B wants
+// it (measured DRAM traffic 1.38x the algorithmic bytes). Running the two passes chunk by chunk keeps a chunk's scratch
+// L2-resident. The chunk is sized to about half of L2 and rounded so that pass A's grid (grid^2 CTAs per image) fills
+// whole waves of the machine.
+static int clahe_chunk_images(int n, int h, int w, int grid) {
+    if (g_k1_chunk == 0) return n;
+    if (g_k1_chunk > 0) return g_k1_chunk < n ? g_k1_chunk : n;
+    const size_t pitch = ((size_t)w + 3) & ~(size_t)3;
+    const size_t scratch_per_image = (size_t)h * pitch * 5;
+    int dev = 0, l2 = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) != cudaSuccess || l2 <= 0)
+        l2 = 64 << 20;
+    long long c = (long long)((size_t)l2 * 9 / 16 / (scratch_per_image ? scratch_per_image : 1));
+    if (c < 1) c = 1;
+    if (c >= n) return n;
+    // whole waves of pass A: 4 resident CTAs per SM
+    const long long slots = 4LL * sm_count_current_device(), per_img = (long long)grid * grid;
+    const long long waves = (c * per_img) / slots;
+    if (waves >= 1) {
+        const long long fit = (waves * slots) / per_img;
+        if (fit >= 1) c = fit;
+    }
+    // balance: the same number of chunks, equal sizes
+    const long long chunks = ceil_div_ll(n, c);
+    return (int)ceil_div_ll(n, chunks);
+}
+
+template <bool U8>
+static int clahe_launch(const void* in, int n, int h, int w, double clip_limit, int grid, const Norm3& in_norm,
+                        const Norm3& out_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (n <= 0 || h <= 0 || w <= 0 || grid < 1 || grid > 16) return GDT_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < gdt_clahe_workspace_bytes(n, h, w, grid)) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    const int chunk = clahe_chunk_images(n, h, w, grid);
+    const size_t in_stride = (size_t)h * w * 3 * (U8 ? 1 : 4), out_stride = (size_t)h * w * 3;
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int m = n - i0 < chunk ? n - i0 : chunk;
+        // every chunk reuses the head of the workspace: the launches are stream-ordered
+        const int rc = clahe_launch_chunk<U8>((const char*)in + (size_t)i0 * in_stride, m, h, w, clip_limit, grid, in_norm,
+                                              out_norm, out + (size_t)i0 * out_stride, ws, ws_bytes, stream);
+        if (rc != GDT_OK) return rc;
+    }
+    return GDT_OK;
+}
+
+// MeanStdPost / MeanStdPre (wrapper.py:149-194): y = ((x * s0 + m0) - m1) / s1 per channel, four separate roundings.
+// One thread per 4 consecutive floats of a plane (planes that are a multiple of 4 long and 16-byte aligned), else scalar.
+__global__ void __launch_bounds__(256)
+meanstd_adapt_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, long long plane, Norm3 in_n,
+                     NormFast out_n, int vec) {
+    const long long per = vec ? plane >> 2 : plane;
+    const long long total = planes * per;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long pl = i / per;
+        const int c = (int)(pl % 3);
+        const float s0 = in_n.std[c], m0 = in_n.mean[c], m1 = out_n.mean[c], s1 = out_n.std[c], r1 = out_n.rstd[c];
+        auto one = [&](float v) {
+            const float t = f_sub(f_add(f_mul(v, s0), m0), m1);
+            return out_n.fast ? div_by_const<2>(t, s1, r1) : f_div(t, s1);
+        };
+        if (vec) {
+            const float4 v = __ldcs((const float4*)x + i);
+            __stcs((float4*)y + i, make_float4(one(v.x), one(v.y), one(v.z), one(v.w)));
+        } else {
+            y[i] = one(x[i]);
+        }
+    }
+}
+
 // debug: count floats a in the bit range [lo_bits, hi_bits] (both signs) for which div_by_const<2> != a / b
 __global__ void __launch_bounds__(256)
 div_check_kernel(float b, float r, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* __restrict__ mismatches) {
@@ -698,6 +770,33 @@ extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, 
     return GDT_OK;
 }
 
+extern "C" int gdt_meanstd_adapt(const float* x, long long n, long long plane, const float* host_in_mean,
+                                 const float* host_in_std, const float* host_out_mean, const float* host_out_std, float* y,
+                                 void* stream) {
+    if (!x || !y || !host_in_mean || !host_in_std || !host_out_mean || !host_out_std || n < 0 || plane < 0)
+        return GDT_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GDT_ERR_NO_DEVICE; }
+    if (n == 0 || plane == 0) return GDT_OK;
+    Norm3 i;
+    NormFast o;
+    o.fast = 0;     // arbitrary input range: always the true division (the kernel is HBM-bound either way)
+    for (int c = 0; c < 3; ++c) {
+        if (host_out_std[c] == 0.f) return GDT_ERR_INVALID_ARGUMENT;
+        i.mean[c] = host_in_mean[c]; i.std[c] = host_in_std[c];
+        o.mean[c] = host_out_mean[c]; o.std[c] = host_out_std[c];
+        o.rstd[c] = 0.f;
+    }
+    const int vec = (plane % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+    const long long work = n * 3 * (vec ? plane / 4 : plane);
+    long long blocks = ceil_div_ll(work, 256);
+    const long long cap = (long long)sm_count_current_device() * 16;
+    if (blocks > cap) blocks = cap;
+    meanstd_adapt_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n * 3, plane, i, o, vec);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
 extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a) {
     if (spltex < 0 || spltex > 1 || (occ_a != 4 && occ_a != 6)) return GDT_ERR_INVALID_ARGUMENT;
     g_k1_texab = texab & 7;
@@ -705,6 +804,12 @@ extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_
     g_k1_fytex = fytex ? 1 : 0;
     g_k1_chroma_a = chroma_a ? 1 : 0;
     g_k1_occ_a = occ_a;
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_chunk(int images_per_launch_pair) {
+    if (images_per_launch_pair < -1) return GDT_ERR_INVALID_ARGUMENT;
+    g_k1_chunk = images_per_launch_pair;
     return GDT_OK;
 }
 

@@ -125,14 +125,29 @@ class _Decode(torch.utils.data.Dataset):
         return torch.from_numpy(load_image(self.images[i], self.imsize, self.bbxs[i] if self.bbxs is not None else None).copy())
 
 
-def _descriptors_for_batch(model, x, ms, msp):
-    """x: [b,3,h,w] normalised CUDA batch -> [b, D]. Mirrors extract_ss (ms == [1]) and extract_ms."""
+def _net_rows(net, x):
+    """`net(input)` of the reference loop (imageretrievalnet.py:341-353) on a whole batch -> [b, D'] rows.
+    A `SingleNetwork` runs its stage wrappers (the hub models' eval stack {cirwhiten, cirmultiscale} is ONE fused K2
+    call, network.py `_forward_fused`); a bare `ImageRetrievalNet` is features -> GeM -> L2N."""
+    if not hasattr(net, "wrappers"):
+        return net.descriptors([net.feature_map(x)])
+    if net._fused_plan() is not None:
+        out = net(x)
+        return out.unsqueeze(0) if out.dim() == 1 else out.t()
+    # arbitrary wrapper stacks follow the reference's calling convention: one image per call
+    rows = [net(x[j:j + 1]).reshape(-1) for j in range(x.shape[0])]
+    return torch.stack(rows)
+
+
+def _descriptors_for_batch(net, x, ms, msp):
+    """x: [b,3,h,w] normalised CUDA batch -> [b, D']. Mirrors extract_ss (ms == [1]) and extract_ms; `net` is called
+    the way the reference calls it, so a SingleNetwork's whitening / multi-scale wrappers take part."""
     if len(ms) == 1 and ms[0] == 1:
-        return model.descriptors([model.feature_map(x)])
+        return _net_rows(net, x)
     per_scale = []
     for s in ms:
         xs = x if s == 1 else torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
-        per_scale.append(model.descriptors([model.feature_map(xs)]))       # net(input_t): GeM + L2N per scale
+        per_scale.append(_net_rows(net, xs).contiguous())                  # net(input_t) per scale
     # v = sum_s d^msp ; v /= len(ms) ; v = v^(1/msp) ; v /= ||v||        (imageretrievalnet.py:344-357)
     return _lib.desc_post(per_scale, msp if isinstance(msp, torch.Tensor) else float(msp))
 
@@ -148,14 +163,14 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
     if device_resize is None:
         device_resize = image_size is not None or (bbxs is not None and any(b for b in bbxs))
     model = getattr(net, "model", net)
-    model.eval()
+    net.eval()                                                  # SingleNetwork.eval() also selects the eval wrappers
     dev = next(model.parameters()).device
     if dev.type != "cuda":
         raise _lib.GdtError("extract_descriptors needs the network on a CUDA device")
     lo, hi = shard_bounds(len(images), world_size, rank)
     local = list(images[lo:hi])
     local_bbxs = list(bbxs[lo:hi]) if bbxs is not None else None
-    out = torch.empty((len(local), model.meta["out_channels"]), dtype=torch.float32, device=dev)
+    out = None            # allocated from the first batch: a whitening wrapper may reduce the dimensionality
     loader = torch.utils.data.DataLoader(_Decode(local, image_size, local_bbxs, device_resize), batch_size=None, shuffle=False,
                                          num_workers=min(workers, max(len(local), 1)) if len(local) > 8 else 0)
     pending, shape, start = [], None, 0
@@ -166,7 +181,7 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
         geometry = DeviceImageLoader(imsize=image_size, device=dev)
 
     def flush():
-        nonlocal pending, start
+        nonlocal pending, start, out
         if not pending:
             return
         batch = torch.stack(pending)                           # device_resize: already on the device
@@ -179,7 +194,10 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
                 staged = uploader.upload(batch)
                 x = transform.batch(staged)
                 uploader.release(staged)                       # K1 was the only reader of the uint8 batch
-            out[start:start + len(pending)] = _descriptors_for_batch(model, x, list(ms), msp)
+            rows = _descriptors_for_batch(net, x, list(ms), msp)
+            if out is None:
+                out = torch.empty((len(local), rows.shape[1]), dtype=torch.float32, device=dev)
+            out[start:start + len(pending)] = rows
         start += len(pending)
         pending = []
 
@@ -197,6 +215,8 @@ def extract_descriptors(net, images, image_size, transform, bbxs=None, ms=(1,), 
     flush()
     if print_freq:
         print("")
+    if out is None:
+        out = torch.empty((0, model.meta["out_channels"]), dtype=torch.float32, device=dev)
     return out
 
 
@@ -214,4 +234,4 @@ def extract_ss(net, input):
 def extract_ms(net, input, ms, msp):
     """imageretrievalnet.py:344-359."""
     model = getattr(net, "model", net)
-    return _descriptors_for_batch(model, input.to(next(model.parameters()).device), list(ms), msp).squeeze(0).cpu()
+    return _descriptors_for_batch(net, input.to(next(model.parameters()).device), list(ms), msp).squeeze(0).cpu()

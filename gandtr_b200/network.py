@@ -18,9 +18,13 @@ The VGG16 / ResNet-101 conv backbones stay stock torchvision modules (BASELINE.j
 There is no CPU path: modules raise on CPU tensors.
 """
 import copy
+import hashlib
 import json
 import pickle
+import random
+import re
 from collections import namedtuple
+from typing import Any, NamedTuple
 
 import numpy as np
 import torch
@@ -32,7 +36,9 @@ from .transforms import initialize_transforms
 
 __all__ = ["GeM", "L2N", "ImageRetrievalNet", "init_network", "init_cirnet", "Wrapper", "Compose",
            "CirMultiscaleAggregation", "FakeBatch", "CirFakeTupleBatch", "CirtorchWhiten", "ClahePost",
-           "WRAPPERS_LABELS", "initialize_wrappers", "SingleNetwork", "OUTPUT_DIM"]
+           "RandomPassThrough", "CirRatioPassThrough", "MeanStdPost", "MeanStdPre", "MetadataTensor", "as_tensor",
+           "as_metadata_tensor", "to_device", "WRAPPERS_LABELS", "initialize_wrappers", "SingleNetwork", "SequentialNetwork",
+           "CirSequentialNetwork", "NETWORKS", "initialize_network", "OUTPUT_DIM"]
 
 OUTPUT_DIM = {"alexnet": 256, "vgg11": 512, "vgg13": 512, "vgg16": 512, "vgg19": 512, "resnet18": 512, "resnet34": 512,
               "resnet50": 2048, "resnet101": 2048, "resnet152": 2048}
@@ -179,14 +185,79 @@ def init_cirnet(**params):
 
 # ---------------------------------------------------------------------------------------------------- wrappers
 
-def _to_device(tensor, device):
+class MetadataTensor(NamedTuple):
+    """(tensor, metadata) pair the reference's datasets hand to `network(x)` (mdir/tools/tensors.py:37-64): a NamedTuple
+    for `default_collate`, with `.to` / `.unsqueeze_` propagated and every other attribute read from the tensor."""
+
+    tensor: Any
+    metadata: Any
+
+    def __repr__(self):
+        return "Data:\n%s\nMetadata:\n%s" % (self.tensor, self.metadata)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        metadata, = (a.metadata for a in args if isinstance(a, cls))
+        args = [a.tensor if isinstance(a, cls) else a for a in args]
+        return MetadataTensor(func(*args, **(kwargs or {})), metadata)
+
+    def __getattr__(self, name):
+        attr = getattr(self.tensor, name)
+        if name not in ["to", "unsqueeze_"]:
+            return attr
+
+        def func(*args, **kwargs):
+            return self.__class__(attr(*args, **kwargs), self.metadata)
+        return func
+
+
+def as_metadata_tensor(tensor, metadata):
+    """tools/tensors.py:67-72."""
+    if isinstance(tensor, MetadataTensor):
+        assert not set(tensor.metadata.keys()) & set(metadata.keys())
+        tensor.metadata.update(dict(metadata))
+        return tensor
+    return MetadataTensor(torch.as_tensor(tensor), dict(metadata))
+
+
+def as_tensor(tensor):
+    """Strip the metadata from tensors nested in lists / tuples / dicts (tools/tensors.py:74-85)."""
+    if tensor is None:
+        return None
+    if isinstance(tensor, MetadataTensor):
+        return tensor.tensor
+    if isinstance(tensor, list):
+        return [as_tensor(x) for x in tensor]
+    if isinstance(tensor, tuple):
+        return tuple(as_tensor(x) for x in tensor)
+    if isinstance(tensor, dict):
+        return {k: as_tensor(v) for k, v in tensor.items()}
+    return torch.as_tensor(tensor)
+
+
+def to_device(tensor, device):
+    """Move tensors nested in lists / tuples / dicts to `device`, keeping the structure (tools/tensors.py:8-20)."""
+    if isinstance(tensor, MetadataTensor):                      # before the tuple test: a NamedTuple is a tuple
+        return MetadataTensor(tensor.tensor.to(device), tensor.metadata)
     if hasattr(tensor, "to"):
         return tensor.to(device)
     if isinstance(tensor, list):
-        return [_to_device(x, device) for x in tensor]
+        return [to_device(x, device) for x in tensor]
     if isinstance(tensor, tuple):
-        return tuple(_to_device(x, device) for x in tensor)
-    return tensor
+        return tuple(to_device(x, device) for x in tensor)
+    if isinstance(tensor, dict):
+        return {k: to_device(v, device) for k, v in tensor.items()}
+    if tensor is None:
+        return None
+    return tensor.to(device)
+
+
+_to_device = to_device
+
+
+def _plain(x):
+    """The torch.Tensor inside a MetadataTensor (kernels take raw device pointers), anything else unchanged."""
+    return x.tensor if isinstance(x, MetadataTensor) else x
 
 
 class Compose(object):
@@ -229,6 +300,110 @@ class Wrapper(object):
         return tensor
 
 
+class RandomPassThrough(Wrapper):
+    """Lets the input through the wrapped network with the given probability, otherwise the input skips it
+    (wrapper.py:97-117)."""
+
+    def __init__(self, probability_through, device):
+        super().__init__(device)
+        self.probability = float(probability_through)
+
+    def preprocess(self, tensor, outputmodel):
+        if isinstance(tensor, list):
+            out = tuple(zip(*[self.preprocess(t, outputmodel) for t in tensor]))
+            return list(out[0]), list(out[1])
+        return (tensor, None) if random.random() < self.probability else (None, tensor)
+
+    def postprocess(self, tensor, outputmodel, tensor_skipping):
+        if isinstance(tensor, list):
+            return [self.postprocess(t, outputmodel, s) for (t, s) in zip(tensor, tensor_skipping)]
+        return tensor if tensor_skipping is None else as_tensor(tensor_skipping)
+
+    def __repr__(self):
+        return "%s(probability=%s)" % (self.__class__.__name__, self.probability)
+
+
+class CirRatioPassThrough(RandomPassThrough):
+    """Deterministic variant for the retrieval training tuples: an image goes through the generator iff its
+    `image_label` matches and the md5 of its name falls below the ratio (wrapper.py:120-146)."""
+
+    def __init__(self, ratio_through, image_label, *, device):
+        super().__init__(ratio_through, device)
+        self.image_label = re.compile(image_label)
+
+    def preprocess(self, tensor, outputmodel):
+        if isinstance(tensor, list):
+            acc = [self.preprocess(x, outputmodel) for x in tensor]
+            return tuple(list(x) for x in zip(*acc))
+        image_label = tensor.metadata["image_label"]            # must be present (sanity check of the reference)
+        if isinstance(image_label, list) and len(image_label) == 1:
+            image_label = image_label[0]
+        if self.image_label.match(image_label) and self._passthrough(tensor.metadata["name"]):
+            return tensor, None
+        return None, tensor
+
+    def _passthrough(self, name):
+        if isinstance(name, list):
+            name, = name
+        digits = 4
+        rand = int(hashlib.md5(name.encode("utf8")).hexdigest()[-digits:], 16) / (16 ** digits)
+        return rand < self.probability
+
+    def __repr__(self):
+        return "%s(probability=%s, train_label=%s)" % (self.__class__.__name__, self.probability, self.image_label)
+
+
+class MeanStdPost(Wrapper):
+    """Adapts the normalisation of the network output: x*std_in + mean_in, then (. - mean_out) / std_out
+    (wrapper.py:149-179). One elementwise kernel (gdt_meanstd_adapt) with the reference's four roundings."""
+
+    def __init__(self, input_meanstd, output_meanstd, device):
+        super().__init__(device)
+        input_meanstd = json.loads(input_meanstd) if isinstance(input_meanstd, str) else input_meanstd
+        output_meanstd = json.loads(output_meanstd) if isinstance(output_meanstd, str) else output_meanstd
+        if any(x == 0 for x in input_meanstd[1]) or any(x == 0 for x in output_meanstd[1]):
+            raise ValueError("Some std element is zero, leading to zero division.")
+        self.input_meanstd = [self.mean2tensor(x, device) for x in input_meanstd]
+        self.output_meanstd = [self.mean2tensor(x, device) for x in output_meanstd]
+        self.device = device
+        self._host = ([float(v) for v in input_meanstd[0]], [float(v) for v in input_meanstd[1]],
+                      [float(v) for v in output_meanstd[0]], [float(v) for v in output_meanstd[1]])
+
+    @staticmethod
+    def mean2tensor(mean, device):
+        mean = torch.as_tensor(mean, device=device)
+        if mean.ndim == 1:
+            mean = mean[:, None, None]
+        return mean
+
+    def postprocess(self, tensor, outputmodel, meta):
+        if isinstance(tensor, list):
+            return [self.postprocess(x, outputmodel, meta) for x in tensor]
+        return self._adapt(tensor)
+
+    def _adapt(self, tensor):
+        if tensor is None:
+            return None
+        t = _plain(tensor)
+        out = _lib.meanstd_adapt(t.detach().to(self.device).contiguous(), *self._host)
+        return MetadataTensor(out, tensor.metadata) if isinstance(tensor, MetadataTensor) else out
+
+    def __repr__(self):
+        return "%s(input_meanstd=%s,output_meanstd=%s)" % (self.__class__.__name__, self.input_meanstd, self.output_meanstd)
+
+
+class MeanStdPre(MeanStdPost):
+    """The same adaptation applied to the network input (wrapper.py:182-194)."""
+
+    def preprocess(self, tensor, _outputmodel):
+        if isinstance(tensor, list):
+            return [self.preprocess(x, _outputmodel) for x in tensor]
+        return self._adapt(tensor), None
+
+    def postprocess(self, tensor, outputmodel, meta):
+        return tensor
+
+
 class CirMultiscaleAggregation(Wrapper):
     """Downscale each image to defined scales and aggregate resulting descriptors (wrapper.py:200-263)."""
 
@@ -244,7 +419,10 @@ class CirMultiscaleAggregation(Wrapper):
 
     @staticmethod
     def interpolate(x, scale):
-        return F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False)   # wrapper.py:225 (stock ATen)
+        """wrapper.py:212-233: stock ATen bilinear resize; a MetadataTensor keeps its metadata (`wrap_metadata`)."""
+        if isinstance(x, MetadataTensor):
+            return MetadataTensor(F.interpolate(x.tensor, scale_factor=scale, mode="bilinear", align_corners=False), x.metadata)
+        return F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False)
 
     def preprocess(self, tensor, _outputmodel):
         if len(self.scales) == 1:
@@ -360,6 +538,7 @@ class ClahePost(Wrapper):
         meanstd = json.loads(meanstd) if isinstance(meanstd, str) else meanstd
         self.mean, self.std = [float(x) for x in meanstd[0]], [float(x) for x in meanstd[1]]
         self.clip_limit, self.grid_size = float(clip_limit), int(grid_size)
+        self.device = device
         if str(colorspace).lower() != "lab":
             raise NotImplementedError("ClahePost: only the 'lab' colorspace is implemented")
 
@@ -369,8 +548,9 @@ class ClahePost(Wrapper):
         if isinstance(tensor, list):
             return [self.postprocess(x, outputmodel, meta) for x in tensor]
         if len(tensor.shape) == 4:
-            return _lib.clahe_f32(tensor.detach().contiguous(), self.mean, self.std, self.mean, self.std,
-                                  clip_limit=self.clip_limit, grid=self.grid_size)
+            # images that skipped the generator (cir_ratio_pass_through) may still be host tensors: CLAHE runs on the device
+            return _lib.clahe_f32(_plain(tensor).detach().to(self.device).contiguous(), self.mean, self.std, self.mean,
+                                  self.std, clip_limit=self.clip_limit, grid=self.grid_size)
         if len(tensor.shape) == 3:
             return self.postprocess(tensor.unsqueeze(0), outputmodel, meta)[0]
         raise ValueError("Unsupported tensor dims: %s" % len(tensor.shape))
@@ -380,6 +560,10 @@ class ClahePost(Wrapper):
 
 
 WRAPPERS_LABELS = {
+    "random_pass_through": RandomPassThrough,
+    "cir_ratio_pass_through": CirRatioPassThrough,
+    "meanstd_post": MeanStdPost,
+    "meanstd_pre": MeanStdPre,
     "cirmultiscale": CirMultiscaleAggregation,
     "fakebatch": FakeBatch,
     "cirfaketuplebatch": CirFakeTupleBatch,
@@ -394,12 +578,29 @@ def initialize_wrappers(net_wrappers, device):
         wraps = []
     elif isinstance(net_wrappers, str):
         wraps = []
-        for wrap in [x.strip() for x in net_wrappers.split(",") if x.strip()]:
+        for wrap in [x.strip() for x in _split_outside_brackets(net_wrappers, ",") if x.strip()]:
             wname, *args = wrap.split(":")
             wraps.append(_wrapper_class(wname)(*args, device=device))
     else:
         wraps = [_wrapper_class(x.split("_", 1)[1])(**net_wrappers[x], device=device) for x in sorted(net_wrappers)]
     return Compose(wraps, device)
+
+
+def _split_outside_brackets(seq, sep):
+    """Split on `sep` outside (), [], {} -- wrapper arguments such as [[0.5,0.5,0.5],[0.5,0.5,0.5]] contain commas
+    (mdir/tools/utils.py:95-112 `splitp` with check_valid_pairs)."""
+    parts, depth, closing = [""], [], {"(": ")", "[": "]", "{": "}"}
+    for ch in seq:
+        if ch == sep and not depth:
+            parts.append("")
+            continue
+        if ch in closing:
+            depth.append(closing[ch])
+        elif depth and ch == depth[-1]:
+            depth.pop()
+        parts[-1] += ch
+    assert not depth, 'Invalid seq "%s": unbalanced brackets' % seq
+    return parts
 
 
 def _wrapper_class(name):
@@ -463,12 +664,16 @@ class SingleNetwork(object):
         return None
 
     def forward(self, image, **params):
+        """`network(x)`: x is a tensor, a MetadataTensor (tools/tensors.py:37), or lists / tuples of them -- whatever the
+        active wrappers' `preprocess` accept (network.py:133-134 of the reference)."""
         plan = None if params else self._fused_plan()
-        if plan is not None and isinstance(image, torch.Tensor) and image.dim() == 4:
-            return self._forward_fused(image, *plan)
-        if plan is not None and isinstance(image, list) and image and all(isinstance(x, torch.Tensor) and x.dim() == 4
-                                                                          for x in image):
-            return [self._forward_fused(x, *plan) for x in image]
+        if plan is not None:
+            # the fused stack reads no metadata: MetadataTensors are unwrapped the way forward_batch's as_tensor does
+            bare = as_tensor(image) if isinstance(image, (MetadataTensor, list)) else image
+            if isinstance(bare, torch.Tensor) and bare.dim() == 4:
+                return self._forward_fused(bare, *plan)
+            if isinstance(bare, list) and bare and all(isinstance(x, torch.Tensor) and x.dim() == 4 for x in bare):
+                return [self._forward_fused(x, *plan) for x in bare]
         return self.wrappers[self.stage](image, self.forward_batch, outputmodel=self.model, tensor_params=params)
 
     def _forward_fused(self, image, whiten, ms):
@@ -490,11 +695,13 @@ class SingleNetwork(object):
         return d.squeeze(0) if d.shape[0] == 1 else d.t()
 
     def forward_batch(self, images, **params):
+        """network.py:136-141: metadata is dropped right before the model (`tensors.as_tensor`); dict / tuple inputs reach
+        the model with their structure intact."""
         if images is None:
             return None
         if isinstance(images, list):
-            return [self.model(x, **params) if x is not None else None for x in images]
-        return self.model(images, **params)
+            return [self.model(as_tensor(x), **params) if x is not None else None for x in images]
+        return self.model(as_tensor(images), **params)
 
     @classmethod
     def initialize(cls, params, device):
@@ -521,8 +728,15 @@ class SingleNetwork(object):
             model = initialize_model(copy.deepcopy(network_params.model))
             if init and isinstance(init, str):
                 model.load_state_dict(torch.load(init, map_location="cpu"))
+            elif isinstance(init, dict) and init.get("weights") in ("normal_p2p", "kaiming_p2p"):
+                # generator.yml:11-13 (mdir/components/model/weight_initialization.py:62-76)
+                from .generator import init_weights_p2p
+                if init.get("seed") is not None:
+                    torch.manual_seed(init["seed"])
+                kind = init["weights"].split("_")[0]
+                model.apply(lambda mod: init_weights_p2p(mod, kind, 0.2))
             elif init:
-                raise NotImplementedError("custom random weight initialisation is outside the hot path")
+                raise NotImplementedError("weight initialisation %s is outside the hot path" % (init,))
         params.pop("type", None)
         assert not params, params.keys()
         return cls(model, network_params, device=device, frozen=False)
@@ -536,9 +750,106 @@ def initialize_model(model_params):
     """mdir/components/model/network/__init__.py: only the 'cirnet' architecture is on the hot path."""
     model_params = dict(model_params)
     arch = model_params.pop("architecture")
+    if arch == "official_resnet_generator":                     # mdir/hub/generator.yml:3-10 (stock PyTorch, north_star)
+        from .generator import ResnetGenerator
+        return ResnetGenerator(**model_params)
     if arch != "cirnet":
-        raise NotImplementedError("architecture '%s' is outside the retrieval hot path (available: cirnet)" % arch)
+        raise NotImplementedError("architecture '%s' is outside the retrieval hot path (available: cirnet, "
+                                  "official_resnet_generator)" % arch)
     return init_cirnet(**model_params)
+
+
+class SequentialNetwork(object):
+    """Two networks run back to back, e.g. `augment,embed` = day-to-night generator -> descriptor network
+    (mdir/learning/network.py:635-677; BASELINE config 5, iccv23/parameters/finetune.yml:5-32). The last network's
+    wrappers become the sequence's own (they see the raw input and the final output); the first network keeps its
+    wrappers (meanstd_post, clahepost, cir_ratio_pass_through for the generator), so everything between the two models
+    stays on the device: generator -> K1' (gdt_clahe_f32) -> gdt_meanstd_adapt -> backbone -> K2."""
+
+    NetworkParams = namedtuple("NetworkParams", ["runtime"])
+
+    def __init__(self, networks, sequence, device, frozen, rearrange_wrappers=True):
+        assert len(networks) == 2
+        assert networks.keys() == set(sequence)
+        self.networks, self.network_order = networks, list(sequence)
+        first_net = networks[sequence[0]]
+        self.last_net = networks[sequence[1]]
+        self.model = self.last_net.model
+        self.device = torch.device(device)
+        self.frozen = frozen
+        if rearrange_wrappers:
+            self.wrappers = self.last_net.wrappers
+            self.last_net.wrappers = {x: initialize_wrappers("", device) for x in ["train", "eval"]}
+            self.network_params = self.NetworkParams({"wrappers": self.last_net.network_params.runtime.get("wrappers", ""),
+                                                      "data": first_net.network_params.runtime["data"]})
+        else:
+            self.wrappers = {x: initialize_wrappers("", device) for x in ["train", "eval"]}
+            self.network_params = self.NetworkParams({"wrappers": "", "data": first_net.network_params.runtime["data"]})
+        assert first_net.meta["out_channels"] == self.last_net.meta["in_channels"]
+        self.meta = {"in_channels": first_net.meta["in_channels"], "out_channels": self.last_net.meta["out_channels"]}
+        self.stage = None
+        if frozen:
+            self.eval()
+
+    def train(self):
+        for net in self.networks.values():
+            net.train()
+        self.stage = SingleNetwork.TRAIN
+        return self
+
+    def eval(self):
+        for net in self.networks.values():
+            net.eval()
+        self.stage = SingleNetwork.EVAL
+        return self
+
+    def __call__(self, image):
+        return self.forward(image)
+
+    def forward(self, image):
+        return self.wrappers[self.stage](image, self.forward_batch, outputmodel=self.model)
+
+    def forward_batch(self, images):
+        if images is None:
+            return None
+        if isinstance(images, list):
+            return [self._forward_all(x) for x in images]
+        return self._forward_all(images)
+
+    def _forward_all(self, image):
+        for net in self.network_order:
+            image = self.networks[net](image)
+        return image
+
+    @classmethod
+    def initialize(cls, params, device):
+        # already built networks may be passed in place of their parameter dicts (they are used, not copied)
+        params = {k: (v if hasattr(v, "forward_batch") else copy.deepcopy(v)) for k, v in params.items()}
+        sequence = params.pop("sequence").split(",")
+        rearrange = params.pop("rearrange_wrappers") if "rearrange_wrappers" in params else True
+        params.pop("type", None)
+        networks = {x: (params[x] if hasattr(params[x], "forward_batch") else initialize_network(params[x], device))
+                    for x in params}
+        return cls(networks, sequence, device=device, frozen=False, rearrange_wrappers=rearrange)
+
+
+class CirSequentialNetwork(SequentialNetwork):
+    """network.py:750-756: the tuple list produced by `cirfaketuplebatch` goes through the sequence as ONE list, so the
+    first network's wrappers see every image of the tuple (and its metadata) at once."""
+
+    def forward_batch(self, images):
+        if images is None:
+            return None
+        return self._forward_all(images)
+
+
+NETWORKS = {"SingleNetwork": SingleNetwork, "SequentialNetwork": SequentialNetwork, "CirSequentialNetwork": CirSequentialNetwork}
+
+
+def initialize_network(params, device):
+    """mdir/learning/network.py `initialize_network`: {type, ...} -> network object."""
+    params = dict(params)
+    return NETWORKS[params.pop("type", "SingleNetwork")].initialize(params, device)
 
 
 def attach_transform(network):

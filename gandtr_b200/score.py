@@ -62,7 +62,6 @@ class CirDatasetAp:
         self.image_size = params.pop("image_size")
         self.dataset = params.pop("dataset")
         self.transforms = initialize_transforms(params.pop("transforms"), params.pop("mean_std"))
-        self.multiscale = params.pop("multiscale", False)
         if isinstance(self.dataset, dict) and {"images", "qimages", "gnd"} <= self.dataset.keys():
             self.images, self.qimages = list(self.dataset["images"]), list(self.dataset["qimages"])
             self.bbxs = list(self.dataset.get("bbxs") or [None] * len(self.qimages))
@@ -82,11 +81,10 @@ class CirDatasetAp:
     def __call__(self, network, device, logger):
         t0 = time.time()
         world, rank = _world()
-        ms, msp = ([1], 1)
-        if self.multiscale:
-            ms, msp = [1, 1. / np.sqrt(2), 1. / 2], network.model.pool.p.detach()
+        # extract_vectors(network, ...) with the default ms=[1] (cirscore.py:56): single- vs multi-scale and whitening are
+        # decided by the network's own eval wrappers, which extract_descriptors runs
         print(">> {}: database images...".format(self.dataset))
-        vecs = extract_descriptors(network, self.images, self.image_size, self.transforms, ms=ms, msp=msp,
+        vecs = extract_descriptors(network, self.images, self.image_size, self.transforms,
                                    rank=rank, world_size=world)                  # local rows of the database shard
         print(">> {}: query images...".format(self.dataset))
         same = len(self.images) == len(self.qimages) and set(self.bbxs) == {None} and \
@@ -94,11 +92,14 @@ class CirDatasetAp:
         if same and world == 1:
             qvecs = vecs.clone()
         else:
-            qvecs = extract_descriptors(network, self.qimages, self.image_size, self.transforms, bbxs=self.bbxs, ms=ms, msp=msp)
+            qvecs = extract_descriptors(network, self.qimages, self.image_size, self.transforms, bbxs=self.bbxs)
         t1 = time.time()
         print(">> {}: Evaluating...".format(self.dataset))
         lo, _ = shard_bounds(len(self.images), world, rank)
         index = ShardedIndex(vecs, n_total=len(self.images), index_base=lo)
+        # the probe-score / histogram exchanges need bit-identical queries on every rank: the stock cuDNN backbone may pick
+        # different algorithms per process, so rank 0's copy is the one everybody scores
+        qvecs = index.broadcast_queries(qvecs.contiguous())
         averages, scores = compute_map_and_print(self.dataset, index, qvecs, self.gnd)
         t2 = time.time()
         first_score = scores[list(scores.keys())[0]]

@@ -79,6 +79,9 @@ int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned lo
 int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a);
 /* debug/test hook: force the image rows per pass-B CTA of K1 (1..64; 0 = the built-in wave-quantisation rule) */
 int gdt_debug_k1_rows(int rows_per_cta);
+/* debug/test hook: images per (pass A, pass B) launch pair of K1: -1 = automatic (a chunk's 5 B/px scratch stays
+ * L2-resident between the passes), 0 = the whole batch at once, > 0 = forced */
+int gdt_debug_k1_chunk(int images_per_launch_pair);
 
 /* ---- K5: dataset image geometry (crop + LANCZOS thumbnail) ---------------------------------------
  * The image-size half of the reference's dataset loader on the device:
@@ -131,6 +134,13 @@ int gdt_clahe_f32(const float* in_chw, int n, int h, int w, double clip_limit, i
                   const float* host_in_mean, const float* host_in_std,
                   const float* host_out_mean, const float* host_out_std, float* out_chw,
                   void* ws, size_t ws_bytes, void* stream);
+
+/* `MeanStdPost._adapt` / `MeanStdPre` (mdir/components/data/wrapper.py:149-194): re-normalisation of a CHW float tensor,
+ *     y = ((x * in_std[c] + in_mean[c]) - out_mean[c]) / out_std[c]
+ * with the reference's four separately rounded fp32 operations (mul, add, sub, true division), bit-exact against the
+ * torch expression `x.mul(s0).add(m0).sub(m1).div(s1)`. x, y : float32 [n][3][plane] (plane = h*w), may alias. */
+int gdt_meanstd_adapt(const float* x, long long n, long long plane, const float* host_in_mean, const float* host_in_std,
+                      const float* host_out_mean, const float* host_out_std, float* y, void* stream);
 
 /* ---- K2: GeM + L2N + multi-scale aggregation + learned whitening ---------------------------------
  * Replaces LF.gem / LF.l2n (mdir/external/cirtorch/layers/functional.py:21-22,130-131),

@@ -180,3 +180,89 @@ def test_inline_gan_clahe_embed_chain_stays_on_device(vgg):
         s0 = torch.tensor(STD, device="cuda").view(1, 3, 1, 1)
         vec = vgg((eq * 0.5 + 0.5 - m0) / s0)
     assert tuple(vec.shape) == (512, 1) and abs(float(vec.norm()) - 1.0) < 1e-5
+
+
+def test_meanstd_post_matches_reference_golden_and_torch_expression():
+    """MeanStdPost (wrapper.py:149-179) as ONE kernel with the reference's four roundings: bit-exact against the
+    unmodified reference's CPU output and against the same torch expression evaluated on the device."""
+    from gandtr_b200.network import MeanStdPost, MeanStdPre
+    g = golden("augment_chain.npz")
+    post = MeanStdPost("[[0.5,0.4,0.3],[0.5,0.25,0.2]]", "[[0.485,0.456,0.406],[0.229,0.224,0.225]]", device="cuda")
+    x = torch.from_numpy(g["ms_x"]).cuda()
+    y = post.postprocess(x, None, None)
+    assert np.array_equal(y.cpu().numpy().view(np.uint32), g["ms_y"].view(np.uint32))
+    expr = x.mul(post.input_meanstd[1]).add(post.input_meanstd[0]).sub(post.output_meanstd[0]).div(post.output_meanstd[1])
+    assert torch.equal(y, expr)
+    # 3-d input, odd plane size (scalar path), list input, and the Pre variant
+    x3 = torch.randn(3, 7, 9, device="cuda")
+    y3 = post.postprocess([x3, x3 * 2], None, None)
+    e3 = x3.mul(post.input_meanstd[1]).add(post.input_meanstd[0]).sub(post.output_meanstd[0]).div(post.output_meanstd[1])
+    assert isinstance(y3, list) and torch.equal(y3[0], e3)
+    pre = MeanStdPre("[[0.5,0.4,0.3],[0.5,0.25,0.2]]", "[[0.485,0.456,0.406],[0.229,0.224,0.225]]", device="cuda")
+    t, meta = pre.preprocess(x3, None)
+    assert meta is None and torch.equal(t, e3) and pre.postprocess(x3, None, None) is x3
+    with pytest.raises(ValueError):
+        MeanStdPost("[[0,0,0],[1,0,1]]", "[[0,0,0],[1,1,1]]", device="cuda")
+
+
+def test_augment_wrapper_stack_matches_reference_golden():
+    """The `augment` network's wrapper string of BASELINE config 5 (finetune.yml:13) built by initialize_wrappers and run
+    through Compose on MetadataTensor inputs: routing (cir_ratio_pass_through), ClahePost (K1', float input) and
+    MeanStdPost, bit-exact against the unmodified reference (tools/gen_golden_chain.py; the generator between the
+    wrappers is the fixture's exactly reproducible stand-in)."""
+    from gandtr_b200 import network as N
+    g = golden("augment_chain.npz")
+    compose = N.initialize_wrappers(str(g["wrappers"]), "cuda")
+    assert [type(w).__name__ for w in compose.wrappers] == ["MeanStdPost", "ClahePost", "CirRatioPassThrough"]
+    inputs = [N.MetadataTensor(torch.from_numpy(x.copy()), {"image_label": [str(lab)], "name": [str(nm)]})
+              for x, lab, nm in zip(g["x"], g["labels"], g["names"])]
+    seen = []
+
+    def stand_in_generator(images):
+        seen.append([x is not None for x in images])
+        assert all(x is None or x.is_cuda for x in images)            # Compose moved the survivors to the device
+        return [None if x is None else N.as_tensor(x).flip(-1) * 0.5 for x in images]
+    with torch.no_grad():
+        outs = compose(inputs, stand_in_generator)
+    assert seen[0] == g["passed"].tolist()
+    for o, ref in zip(outs, g["y"]):
+        assert o.is_cuda and np.array_equal(o.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_sequential_network_chain_config5(vgg):
+    """`CirSequentialNetwork(sequence='augment,embed')` (network.py:635-677,750-756; finetune.yml:5-32): generator
+    SingleNetwork with the augment wrappers + descriptor network with `cirfaketuplebatch`, one object, everything between
+    the two models on the device. Checked against the same chain assembled by hand from its parts."""
+    from gandtr_b200 import network as N
+    wr = ("meanstd_post:[[0.5,0.5,0.5],[0.5,0.5,0.5]]:[[0.485,0.456,0.406],[0.229,0.224,0.225]],"
+          "clahepost:[[0.5,0.5,0.5],[0.5,0.5,0.5]]:1.0,cir_ratio_pass_through:1.0:anc")
+    params = {"type": "CirSequentialNetwork", "sequence": "augment,embed",
+              "augment": {"type": "SingleNetwork",
+                          "model": {"architecture": "official_resnet_generator", "no_antialias": True, "no_antialias_up": True,
+                                    "input_nc": 3, "output_nc": 3, "n_blocks": 2, "norm_layer": "instance"},
+                          "initialize": {"weights": "normal_p2p", "seed": 0},
+                          "runtime": {"frozen": True, "wrappers": wr,
+                                      "data": {"transforms": "pil2np | totensor | normalize",
+                                               "mean_std": [[0.5, 0.5, 0.5], [0.5, 0.5, 0.5]]}}},
+              "embed": vgg}
+    net = N.initialize_network(params, "cuda").eval()
+    assert isinstance(net, N.CirSequentialNetwork) and net.meta == {"in_channels": 3, "out_channels": 512}
+    assert [type(w).__name__ for w in net.wrappers["eval"].wrappers] == ["CirFakeTupleBatch"]   # the embed net's, re-homed
+    gen = net.networks["augment"]
+    tf = N.initialize_transforms("pil2np | totensor | normalize", [[0.5] * 3, [0.5] * 3], device="cuda")
+    imgs = [synth_image(40 + i, 64, 96, "smooth") for i in range(3)]
+    labels = ["anc", "pos", "neg"]
+    tuple_ = [N.MetadataTensor(tf(im), {"image_label": lab, "name": "t%d" % i}) for i, (im, lab) in enumerate(zip(imgs, labels))]
+    try:
+        with torch.no_grad():
+            out = net([tuple_])                                       # one training tuple -> D x 3
+            assert tuple(out.shape) == (512, 3)
+            # by hand: only the anchor goes through the generator (ratio 1.0, label 'anc'); ClahePost + MeanStdPost on all
+            post, clahe = gen.wrappers["eval"].wrappers[0], gen.wrappers["eval"].wrappers[1]
+            xs = [tf(im).unsqueeze(0) for im in imgs]
+            xs[0] = gen.model(xs[0])
+            ys = [post.postprocess(clahe.postprocess(x, None, None), None, None) for x in xs]
+            ref = torch.stack([vgg.model(y).reshape(-1) for y in ys], dim=1)
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    finally:
+        vgg.wrappers = net.wrappers                                   # give the shared fixture its wrappers back

@@ -150,6 +150,47 @@ def test_cirdatasetap_and_validate_stage(vgg):
     assert abs(out["eval"]["synthetic/validation/score_avg:map"] - m) < 1e-12
 
 
+def test_cirdatasetap_runs_the_networks_eval_wrappers(vgg):
+    """`extract_vectors(network, ...)` calls `net(input)` (imageretrievalnet.py:326-343), so a SingleNetwork's eval
+    wrappers -- {0_cirwhiten, 1_cirmultiscale} for the pretrained hub models (embedding.yml:24-25) -- shape the
+    descriptors CirDatasetAp ranks. Batched extraction must equal the per-image `net(transform(img))` descriptors and
+    validate() and infer() must agree on them."""
+    from gandtr_b200 import network as N
+    from gandtr_b200.extract import extract_descriptors
+    from gandtr_b200.score import SCORES, infer
+    rs = np.random.RandomState(11)
+    c = 512
+    whit = {"P": rs.normal(0, 1, (c, c)) / np.sqrt(c), "m": 0.05 * rs.rand(c, 1)}
+    data = vgg.network_params.runtime["data"]
+    runtime = {"data": data, "wrappers": {"train": None, "eval": {"0_cirwhiten": {"whitening": whit, "dimensions": 96},
+                                                                  "1_cirmultiscale": {"scales": True}}}}
+    net = N.SingleNetwork(vgg.model, N.SingleNetwork.NetworkParams(vgg.network_params.model, runtime), "cuda", frozen=True)
+    net.transform = vgg.transform
+    images, qimages, gnd = _dataset(12, 4)
+    d = extract_descriptors(net, images, None, vgg.transform, batch_size=4)
+    assert tuple(d.shape) == (12, 96)                              # whitened, reduced dimensionality
+    with torch.no_grad():
+        per_image = torch.stack([net(vgg.transform(im).unsqueeze(0)).reshape(-1) for im in images])
+        plain = extract_descriptors(vgg, images, None, vgg.transform, batch_size=4)
+    torch.testing.assert_close(d, per_image, rtol=1e-4, atol=1e-5)   # batch size changes the cuDNN algorithm
+    assert plain.shape[1] == 512                                    # the wrapper-less network is untouched
+    # the score object ranks the wrapped descriptors
+    ds = {"name": "synthetic", "images": images, "qimages": qimages, "bbxs": [None] * len(qimages), "gnd": gnd}
+    score = SCORES["cirdatasetap"]({"image_size": None, "dataset": ds, "transforms": data.get("transforms", data.get("augmentations")),
+                                    "mean_std": data["mean_std"]})
+    avg = score(net, "cuda", lambda *a: None)
+    q = extract_descriptors(net, qimages, None, vgg.transform).cpu().numpy()
+    m, _, _, _ = R.compute_map(R.full_ranks(R.scores_exact(q, d.cpu().numpy())), gnd)
+    assert abs(avg["map"] - m) < 1e-12
+    # infer() goes through the same wrappers: both stages see the same vectors
+    _, _, vecs = infer({"network": net}, (images[:3],))
+    np.testing.assert_allclose(vecs, d[:3].double().cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # the reference rejects unknown criterion keys (`assert not params`, cirscore.py:48)
+    with pytest.raises(AssertionError):
+        SCORES["cirdatasetap"]({"image_size": None, "dataset": ds, "transforms": "pil2np | totensor", "mean_std": data["mean_std"],
+                                "multiscale": True})
+
+
 def test_infer_stage_and_whitening_learning_chain(vgg, tmp_path):
     from gandtr_b200.score import infer, infer_and_learn_whitening
     images, _, _ = _dataset(12, 2)

@@ -69,6 +69,14 @@ def test_wrapper_registry_and_scales():
     assert c2.wrappers[0].dimensions == 8 and c2.wrappers[0].P.dtype == torch.float32
     with pytest.raises(NotImplementedError):
         N.initialize_wrappers("reflectpad_divisible:32", "cpu")
+    # the `augment` wrapper string of finetune.yml:13: commas inside the bracketed arguments do not split (utils.splitp)
+    c3 = N.initialize_wrappers("meanstd_post:[[0.5,0.5,0.5],[0.5,0.5,0.5]]:[[0.485,0.456,0.406],[0.229,0.224,0.225]],"
+                               "clahepost:[[0.5,0.5,0.5],[0.5,0.5,0.5]]:1.0,cir_ratio_pass_through:0.25:anc", "cpu")
+    assert [type(w).__name__ for w in c3.wrappers] == ["MeanStdPost", "ClahePost", "CirRatioPassThrough"]
+    assert c3.wrappers[1].clip_limit == 1.0 and c3.wrappers[2].probability == 0.25
+    assert repr(c3.wrappers[2]).startswith("CirRatioPassThrough(probability=0.25, train_label=")
+    with pytest.raises(AssertionError):
+        N.initialize_wrappers("meanstd_post:[[0.5,0.5", "cpu")
     # FakeBatch stacks per-image vectors into D x n (wrapper.py:266-280)
     out = N.FakeBatch("cpu").postprocess([torch.arange(4.0).reshape(4, 1), torch.ones(4)], None, None)
     assert tuple(out.shape) == (4, 2)
@@ -115,3 +123,42 @@ def test_descriptor_store_roundtrip_and_resharding(tmp_path):
     np.testing.assert_array_equal(np.concatenate(parts), x)
     w = store.load_whitening(str(tmp_path))
     np.testing.assert_array_equal(w["P"], whit["P"])
+
+
+def test_metadata_tensor_and_pass_through_routing():
+    """tools/tensors.py:8-30,37-85 and wrapper.py:97-146 on the host: structure-preserving helpers, metadata propagation
+    and the md5-based routing of CirRatioPassThrough (no kernels involved)."""
+    import hashlib
+    from gandtr_b200 import network as N
+    t = N.MetadataTensor(torch.zeros(1, 3, 4, 4), {"image_label": ["anc"], "name": ["img_000"]})
+    assert tuple(t.shape) == (1, 3, 4, 4)                                  # tensor attributes shine through
+    moved = t.to("cpu")
+    assert isinstance(moved, N.MetadataTensor) and moved.metadata is t.metadata
+    up = torch.nn.functional.interpolate(t, scale_factor=2.0)              # __torch_function__ keeps the metadata
+    assert isinstance(up, N.MetadataTensor) and tuple(up.tensor.shape) == (1, 3, 8, 8)
+    nested = {"a": [t, None], "b": (t, torch.ones(2))}
+    bare = N.as_tensor(nested)
+    assert isinstance(bare["a"][0], torch.Tensor) and bare["a"][1] is None and isinstance(bare["b"], tuple)
+    dev = N.to_device(nested, "cpu")
+    assert isinstance(dev["a"][0], N.MetadataTensor) and dev["a"][1] is None
+    m2 = N.as_metadata_tensor(torch.ones(2), {"k": 1})
+    assert m2.metadata == {"k": 1} and N.as_metadata_tensor(m2, {"j": 2}).metadata == {"k": 1, "j": 2}
+    ms = N.CirMultiscaleAggregation(True, device="cpu")
+    scaled, waslist = ms.preprocess(N.MetadataTensor(torch.zeros(1, 3, 8, 8), {"name": "x"}), None)
+    assert not waslist and all(isinstance(s, N.MetadataTensor) for s in scaled) and tuple(scaled[2].tensor.shape) == (1, 3, 4, 4)
+    # routing
+    w = N.CirRatioPassThrough("0.25", "anc", device="cpu")
+    names = ["img_%03d" % i for i in range(64)]
+    expect = [int(hashlib.md5(n.encode("utf8")).hexdigest()[-4:], 16) / 65536 < 0.25 for n in names]
+    assert [w._passthrough(n) for n in names] == expect and 4 < sum(expect) < 28
+    items = [N.MetadataTensor(torch.full((1,), float(i)), {"image_label": "anc" if i % 2 == 0 else "pos", "name": n})
+             for i, n in enumerate(names[:8])]
+    through, skipped = w.preprocess(items, None)
+    for i in range(8):
+        goes = (i % 2 == 0) and expect[i]
+        assert (through[i] is not None) == goes and (skipped[i] is None) == goes
+    out = w.postprocess([None if x is None else x.tensor + 100 for x in through], None, skipped)
+    for i in range(8):
+        assert float(out[i]) == (i + 100 if (i % 2 == 0 and expect[i]) else i) and isinstance(out[i], torch.Tensor)
+    rp = N.RandomPassThrough("1.0", "cpu")
+    assert rp.preprocess(torch.ones(1), None)[1] is None and repr(rp) == "RandomPassThrough(probability=1.0)"
