@@ -59,6 +59,8 @@ SYMBOLS = [
     ("gdt_score_topk_filter", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _P, _P, _c.c_size_t, _P]),
     ("gdt_score_topk_finalize", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P, _P,
                                            _P, _c.c_size_t, _P]),
+    ("gdt_debug_k3_coarse_scores", _c.c_int, [_P, _P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _P, _P, _P, _P,
+                                              _c.c_size_t, _P]),
     ("gdt_score_topk_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_longlong, _c.c_int, _c.c_int]),
     ("gdt_score_topk", _c.c_int, [_P, _P, _P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P,
                                   _P, _P, _c.c_size_t, _P]),
@@ -66,9 +68,11 @@ SYMBOLS = [
     ("gdt_score_topk_exact", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_longlong, _P, _P, _P,
                                         _c.c_size_t, _P]),
     ("gdt_topk_merge", _c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
+    ("gdt_topk_pack", _c.c_int, [_P, _P, _c.c_longlong, _P, _P]),
+    ("gdt_topk_merge_packed", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
     ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P]),
-    ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
+    ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
     ("gdt_thumbnail_geometry", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P, _P, _P, _P]),
     ("gdt_resize_plan_create", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P]),
     ("gdt_resize_plan_destroy", None, [_P]),
@@ -85,7 +89,7 @@ launch_count = 0  # number of library compute calls made by this process (bench.
 
 # kernels launched by each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"clahe": 2, "meanstd_adapt": 1, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
-                    "topk_merge": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1, "resize": 2}
+                    "topk_merge": 1, "topk_pack": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1, "resize": 2}
 
 
 class GdtError(RuntimeError):
@@ -410,34 +414,92 @@ def db_prepare_sharded(db, allreduce_max):
     return shadow, stats
 
 
-def score_topk_two_phase(q, db, shadow, stats, k, index_base=0, exchange=None):
-    """Filter -> `exchange(hist)` (an in-place SUM all-reduce of the int32 [nq, 256] histogram view) -> finalize."""
+def _filter_launches(ndb, k):
+    seed = max(32, (16 * k + 255) // 256)
+    return 2 + (1 if (ndb + 255) // 256 > seed else 0)        # q_prepare, seed (+ main) filter pass
+
+
+class FilterState:
+    """What lives between gdt_score_topk_filter and gdt_score_topk_finalize of one shard: the workspace (candidate
+    segments, thresholds), the status words and `hist`, the int32 [nq, 256] view of the per-query score histogram that
+    the ranks sum (in place) before finalising."""
+
+    def __init__(self, ws, status, hist, nq, ndb, d, k):
+        self.ws, self.status, self.hist, self.nq, self.ndb, self.d, self.k = ws, status, hist, nq, ndb, d, k
+
+
+def score_topk_filter(q, shadow, stats, k):
+    """First phase of the row-sharded search on one shard: tcgen05 coarse pass, candidates + histogram in the workspace."""
+    global launch_count
     _require(q, torch.float32, "q")
-    _require(db, torch.float32, "db")
     _require(shadow, torch.float16, "shadow")
     _require(stats, torch.float32, "stats")
     nq, d = q.shape
-    ndb = db.shape[0]
+    ndb = shadow.shape[0]
+    if shadow.shape[1] != d:
+        raise GdtError("q and shadow dimensions differ")
     lib = load()
     dev = q.device
-    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
     status = torch.empty(4, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         ws = _workspace(lib.gdt_score_topk_workspace_bytes(nq, ndb, d, k), dev)
         check(lib.gdt_score_topk_filter(_ptr(q), _ptr(shadow), _ptr(stats), nq, ndb, d, k, _ptr(status), _ptr(ws), ws.numel(),
                                         _stream()), "gdt_score_topk_filter")
-        if exchange is not None:
-            off, nbytes = ctypes.c_size_t(), ctypes.c_size_t()
-            check(lib.gdt_score_topk_exchange_layout(nq, ndb, d, k, ctypes.byref(off), ctypes.byref(nbytes)),
-                  "gdt_score_topk_exchange_layout")
-            exchange(ws[off.value:off.value + nbytes.value].view(torch.int32).view(nq, 256))
-        check(lib.gdt_score_topk_finalize(_ptr(q), _ptr(db), nq, ndb, d, k, int(index_base), _ptr(scores), _ptr(idx),
-                                          _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_score_topk_finalize")
+        off, nbytes = ctypes.c_size_t(), ctypes.c_size_t()
+        check(lib.gdt_score_topk_exchange_layout(nq, ndb, d, k, ctypes.byref(off), ctypes.byref(nbytes)),
+              "gdt_score_topk_exchange_layout")
+    hist = ws[off.value:off.value + nbytes.value].view(torch.int32).view(nq, 256)
+    launch_count += _filter_launches(ndb, k)
+    return FilterState(ws, status, hist, nq, ndb, d, k)
+
+
+def score_topk_finalize(q, db, state, index_base=0):
+    """Second phase: survivors above the threshold implied by `state.hist` (local, or summed over the shards) are
+    re-scored exactly. Returns (scores [nq,k], idx [nq,k], status [4]) on the device."""
     global launch_count
-    seed = max(32, (16 * k + 255) // 256)
-    launch_count += 3 + (1 if (ndb + 255) // 256 > seed else 0)
-    return scores, idx, status
+    _require(q, torch.float32, "q")
+    _require(db, torch.float32, "db")
+    nq, d = q.shape
+    k = state.k
+    if (nq, db.shape[0], d) != (state.nq, state.ndb, state.d) or db.shape[1] != d:
+        raise GdtError("finalize arguments do not match the filter pass")
+    dev = q.device
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(load().gdt_score_topk_finalize(_ptr(q), _ptr(db), nq, state.ndb, d, k, int(index_base), _ptr(scores), _ptr(idx),
+                                             _ptr(state.status), _ptr(state.ws), state.ws.numel(), _stream()),
+              "gdt_score_topk_finalize")
+    launch_count += 1
+    return scores, idx, state.status
+
+
+def score_topk_two_phase(q, db, shadow, stats, k, index_base=0, exchange=None):
+    """Filter -> `exchange(hist)` (an in-place SUM all-reduce of the int32 [nq, 256] histogram view) -> finalize."""
+    _require(db, torch.float32, "db")
+    state = score_topk_filter(q, shadow, stats, k)
+    if exchange is not None:
+        exchange(state.hist)
+    return score_topk_finalize(q, db, state, index_base=index_base)
+
+
+def debug_k3_coarse_scores(q, shadow, stats, k):
+    """Test hook: (coarse [nq, ndb] raw tensor-core scores, meta [nq, 4] = scale, 1/scale, margin = 2*E_q, sq)."""
+    _require(q, torch.float32, "q")
+    _require(shadow, torch.float16, "shadow")
+    _require(stats, torch.float32, "stats")
+    nq, d = q.shape
+    ndb = shadow.shape[0]
+    lib = load()
+    dev = q.device
+    coarse = torch.full((nq, ndb), float("nan"), dtype=torch.float32, device=dev)
+    meta = torch.empty((nq, 4), dtype=torch.float32, device=dev)
+    status = torch.empty(4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_score_topk_workspace_bytes(nq, ndb, d, k), dev)
+        check(lib.gdt_debug_k3_coarse_scores(_ptr(q), _ptr(shadow), _ptr(stats), nq, ndb, d, k, _ptr(coarse), _ptr(meta),
+                                             _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_debug_k3_coarse_scores")
+    return coarse, meta
 
 
 def score_topk_workspace_bytes(nq, ndb, d, k):
@@ -468,8 +530,7 @@ def score_topk(q, db, shadow, norm_max, k, index_base=0, ws=None, out=None):
         check(lib.gdt_score_topk(_ptr(q), _ptr(db), _ptr(shadow), _ptr(norm_max), nq, ndb, d, k, int(index_base),
                                  _ptr(scores), _ptr(idx), _ptr(status), _ptr(ws), ws.numel(), _stream()), "gdt_score_topk")
     global launch_count
-    seed = max(32, (16 * k + 255) // 256)
-    launch_count += 3 + (1 if (ndb + 255) // 256 > seed else 0)   # q_prepare, seed (+ main) filter pass, finalize
+    launch_count += _filter_launches(ndb, k) + 1                  # q_prepare, seed (+ main) filter pass, finalize
     return scores, idx, status
 
 
@@ -507,6 +568,29 @@ def topk_merge(scores, idx):
     return out_s, out_i
 
 
+def topk_pack(scores, idx):
+    """(scores, GLOBAL idx) lists of any shape -> uint64 rank keys (as an int64 tensor): the 8-byte exchange format."""
+    _require(scores, torch.float32, "scores")
+    _require(idx, torch.int64, "idx")
+    keys = torch.empty(scores.shape, dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(load().gdt_topk_pack(_ptr(scores), _ptr(idx), scores.numel(), _ptr(keys), _stream()), "gdt_topk_pack")
+    _count("topk_pack")
+    return keys
+
+
+def topk_merge_packed(keys):
+    """[g, nq, k] packed per-shard lists -> merged (scores [nq, k], idx [nq, k]); idx[q, 0] == -2 marks an overflow."""
+    _require(keys, torch.int64, "keys")
+    g, nq, k = keys.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        check(load().gdt_topk_merge_packed(_ptr(keys), g, nq, k, _ptr(out_s), _ptr(out_i), _stream()), "gdt_topk_merge_packed")
+    _count("topk_merge")
+    return out_s, out_i
+
+
 # ---- K4 ----------------------------------------------------------------------------------------------
 
 def probe_scores(q, db, probe_idx, index_base=0, out=None):
@@ -540,20 +624,27 @@ def rank_counts(q, db, probe_idx, probe_score, index_base=0, out=None):
     return out
 
 
-def map_eval(pos_rank, junk_rank, npos, njunk, kappas):
+def map_eval(pos_rank, junk_rank, npos, njunk, kappas, nres=None):
+    """-> (ap [nq] float64, prk [nq, nk] float64). kappas: list of ints or an int32 CUDA tensor; nres: optional int32 [nq]
+    recall denominators (defaults to npos)."""
     _require(pos_rank, torch.int64, "pos_rank")
     _require(junk_rank, torch.int64, "junk_rank")
     _require(npos, torch.int32, "npos")
     _require(njunk, torch.int32, "njunk")
+    if nres is not None:
+        _require(nres, torch.int32, "nres")
     nq = pos_rank.shape[0]
     dev = pos_rank.device
-    kap = torch.tensor(list(kappas) or [1], dtype=torch.int32, device=dev)
-    nk = len(kappas)
+    if isinstance(kappas, torch.Tensor):
+        kap, nk = _require(kappas, torch.int32, "kappas"), kappas.numel()
+    else:
+        kap, nk = torch.tensor(list(kappas) or [1], dtype=torch.int32, device=dev), len(kappas)
     ap = torch.empty(nq, dtype=torch.float64, device=dev)
     prk = torch.empty((nq, max(nk, 1)), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         check(load().gdt_map_eval(_ptr(pos_rank), pos_rank.shape[1], _ptr(junk_rank), junk_rank.shape[1], _ptr(npos),
-                                  _ptr(njunk), nq, _ptr(kap), nk, _ptr(ap), _ptr(prk), _stream()), "gdt_map_eval")
+                                  _ptr(njunk), _ptr(nres) if nres is not None else None, nq, _ptr(kap), nk, _ptr(ap),
+                                  _ptr(prk), _stream()), "gdt_map_eval")
     _count("map_eval")
     return ap, prk[:, :nk]
 

@@ -49,8 +49,9 @@ static ClaheTables g_tables[32];
 // under pass B's arithmetic; in pass A it is exposed: 1.03 vs 1.20 ms per 128 images), everything else recomputed.
 static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_chroma_a = 0, g_k1_occ_a = 4;
 static int g_k1_rows = 0;     // > 0: rows per pass-B CTA forced (gdt_debug_k1_rows), 0: pass_b_rows()
-static int g_k1_chunk = -1;   // images per (pass A, pass B) launch pair: -1 automatic (scratch of a chunk stays in L2),
-                              // 0 whole batch at once, > 0 forced (gdt_debug_k1_chunk)
+static int g_k1_chunk = 0;    // images per (pass A, pass B) launch pair: 0 whole batch at once (default: measured fastest,
+                              // profiles/k1_chunk_ab_r2a.log), -1 sized so that a chunk's scratch stays in L2, > 0 forced
+                              // (gdt_debug_k1_chunk)
 
 const ClaheTables* clahe_tables_for_current_device() {
     int dev = -1;
@@ -677,9 +678,11 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
 
 // Images per launch pair. Pass A writes 5 B/px of scratch that pass B reads back: when the whole batch goes through pass
 // A first, the scratch of a large batch (128 images of 1024x768: 503 MB) has left the 126 MB L2 long before pass B wants
-// it (measured DRAM traffic 1.38x the algorithmic bytes). Running the two passes chunk by chunk keeps a chunk's scratch
-// L2-resident. The chunk is sized to about half of L2 and rounded so that pass A's grid (grid^2 CTAs per image) fills
-// whole waves of the machine.
+// it (measured DRAM traffic 1.38x the algorithmic bytes). Running the two passes chunk by chunk (-1: a chunk sized to
+// about half of L2, rounded to whole waves of pass A) keeps a chunk's scratch L2-resident -- and is SLOWER on B200
+// (1.10 - 1.25 ms against 1.03 ms per 128 images, profiles/k1_chunk_ab_r2a.log): the kernels are bound by the SM's
+// issue / LSU / texture pipes, not by DRAM (22 % busy), and every extra launch pair adds a partially filled last wave.
+// The whole batch at once stays the default; the hook remains for A/B runs.
 static int clahe_chunk_images(int n, int h, int w, int grid) {
     if (g_k1_chunk == 0) return n;
     if (g_k1_chunk > 0) return g_k1_chunk < n ? g_k1_chunk : n;

@@ -94,13 +94,17 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
 // one CTA per query; sorts the two rank lists in shared memory, thread 0 runs the reference's loops
 __global__ void __launch_bounds__(128)
 map_eval_kernel(const int64_t* __restrict__ pos_rank, int pmax_pos, const int64_t* __restrict__ junk_rank, int pmax_junk,
-                const int32_t* __restrict__ npos, const int32_t* __restrict__ njunk, const int32_t* __restrict__ kappas,
-                int nk, int np_pos, int np_junk, double* __restrict__ ap, double* __restrict__ prk) {
+                const int32_t* __restrict__ npos, const int32_t* __restrict__ njunk, const int32_t* __restrict__ nres,
+                const int32_t* __restrict__ kappas, int nk, int np_pos, int np_junk, double* __restrict__ ap,
+                double* __restrict__ prk) {
     extern __shared__ __align__(16) uint64_t lists[];  // [np_pos] ascending positives, then [np_junk] ascending junk
     uint64_t* pos = lists;
     uint64_t* junk = lists + np_pos;
     const int tid = threadIdx.x, qi = blockIdx.x;
     const int n_p = npos[qi], n_j = njunk[qi];
+    // evaluate.py:75-80: positions come from the ids FOUND in the ranking (np.in1d: set semantics), the recall step from
+    // the length of the ground-truth list as given (nres = len(qgnd)); the two differ for duplicated / foreign ids
+    const int n_res = nres ? nres[qi] : n_p;
     // descending bitonic sort on (~rank) == ascending on rank; padding key 0 sorts last
     for (int i = tid; i < np_pos; i += 128) pos[i] = i < n_p ? ~(uint64_t)pos_rank[(size_t)qi * pmax_pos + i] : 0ull;
     for (int i = tid; i < np_junk; i += 128) junk[i] = i < n_j ? ~(uint64_t)junk_rank[(size_t)qi * pmax_junk + i] : 0ull;
@@ -108,7 +112,7 @@ map_eval_kernel(const int64_t* __restrict__ pos_rank, int pmax_pos, const int64_
     block_bitonic_sort_desc(junk, np_junk, tid, 128);
     if (tid != 0) return;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    if (n_p == 0) {  // evaluate.py:68-72
+    if (n_res == 0 || n_p == 0) {  // evaluate.py:68-72 (empty ground truth); no id found: nothing to average either
         ap[qi] = nan;
         for (int j = 0; j < nk; ++j) prk[(size_t)qi * nk + j] = nan;
         return;
@@ -117,7 +121,7 @@ map_eval_kernel(const int64_t* __restrict__ pos_rank, int pmax_pos, const int64_
     long long kshift = 0;
     int ij = 0;
     double acc = 0.0;
-    const double recall_step = 1.0 / (double)n_p;
+    const double recall_step = 1.0 / (double)n_res;
     long long maxpos = 0;
     for (int ip = 0; ip < n_p; ++ip) {
         long long r = (long long)(~pos[ip]);
@@ -198,8 +202,8 @@ extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long lon
 }
 
 extern "C" int gdt_map_eval(const int64_t* pos_rank, int pmax_pos, const int64_t* junk_rank, int pmax_junk,
-                            const int32_t* npos, const int32_t* njunk, int nq, const int32_t* kappas, int nk,
-                            double* ap, double* prk, void* stream_) {
+                            const int32_t* npos, const int32_t* njunk, const int32_t* nres, int nq, const int32_t* kappas,
+                            int nk, double* ap, double* prk, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!pos_rank || !junk_rank || !npos || !njunk || !ap) return GDT_ERR_INVALID_ARGUMENT;
     if (nq <= 0 || pmax_pos <= 0 || pmax_junk <= 0 || nk < 0 || (nk > 0 && (!kappas || !prk))) return GDT_ERR_INVALID_ARGUMENT;
@@ -213,8 +217,8 @@ extern "C" int gdt_map_eval(const int64_t* pos_rank, int pmax_pos, const int64_t
         GDT_CUDA(cudaFuncSetAttribute(map_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;
     }
-    map_eval_kernel<<<nq, 128, smem, stream>>>(pos_rank, pmax_pos, junk_rank, pmax_junk, npos, njunk, kappas, nk, np_pos,
-                                               np_junk, ap, prk);
+    map_eval_kernel<<<nq, 128, smem, stream>>>(pos_rank, pmax_pos, junk_rank, pmax_junk, npos, njunk, nres, kappas, nk,
+                                               np_pos, np_junk, ap, prk);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

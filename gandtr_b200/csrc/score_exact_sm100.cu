@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int g, int nq, int k, int np,
                   float* __restrict__ out_s, int64_t* __restrict__ out_i) {
     extern __shared__ __align__(16) uint64_t keys[];  // [np]
+    __shared__ int s_overflow;
     const int tid = threadIdx.x, q = blockIdx.x;
     const int total = g * k;
+    if (tid == 0) s_overflow = 0;
+    __syncthreads();
     for (int i = tid; i < np; i += 256) {
         uint64_t key = 0ull;
         if (i < total) {
@@ -165,15 +168,67 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
             const size_t off = ((size_t)s * nq + q) * k + j;
             const int64_t id = idx[off];
             if (id >= 0) key = rank_key(scores[off], (uint32_t)id);
+            else if (id == -2) s_overflow = 1;      // a shard's list overflowed (topk_finalize_kernel's marker)
         }
         keys[i] = key;
     }
     block_bitonic_sort_desc(keys, np, tid, 256);
+    const bool overflow = s_overflow != 0;
     for (int i = tid; i < k; i += 256) {
         const uint64_t key = keys[i];
         const bool valid = key != 0ull;
         out_s[(size_t)q * k + i] = valid ? key_score(key) : __int_as_float(0xff800000);
-        out_i[(size_t)q * k + i] = valid ? (int64_t)key_index(key) : (int64_t)-1;
+        int64_t id = valid ? (int64_t)key_index(key) : (int64_t)-1;
+        if (overflow && i == 0) id = -2;
+        out_i[(size_t)q * k + i] = id;
+    }
+}
+
+// ---- packed exchange format ---------------------------------------------------------------------
+// One 64-bit word per list entry instead of (fp32 score, int64 index): the library's rank key (select.cuh) of
+// (score, GLOBAL index) -- larger key == sorts first -- so per-shard lists travel as 8 bytes per entry in ONE
+// all-gather and merge without unpacking. Keys with a zero high word cannot be rank keys (ordered_bits() is zero only
+// for a negative NaN): 0 = padding, kKeyOverflow = "this shard's list overflowed, the query needs the exact fallback".
+constexpr uint64_t kKeyOverflow = 2ull;
+
+__global__ void __launch_bounds__(256)
+topk_pack_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, long long n, uint64_t* __restrict__ keys) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const int64_t id = idx[i];
+        keys[i] = id >= 0 ? rank_key(scores[i], (uint32_t)id) : (id == -2 ? kKeyOverflow : 0ull);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, int np, float* __restrict__ out_s,
+                         int64_t* __restrict__ out_i) {
+    extern __shared__ __align__(16) uint64_t keys[];  // [np]
+    __shared__ int s_overflow;
+    const int tid = threadIdx.x, q = blockIdx.x;
+    const int total = g * k;
+    if (tid == 0) s_overflow = 0;
+    __syncthreads();
+    for (int i = tid; i < np; i += 256) {
+        uint64_t key = 0ull;
+        if (i < total) {
+            const int s = i / k, j = i - s * k;
+            key = in[((size_t)s * nq + q) * k + j];
+            if ((key >> 32) == 0ull) {
+                if (key == kKeyOverflow) s_overflow = 1;
+                key = 0ull;
+            }
+        }
+        keys[i] = key;
+    }
+    block_bitonic_sort_desc(keys, np, tid, 256);
+    const bool overflow = s_overflow != 0;
+    for (int i = tid; i < k; i += 256) {
+        const uint64_t key = keys[i];
+        const bool valid = key != 0ull;
+        out_s[(size_t)q * k + i] = valid ? key_score(key) : __int_as_float(0xff800000);
+        int64_t id = valid ? (int64_t)key_index(key) : (int64_t)-1;
+        if (overflow && i == 0) id = -2;      // same marker as topk_finalize_kernel: the caller repairs this query
+        out_i[(size_t)q * k + i] = id;
     }
 }
 
@@ -261,6 +316,39 @@ extern "C" int gdt_topk_merge(const float* scores, const int64_t* idx, int g, in
         attr_bytes = smem;
     }
     topk_merge_kernel<<<nq, 256, smem, stream>>>(scores, idx, g, nq, k, np, out_scores, out_idx);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
+extern "C" int gdt_topk_pack(const float* scores, const int64_t* idx, long long n, uint64_t* keys, void* stream_) {
+    if (!scores || !idx || !keys || n < 0) return GDT_ERR_INVALID_ARGUMENT;
+    if (!have_device()) return GDT_ERR_NO_DEVICE;
+    if (n == 0) return GDT_OK;
+    long long blocks = ceil_div_ll(n, 256);
+    const long long cap = (long long)sm_count_current_device() * 8;
+    if (blocks > cap) blocks = cap;
+    topk_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(scores, idx, n, keys);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
+extern "C" int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k, float* out_scores, int64_t* out_idx,
+                                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!keys || !out_scores || !out_idx) return GDT_ERR_INVALID_ARGUMENT;
+    if (g <= 0 || nq <= 0 || k <= 0) return GDT_ERR_INVALID_ARGUMENT;
+    const long long total = (long long)g * k;
+    if (total > 16384) return GDT_ERR_UNSUPPORTED;
+    if (!have_device()) return GDT_ERR_NO_DEVICE;
+    const int np = next_pow2((int)total);
+    const size_t smem = (size_t)np * sizeof(uint64_t);
+    static size_t attr_bytes_dev[32] = {0};
+    size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
+    if (smem > 48 * 1024 && smem > attr_bytes) {
+        GDT_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes = smem;
+    }
+    topk_merge_packed_kernel<<<nq, 256, smem, stream>>>(keys, g, nq, k, np, out_scores, out_idx);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

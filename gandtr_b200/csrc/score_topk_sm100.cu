@@ -248,6 +248,8 @@ struct FilterParams {
     uint32_t* cnt;                     // [nq][n_segs]
     uint32_t* hist;
     uint64_t* cand;                    // [nq][n_seed * cap0 + (n_segs - n_seed) * cap1]
+    float* dump;                       // debug (gdt_debug_k3_coarse_scores): every coarse score, [nq][dump_ld]; else null
+    long long dump_ld;
 };
 
 // per-query threshold from the global histogram (scanned from the top, 128-bit loads through L2)
@@ -419,6 +421,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll                                  // NaN fails every `>= tau` test, even while tau is still -inf
                         for (int j = 0; j < 32; ++j)
                             if (c * 32 + j >= ncols) v[j] = 0x7fc00000u;
+                    }
+                    if (P.dump != nullptr && valid) {      // debug only: the raw tensor-core scores, for the error-bound tests
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j < ncols) P.dump[(size_t)qrow * P.dump_ld + col0 + c * 32 + j] = __uint_as_float(v[j]);
                     }
                     float mg[4];
 #pragma unroll
@@ -657,11 +664,25 @@ static TopkPlan topk_plan(int nq, long long ndb, int d, int k) {
     L.n_units = max_active_clusters(L.cluster);
     (void)sms;
     plan_items(L.n_qgroups, L.n_dtiles - L.seed_tiles, L.n_units, L.n_stripes, L.stripe_len);
-    // the seed range itself is striped over idle SMs when there are few query tiles; a seed segment can hold every row of
-    // its stripe, so it cannot overflow however cold the threshold is
-    L.n_seed = L.n_units / L.n_qgroups;
-    if (L.n_seed > L.seed_tiles / 8) L.n_seed = L.seed_tiles / 8;
-    if (L.n_seed < 1) L.n_seed = 1;
+    // The seed range itself is striped over the machine: every seed stripe starts cold and its segment can hold every row
+    // of the stripe, so it cannot overflow however cold the threshold is. The stripe count minimises the makespan
+    // waves x (stripe length + pipeline fill) -- e.g. 40 query groups on 74 clusters: 1 stripe of 32 tiles leaves 34
+    // clusters idle for 32 tile times, 3 stripes of 11 run in 2 waves of 11 -- with at least 8 tiles (2048 rows) per
+    // stripe so that a cold stripe still reaches a useful threshold.
+    {
+        int best_s = 1;
+        double best_cost = 1e300;
+        const int max_s = L.seed_tiles / 8 > 1 ? L.seed_tiles / 8 : 1;
+        for (int sd = 1; sd <= max_s; ++sd) {
+            const int len = ceil_div(L.seed_tiles, sd);
+            const int s_eff = ceil_div(L.seed_tiles, len);
+            const long long items = (long long)s_eff * L.n_qgroups;
+            const long long waves = (items + L.n_units - 1) / L.n_units;
+            const double cost = (double)waves * (len + 0.5);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s_eff; }
+        }
+        L.n_seed = best_s;
+    }
     L.seed_len = ceil_div(L.seed_tiles, L.n_seed);
     L.n_seed = ceil_div(L.seed_tiles, L.seed_len);
     L.n_segs = L.n_seed + L.n_stripes;
@@ -782,8 +803,9 @@ extern "C" int gdt_score_topk_exchange_layout(int nq, long long ndb, int d, int 
     return GDT_OK;
 }
 
-extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb,
-                                     int d, int k, int32_t* status_dev, void* ws, size_t ws_bytes, void* stream_) {
+static int score_topk_filter_impl(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb,
+                                  int d, int k, int32_t* status_dev, void* ws, size_t ws_bytes, float* dump,
+                                  void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!db_f16 || !db_stats || !status_dev) return GDT_ERR_INVALID_ARGUMENT;
     if ((((uintptr_t)db_f16) & 15) != 0) return GDT_ERR_INVALID_ARGUMENT;
@@ -815,6 +837,7 @@ extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const f
     P.n_kblocks = ceil_div(d, kBlockK);
     P.n_segs = L.n_segs; P.n_seed = L.n_seed; P.cap0 = L.cap0; P.cap1 = L.cap1;
     P.meta = meta; P.tau = tau; P.cnt = cnt; P.hist = hist; P.cand = cand;
+    P.dump = dump; P.dump_ld = ndb;
     (void)sms;
     // seed pass: the first tiles of the shard against every query tile establish the thresholds
     P.tile_begin = 0; P.tile_end = L.seed_tiles;
@@ -827,6 +850,26 @@ extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const f
         rc = launch_filter(L.cluster, L.n_units, map_q, map_db, P, stream);
         if (rc != GDT_OK) return rc;
     }
+    return GDT_OK;
+}
+
+extern "C" int gdt_score_topk_filter(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb,
+                                     int d, int k, int32_t* status_dev, void* ws, size_t ws_bytes, void* stream) {
+    return score_topk_filter_impl(q, db_f16, db_stats, nq, ndb, d, k, status_dev, ws, ws_bytes, nullptr, stream);
+}
+
+// Debug / test hook: the filter pass with every raw tensor-core score written to coarse[nq][ndb], plus the per-query
+// bound the filter relies on: meta[q] = {scale, 1/scale, margin = 2 * E_q, sq}. tests/ compare
+// |coarse - sq * sx * <q, x>| (exact, fp64) with E_q = margin / 2.
+extern "C" int gdt_debug_k3_coarse_scores(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb,
+                                          int d, int k, float* coarse, float* meta_out, int32_t* status_dev, void* ws,
+                                          size_t ws_bytes, void* stream) {
+    if (!coarse || !meta_out) return GDT_ERR_INVALID_ARGUMENT;
+    int rc = score_topk_filter_impl(q, db_f16, db_stats, nq, ndb, d, k, status_dev, ws, ws_bytes, coarse, stream);
+    if (rc != GDT_OK) return rc;
+    const TopkPlan L = topk_plan(nq, ndb, d, k);
+    GDT_CUDA(cudaMemcpyAsync(meta_out, (const char*)ws + L.meta, (size_t)nq * sizeof(QMeta), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
     return GDT_OK;
 }
 

@@ -19,11 +19,17 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "CudaOps", "DatabaseShard", "ShardedIndex", "evaluate_map", "evaluate_protocols", "compute_map_and_print",
-           "TC_MIN_WORK"]
+__all__ = ["shard_bounds", "DistComm", "CudaOps", "DatabaseShard", "ShardedIndex", "evaluate_map", "evaluate_protocols",
+           "compute_map_and_print", "TC_MIN_WORK", "EXACT_MAX_K", "MERGE_MAX_ENTRIES"]
 
 # below this many multiply-adds the exact CUDA-core kernel is used instead of the tcgen05 pipeline
 TC_MIN_WORK = 1 << 24
+# kernel limits (score_exact_sm100.cu): lists longer than EXACT_MAX_K take the full-sort path, merges of more than
+# MERGE_MAX_ENTRIES (= shards x k) entries run in rounds
+EXACT_MAX_K = 4096
+MERGE_MAX_ENTRIES = 16384
+# the exact fallback streams the database in row blocks so that its score workspace stays below this many floats
+EXACT_WS_FLOATS = 1 << 26
 
 
 def shard_bounds(n_total, world_size, rank):
@@ -39,65 +45,120 @@ def _world(group):
     return 1, 0
 
 
+class DistComm:
+    """The collectives of the sharded path over one torch.distributed process group (NCCL over NVLink on GPUs, gloo in
+    the CPU tests). Tests may inject another object with the same five methods (tests/util.py `ThreadComm` emulates
+    several ranks on ONE GPU)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world, self.rank = _world(group)
+
+    def _nccl(self):
+        return self.world > 1 and dist.get_backend(self.group) == "nccl"
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def all_reduce_max(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather(self, t):
+        """-> [world, *t.shape], rank-major."""
+        t = t.contiguous()
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        if self.world == 1:
+            out[0] = t
+        elif self._nccl():
+            dist.all_gather_into_tensor(out, t, group=self.group)      # one collective, no staging copies
+        else:
+            dist.all_gather(list(out.unbind(0)), t, group=self.group)   # gloo (CPU tests)
+        return out
+
+    def broadcast(self, t, src=0):
+        if self.world > 1:
+            dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def sum_int(self, v):
+        if self.world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], dtype=torch.int64)
+        if self._nccl():
+            t = t.cuda()
+        dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+
 class CudaOps:
     """The product's compute: every method is one or more launches of libgandtr_b200.so kernels."""
 
-    def prepare(self, db, group=None, world=1):
+    def prepare(self, db, comm=None):
         from . import _lib
         d = db.shape[1]
         if d % 8 != 0 or d > 8192:
             return {}
-        if world > 1:
+        if comm is not None and comm.world > 1:
             # common scale / error bound on every rank, so that the per-query score histograms can be summed
-            shadow, stats = _lib.db_prepare_sharded(db, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group))
-            return {"shadow": shadow, "norm_max": stats, "group": group}
+            shadow, stats = _lib.db_prepare_sharded(db, comm.all_reduce_max)
+            return {"shadow": shadow, "norm_max": stats, "comm": comm}
         if db.shape[0] > 0:
             shadow, norm_max = _lib.db_prepare(db)
             return {"shadow": shadow, "norm_max": norm_max}
         return {}
 
+    @staticmethod
+    def _empty_lists(nq, k, device):
+        return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=device),
+                torch.full((nq, k), -1, dtype=torch.int64, device=device))
+
     def local_topk(self, q, shard, k):
-        """(scores [nq,k], global idx [nq,k]) of one shard; exact ordering (score desc, index asc). On a sharded index
-        the lists hold this shard's members of the GLOBAL top k (fewer than k valid entries, (-inf, -1) padding)."""
-        if "group" in shard.aux:
+        """(scores [nq,k], global idx [nq,k]) of one shard; exact ordering (score desc, index asc).
+        Single shard: complete and repaired. On a sharded index the lists hold this shard's members of the GLOBAL top k
+        (fewer than k valid entries, (-inf, -1) padding) and are returned WITHOUT a host sync: a query whose candidate
+        lists overflowed carries idx[q, 0] == -2, which the merge propagates and `ShardedIndex.search` repairs after one
+        check at the very end of the search."""
+        if "comm" in shard.aux:
             return self._local_topk_exchanged(q, shard, k)
         from . import _lib
         db, aux, base = shard.db, shard.aux, shard.index_base
         nq, d = q.shape
         ndb = db.shape[0]
         if ndb == 0:
-            return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device),
-                    torch.full((nq, k), -1, dtype=torch.int64, device=q.device))
+            return self._empty_lists(nq, k, q.device)
         use_tc = "shadow" in aux and k <= 1024 and nq * ndb * d >= TC_MIN_WORK and base + ndb <= 0xFFFFFFFF
         if not use_tc:
-            return self._exact_chunked(q, db, k, base)
+            return self.exact_topk(q, shard, k)
         s, i, st = _lib.score_topk(q, db, aux["shadow"], aux["norm_max"], k, index_base=base)
         status = st.cpu()  # one small sync per search: the status word decides whether a repair pass is needed
         shard.last_status = status.tolist()
         if int(status[0]) != 0:
-            self._repair(q, shard, k, s, i)
+            bad = torch.nonzero(i[:, 0] == -2).flatten()
+            if bad.numel():
+                s[bad], i[bad] = self.repair_topk(q[bad].contiguous(), shard, k)
         return s, i
 
-    def _repair(self, q, shard, k, s, i):
-        """Candidate overflow (dense near-ties, duplicated rows): first retry the flagged queries alone with a much larger
-        k -- that multiplies the candidate and survivor capacities and spreads the shard over more stripes -- and only
-        what still overflows goes to the exact CUDA-core scan."""
+    def repair_topk(self, q, shard, k):
+        """Exact local lists of queries whose candidate segments overflowed (dense near-ties, duplicated rows): first a
+        retry with a much larger k -- that multiplies the candidate and survivor capacities and spreads the shard over
+        more stripes -- and only what still overflows goes to the exact CUDA-core scan. No collective in here."""
         from . import _lib
         db, aux, base = shard.db, shard.aux, shard.index_base
-        bad = torch.nonzero(i[:, 0] == -2).flatten()
-        if not bad.numel():
-            return
+        if db.shape[0] == 0:
+            return self._empty_lists(q.shape[0], k, q.device)
         kk = 1024              # 8192-entry candidate segments per stripe, 8192 survivors
-        if kk > k:
-            s2, i2, st2 = _lib.score_topk(q[bad].contiguous(), db, aux["shadow"], aux["norm_max"], kk, index_base=base)
-            ok = i2[:, 0] != -2
-            s[bad[ok]] = s2[ok, :k]
-            i[bad[ok]] = i2[ok, :k]
-            bad = bad[~ok]
-        if bad.numel():
-            se, ie = self._exact_chunked(q[bad].contiguous(), db, k, base)
-            s[bad] = se
-            i[bad] = ie
+        if kk > k and "shadow" in aux:
+            s2, i2, _ = _lib.score_topk(q, db, aux["shadow"], aux["norm_max"], kk, index_base=base)
+            s, i = s2[:, :k].contiguous(), i2[:, :k].contiguous()
+            bad = torch.nonzero(i2[:, 0] == -2).flatten()
+            if bad.numel():
+                s[bad], i[bad] = self.exact_topk(q[bad].contiguous(), shard, k)
+            return s, i
+        return self.exact_topk(q, shard, k)
 
     def _local_topk_exchanged(self, q, shard, k):
         """Row-sharded search with the histogram exchange (include/gandtr_b200.h, two-phase form). Every rank takes the
@@ -105,40 +166,85 @@ class CudaOps:
         from . import _lib
         db, aux, base = shard.db, shard.aux, shard.index_base
         nq, d = q.shape
-        group = aux["group"]
+        comm = aux["comm"]
         ndb = db.shape[0]
-        use_tc = k <= 1024 and nq * shard.n_total * d >= TC_MIN_WORK * dist.get_world_size(group) and shard.n_total <= 0xFFFFFFFF
+        use_tc = k <= 1024 and nq * shard.n_total * d >= TC_MIN_WORK * comm.world and shard.n_total <= 0xFFFFFFFF
         if not use_tc:
-            if ndb == 0:
-                return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device),
-                        torch.full((nq, k), -1, dtype=torch.int64, device=q.device))
-            return self._exact_chunked(q, db, k, base)
+            return self.exact_topk(q, shard, k)
         if ndb == 0:
             hist = torch.zeros((nq, 256), dtype=torch.int32, device=q.device)
-            dist.all_reduce(hist, group=group)          # take part in the histogram exchange with an empty contribution
-            return (torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device),
-                    torch.full((nq, k), -1, dtype=torch.int64, device=q.device))
-        s, i, st = _lib.score_topk_two_phase(q, db, aux["shadow"], aux["norm_max"], k, index_base=base,
-                                             exchange=lambda h: dist.all_reduce(h, group=group))
-        status = st.cpu()
-        shard.last_status = status.tolist()
-        if int(status[0]) != 0:
-            self._repair(q, shard, k, s, i)      # local, no collective: the repaired lists are supersets of what is needed
+            comm.all_reduce_sum(hist)                    # take part in the histogram exchange with an empty contribution
+            return self._empty_lists(nq, k, q.device)
+        state = _lib.score_topk_filter(q, aux["shadow"], aux["norm_max"], k)
+        comm.all_reduce_sum(state.hist)
+        s, i, st = _lib.score_topk_finalize(q, db, state, index_base=base)
+        shard.last_status = st                           # device tensor: read lazily (bench / diagnostics), no sync here
         return s, i
 
-    @staticmethod
-    def _exact_chunked(q, db, k, base):
+    def exact_topk(self, q, shard, k):
+        """CUDA-core exact lists of one shard (fallback and small problems). The database is streamed in row blocks so the
+        score workspace stays bounded (EXACT_WS_FLOATS), block lists are merged on the device."""
         from . import _lib
-        # the exact kernel materialises [nq_chunk, ndb] scores in its workspace: bound it to ~1 GiB
-        ndb = db.shape[0]
-        step = max(1, min(q.shape[0], (1 << 28) // max(ndb, 1)))
-        outs = [_lib.score_topk_exact(q[a:a + step].contiguous(), db, k, index_base=base)
-                for a in range(0, q.shape[0], step)]
-        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+        db, base = shard.db, shard.index_base
+        nq, ndb = q.shape[0], db.shape[0]
+        if ndb == 0:
+            return self._empty_lists(nq, k, q.device)
+        if k > EXACT_MAX_K:
+            return self._full_sort_topk(q, db, k, base)
+        rows = min(ndb, max(4 * k, 1 << 20))
+        qstep = max(1, min(nq, EXACT_WS_FLOATS // rows))
+        out_s, out_i = [], []
+        for a in range(0, nq, qstep):
+            qa = q[a:a + qstep].contiguous()
+            parts = [_lib.score_topk_exact(qa, db[r0:r0 + rows], k, index_base=base + r0) for r0 in range(0, ndb, rows)]
+            if len(parts) == 1:
+                s, i = parts[0]
+            else:
+                s, i = self.merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+            out_s.append(s)
+            out_i.append(i)
+        return (out_s[0], out_i[0]) if len(out_s) == 1 else (torch.cat(out_s), torch.cat(out_i))
+
+    @staticmethod
+    def _full_sort_topk(q, db, k, base):
+        """k > EXACT_MAX_K (deep mining walks): outside the hot path -- fp64 library GEMM rounded once to fp32, stable
+        descending sort (ties -> lower index first), query blocks bounded like the exact kernel's workspace."""
+        nq, ndb = q.shape[0], db.shape[0]
+        kk = min(k, ndb)
+        s = torch.full((nq, k), float("-inf"), dtype=torch.float32, device=q.device)
+        i = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
+        step = max(1, EXACT_WS_FLOATS // (2 * max(ndb, 1)))
+        dbd = db.double()
+        for a in range(0, nq, step):
+            sc = (q[a:a + step].double() @ dbd.t()).float()
+            v, o = torch.sort(sc, dim=1, descending=True, stable=True)
+            s[a:a + step, :kk], i[a:a + step, :kk] = v[:, :kk], o[:, :kk] + base
+        return s, i
 
     def merge(self, scores, idx):
+        """[g, nq, k] lists -> [nq, k]; more than MERGE_MAX_ENTRIES entries per query are merged in rounds."""
         from . import _lib
-        return _lib.topk_merge(scores.contiguous(), idx.contiguous())
+        scores, idx = scores.contiguous(), idx.contiguous()
+        g, nq, k = scores.shape
+        if k > MERGE_MAX_ENTRIES // 2:
+            raise _lib.GdtError("top-k lists longer than %d entries cannot be merged on the device" % (MERGE_MAX_ENTRIES // 2))
+        gmax = max(2, MERGE_MAX_ENTRIES // k)
+        while g > gmax:
+            parts = [_lib.topk_merge(scores[a:a + gmax].contiguous(), idx[a:a + gmax].contiguous()) for a in range(0, g, gmax)]
+            scores, idx = torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts])
+            g = scores.shape[0]
+        return _lib.topk_merge(scores, idx)
+
+    def pack(self, scores, idx):
+        from . import _lib
+        return _lib.topk_pack(scores.contiguous(), idx.contiguous())
+
+    def merge_packed(self, keys):
+        from . import _lib
+        g, nq, k = keys.shape
+        if g * k > MERGE_MAX_ENTRIES:
+            raise _lib.GdtError("packed merge of %d x %d entries exceeds %d" % (g, k, MERGE_MAX_ENTRIES))
+        return _lib.topk_merge_packed(keys.contiguous())
 
     def probe_scores(self, q, shard, probe_idx, out):
         from . import _lib
@@ -161,143 +267,173 @@ class DatabaseShard:
     """Rows [index_base, index_base + n) of the database, resident in HBM: fp32 rows + the fp16 shadow used by the
     tcgen05 coarse pass (6 bytes per element in total)."""
 
-    def __init__(self, db, index_base=0, ops=None, group=None, world=1, n_total=None):
+    def __init__(self, db, index_base=0, ops=None, comm=None, n_total=None):
         self.ops = ops or CudaOps()
         self.db = db.contiguous()
         self.index_base = int(index_base)
         self.n_total = int(n_total if n_total is not None else db.shape[0])
         try:
-            self.aux = self.ops.prepare(self.db, group=group, world=world)
+            self.aux = self.ops.prepare(self.db, comm=comm)
         except TypeError:          # injected ops with the single-argument signature (tests)
             self.aux = self.ops.prepare(self.db)
-        self.last_status = None
+        self._last_status = None
 
     @property
     def rows(self):
         return self.db.shape[0]
+
+    @property
+    def last_status(self):
+        """[overflow status, max survivors re-scored per query, overflowed queries, max candidates per query] of the last
+        tcgen05 search as a list (reads the device words on demand)."""
+        st = self._last_status
+        return st.tolist() if isinstance(st, torch.Tensor) else st
+
+    @last_status.setter
+    def last_status(self, value):
+        self._last_status = value
 
 
 class ShardedIndex:
     """Row-sharded database over a process group. `search` is the drop-in for
     `np.argsort(-np.dot(vecs.T, qvecs), axis=0)[:k]` (cirscore.py:71-72), returned query-major."""
 
-    def __init__(self, local_db, n_total=None, group=None, ops=None, index_base=None):
+    def __init__(self, local_db, n_total=None, group=None, ops=None, index_base=None, comm=None):
+        self.comm = comm if comm is not None else DistComm(group)
         self.group = group
-        self.world, self.rank = _world(group)
+        self.world, self.rank = self.comm.world, self.comm.rank
         self.ops = ops or CudaOps()
         if n_total is None:
-            n_total = self._sum_int(local_db.shape[0])
+            n_total = self.comm.sum_int(local_db.shape[0])
         self.n_total = int(n_total)
         if index_base is None:
             index_base = shard_bounds(self.n_total, self.world, self.rank)[0]
             if self.world > 1:
                 assert local_db.shape[0] == shard_bounds(self.n_total, self.world, self.rank)[1] - index_base, \
                     "local shard does not match shard_bounds(); pass index_base explicitly for custom partitions"
-        self.shard = DatabaseShard(local_db, index_base, self.ops, group=group, world=self.world, n_total=self.n_total)
+        self.shard = DatabaseShard(local_db, index_base, self.ops, comm=self.comm, n_total=self.n_total)
 
     @classmethod
-    def from_full(cls, db, group=None, ops=None):
+    def from_full(cls, db, group=None, ops=None, comm=None):
         """Every rank holds (or can produce) the full [ndb, d] matrix: keep only this rank's rows."""
-        world, rank = _world(group)
-        lo, hi = shard_bounds(db.shape[0], world, rank)
-        return cls(db[lo:hi].contiguous(), n_total=db.shape[0], group=group, ops=ops, index_base=lo)
-
-    def _sum_int(self, v):
-        if self.world == 1:
-            return int(v)
-        t = torch.tensor([int(v)], dtype=torch.int64)
-        if dist.get_backend(self.group) == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, group=self.group)
-        return int(t.item())
+        comm = comm if comm is not None else DistComm(group)
+        lo, hi = shard_bounds(db.shape[0], comm.world, comm.rank)
+        return cls(db[lo:hi].contiguous(), n_total=db.shape[0], group=group, ops=ops, index_base=lo, comm=comm)
 
     def broadcast_queries(self, q, src=0):
-        if self.world > 1:
-            dist.broadcast(q, src=src, group=self.group)
-        return q
+        return self.comm.broadcast(q, src=src)
+
+    def _exchange_and_merge(self, s, i):
+        """Per-shard lists -> the same merged [nq, k] lists on every rank. With the product's ops the lists travel packed
+        (8 bytes per entry, ONE all-gather); injected test ops without `pack` use the two-tensor form."""
+        if hasattr(self.ops, "pack") and s.shape[1] * self.world <= MERGE_MAX_ENTRIES:
+            return self.ops.merge_packed(self.comm.all_gather(self.ops.pack(s, i)))
+        return self.ops.merge(self.comm.all_gather(s), self.comm.all_gather(i))
 
     def search(self, q, k, broadcast=False):
         """q: [nq, d] float32 (identical on every rank, or rank 0's copy with broadcast=True).
-        Returns (scores [nq, k], global indices [nq, k] int64) on every rank."""
+        Returns (scores [nq, k], global indices [nq, k] int64) on every rank.
+        Sharded: filter -> histogram all-reduce -> finalize -> pack -> all-gather -> merge are enqueued back to back; the
+        only host read is the overflow check on the MERGED lists at the end (identical on every rank, so every rank takes
+        the same repair decision)."""
         if broadcast:
             q = self.broadcast_queries(q)
         s, i = self.ops.local_topk(q, self.shard, k)
         if self.world == 1:
             return s, i
-        all_s = torch.empty((self.world,) + tuple(s.shape), dtype=s.dtype, device=s.device)
-        all_i = torch.empty((self.world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
-        # list-of-views form: one collective on NCCL (equal sizes), and also supported by gloo (CPU tests)
-        dist.all_gather(list(all_s.unbind(0)), s.contiguous(), group=self.group)
-        dist.all_gather(list(all_i.unbind(0)), i.contiguous(), group=self.group)
-        return self.ops.merge(all_s, all_i)
+        s, i = self._exchange_and_merge(s, i)
+        if hasattr(self.ops, "repair_topk"):
+            bad = i[:, 0] == -2
+            if bool(bad.any()):                      # the search's single host sync
+                rows = torch.nonzero(bad).flatten()
+                rs, ri = self.ops.repair_topk(q[rows].contiguous(), self.shard, k)     # exact local lists, no collective
+                rs, ri = self._exchange_and_merge(rs, ri)
+                s[rows], i[rows] = rs, ri
+        return s, i
 
     def positions(self, q, probe_idx):
         """0-based position every probe id would take in the full descending ranking of its query
         (= what `np.flatnonzero(np.in1d(ranks[:, i], ids))` reads, evaluate.py:75-76). probe_idx: [nq, pmax] int64, -1 pad."""
         ps = torch.zeros(probe_idx.shape, dtype=torch.float32, device=q.device)
         self.ops.probe_scores(q, self.shard, probe_idx, ps)
-        if self.world > 1:
-            dist.all_reduce(ps, group=self.group)       # non-owners contributed exact zeros
+        self.comm.all_reduce_sum(ps)                    # non-owners contributed exact zeros
         before = torch.zeros(probe_idx.shape, dtype=torch.int64, device=q.device)
         self.ops.rank_counts(q, self.shard, probe_idx, ps, before)
-        if self.world > 1:
-            dist.all_reduce(before, group=self.group)
+        self.comm.all_reduce_sum(before)
         return before
 
 
-def _pad_ids(lists, device, fill=-1):
+def _pad_rows(lists, fill=-1):
     n = max(1, max((len(x) for x in lists), default=1))
     arr = np.full((len(lists), n), fill, dtype=np.int64)
     for r, x in enumerate(lists):
         arr[r, :len(x)] = np.asarray(x, dtype=np.int64)
-    return torch.from_numpy(arr).to(device)
+    return arr
 
 
-def _map_from_positions(ops, before, ok_cols, junk_cols, kappas, device):
-    """before: [nq, pu] positions of the probe ids; ok_cols / junk_cols: per query, the columns of `before` that hold its
-    positives / junk ids. Runs gdt_map_eval and averages like the reference loop."""
-    nq = len(ok_cols)
-    npos_h = [len(c) for c in ok_cols]
-    njunk_h = [len(c) for c in junk_cols]
-    pos_rank = torch.gather(before, 1, _pad_ids(ok_cols, device, fill=0)).contiguous()
-    junk_rank = torch.gather(before, 1, _pad_ids(junk_cols, device, fill=0)).contiguous()
-    npos = torch.tensor(npos_h, dtype=torch.int32, device=device)
-    njunk = torch.tensor(njunk_h, dtype=torch.int32, device=device)
-    ap, prk = ops.map_eval(pos_rank, junk_rank, npos, njunk, list(kappas))
-    ap, prk = ap.cpu().numpy(), prk.cpu().numpy()
-    # same accumulation order as the reference loop (evaluate.py:98,106,108-109): sequential, empty queries skipped
-    total, pr, nempty = 0.0, np.zeros(len(kappas)), 0
-    for i in range(nq):
-        if npos_h[i] == 0:
-            nempty += 1
-            continue
-        total = total + ap[i]
-        pr = pr + prk[i, :]
-    nvalid = nq - nempty
-    return (total / nvalid if nvalid else float("nan")), ap, (pr / nvalid if nvalid else pr * np.nan), prk
+def _to_device(arr, device):
+    t = torch.from_numpy(arr)
+    if torch.device(device).type == "cuda":
+        t = t.pin_memory().to(device, non_blocking=True)
+    return t
 
 
 def evaluate_protocols(index, q, groups, protocols, kappas=()):
-    """Several (ok, junk) partitions of the same id groups with ONE pass over the database.
+    """Several (ok, junk) partitions of the same id groups with ONE pass over the database and ONE evaluation launch.
     groups: per query {name: ids}; protocols: {protocol: (ok group names, junk group names)}.
-    Returns {protocol: (map, aps, mean P@k, P@k)}."""
+    Returns {protocol: (map, aps, mean P@k, P@k)}.
+    Ids follow `np.in1d(ranks[:, i], ids)` (evaluate.py:75-76): set semantics -- a duplicated id is found once, an id
+    outside the database never -- while the recall step stays 1 / len(list as given) (evaluate.py:77-78)."""
     names = sorted({n for ok, jk in protocols.values() for n in tuple(ok) + tuple(jk)})
-    ids, spans = [], []
+    nq = len(groups)
+    ids, spans, given = [], [], []
     for g in groups:
-        off, span, parts = 0, {}, []
+        off, span, parts, glen = 0, {}, [], {}
         for n in names:
-            a = np.asarray(g.get(n, []), dtype=np.int64).reshape(-1)
-            span[n] = (off, off + len(a))
+            raw = np.asarray(g.get(n, []), dtype=np.int64).reshape(-1)
+            a = np.unique(raw[(raw >= 0) & (raw < index.n_total)])
+            span[n], glen[n] = (off, off + len(a)), len(raw)
             off += len(a)
             parts.append(a)
         ids.append(np.concatenate(parts) if parts else np.zeros(0, np.int64))
         spans.append(span)
-    before = index.positions(q, _pad_ids(ids, q.device))
+        given.append(glen)
+    before = index.positions(q, _to_device(_pad_rows(ids), q.device))              # [nq, pu]
+    # every protocol's rows stacked: one gather pair, one gdt_map_eval launch, one read-back
+    prots = list(protocols.items())
+    ok_cols, junk_cols, nres = [], [], []
+    for _, (ok_names, junk_names) in prots:
+        for sp, gl in zip(spans, given):
+            ok_cols.append(np.concatenate([np.arange(*sp[n]) for n in ok_names]) if ok_names else np.zeros(0, np.int64))
+            junk_cols.append(np.concatenate([np.arange(*sp[n]) for n in junk_names]) if junk_names else np.zeros(0, np.int64))
+            nres.append(sum(gl[n] for n in ok_names))
+    npos_h, njunk_h = [len(c) for c in ok_cols], [len(c) for c in junk_cols]
+    okm, jkm = _pad_rows(ok_cols, fill=0), _pad_rows(junk_cols, fill=0)
+    counts = np.stack([npos_h, njunk_h, nres]).astype(np.int32)
+    dev = q.device
+    rep = before.repeat(len(prots), 1) if len(prots) > 1 else before
+    pos_rank = torch.gather(rep, 1, _to_device(okm, dev)).contiguous()
+    junk_rank = torch.gather(rep, 1, _to_device(jkm, dev)).contiguous()
+    cnt = _to_device(counts, dev)
+    try:
+        ap, prk = index.ops.map_eval(pos_rank, junk_rank, cnt[0].contiguous(), cnt[1].contiguous(), list(kappas),
+                                     nres=cnt[2].contiguous())
+    except TypeError:                  # injected test ops with the five-argument signature
+        ap, prk = index.ops.map_eval(pos_rank, junk_rank, cnt[0].contiguous(), cnt[1].contiguous(), list(kappas))
+    ap, prk = ap.cpu().numpy(), prk.cpu().numpy()
     out = {}
-    for prot, (ok_names, junk_names) in protocols.items():
-        ok_cols = [np.concatenate([np.arange(*sp[n]) for n in ok_names]) if ok_names else np.zeros(0, np.int64) for sp in spans]
-        junk_cols = [np.concatenate([np.arange(*sp[n]) for n in junk_names]) if junk_names else np.zeros(0, np.int64) for sp in spans]
-        out[prot] = _map_from_positions(index.ops, before, ok_cols, junk_cols, kappas, q.device)
+    for pi, (prot, _) in enumerate(prots):
+        a, pk = ap[pi * nq:(pi + 1) * nq], prk[pi * nq:(pi + 1) * nq]
+        # same accumulation order as the reference loop (evaluate.py:98,106,108-109): sequential, empty queries skipped
+        total, pr, nempty = 0.0, np.zeros(len(kappas)), 0
+        for i in range(nq):
+            if nres[pi * nq + i] == 0:
+                nempty += 1
+                continue
+            total = total + a[i]
+            pr = pr + pk[i, :]
+        nvalid = nq - nempty
+        out[prot] = ((total / nvalid if nvalid else float("nan")), a, (pr / nvalid if nvalid else pr * np.nan), pk)
     return out
 
 

@@ -79,8 +79,8 @@ int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned lo
 int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a);
 /* debug/test hook: force the image rows per pass-B CTA of K1 (1..64; 0 = the built-in wave-quantisation rule) */
 int gdt_debug_k1_rows(int rows_per_cta);
-/* debug/test hook: images per (pass A, pass B) launch pair of K1: -1 = automatic (a chunk's 5 B/px scratch stays
- * L2-resident between the passes), 0 = the whole batch at once, > 0 = forced */
+/* debug/test hook: images per (pass A, pass B) launch pair of K1: 0 = the whole batch at once (default), -1 = sized so
+ * that a chunk's 5 B/px scratch stays L2-resident between the passes, > 0 = forced */
 int gdt_debug_k1_chunk(int images_per_launch_pair);
 
 /* ---- K5: dataset image geometry (crop + LANCZOS thumbnail) ---------------------------------------
@@ -233,6 +233,12 @@ int gdt_score_topk_filter(const float* q, const void* db_f16, const float* db_st
 int gdt_score_topk_finalize(const float* q, const float* db, int nq, long long ndb, int d, int k, long long index_base,
                             float* top_scores, int64_t* top_idx, int32_t* status_dev,
                             void* ws, size_t ws_bytes, void* stream);
+/* debug/test hook: gdt_score_topk_filter that also writes every raw tensor-core (coarse) score to coarse[nq][ndb] and the
+ * per-query filter constants to meta_out[nq][4] = {scale, 1/scale, margin = 2*E_q, sq}. The exactness of K3 rests on
+ * |coarse - sq*sx*<q,x>| <= E_q; tests/test_gpu_topk.py measures the left side against fp64 on adversarial data. */
+int gdt_debug_k3_coarse_scores(const float* q, const void* db_f16, const float* db_stats, int nq, long long ndb, int d,
+                               int k, float* coarse, float* meta_out, int32_t* status_dev, void* ws, size_t ws_bytes,
+                               void* stream);
 size_t gdt_score_topk_workspace_bytes(int nq, long long ndb, int d, int k);
 int gdt_score_topk(const float* q, const float* db, const void* db_f16, const float* db_stats,
                    int nq, long long ndb, int d, int k, long long index_base,
@@ -250,6 +256,15 @@ int gdt_score_topk_exact(const float* q, const float* db, int nq, long long ndb,
  * scores/idx : [g][nq][k] -> out : [nq][k], same ordering rule; entries with idx < 0 are padding. */
 int gdt_topk_merge(const float* scores, const int64_t* idx, int g, int nq, int k,
                    float* out_scores, int64_t* out_idx, void* stream);
+
+/* Packed exchange form of the per-shard lists: one uint64 per entry = the library's rank key of (score, GLOBAL index)
+ * (larger key sorts first; 0 = padding, 2 = "this shard overflowed"), so that the row-sharded search needs ONE
+ * all-gather of 8 bytes per entry instead of two (fp32 scores + int64 indices, 12 bytes).
+ *   gdt_topk_pack          scores/idx [n] -> keys [n]; idx -1 -> padding, idx -2 (overflow marker) -> overflow key
+ *   gdt_topk_merge_packed  keys [g][nq][k] -> merged (scores, idx) [nq][k]; a query for which any shard reported an
+ *                          overflow comes back with idx[q][0] == -2, as gdt_score_topk_finalize marks it. */
+int gdt_topk_pack(const float* scores, const int64_t* idx, long long n, uint64_t* keys, void* stream);
+int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k, float* out_scores, int64_t* out_idx, void* stream);
 
 /* ---- K4: ranks of ground-truth ids + mAP ------------------------------------------------------------
  * Replaces the use of the full `ranks` matrix inside compute_map
@@ -272,10 +287,13 @@ int gdt_rank_counts(const float* q, const float* db, int nq, long long ndb, int 
 
 /* compute_ap / compute_map body (evaluate.py:3-37,60-106) for nq queries:
  * pos_rank [nq][pmax_pos], junk_rank [nq][pmax_junk] : 0-based full-ranking positions (any order,
- * first npos[q] / njunk[q] entries valid). kappas [nk] (device). Outputs (float64, as the
- * reference): ap [nq] (NaN when npos == 0), prk [nq][nk]. */
+ * first npos[q] / njunk[q] entries valid). nres [nq] (nullable -> npos): length of the positive list as given, the
+ * recall denominator `compute_ap(pos, len(qgnd))` uses (evaluate.py:75-98; differs from npos when the list holds
+ * duplicated or foreign ids, which np.in1d finds once or never). kappas [nk] (device). Outputs (float64, as the
+ * reference): ap [nq] (NaN when nres == 0 or npos == 0), prk [nq][nk]. Several protocols (easy / medium / hard) are
+ * evaluated in one launch by stacking their rows. */
 int gdt_map_eval(const int64_t* pos_rank, int pmax_pos, const int64_t* junk_rank, int pmax_junk,
-                 const int32_t* npos, const int32_t* njunk, int nq,
+                 const int32_t* npos, const int32_t* njunk, const int32_t* nres, int nq,
                  const int32_t* kappas, int nk, double* ap, double* prk, void* stream);
 
 #ifdef __cplusplus

@@ -252,7 +252,9 @@ def test_sequential_network_chain_config5(vgg):
     tf = N.initialize_transforms("pil2np | totensor | normalize", [[0.5] * 3, [0.5] * 3], device="cuda")
     imgs = [synth_image(40 + i, 64, 96, "smooth") for i in range(3)]
     labels = ["anc", "pos", "neg"]
-    tuple_ = [N.MetadataTensor(tf(im), {"image_label": lab, "name": "t%d" % i}) for i, (im, lab) in enumerate(zip(imgs, labels))]
+    # the training loop hands 4-d tensors to the network (CirFakeTupleBatch.unsqueeze, wrapper.py:286-294)
+    tuple_ = N.CirFakeTupleBatch.unsqueeze([tf(im) for im in imgs])
+    tuple_ = [N.MetadataTensor(t, {"image_label": lab, "name": "t%d" % i}) for i, (t, lab) in enumerate(zip(tuple_, labels))]
     try:
         with torch.no_grad():
             out = net([tuple_])                                       # one training tuple -> D x 3

@@ -118,3 +118,39 @@ def test_roxford_shaped_eval_full_size_matches_oracle():
         assert abs(avg["map_" + name] - oavg["map_" + name]) < 1e-12
         np.testing.assert_array_equal(per["ap_" + name], oaps["ap_" + name])
     assert np.isnan(per["ap_hard"][8]) and 0.2 < avg["map_medium"] <= 1.0
+
+
+def test_duplicated_and_foreign_ground_truth_ids_follow_in1d_semantics():
+    """`np.in1d(ranks[:, i], qgnd)` (evaluate.py:75-76) finds a duplicated id once and an id outside the database never,
+    while `compute_ap(pos, len(qgnd))` keeps the list length as given: evaluate_map must do the same."""
+    from gandtr_b200.retrieval import ShardedIndex, evaluate_map, compute_map_and_print
+    from tests.util import unit_rows
+    rs = np.random.RandomState(17)
+    ndb, nq, d = 3000, 12, 64
+    db, q = unit_rows(rs, ndb, d), unit_rows(rs, nq, d)
+    gnd = []
+    for i in range(nq):
+        ok = rs.permutation(ndb)[:9]
+        junk = rs.permutation(ndb)[:5]
+        if i % 3 == 0:
+            ok = np.concatenate([ok, ok[:3]])                           # duplicates
+        if i % 4 == 1:
+            ok = np.concatenate([ok, [ndb + 5, ndb + 77]])              # ids no shard owns
+            junk = np.concatenate([junk, junk[:2], [ndb + 1]])
+        gnd.append({"ok": ok, "junk": junk})
+    gnd[7]["ok"] = np.array([], dtype=np.int64)                         # empty query: NaN, excluded
+    index = ShardedIndex(torch.from_numpy(db).cuda())
+    qd = torch.from_numpy(q).cuda()
+    m, aps, mpr, prs = evaluate_map(index, qd, gnd, [1, 5, 10])
+    mo, apo, mpro, prso = R.compute_map(R.full_ranks(R.scores_exact(q, db)), gnd, [1, 5, 10])
+    assert np.array_equal(aps, apo, equal_nan=True) and np.isnan(aps[7])
+    assert abs(m - mo) < 1e-15
+    np.testing.assert_array_equal(prs, prso)
+    np.testing.assert_allclose(mpr, mpro, rtol=0, atol=1e-15)
+    # the three revisited protocols in one pass (one rank_counts + one map_eval launch) equal three separate evaluations
+    rg = [{"bbx": None, "easy": g["ok"][:4], "hard": g["ok"][4:], "junk": g["junk"]} for g in gnd]
+    avg, per = compute_map_and_print("roxford5k", index, qd, rg, printer=lambda *_: None)
+    oavg, oper, _ = R.compute_map_protocols("roxford5k", R.full_ranks(R.scores_exact(q, db)), rg)
+    for name in ("easy", "medium", "hard"):
+        assert np.array_equal(per["ap_" + name], oper["ap_" + name], equal_nan=True)
+        assert abs(avg["map_" + name] - oavg["map_" + name]) < 1e-15

@@ -168,8 +168,8 @@ def test_index_repairs_duplicate_clusters_on_the_tensor_path(monkeypatch):
     q = unit_rows(rs, 5, 128)
     q[2] = base[0]
     calls = []
-    orig = retrieval.CudaOps._exact_chunked
-    monkeypatch.setattr(retrieval.CudaOps, "_exact_chunked", staticmethod(lambda *a, **k: calls.append(1) or orig(*a, **k)))
+    orig = retrieval.CudaOps.exact_topk
+    monkeypatch.setattr(retrieval.CudaOps, "exact_topk", lambda self, *a, **k: calls.append(1) or orig(self, *a, **k))
     monkeypatch.setattr(retrieval, "TC_MIN_WORK", 1)
     index = retrieval.ShardedIndex(torch.from_numpy(db).cuda())
     s, i = index.search(torch.from_numpy(q).cuda(), 50)
