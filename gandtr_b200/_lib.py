@@ -71,8 +71,12 @@ SYMBOLS = [
     ("gdt_topk_pack", _c.c_int, [_P, _P, _c.c_longlong, _P, _P]),
     ("gdt_topk_merge_packed", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
-    ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P]),
+    ("gdt_rank_counts_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int]),
+    ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P,
+                                   _c.c_size_t, _P]),
     ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
+    ("gdt_diverse_anchors_workspace_bytes", _c.c_size_t, [_c.c_int]),
+    ("gdt_diverse_anchors", _c.c_int, [_P, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _P, _P, _P, _c.c_size_t, _P]),
     ("gdt_thumbnail_geometry", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P, _P, _P, _P]),
     ("gdt_resize_plan_create", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P]),
     ("gdt_resize_plan_destroy", None, [_P]),
@@ -89,7 +93,7 @@ launch_count = 0  # number of library compute calls made by this process (bench.
 
 # kernels launched by each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"clahe": 2, "meanstd_adapt": 1, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
-                    "topk_merge": 1, "topk_pack": 1, "probe_scores": 1, "rank_counts": 1, "map_eval": 1, "resize": 2}
+                    "topk_merge": 1, "topk_pack": 1, "probe_scores": 1, "rank_counts": 3, "map_eval": 1, "resize": 2}
 
 
 class GdtError(RuntimeError):
@@ -617,9 +621,11 @@ def rank_counts(q, db, probe_idx, probe_score, index_base=0, out=None):
     pmax = probe_idx.shape[1]
     if out is None:
         out = torch.zeros((nq, pmax), dtype=torch.int64, device=q.device)
+    lib = load()
     with torch.cuda.device(q.device):
-        check(load().gdt_rank_counts(_ptr(q), _ptr(db), nq, db.shape[0], d, int(index_base), _ptr(probe_idx),
-                                     _ptr(probe_score), pmax, _ptr(out), _stream()), "gdt_rank_counts")
+        ws = _workspace(lib.gdt_rank_counts_workspace_bytes(nq, pmax), q.device)
+        check(lib.gdt_rank_counts(_ptr(q), _ptr(db), nq, db.shape[0], d, int(index_base), _ptr(probe_idx),
+                                  _ptr(probe_score), pmax, _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_rank_counts")
     _count("rank_counts")
     return out
 
@@ -647,6 +653,28 @@ def map_eval(pos_rank, junk_rank, npos, njunk, kappas, nres=None):
                                   _ptr(prk), _stream()), "gdt_map_eval")
     _count("map_eval")
     return ap, prk[:, :nk]
+
+
+# ---- N3: mining ------------------------------------------------------------------------------------
+
+def diverse_anchors(pool, ranks, first=0):
+    """pool: [n, d] float32 CUDA rows; ranks: int32 CUDA [steps] ascending rank picked per round.
+    -> (picked int32 [steps + 1], picked_score float32 [steps]) on the device, no host sync."""
+    global launch_count
+    _require(pool, torch.float32, "pool")
+    _require(ranks, torch.int32, "ranks")
+    n, d = pool.shape
+    steps = ranks.numel()
+    dev = pool.device
+    picked = torch.empty(steps + 1, dtype=torch.int32, device=dev)
+    score = torch.empty(max(steps, 1), dtype=torch.float32, device=dev)
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_diverse_anchors_workspace_bytes(n), dev)
+        check(lib.gdt_diverse_anchors(_ptr(pool), n, d, _ptr(ranks), steps, int(first), _ptr(picked), _ptr(score), _ptr(ws),
+                                      ws.numel(), _stream()), "gdt_diverse_anchors")
+    launch_count += 2 * steps
+    return picked, score[:steps]
 
 
 # ---- K5: dataset image geometry ------------------------------------------------------------------

@@ -7,9 +7,12 @@
 // never materialise the ndb x nq rank matrix.
 //
 //   probe_scores_kernel  exact score of every (query, probe id) pair owned by this shard
-//   rank_counts_kernel   8 queries per CTA in shared memory, one warp per database row (read once),
-//                        exact scores compared against the probes of each query; per-CTA shared-memory
-//                        counters, one global atomicAdd per (query, probe) per CTA
+//   probe_sort_kernel    per query: the probes' rank keys sorted once (descending)
+//   rank_counts_kernel   8 queries per CTA in shared memory, one warp per database row (read once): exact scores,
+//                        then ONE binary search per (row, query) into the sorted probe keys and ONE bucket increment
+//                        ("this row sorts before the probes from slot m on") -- O(log pmax) instead of pmax compares and
+//                        up to pmax shared-memory atomics per (row, query)
+//   rank_finish_kernel   per query: prefix sum over the buckets, scattered back to the probes' columns
 //   map_eval_kernel      junk shift + trapezoidal AP + precision@k in fp64, same operation order as
 //                        the reference so the per-query numbers are bit-identical
 #include "common.cuh"
@@ -36,15 +39,41 @@ probe_scores_kernel(const float* __restrict__ q, const float* __restrict__ db, i
     }
 }
 
+// rank key of a probe: 0 for padding / ids this library cannot address
+__device__ __forceinline__ uint64_t probe_key(long long id, float score) {
+    return (id >= 0 && id <= 0xffffffffLL) ? rank_key(score, (uint32_t)id) : 0ull;
+}
+
+__global__ void __launch_bounds__(256)
+probe_sort_kernel(const int64_t* __restrict__ probe_idx, const float* __restrict__ probe_score, int pmax, int pp,
+                  uint64_t* __restrict__ skeys, unsigned long long* __restrict__ gbucket) {
+    extern __shared__ __align__(16) uint64_t keys[];   // [pp]
+    const int tid = threadIdx.x, qi = blockIdx.x;
+    for (int i = tid; i < pp; i += 256)
+        keys[i] = i < pmax ? probe_key(probe_idx[(size_t)qi * pmax + i], probe_score[(size_t)qi * pmax + i]) : 0ull;
+    block_bitonic_sort_desc(keys, pp, tid, 256);
+    for (int i = tid; i < pp; i += 256) skeys[(size_t)qi * pp + i] = keys[i];
+    for (int i = tid; i <= pp; i += 256) gbucket[(size_t)qi * (pp + 1) + i] = 0ull;
+}
+
+// number of sorted (descending) keys that are >= key: the row sorts before the probes in the slots from there on
+__device__ __forceinline__ int slots_not_after(const uint64_t* __restrict__ sk, int pp, uint64_t key) {
+    int lo = 0, n = pp;                       // first index with sk[i] < key
+    while (n > 0) {
+        const int half = n >> 1;
+        if (__ldg(sk + lo + half) >= key) { lo += half + 1; n -= half + 1; }
+        else n = half;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256)
 rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, int nq, long long ndb, int d, int dpad,
-                   long long index_base, const int64_t* __restrict__ probe_idx, const float* __restrict__ probe_score,
-                   int pmax, unsigned long long* __restrict__ before, int rows_per_cta) {
+                   long long index_base, const uint64_t* __restrict__ skeys, int pp,
+                   unsigned long long* __restrict__ gbucket, int rows_per_cta) {
     extern __shared__ __align__(16) uint8_t rsm[];
     float* qs = (float*)rsm;                                              // [kRankQB][dpad]
-    float* ps = qs + (size_t)kRankQB * dpad;                              // [kRankQB][pmax]
-    long long* pi = (long long*)(ps + (size_t)kRankQB * ((pmax + 1) & ~1));  // [kRankQB][pmax]
-    uint32_t* cnt = (uint32_t*)(pi + (size_t)kRankQB * pmax);             // [kRankQB][pmax]
+    uint32_t* bucket = (uint32_t*)(qs + (size_t)kRankQB * dpad);          // [kRankQB][pp + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qb0 = blockIdx.y * kRankQB;
     const int nqb = min(kRankQB, nq - qb0);
@@ -52,42 +81,72 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
         const int j = i / dpad, c = i - j * dpad;
         qs[i] = (j < nqb && c < d) ? q[(size_t)(qb0 + j) * d + c] : 0.0f;
     }
-    for (int i = tid; i < kRankQB * pmax; i += 256) {
-        const int j = i / pmax, p = i - j * pmax;
-        long long id = -1;
-        float s = 0.f;
-        if (j < nqb) {
-            id = probe_idx[(size_t)(qb0 + j) * pmax + p];
-            s = probe_score[(size_t)(qb0 + j) * pmax + p];
-        }
-        pi[i] = id;
-        ps[i] = s;
-        cnt[i] = 0;
-    }
+    for (int i = tid; i < kRankQB * (pp + 1); i += 256) bucket[i] = 0;
     __syncthreads();
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min(r0 + (long long)rows_per_cta, ndb);
     for (long long r = r0 + warp; r < r1; r += 8) {
         float out[kRankQB];
         warp_exact_dot_multi<kRankQB>(qs, dpad, db + (size_t)r * d, d, lane, out);
-        const long long gid = index_base + r;
+        float mine = 0.f;
 #pragma unroll
-        for (int j = 0; j < kRankQB; ++j) {
-            if (j < nqb) {
-                const float s = out[j] + 0.0f;
-                for (int p = lane; p < pmax; p += 32) {
-                    const long long id = pi[j * pmax + p];
-                    if (id < 0) continue;
-                    const float t = ps[j * pmax + p] + 0.0f;
-                    if (s > t || (s == t && gid < id)) atomicAdd(&cnt[j * pmax + p], 1u);
-                }
-            }
+        for (int j = 0; j < kRankQB; ++j)
+            if (lane == j) mine = out[j];
+        if (lane < nqb) {                     // lane j ranks this row among query j's probes
+            const uint64_t key = rank_key(mine, (uint32_t)(index_base + r));
+            const int m = slots_not_after(skeys + (size_t)(qb0 + lane) * pp, pp, key);
+            atomicAdd(&bucket[lane * (pp + 1) + m], 1u);
         }
     }
     __syncthreads();
-    for (int i = tid; i < nqb * pmax; i += 256) {
-        const uint32_t c = cnt[i];
-        if (c) atomicAdd(before + (size_t)qb0 * pmax + i, (unsigned long long)c);
+    for (int i = tid; i < nqb * (pp + 1); i += 256) {
+        const uint32_t c = bucket[i];
+        if (c) atomicAdd(gbucket + (size_t)qb0 * (pp + 1) + i, (unsigned long long)c);
+    }
+}
+
+// before[q][p] += rows of this shard that sort before probe p = inclusive prefix sum of the buckets up to the probe's slot
+__global__ void __launch_bounds__(256)
+rank_finish_kernel(const int64_t* __restrict__ probe_idx, const float* __restrict__ probe_score, int pmax, int pp,
+                   const uint64_t* __restrict__ skeys, const unsigned long long* __restrict__ gbucket,
+                   unsigned long long* __restrict__ before) {
+    extern __shared__ __align__(16) unsigned long long pre[];   // [pp + 1] inclusive prefix sums
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, qi = blockIdx.x;
+    if (tid == 0) carry = 0ull;
+    __syncthreads();
+    // chunked scan: 256 buckets at a time (pp + 1 <= 2049)
+    for (int base = 0; base <= pp; base += 256) {
+        const int i = base + tid;
+        unsigned long long v = i <= pp ? gbucket[(size_t)qi * (pp + 1) + i] : 0ull;
+        const int lane = tid & 31, wid = tid >> 5;
+        __shared__ unsigned long long wtot[8];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) wtot[wid] = v;
+        __syncthreads();
+        unsigned long long add = carry;
+        for (int w = 0; w < wid; ++w) add += wtot[w];
+        if (i <= pp) pre[i] = v + add;
+        __syncthreads();
+        if (tid == 255) carry = v + add;
+        __syncthreads();
+    }
+    for (int p = tid; p < pmax; p += 256) {
+        const uint64_t key = probe_key(probe_idx[(size_t)qi * pmax + p], probe_score[(size_t)qi * pmax + p]);
+        if (key == 0ull) continue;
+        // slot of the probe = number of sorted keys strictly greater than its own
+        int lo = 0, n = pp;
+        const uint64_t* sk = skeys + (size_t)qi * pp;
+        while (n > 0) {
+            const int half = n >> 1;
+            if (sk[lo + half] > key) { lo += half + 1; n -= half + 1; }
+            else n = half;
+        }
+        before[(size_t)qi * pmax + p] += pre[lo];
     }
 }
 
@@ -170,16 +229,30 @@ extern "C" int gdt_probe_scores(const float* q, const float* db, int nq, long lo
     return GDT_OK;
 }
 
+extern "C" size_t gdt_rank_counts_workspace_bytes(int nq, int pmax) {
+    if (nq <= 0 || pmax <= 0) return 0;
+    const size_t pp = (size_t)next_pow2(pmax);
+    return align_up((size_t)nq * pp * 8, 256) + align_up((size_t)nq * (pp + 1) * 8, 256) + 256;
+}
+
 extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long long ndb, int d, long long index_base,
-                               const int64_t* probe_idx, const float* probe_score, int pmax, int64_t* before,
-                               void* stream_) {
+                               const int64_t* probe_idx, const float* probe_score, int pmax, int64_t* before, void* ws,
+                               size_t ws_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!q || !db || !probe_idx || !probe_score || !before) return GDT_ERR_INVALID_ARGUMENT;
+    if (!q || !db || !probe_idx || !probe_score || !before || !ws) return GDT_ERR_INVALID_ARGUMENT;
     if (nq <= 0 || ndb <= 0 || d <= 0 || pmax <= 0) return GDT_ERR_INVALID_ARGUMENT;
+    if (pmax > 2048 || index_base < 0 || index_base + ndb > 0xffffffffLL) return GDT_ERR_UNSUPPORTED;
     if (!have_device_k4()) return GDT_ERR_NO_DEVICE;
+    if (ws_bytes < gdt_rank_counts_workspace_bytes(nq, pmax) || (((uintptr_t)ws) & 255)) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    const int pp = next_pow2(pmax);
+    Workspace W(ws, ws_bytes);
+    uint64_t* skeys = W.take<uint64_t>((size_t)nq * pp);
+    unsigned long long* gbucket = W.take<unsigned long long>((size_t)nq * (pp + 1));
+    if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
+    probe_sort_kernel<<<nq, 256, (size_t)pp * 8, stream>>>(probe_idx, probe_score, pmax, pp, skeys, gbucket);
+    GDT_LAUNCH_CHECK();
     const int dpad = (d + 3) & ~3;
-    const size_t smem = (size_t)kRankQB * dpad * 4 + (size_t)kRankQB * ((pmax + 1) & ~1) * 4 + (size_t)kRankQB * pmax * 8 +
-                        (size_t)kRankQB * pmax * 4;
+    const size_t smem = (size_t)kRankQB * dpad * 4 + (size_t)kRankQB * (pp + 1) * 4;
     if (smem > 200 * 1024) return GDT_ERR_UNSUPPORTED;
     static size_t attr_bytes_dev[32] = {0};
     size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
@@ -195,8 +268,10 @@ extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long lon
     if (rows < 256) rows = 256;
     rows = (rows + 7) / 8 * 8;
     dim3 grid((unsigned)ceil_div_ll(ndb, rows), (unsigned)qblocks);
-    rank_counts_kernel<<<grid, 256, smem, stream>>>(q, db, nq, ndb, d, dpad, index_base, probe_idx, probe_score, pmax,
-                                                     (unsigned long long*)before, (int)rows);
+    rank_counts_kernel<<<grid, 256, smem, stream>>>(q, db, nq, ndb, d, dpad, index_base, skeys, pp, gbucket, (int)rows);
+    GDT_LAUNCH_CHECK();
+    rank_finish_kernel<<<nq, 256, (size_t)(pp + 1) * 8, stream>>>(probe_idx, probe_score, pmax, pp, skeys, gbucket,
+                                                                  (unsigned long long*)before);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

@@ -258,9 +258,9 @@ class CudaOps:
             _lib.rank_counts(q, shard.db, probe_idx, probe_score, index_base=shard.index_base, out=out)
         return out
 
-    def map_eval(self, pos_rank, junk_rank, npos, njunk, kappas):
+    def map_eval(self, pos_rank, junk_rank, npos, njunk, kappas, nres=None):
         from . import _lib
-        return _lib.map_eval(pos_rank, junk_rank, npos, njunk, kappas)
+        return _lib.map_eval(pos_rank, junk_rank, npos, njunk, kappas, nres=nres)
 
 
 class DatabaseShard:
@@ -386,27 +386,28 @@ def evaluate_protocols(index, q, groups, protocols, kappas=()):
     outside the database never -- while the recall step stays 1 / len(list as given) (evaluate.py:77-78)."""
     names = sorted({n for ok, jk in protocols.values() for n in tuple(ok) + tuple(jk)})
     nq = len(groups)
-    ids, spans, given = [], [], []
-    for g in groups:
-        off, span, parts, glen = 0, {}, [], {}
-        for n in names:
-            raw = np.asarray(g.get(n, []), dtype=np.int64).reshape(-1)
-            a = np.unique(raw[(raw >= 0) & (raw < index.n_total)])
-            span[n], glen[n] = (off, off + len(a)), len(raw)
-            off += len(a)
-            parts.append(a)
-        ids.append(np.concatenate(parts) if parts else np.zeros(0, np.int64))
-        spans.append(span)
-        given.append(glen)
+    raw = [{n: np.asarray(g.get(n, []), dtype=np.int64).reshape(-1) for n in names} for g in groups]
+    # one probe column per distinct in-range id of a query, whatever groups it appears in
+    ids = []
+    for r in raw:
+        allv = np.concatenate([r[n] for n in names]) if names else np.zeros(0, np.int64)
+        ids.append(np.unique(allv[(allv >= 0) & (allv < index.n_total)]))
     before = index.positions(q, _to_device(_pad_rows(ids), q.device))              # [nq, pu]
     # every protocol's rows stacked: one gather pair, one gdt_map_eval launch, one read-back
     prots = list(protocols.items())
     ok_cols, junk_cols, nres = [], [], []
+
+    def cols(r, uniq, group_names):
+        given = np.concatenate([r[n] for n in group_names]) if group_names else np.zeros(0, np.int64)
+        found = np.unique(given[(given >= 0) & (given < index.n_total)])           # np.in1d: a set, foreign ids never found
+        return np.searchsorted(uniq, found), len(given)
     for _, (ok_names, junk_names) in prots:
-        for sp, gl in zip(spans, given):
-            ok_cols.append(np.concatenate([np.arange(*sp[n]) for n in ok_names]) if ok_names else np.zeros(0, np.int64))
-            junk_cols.append(np.concatenate([np.arange(*sp[n]) for n in junk_names]) if junk_names else np.zeros(0, np.int64))
-            nres.append(sum(gl[n] for n in ok_names))
+        for r, uniq in zip(raw, ids):
+            oc, n_given = cols(r, uniq, ok_names)
+            jc, _ = cols(r, uniq, junk_names)
+            ok_cols.append(oc)
+            junk_cols.append(jc)
+            nres.append(n_given)
     npos_h, njunk_h = [len(c) for c in ok_cols], [len(c) for c in junk_cols]
     okm, jkm = _pad_rows(ok_cols, fill=0), _pad_rows(junk_cols, fill=0)
     counts = np.stack([npos_h, njunk_h, nres]).astype(np.int32)

@@ -277,13 +277,16 @@ int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k, float* out
  *              summed across shards by the caller since non-owners contribute 0)
  * before     : int64 [nq][pmax], += number of rows of THIS shard that sort before the probe
  *              (caller zero-initialises and sums across shards)
+ * The probes of a query are sorted once; every (row, query) pair then costs one binary search and one counter
+ * increment, whatever pmax is (pmax <= 2048, global ids < 2^32). Probes with equal (score, id) get equal counts.
  */
 int gdt_probe_scores(const float* q, const float* db, int nq, long long ndb, int d,
                      long long index_base, const int64_t* probe_idx, int pmax,
                      float* probe_score, void* stream);
+size_t gdt_rank_counts_workspace_bytes(int nq, int pmax);
 int gdt_rank_counts(const float* q, const float* db, int nq, long long ndb, int d,
                     long long index_base, const int64_t* probe_idx, const float* probe_score,
-                    int pmax, int64_t* before, void* stream);
+                    int pmax, int64_t* before, void* ws, size_t ws_bytes, void* stream);
 
 /* compute_ap / compute_map body (evaluate.py:3-37,60-106) for nq queries:
  * pos_rank [nq][pmax_pos], junk_rank [nq][pmax_junk] : 0-based full-ranking positions (any order,
@@ -295,6 +298,19 @@ int gdt_rank_counts(const float* q, const float* db, int nq, long long ndb, int 
 int gdt_map_eval(const int64_t* pos_rank, int pmax_pos, const int64_t* junk_rank, int pmax_junk,
                  const int32_t* npos, const int32_t* njunk, const int32_t* nres, int nq,
                  const int32_t* kappas, int nk, double* ap, double* prk, void* stream);
+
+/* ---- N3: diverse-anchor mining -------------------------------------------------------
+ * The greedy loop of `DiverseAnchorsDataset._select_positive_pairs_db`
+ * (mdir/components/data/dataset/cirtorch_datasets.py:68-100) without a host round trip per round:
+ *   pool      float32 [n][d] rows (the reference's qvecs is the D x n transpose)
+ *   ranks_dev int32 [steps]: the ascending rank (under value asc, index asc) of `most_similar` to pick in each round --
+ *             `dissimilar_split + choice` of the reference, data-independent, computed by the caller
+ *   first     index picked before the first round (the reference starts from 0)
+ * Outputs: picked_dev int32 [steps + 1] (first, then one index per round), picked_score_dev float32 [steps] (the
+ * reference's qscore_acc). Scores are the library's exact fp32 scores (fp64-accumulated). ws: n floats. */
+size_t gdt_diverse_anchors_workspace_bytes(int n);
+int gdt_diverse_anchors(const float* pool, int n, int d, const int32_t* ranks_dev, int steps, int first,
+                        int32_t* picked_dev, float* picked_score_dev, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -265,6 +265,9 @@ def test_sequential_network_chain_config5(vgg):
             xs[0] = gen.model(xs[0])
             ys = [post.postprocess(clahe.postprocess(x, None, None), None, None) for x in xs]
             ref = torch.stack([vgg.model(y).reshape(-1) for y in ys], dim=1)
-        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+        # images that skip the generator take exactly the same kernels: bit-identical. The anchor's generator output is
+        # not bit-reproducible between two cuDNN calls (atomics in the transposed convolutions) and CLAHE quantises it
+        assert torch.equal(out[:, 1:], ref[:, 1:])
+        torch.testing.assert_close(out[:, 0], ref[:, 0], rtol=1e-2, atol=2e-5)
     finally:
         vgg.wrappers = net.wrappers                                   # give the shared fixture its wrappers back

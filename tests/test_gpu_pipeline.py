@@ -187,8 +187,8 @@ def test_cirdatasetap_runs_the_networks_eval_wrappers(vgg):
     np.testing.assert_allclose(vecs, d[:3].double().cpu().numpy(), rtol=1e-4, atol=1e-5)
     # the reference rejects unknown criterion keys (`assert not params`, cirscore.py:48)
     with pytest.raises(AssertionError):
-        SCORES["cirdatasetap"]({"image_size": None, "dataset": ds, "transforms": "pil2np | totensor", "mean_std": data["mean_std"],
-                                "multiscale": True})
+        SCORES["cirdatasetap"]({"image_size": None, "dataset": ds, "transforms": data.get("transforms", data.get("augmentations")),
+                                "mean_std": data["mean_std"], "multiscale": True})
 
 
 def test_infer_stage_and_whitening_learning_chain(vgg, tmp_path):
@@ -282,3 +282,82 @@ def test_file_formats_checkpoint_whitening_gnd_and_jpeg_paths(vgg, tmp_path, mon
     oavg, _, _ = R.compute_map_protocols("roxford5k", R.full_ranks(R.scores_exact(q, db)), gnd)
     for k in avg:
         assert abs(avg[k] - oavg[k]) < 1e-12
+
+
+def test_diverse_anchor_mining_equals_reference_loop():
+    """SURVEY 8(f) N3, second half: the device loop (gdt_diverse_anchors) against the reference algorithm
+    (cirtorch_datasets.py:78-96: matrix-vector product, running maximum, argsort slice, random choice) restated on the
+    host with the library's exact scores and total order, driven by the same random draws."""
+    from gandtr_b200.mining import diverse_anchor_ranks, mark_easy_pairs, select_diverse_anchors
+    from tests.util import unit_rows
+    rs = np.random.RandomState(6)
+    d, npool, qsize = 96, 1500, 120
+    centres = unit_rows(rs, 40, d)
+    pool = centres[rs.randint(0, 40, npool)] + 0.35 * rs.normal(0, 1, (npool, d)).astype(np.float32) / np.sqrt(d)
+    pool[700] = pool[3]                                               # exact duplicates: ties broken by index
+    pool = (pool / np.linalg.norm(pool, axis=1, keepdims=True)).astype(np.float32)
+    qvecs = torch.from_numpy(pool.T.copy()).cuda()
+    for shuffle, (excl, incl) in ((True, (0.02, 0.3)), (False, (0.0, 0.1)), (True, (0.0, 1.0))):
+        gen = torch.Generator().manual_seed(123)
+        idxs, scores = select_diverse_anchors(qvecs, qsize, excl, incl, shuffle=shuffle, generator=gen)
+        ranks = diverse_anchor_ranks(npool, qsize, excl, incl, shuffle, torch.Generator().manual_seed(123))
+        # reference loop
+        S = R.scores_exact(pool, pool)                               # [npool, npool], fp64-accumulated, rounded once
+        idx, ref_idxs, ref_scores = 0, [0], []
+        most = None
+        for t in range(qsize - 1):
+            dist = S[:, idx]
+            most = dist.copy() if most is None else np.maximum(most, dist)
+            order = np.lexsort((np.arange(npool), most))             # value asc, index asc
+            idx = int(order[ranks[t]])
+            ref_scores.append(float(most[idx]))
+            ref_idxs.append(idx)
+        assert idxs == ref_idxs
+        assert scores == ref_scores
+        assert len(set(idxs)) >= qsize - 1                           # only the planted exact duplicate can repeat (as in the reference)
+    easy = mark_easy_pairs(qvecs[:, :20], qvecs[:, 20:40], 0.25)
+    sim = (pool[:20] * pool[20:40]).sum(1)
+    assert easy.count("-easy") == 5 and all((lab == "-easy") == (i in set(np.argsort(sim)[-5:].tolist())) for i, lab in enumerate(easy))
+
+
+def test_descriptor_store_roundtrip_into_sharded_index(tmp_path):
+    """SURVEY 8(f) N4 on the device: descriptors written by 3 'ranks', read back as 2 shards through the pinned
+    double-buffered loader, searched through ShardedIndex -- identical to searching the matrix that was saved; the bf16
+    payload reproduces the bf16-rounded rows exactly and still ranks the planted neighbours first."""
+    from gandtr_b200 import store
+    from gandtr_b200.retrieval import ShardedIndex, shard_bounds
+    from tests.util import run_ranks, unit_rows
+    rs = np.random.RandomState(10)
+    n, d, nq, k = 50000, 128, 40, 20
+    db = unit_rows(rs, n, d)
+    src = rs.randint(0, n, nq)
+    q = db[src] + 0.3 * rs.normal(0, 1, (nq, d)).astype(np.float32) / np.sqrt(d)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    dbd = torch.from_numpy(db).cuda()
+    for dtype in ("float32", "bfloat16"):
+        path = str(tmp_path / dtype)
+        for r in range(3):
+            lo, hi = shard_bounds(n, 3, r)
+            store.save(path, dbd[lo:hi], ids=["img%d" % i for i in range(n)] if r == 0 else None, rows_per_file=7000,
+                       lo=lo, n_total=n, dtype=dtype)
+        man = store.load_manifest(path)
+        assert man["rows"] == n and man["dtype"] == dtype
+        parts = [store.load_shard(path, r, 2, device="cuda", block_rows=3000) for r in range(2)]
+        full = torch.cat([p[0] for p in parts])
+        assert parts[1][1] == shard_bounds(n, 2, 1)[0] and parts[0][2] == n and full.is_cuda
+        if dtype == "float32":
+            assert torch.equal(full, dbd)
+        else:
+            assert torch.equal(full, dbd.to(torch.bfloat16).to(torch.float32))
+            assert float((full - dbd).abs().max()) < 2e-3
+        expect = full.cpu().numpy()
+        os_, oi = R.topk(R.scores_exact(q, expect), k)
+
+        def rank_fn(rank, comm):
+            rows, lo, total = store.load_shard(path, rank, 2, device="cuda")
+            index = ShardedIndex(rows, n_total=total, index_base=lo, comm=comm)
+            s, i = index.search(torch.from_numpy(q).cuda(), k)
+            assert np.array_equal(i.cpu().numpy(), oi) and np.abs(s.cpu().numpy() - os_).max() < 1e-6
+            return int((i[:, 0].cpu() == torch.from_numpy(src)).sum())
+        hits = run_ranks(2, rank_fn)
+        assert hits[0] == nq                                          # planted neighbours rank first, also from bf16 rows

@@ -243,10 +243,15 @@ def test_k3_coarse_score_error_stays_inside_the_filter_bound(kind, nq, ndb, d, r
     print("K3 bound check %-10s d=%-5d max|coarse-exact|/E_q = %.4f   accumulation / allowance = %.4f" % (kind, d, ratio, acc_ratio))
     assert ratio < 1.0, "coarse scores leave the bound the filter relies on"
     assert acc_ratio < 0.5, "the accumulation allowance (2x an estimate) has less than 2x head-room"
-    # and the end result on the same data is the oracle ranking
+    # and the end result on the same data is the oracle ranking. Scores that crowd into one histogram bin (near-ties;
+    # all-positive vectors, whose cosines sit within a few percent of each other) overflow the candidate segments: that
+    # is reported, never hidden, and ShardedIndex repairs those queries exactly
+    from gandtr_b200.retrieval import ShardedIndex
     s, i, st = _lib.score_topk(qd, dbd, shadow, stats, 100)
+    os_, oi = R.topk(R.scores_exact(q, db), 100)
     if int(st[0]) == 0:
-        os_, oi = R.topk(R.scores_exact(q, db), 100)
         _check_lists(s, i, os_, oi, q, db)
     else:
-        assert kind == "near_ties"                                         # dense ties overflow; ShardedIndex repairs (other tests)
+        assert kind in ("near_ties", "positive") and int(st[0]) == -7
+        s, i = ShardedIndex(dbd).search(qd, 100)
+        _check_lists(s, i, os_, oi, q, db)

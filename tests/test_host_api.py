@@ -123,6 +123,14 @@ def test_descriptor_store_roundtrip_and_resharding(tmp_path):
     np.testing.assert_array_equal(np.concatenate(parts), x)
     w = store.load_whitening(str(tmp_path))
     np.testing.assert_array_equal(w["P"], whit["P"])
+    # bf16 payload: half the bytes, rows come back as the bf16-rounded values
+    bdir = str(tmp_path / "bf16")
+    store.save(bdir, x, rows_per_file=300, dtype="bfloat16")
+    assert store.load_manifest(bdir)["dtype"] == "bfloat16"
+    rows, lo, total = store.load_shard(bdir, 0, 1, device="cpu")
+    np.testing.assert_array_equal(rows.numpy(), torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy())
+    with pytest.raises(ValueError):
+        store.save(bdir, x, dtype="float16")
 
 
 def test_metadata_tensor_and_pass_through_routing():

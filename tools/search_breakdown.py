@@ -1,9 +1,9 @@
 """Per-phase timing of the row-sharded search (one process per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/search_breakdown.py [rows d nq]
-Prints, per rank 0 and as the max over ranks, the CUDA-event time of: filter (seed + main tcgen05 pass), histogram
-all-reduce, finalize (exact re-score), status read-back (host round trip), all_gather of the [nq, k] lists, merge.
+Prints, per rank 0 and as the max over ranks, the CUDA-event time of: filter (query preparation + seed + main tcgen05
+pass), histogram all-reduce, finalize (exact re-score), pack, all_gather of the packed [nq, k] lists, merge, and the
+overflow-flag read (the search's one host round trip). With one process it times one shard of the given size.
 Answers "where do the ~2.3 ms of fixed cost per search go" (lead 3)."""
-import ctypes
 import os
 import sys
 import time
@@ -36,53 +36,41 @@ def main():
         shadow, stats = _lib.db_prepare_sharded(db, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MAX))
     else:
         shadow, stats = _lib.db_prepare(db)
-    lib = _lib.load()
     ndb = db.shape[0]
-    ws = torch.empty(lib.gdt_score_topk_workspace_bytes(nq, ndb, d, k), dtype=torch.uint8, device=dev)
-    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    status = torch.empty(4, dtype=torch.int32, device=dev)
-    off, nbytes = ctypes.c_size_t(), ctypes.c_size_t()
-    _lib.check(lib.gdt_score_topk_exchange_layout(nq, ndb, d, k, ctypes.byref(off), ctypes.byref(nbytes)), "layout")
-    hist = ws[off.value:off.value + nbytes.value].view(torch.int32).view(nq, 256)
-    all_s = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-    all_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-    P = lambda t: ctypes.c_void_p(t.data_ptr())
-    stream = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    names = ["filter", "hist_allreduce", "finalize", "status_readback", "all_gather", "merge", "total"]
+    all_k = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+    names = ["filter", "hist_allreduce", "finalize", "pack", "all_gather", "merge", "flag_check", "total"]
     acc = {n: 0.0 for n in names}
     iters, warm = 8, 3
     for it in range(warm + iters):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
         ev[0].record()
-        _lib.check(lib.gdt_score_topk_filter(P(q), P(shadow), P(stats), nq, ndb, d, k, P(status), P(ws), ws.numel(), stream()), "filter")
+        state = _lib.score_topk_filter(q, shadow, stats, k)
         ev[1].record()
         if world > 1:
-            dist.all_reduce(hist)
+            dist.all_reduce(state.hist)
         ev[2].record()
-        _lib.check(lib.gdt_score_topk_finalize(P(q), P(db), nq, ndb, d, k, lo, P(scores), P(idx), P(status), P(ws), ws.numel(), stream()), "finalize")
+        scores, idx, status = _lib.score_topk_finalize(q, db, state, index_base=lo)
         ev[3].record()
-        t0 = time.perf_counter()
-        st = status.cpu()
-        t_host = (time.perf_counter() - t0) * 1e3        # includes waiting for everything queued before it
+        keys = _lib.topk_pack(scores, idx)
         ev[4].record()
         if world > 1:
-            dist.all_gather_into_tensor(all_s.view(-1), scores.view(-1))
-            dist.all_gather_into_tensor(all_i.view(-1), idx.view(-1))
+            dist.all_gather_into_tensor(all_k, keys)
         else:
-            all_s[0].copy_(scores)
-            all_i[0].copy_(idx)
+            all_k[0].copy_(keys)
         ev[5].record()
-        _lib.topk_merge(all_s, all_i)
+        ms, mi = _lib.topk_merge_packed(all_k)
         ev[6].record()
+        bad = bool((mi[:, 0] == -2).any())                # the search's single host read
+        ev[7].record()
         torch.cuda.synchronize()
+        st = status.cpu()
         if it >= warm:
-            for n, (a, b) in zip(names[:6], [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6)]):
+            for n, (a, b) in zip(names[:7], [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7)]):
                 acc[n] += ev[a].elapsed_time(ev[b]) / iters
-            acc["total"] += ev[0].elapsed_time(ev[6]) / iters
+            acc["total"] += ev[0].elapsed_time(ev[7]) / iters
     t = torch.tensor([acc[n] for n in names], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if world > 1:
