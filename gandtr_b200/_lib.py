@@ -72,6 +72,7 @@ SYMBOLS = [
     ("gdt_topk_merge_packed", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
     ("gdt_rank_counts_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int]),
+    ("gdt_debug_k4_exact", _c.c_int, [_c.c_int]),
     ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P,
                                    _c.c_size_t, _P]),
     ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
@@ -83,6 +84,9 @@ SYMBOLS = [
     ("gdt_resize_plan_info", _c.c_int, [_P, _P, _P, _P, _P]),
     ("gdt_resize_workspace_bytes", _c.c_size_t, [_P]),
     ("gdt_resize_u8", _c.c_int, [_P, _P, _c.c_size_t, _P, _P, _c.c_size_t, _P]),
+    ("gdt_resize_batch_workspace_bytes", _c.c_size_t, [_P, _c.c_int]),
+    ("gdt_resize_u8_batch", _c.c_int, [_P, _P, _P, _c.c_int, _P, _P, _c.c_size_t, _P]),
+    ("gdt_debug_k5_bytewise", _c.c_int, [_c.c_int]),
     ("gdt_debug_resize_coeffs", _c.c_int, [_c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P, _P, _c.c_size_t]),
 ]
 
@@ -726,5 +730,32 @@ def resize_u8(plan, src, out=None):
     with torch.cuda.device(src.device):
         ws = _workspace(plan.ws_bytes, src.device)
         check(load().gdt_resize_u8(plan._h, _ptr(src), src.stride(0), _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_resize_u8")
+    _count("resize")
+    return out
+
+
+def resize_u8_batch(plan, srcs, out=None):
+    """srcs: list of uint8 CUDA tensors [h, w, 3] of the plan's geometry (any row stride each) -> [n, out_h, out_w, 3]
+    contiguous, one launch per pass for the whole list."""
+    n = len(srcs)
+    if n == 0:
+        raise GdtError("resize_u8_batch needs at least one image")
+    for src in srcs:
+        if not isinstance(src, torch.Tensor) or not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 3 or src.shape[2] != 3:
+            raise GdtError("resize_u8_batch needs uint8 CUDA tensors [h, w, 3] (gandtr_b200 has no CPU path)")
+        if src.stride(2) != 1 or src.stride(1) != 3:
+            raise GdtError("resize_u8_batch: pixels must be packed RGB (strides (*, 3, 1)), got %s" % (src.stride(),))
+        if (src.shape[1], src.shape[0]) != plan.in_size:
+            raise GdtError("resize_u8_batch: plan is for %s, image is %s" % (plan.in_size, (src.shape[1], src.shape[0])))
+    ow, oh = plan.out_size
+    dev = srcs[0].device
+    if out is None:
+        out = torch.empty((n, oh, ow, 3), dtype=torch.uint8, device=dev)
+    ptrs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    strides = (ctypes.c_size_t * n)(*[int(s.stride(0)) for s in srcs])
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.gdt_resize_batch_workspace_bytes(plan._h, n), dev)
+        check(lib.gdt_resize_u8_batch(plan._h, ptrs, strides, n, _ptr(out), _ptr(ws), ws.numel(), _stream()), "gdt_resize_u8_batch")
     _count("resize")
     return out

@@ -67,13 +67,24 @@ __device__ __forceinline__ int slots_not_after(const uint64_t* __restrict__ sk, 
     return lo;
 }
 
+// Rows per warp and iteration: the query float4 read from shared memory is reused for 4 database rows (16 FMAs per
+// 16-byte shared-memory load), which balances the FMA pipe against the shared-memory bandwidth.
+constexpr int kRankRows = 4;
+
+// Scores are computed in fp32 (FMA, 128 lanes / clk / SM -- the fp64 pipe of this part is >10x slower) together with a
+// rigorous bound on their distance to the library's exact score (fp64-accumulated, rounded once):
+//     |s32 - s_exact| <= tol = 1.1 * (d + 8) * 2^-24 * ||q|| * ||x||      (recursive-summation bound, Cauchy-Schwarz)
+// A row is ranked from s32 alone when no probe key lies between the keys of (s32 - tol) and (s32 + tol); only the rare
+// rows that come that close to a probe are re-scored exactly (warp_exact_dot), so the counts are those of the exact
+// kernel. One lane per (row, query) pair does the binary search: all 32 lanes of a warp are busy.
 __global__ void __launch_bounds__(256)
 rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, int nq, long long ndb, int d, int dpad,
                    long long index_base, const uint64_t* __restrict__ skeys, int pp,
-                   unsigned long long* __restrict__ gbucket, int rows_per_cta) {
+                   unsigned long long* __restrict__ gbucket, int rows_per_cta, int force_exact) {
     extern __shared__ __align__(16) uint8_t rsm[];
     float* qs = (float*)rsm;                                              // [kRankQB][dpad]
     uint32_t* bucket = (uint32_t*)(qs + (size_t)kRankQB * dpad);          // [kRankQB][pp + 1]
+    __shared__ float qnorm[kRankQB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qb0 = blockIdx.y * kRankQB;
     const int nqb = min(kRankQB, nq - qb0);
@@ -83,20 +94,101 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
     }
     for (int i = tid; i < kRankQB * (pp + 1); i += 256) bucket[i] = 0;
     __syncthreads();
+    {   // ||q_j||, one warp per query
+        float ss = 0.f;
+        for (int i = lane; i < dpad; i += 32) { const float v = qs[warp * dpad + i]; ss = fmaf(v, v, ss); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) qnorm[warp] = sqrtf(ss) * 1.0001f;
+    }
+    __syncthreads();
+    const float cd = 1.1f * (float)(d + 8) * 5.9604644775390625e-08f;
+    const bool vec = (d & 3) == 0 && (((uintptr_t)db) & 15) == 0;
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min(r0 + (long long)rows_per_cta, ndb);
-    for (long long r = r0 + warp; r < r1; r += 8) {
-        float out[kRankQB];
-        warp_exact_dot_multi<kRankQB>(qs, dpad, db + (size_t)r * d, d, lane, out);
-        float mine = 0.f;
+    const int my_row = lane >> 3, my_q = lane & 7;                          // the (row, query) pair this lane ranks
+    for (long long rb = r0 + warp * kRankRows; rb < r1; rb += 8 * kRankRows) {
+        float acc[kRankRows * kRankQB];
+        float xx[kRankRows];
 #pragma unroll
-        for (int j = 0; j < kRankQB; ++j)
-            if (lane == j) mine = out[j];
-        if (lane < nqb) {                     // lane j ranks this row among query j's probes
-            const uint64_t key = rank_key(mine, (uint32_t)(index_base + r));
-            const int m = slots_not_after(skeys + (size_t)(qb0 + lane) * pp, pp, key);
-            atomicAdd(&bucket[lane * (pp + 1) + m], 1u);
+        for (int a = 0; a < kRankRows * kRankQB; ++a) acc[a] = 0.f;
+#pragma unroll
+        for (int r = 0; r < kRankRows; ++r) xx[r] = 0.f;
+        const float* xrow[kRankRows];
+#pragma unroll
+        for (int r = 0; r < kRankRows; ++r) xrow[r] = db + (size_t)min(rb + r, r1 - 1) * d;   // ragged tail: clamped
+        if (vec) {
+#pragma unroll 2
+            for (int i = lane; i < (d >> 2); i += 32) {
+                float4 x[kRankRows];
+#pragma unroll
+                for (int r = 0; r < kRankRows; ++r) {
+                    x[r] = __ldg((const float4*)xrow[r] + i);
+                    xx[r] = fmaf(x[r].x, x[r].x, fmaf(x[r].y, x[r].y, fmaf(x[r].z, x[r].z, fmaf(x[r].w, x[r].w, xx[r]))));
+                }
+#pragma unroll
+                for (int j = 0; j < kRankQB; ++j) {
+                    const float4 a = *(const float4*)(qs + (size_t)j * dpad + (i << 2));
+#pragma unroll
+                    for (int r = 0; r < kRankRows; ++r)
+                        acc[r * kRankQB + j] = fmaf(a.x, x[r].x, fmaf(a.y, x[r].y, fmaf(a.z, x[r].z, fmaf(a.w, x[r].w, acc[r * kRankQB + j]))));
+                }
+            }
+        } else {
+            for (int i = lane; i < d; i += 32) {
+#pragma unroll
+                for (int r = 0; r < kRankRows; ++r) {
+                    const float x = __ldg(xrow[r] + i);
+                    xx[r] = fmaf(x, x, xx[r]);
+#pragma unroll
+                    for (int j = 0; j < kRankQB; ++j) acc[r * kRankQB + j] = fmaf(qs[(size_t)j * dpad + i], x, acc[r * kRankQB + j]);
+                }
+            }
         }
+        // transposing butterfly: 32 partial sums per lane -> lane L holds the total of pair L (31 shuffles instead of 160)
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const bool upper = (lane & step) != 0;
+#pragma unroll
+            for (int i = 0; i < step; ++i) {
+                const float send = upper ? acc[i] : acc[i + step];
+                const float keep = upper ? acc[i + step] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+            }
+        }
+        float xn = 0.f;
+#pragma unroll
+        for (int r = 0; r < kRankRows; ++r) {
+            float v = xx[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (r == my_row) xn = v;
+        }
+        const long long row = rb + my_row;
+        const bool live = row < r1 && my_q < nqb;
+        const uint64_t* sk = skeys + (size_t)(qb0 + (my_q < nqb ? my_q : 0)) * pp;
+        const uint32_t gid = (uint32_t)(index_base + row);
+        float s = acc[0];
+        int m = 0;
+        bool need_exact = false;
+        if (live) {
+            const float tol = cd * qnorm[my_q] * (sqrtf(xn) * 1.0001f);
+            // keys of the interval ends: (s + tol, best index) is the largest key the row can have, (s - tol, worst
+            // index) the smallest; m(K) = number of probe keys >= K is non-increasing in K
+            const int m_lo = slots_not_after(sk, pp, rank_key(__fadd_ru(s, tol), 0u));
+            const int m_hi = slots_not_after(sk, pp, rank_key(__fadd_rd(s, -tol), 0xffffffffu));
+            m = m_lo;
+            need_exact = (m_lo != m_hi) || force_exact || !(tol >= 0.f);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, need_exact);
+        while (todo) {                                    // rare: the whole warp re-scores one pair exactly
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long er = rb + (l >> 3);
+            const float es = warp_exact_dot(qs + (size_t)(l & 7) * dpad, db + (size_t)er * d, d, lane);
+            if (lane == l) m = slots_not_after(sk, pp, rank_key(es, gid));
+        }
+        if (live) atomicAdd(&bucket[my_q * (pp + 1) + m], 1u);
     }
     __syncthreads();
     for (int i = tid; i < nqb * (pp + 1); i += 256) {
@@ -229,6 +321,13 @@ extern "C" int gdt_probe_scores(const float* q, const float* db, int nq, long lo
     return GDT_OK;
 }
 
+static int g_k4_force_exact = 0;     // debug (gdt_debug_k4_exact): 1 = every (row, query) pair is re-scored exactly
+
+extern "C" int gdt_debug_k4_exact(int on) {
+    g_k4_force_exact = on ? 1 : 0;
+    return GDT_OK;
+}
+
 extern "C" size_t gdt_rank_counts_workspace_bytes(int nq, int pmax) {
     if (nq <= 0 || pmax <= 0) return 0;
     const size_t pp = (size_t)next_pow2(pmax);
@@ -266,9 +365,10 @@ extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long lon
     if (want < 1) want = 1;
     long long rows = ceil_div_ll(ndb, want);
     if (rows < 256) rows = 256;
-    rows = (rows + 7) / 8 * 8;
+    rows = (rows + 31) / 32 * 32;
     dim3 grid((unsigned)ceil_div_ll(ndb, rows), (unsigned)qblocks);
-    rank_counts_kernel<<<grid, 256, smem, stream>>>(q, db, nq, ndb, d, dpad, index_base, skeys, pp, gbucket, (int)rows);
+    rank_counts_kernel<<<grid, 256, smem, stream>>>(q, db, nq, ndb, d, dpad, index_base, skeys, pp, gbucket, (int)rows,
+                                                     g_k4_force_exact);
     GDT_LAUNCH_CHECK();
     rank_finish_kernel<<<nq, 256, (size_t)(pp + 1) * 8, stream>>>(probe_idx, probe_score, pmax, pp, skeys, gbucket,
                                                                   (unsigned long long*)before);

@@ -79,6 +79,20 @@ class DeviceImageLoader:
         size = imsize * max(w, h) / full if bbx else imsize
         return _lib.resize_u8(self._plan(w, h, size), img)
 
+    def resize_batch(self, imgs, imsize=None):
+        """Decoded uint8 [h, w, 3] tensors of ONE size (host or device, no bounding boxes) -> uint8 CUDA [n, h', w', 3]:
+        the whole list goes through K5 in one launch per pass (gdt_resize_u8_batch)."""
+        imsize = self.imsize if imsize is None else imsize
+        dev_imgs = []
+        for img in imgs:
+            if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3 or img.shape != imgs[0].shape:
+                raise _lib.GdtError("DeviceImageLoader.resize_batch: uint8 [h, w, 3] images of one size expected")
+            dev_imgs.append(img if img.is_cuda else (img if img.is_pinned() else img.pin_memory()).to(self.device, non_blocking=True))
+        if imsize is None:
+            return torch.stack([i.contiguous() for i in dev_imgs])
+        h, w = int(dev_imgs[0].shape[0]), int(dev_imgs[0].shape[1])
+        return _lib.resize_u8_batch(self._plan(w, h, imsize), dev_imgs)
+
     def crop_only(self, img, bbx=None):
         """Arrays are cropped but never resized by the reference (datahelpers.py:76-79)."""
         if not img.is_cuda:

@@ -108,6 +108,13 @@ int gdt_resize_plan_info(const gdt_resize_plan* plan, int* out_w, int* out_h, in
 size_t gdt_resize_workspace_bytes(const gdt_resize_plan* plan);
 int gdt_resize_u8(const gdt_resize_plan* plan, const uint8_t* src, size_t src_stride, uint8_t* dst, void* ws,
                   size_t ws_bytes, void* stream);
+/* Batched form: n decoded images of ONE geometry (one plan), each with its own base pointer and row stride (host arrays
+ * of device pointers / strides), resized by one launch per pass; dst = uint8 [n][out_h][out_w][3] contiguous. */
+size_t gdt_resize_batch_workspace_bytes(const gdt_resize_plan* plan, int n);
+int gdt_resize_u8_batch(const gdt_resize_plan* plan, const uint8_t* const* host_srcs, const size_t* host_strides, int n,
+                        uint8_t* dst, void* ws, size_t ws_bytes, void* stream);
+/* debug/test hook: 1 = K5 runs its byte-wise kernels only (the dp4a kernels off), for A/B timing and parity */
+int gdt_debug_k5_bytewise(int on);
 /* debug/test hook (host only): Pillow's precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter.
  * bounds: out_size x (first input index, tap count); kk: out_size x ksize int32 (capacity in elements). */
 int gdt_debug_resize_coeffs(int in_size, float in0, float in1, int out_size, int* ksize, int* bounds, int32_t* kk,
@@ -284,6 +291,9 @@ int gdt_probe_scores(const float* q, const float* db, int nq, long long ndb, int
                      long long index_base, const int64_t* probe_idx, int pmax,
                      float* probe_score, void* stream);
 size_t gdt_rank_counts_workspace_bytes(int nq, int pmax);
+/* debug/test hook: 1 = gdt_rank_counts re-scores every (row, query) pair exactly (fp64-accumulated) instead of ranking from
+ * the fp32 score + error bound; the counts must not change */
+int gdt_debug_k4_exact(int on);
 int gdt_rank_counts(const float* q, const float* db, int nq, long long ndb, int d,
                     long long index_base, const int64_t* probe_idx, const float* probe_score,
                     int pmax, int64_t* before, void* ws, size_t ws_bytes, void* stream);

@@ -154,3 +154,50 @@ def test_duplicated_and_foreign_ground_truth_ids_follow_in1d_semantics():
     for name in ("easy", "medium", "hard"):
         assert np.array_equal(per["ap_" + name], oper["ap_" + name], equal_nan=True)
         assert abs(avg["map_" + name] - oavg["map_" + name]) < 1e-15
+
+
+@pytest.mark.parametrize("d,ndb", [(64, 5000), (512, 20001), (2048, 3000), (130, 4000)])
+def test_rank_counts_fp32_bound_path_equals_exact_rescoring(d, ndb):
+    """gdt_rank_counts ranks a row from its fp32 score when the rigorous error interval contains no probe key, and
+    re-scores exactly otherwise. Counts must equal (a) the same kernel with every pair re-scored exactly
+    (gdt_debug_k4_exact) and (b) the oracle's positions -- including exact ties (duplicated rows: index order decides) and
+    near-ties a few float32 ulps apart."""
+    from gandtr_b200 import _lib
+    from tests.util import unit_rows
+    lib = _lib.load()
+    rs = np.random.RandomState(d + ndb)
+    nq, pmax = 19, 37
+    db = unit_rows(rs, ndb, d)
+    q = unit_rows(rs, nq, d)
+    probes = np.stack([rs.permutation(ndb)[:pmax] for _ in range(nq)]).astype(np.int64)
+    probes[:, -3:] = -1                                                   # padding
+    for i in range(nq):                                                   # exact ties and near-ties around the probes
+        db[(probes[i, 0] + 1) % ndb] = db[probes[i, 0]]
+        db[(probes[i, 1] + 2) % ndb] = db[probes[i, 1]] * np.float32(1 + 2e-7)
+    qd, dbd, pd = torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda(), torch.from_numpy(probes).cuda()
+    ps = _lib.probe_scores(qd, dbd, pd)
+    fast = _lib.rank_counts(qd, dbd, pd, ps)
+    try:
+        _lib.check(lib.gdt_debug_k4_exact(1), "exact")
+        exact = _lib.rank_counts(qd, dbd, pd, ps)
+    finally:
+        _lib.check(lib.gdt_debug_k4_exact(0), "exact")
+    assert torch.equal(fast, exact)
+    ranks = R.full_ranks(R.scores_exact(q, db))                           # [ndb, nq]
+    inv = np.empty_like(ranks)
+    for i in range(nq):
+        inv[ranks[:, i], i] = np.arange(ndb)
+    got = fast.cpu().numpy()
+    for i in range(nq):
+        valid = probes[i] >= 0
+        assert np.array_equal(got[i, valid], inv[probes[i, valid], i]), "query %d" % i
+        assert (got[i, ~valid] == 0).all()
+    # accumulation across shards: two calls with different index_base add up to the single-shard counts
+    half = ndb // 2
+    acc = torch.zeros_like(fast)
+    ps2 = torch.zeros_like(ps)
+    _lib.probe_scores(qd, dbd[:half].contiguous(), pd, index_base=0, out=ps2)
+    _lib.probe_scores(qd, dbd[half:].contiguous(), pd, index_base=half, out=ps2)
+    _lib.rank_counts(qd, dbd[:half].contiguous(), pd, ps2, index_base=0, out=acc)
+    _lib.rank_counts(qd, dbd[half:].contiguous(), pd, ps2, index_base=half, out=acc)
+    assert torch.equal(acc, fast)

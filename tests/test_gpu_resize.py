@@ -106,3 +106,32 @@ def test_errors_are_loud():
     plan = _lib.ResizePlan(80, 60, 40, "cuda")
     with pytest.raises(_lib.GdtError):
         _lib.resize_u8(plan, torch.zeros((61, 80, 3), dtype=torch.uint8, device="cuda"))
+
+
+@pytest.mark.parametrize("h,w,imsize,n", [(300, 400, 128, 5), (257, 515, 64, 3), (480, 640, 512, 2), (90, 1100, 60, 4),
+                                          (1200, 1600, 200, 3), (61, 83, 50, 37)])
+def test_batched_launch_equals_per_image_and_bytewise_kernels(h, w, imsize, n):
+    """gdt_resize_u8_batch: n images of one geometry in one launch per pass (incl. more than one 32-image chunk) give the
+    per-image results, the dp4a kernels (coefficients split into byte planes) give the byte-wise kernels' bits, and both
+    equal the oracle. Sources with different row strides (crop views) may share a batch."""
+    from gandtr_b200 import _lib
+    from gandtr_b200.loader import DeviceImageLoader
+    lib = _lib.load()
+    imgs = [synth_image(900 + i, h, w, "noise" if i % 2 else "smooth") for i in range(n)]
+    ld = DeviceImageLoader(imsize=imsize, device="cuda")
+    dev = [torch.from_numpy(im).cuda() for im in imgs]
+    wide = torch.zeros((h, w + 7, 3), dtype=torch.uint8, device="cuda")            # image 0 as a view with a longer row stride
+    wide[:, 3:3 + w] = dev[0]
+    dev[0] = wide[:, 3:3 + w]
+    batch = ld.resize_batch(dev)
+    assert tuple(batch.shape[:1]) == (n,) and batch.is_contiguous()
+    for i in range(n):
+        ref = R.thumbnail_u8(imgs[i], imsize)
+        assert np.array_equal(batch[i].cpu().numpy(), ref), "image %d" % i
+    try:
+        _lib.check(lib.gdt_debug_k5_bytewise(1), "bytewise")
+        slow = ld.resize_batch(dev)
+    finally:
+        _lib.check(lib.gdt_debug_k5_bytewise(0), "bytewise")
+    assert torch.equal(slow, batch)
+    assert torch.equal(ld.resize(dev[1]), batch[1])
