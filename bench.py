@@ -617,7 +617,7 @@ def main():
 
     # ---- BASELINE config 3: revisited-Oxford-shaped ranking + mAP (latency-bound; reported in ms) ----
     if world == 1 and not args.no_retrieval:
-        from gandtr_b200.retrieval import compute_map_and_print
+        from gandtr_b200.retrieval import PreparedGroundTruth, compute_map_and_print
         rq, rdb, rgnd = roxford_shaped()
         rindex = ShardedIndex(torch.from_numpy(rdb).to(dev))
         rqd = torch.from_numpy(rq).to(dev)
@@ -628,8 +628,16 @@ def main():
             res["avg"], _ = compute_map_and_print("roxford5k", rindex, rqd, rgnd, printer=lambda *_: None)
         m_ms, w = timed(evalmap, 5, 2)
         windows.append(w)
+        raw_avg = dict(res["avg"])
+        prepared = PreparedGroundTruth("roxford5k", rgnd, rindex.n_total, dev)       # once per dataset, as a validation loop would
+        def evalmap_prepared():
+            res["avg"], _ = compute_map_and_print("roxford5k", rindex, rqd, prepared, printer=lambda *_: None)
+        mp_ms, w = timed(evalmap_prepared, 10, 3)
+        windows.append(w)
+        assert res["avg"] == raw_avg
         line["roxford_shaped_eval"] = {"queries": 70, "db_rows": 104993, "dim": 512, "search_top100_ms": s_ms / 10,
                                        "map_easy_medium_hard_ms": m_ms / 5,
+                                       "map_easy_medium_hard_prepared_gnd_ms": mp_ms / 10,
                                        "map": {k: round(float(v), 6) for k, v in res["avg"].items()}}
         del rindex
 

@@ -78,6 +78,8 @@ SYMBOLS = [
     ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
     ("gdt_diverse_anchors_workspace_bytes", _c.c_size_t, [_c.c_int]),
     ("gdt_diverse_anchors", _c.c_int, [_P, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _P, _P, _P, _c.c_size_t, _P]),
+    ("gdt_syrk_f64_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_longlong]),
+    ("gdt_syrk_f64", _c.c_int, [_P, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_double, _P, _P, _c.c_size_t, _P]),
     ("gdt_thumbnail_geometry", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P, _P, _P, _P]),
     ("gdt_resize_plan_create", _c.c_int, [_c.c_int, _c.c_int, _c.c_double, _P]),
     ("gdt_resize_plan_destroy", None, [_P]),
@@ -679,6 +681,26 @@ def diverse_anchors(pool, ranks, first=0):
                                       ws.numel(), _stream()), "gdt_diverse_anchors")
     launch_count += 2 * steps
     return picked, score[:steps]
+
+
+# ---- N2: whitening learning ------------------------------------------------------------------------
+
+def syrk_f64(A, alpha=1.0):
+    """A: [d, n] float64 CUDA (rows contiguous) -> alpha * A @ A.T as a symmetric [d, d] float64 tensor."""
+    global launch_count
+    if not isinstance(A, torch.Tensor) or not A.is_cuda or A.dtype != torch.float64 or A.dim() != 2 or A.stride(1) != 1:
+        raise GdtError("A must be a float64 CUDA matrix [d, n] with contiguous rows (gandtr_b200 has no CPU path)")
+    d, n = A.shape
+    C = torch.empty((d, d), dtype=torch.float64, device=A.device)
+    if n == 0:
+        return C.zero_()
+    lib = load()
+    with torch.cuda.device(A.device):
+        ws = _workspace(lib.gdt_syrk_f64_workspace_bytes(d, n), A.device)
+        check(lib.gdt_syrk_f64(_ptr(A), d, n, int(A.stride(0)), float(alpha), _ptr(C), _ptr(ws), ws.numel(), _stream()),
+              "gdt_syrk_f64")
+    launch_count += 2
+    return C
 
 
 # ---- K5: dataset image geometry ------------------------------------------------------------------

@@ -57,11 +57,11 @@ probe_sort_kernel(const int64_t* __restrict__ probe_idx, const float* __restrict
 }
 
 // number of sorted (descending) keys that are >= key: the row sorts before the probes in the slots from there on
-__device__ __forceinline__ int slots_not_after(const uint64_t* __restrict__ sk, int pp, uint64_t key) {
+__device__ __forceinline__ int slots_not_after(const uint64_t* sk, int pp, uint64_t key) {
     int lo = 0, n = pp;                       // first index with sk[i] < key
     while (n > 0) {
         const int half = n >> 1;
-        if (__ldg(sk + lo + half) >= key) { lo += half + 1; n -= half + 1; }
+        if (sk[lo + half] >= key) { lo += half + 1; n -= half + 1; }
         else n = half;
     }
     return lo;
@@ -80,10 +80,11 @@ constexpr int kRankRows = 4;
 __global__ void __launch_bounds__(256)
 rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, int nq, long long ndb, int d, int dpad,
                    long long index_base, const uint64_t* __restrict__ skeys, int pp,
-                   unsigned long long* __restrict__ gbucket, int rows_per_cta, int force_exact) {
+                   unsigned long long* __restrict__ gbucket, int rows_per_cta, int force_exact, int keys_in_smem) {
     extern __shared__ __align__(16) uint8_t rsm[];
     float* qs = (float*)rsm;                                              // [kRankQB][dpad]
-    uint32_t* bucket = (uint32_t*)(qs + (size_t)kRankQB * dpad);          // [kRankQB][pp + 1]
+    uint64_t* sk_s = (uint64_t*)(qs + (size_t)kRankQB * dpad);            // [kRankQB][pp] sorted probe keys (keys_in_smem)
+    uint32_t* bucket = (uint32_t*)(sk_s + (keys_in_smem ? (size_t)kRankQB * pp : 0));   // [kRankQB][pp + 1]
     __shared__ float qnorm[kRankQB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qb0 = blockIdx.y * kRankQB;
@@ -93,6 +94,8 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
         qs[i] = (j < nqb && c < d) ? q[(size_t)(qb0 + j) * d + c] : 0.0f;
     }
     for (int i = tid; i < kRankQB * (pp + 1); i += 256) bucket[i] = 0;
+    if (keys_in_smem)      // the binary searches are chains of dependent loads: from shared memory, not from L2
+        for (int i = tid; i < kRankQB * pp; i += 256) sk_s[i] = i < nqb * pp ? skeys[(size_t)qb0 * pp + i] : 0ull;
     __syncthreads();
     {   // ||q_j||, one warp per query
         float ss = 0.f;
@@ -118,14 +121,21 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
 #pragma unroll
         for (int r = 0; r < kRankRows; ++r) xrow[r] = db + (size_t)min(rb + r, r1 - 1) * d;   // ragged tail: clamped
         if (vec) {
-#pragma unroll 2
-            for (int i = lane; i < (d >> 2); i += 32) {
+            const int nv = d >> 2;
+            float4 xnext[kRankRows];
+#pragma unroll
+            for (int r = 0; r < kRankRows; ++r) xnext[r] = lane < nv ? __ldg((const float4*)xrow[r] + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = lane; i < nv; i += 32) {
                 float4 x[kRankRows];
 #pragma unroll
-                for (int r = 0; r < kRankRows; ++r) {
-                    x[r] = __ldg((const float4*)xrow[r] + i);
-                    xx[r] = fmaf(x[r].x, x[r].x, fmaf(x[r].y, x[r].y, fmaf(x[r].z, x[r].z, fmaf(x[r].w, x[r].w, xx[r]))));
+                for (int r = 0; r < kRankRows; ++r) x[r] = xnext[r];
+                if (i + 32 < nv) {                      // next step's rows are in flight while this step's FMAs issue
+#pragma unroll
+                    for (int r = 0; r < kRankRows; ++r) xnext[r] = __ldg((const float4*)xrow[r] + i + 32);
                 }
+#pragma unroll
+                for (int r = 0; r < kRankRows; ++r)
+                    xx[r] = fmaf(x[r].x, x[r].x, fmaf(x[r].y, x[r].y, fmaf(x[r].z, x[r].z, fmaf(x[r].w, x[r].w, xx[r]))));
 #pragma unroll
                 for (int j = 0; j < kRankQB; ++j) {
                     const float4 a = *(const float4*)(qs + (size_t)j * dpad + (i << 2));
@@ -166,7 +176,7 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
         }
         const long long row = rb + my_row;
         const bool live = row < r1 && my_q < nqb;
-        const uint64_t* sk = skeys + (size_t)(qb0 + (my_q < nqb ? my_q : 0)) * pp;
+        const uint64_t* sk = keys_in_smem ? sk_s + (size_t)my_q * pp : skeys + (size_t)(qb0 + (my_q < nqb ? my_q : 0)) * pp;
         const uint32_t gid = (uint32_t)(index_base + row);
         float s = acc[0];
         int m = 0;
@@ -351,7 +361,9 @@ extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long lon
     probe_sort_kernel<<<nq, 256, (size_t)pp * 8, stream>>>(probe_idx, probe_score, pmax, pp, skeys, gbucket);
     GDT_LAUNCH_CHECK();
     const int dpad = (d + 3) & ~3;
-    const size_t smem = (size_t)kRankQB * dpad * 4 + (size_t)kRankQB * (pp + 1) * 4;
+    size_t smem = (size_t)kRankQB * dpad * 4 + (size_t)kRankQB * (pp + 1) * 4;
+    const int keys_in_smem = smem + (size_t)kRankQB * pp * 8 <= 96 * 1024;
+    if (keys_in_smem) smem += (size_t)kRankQB * pp * 8;
     if (smem > 200 * 1024) return GDT_ERR_UNSUPPORTED;
     static size_t attr_bytes_dev[32] = {0};
     size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
@@ -368,7 +380,7 @@ extern "C" int gdt_rank_counts(const float* q, const float* db, int nq, long lon
     rows = (rows + 31) / 32 * 32;
     dim3 grid((unsigned)ceil_div_ll(ndb, rows), (unsigned)qblocks);
     rank_counts_kernel<<<grid, 256, smem, stream>>>(q, db, nq, ndb, d, dpad, index_base, skeys, pp, gbucket, (int)rows,
-                                                     g_k4_force_exact);
+                                                     g_k4_force_exact, keys_in_smem);
     GDT_LAUNCH_CHECK();
     rank_finish_kernel<<<nq, 256, (size_t)(pp + 1) * 8, stream>>>(probe_idx, probe_score, pmax, pp, skeys, gbucket,
                                                                   (unsigned long long*)before);

@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_bounds", "DistComm", "CudaOps", "DatabaseShard", "ShardedIndex", "evaluate_map", "evaluate_protocols",
-           "compute_map_and_print", "TC_MIN_WORK", "EXACT_MAX_K", "MERGE_MAX_ENTRIES"]
+           "compute_map_and_print", "PreparedProtocols", "PreparedGroundTruth", "TC_MIN_WORK", "EXACT_MAX_K", "MERGE_MAX_ENTRIES"]
 
 # below this many multiply-adds the exact CUDA-core kernel is used instead of the tcgen05 pipeline
 TC_MIN_WORK = 1 << 24
@@ -378,64 +378,83 @@ def _to_device(arr, device):
     return t
 
 
+class PreparedProtocols:
+    """The ground truth of a dataset turned, ONCE, into what the device needs: the probe ids per query, the columns of
+    every protocol's positives / junk in the probe matrix, and the recall denominators. A dataset's ground truth does
+    not change between evaluations (validation every few epochs), so the set logic of evaluate.py:75-80 (`np.in1d`,
+    duplicated / foreign ids) need not be redone per call; `evaluate()` is then a handful of launches and one read-back.
+    groups: per query {name: ids}; protocols: {protocol: (ok group names, junk group names)}."""
+
+    def __init__(self, groups, protocols, n_total, device):
+        names = sorted({n for ok, jk in protocols.values() for n in tuple(ok) + tuple(jk)})
+        self.nq = nq = len(groups)
+        self.n_total = int(n_total)
+        raw = [{n: np.asarray(g.get(n, []), dtype=np.int64).reshape(-1) for n in names} for g in groups]
+        # one probe column per distinct in-range id of a query, whatever groups it appears in
+        ids = []
+        for r in raw:
+            allv = np.concatenate([r[n] for n in names]) if names else np.zeros(0, np.int64)
+            ids.append(np.unique(allv[(allv >= 0) & (allv < self.n_total)]))
+        self.prots = list(protocols.keys())
+        ok_cols, junk_cols, nres = [], [], []
+
+        def cols(r, uniq, group_names):
+            given = np.concatenate([r[n] for n in group_names]) if group_names else np.zeros(0, np.int64)
+            found = np.unique(given[(given >= 0) & (given < self.n_total)])       # np.in1d: a set, foreign ids never found
+            return np.searchsorted(uniq, found), len(given)
+        for prot in self.prots:
+            ok_names, junk_names = protocols[prot]
+            for r, uniq in zip(raw, ids):
+                oc, n_given = cols(r, uniq, ok_names)
+                jc, _ = cols(r, uniq, junk_names)
+                ok_cols.append(oc)
+                junk_cols.append(jc)
+                nres.append(n_given)
+        self.nres = nres
+        counts = np.stack([[len(c) for c in ok_cols], [len(c) for c in junk_cols], nres]).astype(np.int32)
+        self.probe_idx = _to_device(_pad_rows(ids), device)                       # [nq, pu]
+        self.okm = _to_device(_pad_rows(ok_cols, fill=0), device)                 # [nprot * nq, max positives]
+        self.jkm = _to_device(_pad_rows(junk_cols, fill=0), device)
+        cnt = _to_device(counts, device)
+        self.npos, self.njunk, self.nres_dev = cnt[0].contiguous(), cnt[1].contiguous(), cnt[2].contiguous()
+
+    def evaluate(self, index, q, kappas=()):
+        """-> {protocol: (map, aps, mean P@k, P@k)}: ONE pass over the database, ONE evaluation launch, ONE read-back."""
+        assert index.n_total == self.n_total, "ground truth was prepared for another database size"
+        nq, nk = self.nq, len(kappas)
+        before = index.positions(q, self.probe_idx)                               # [nq, pu]
+        rep = before.repeat(len(self.prots), 1) if len(self.prots) > 1 else before
+        pos_rank = torch.gather(rep, 1, self.okm).contiguous()
+        junk_rank = torch.gather(rep, 1, self.jkm).contiguous()
+        try:
+            ap, prk = index.ops.map_eval(pos_rank, junk_rank, self.npos, self.njunk, list(kappas), nres=self.nres_dev)
+        except TypeError:                  # injected test ops with the five-argument signature
+            ap, prk = index.ops.map_eval(pos_rank, junk_rank, self.npos, self.njunk, list(kappas))
+        both = torch.cat([ap.reshape(-1, 1), prk.reshape(ap.shape[0], -1)], dim=1).cpu().numpy()
+        ap, prk = both[:, 0], both[:, 1:1 + nk]
+        out = {}
+        for pi, prot in enumerate(self.prots):
+            a, pk = ap[pi * nq:(pi + 1) * nq], prk[pi * nq:(pi + 1) * nq]
+            # same accumulation order as the reference loop (evaluate.py:98,106,108-109): sequential, empty queries skipped
+            total, pr, nempty = 0.0, np.zeros(nk), 0
+            for i in range(nq):
+                if self.nres[pi * nq + i] == 0:
+                    nempty += 1
+                    continue
+                total = total + a[i]
+                pr = pr + pk[i, :]
+            nvalid = nq - nempty
+            out[prot] = ((total / nvalid if nvalid else float("nan")), a, (pr / nvalid if nvalid else pr * np.nan), pk)
+        return out
+
+
 def evaluate_protocols(index, q, groups, protocols, kappas=()):
     """Several (ok, junk) partitions of the same id groups with ONE pass over the database and ONE evaluation launch.
     groups: per query {name: ids}; protocols: {protocol: (ok group names, junk group names)}.
     Returns {protocol: (map, aps, mean P@k, P@k)}.
     Ids follow `np.in1d(ranks[:, i], ids)` (evaluate.py:75-76): set semantics -- a duplicated id is found once, an id
     outside the database never -- while the recall step stays 1 / len(list as given) (evaluate.py:77-78)."""
-    names = sorted({n for ok, jk in protocols.values() for n in tuple(ok) + tuple(jk)})
-    nq = len(groups)
-    raw = [{n: np.asarray(g.get(n, []), dtype=np.int64).reshape(-1) for n in names} for g in groups]
-    # one probe column per distinct in-range id of a query, whatever groups it appears in
-    ids = []
-    for r in raw:
-        allv = np.concatenate([r[n] for n in names]) if names else np.zeros(0, np.int64)
-        ids.append(np.unique(allv[(allv >= 0) & (allv < index.n_total)]))
-    before = index.positions(q, _to_device(_pad_rows(ids), q.device))              # [nq, pu]
-    # every protocol's rows stacked: one gather pair, one gdt_map_eval launch, one read-back
-    prots = list(protocols.items())
-    ok_cols, junk_cols, nres = [], [], []
-
-    def cols(r, uniq, group_names):
-        given = np.concatenate([r[n] for n in group_names]) if group_names else np.zeros(0, np.int64)
-        found = np.unique(given[(given >= 0) & (given < index.n_total)])           # np.in1d: a set, foreign ids never found
-        return np.searchsorted(uniq, found), len(given)
-    for _, (ok_names, junk_names) in prots:
-        for r, uniq in zip(raw, ids):
-            oc, n_given = cols(r, uniq, ok_names)
-            jc, _ = cols(r, uniq, junk_names)
-            ok_cols.append(oc)
-            junk_cols.append(jc)
-            nres.append(n_given)
-    npos_h, njunk_h = [len(c) for c in ok_cols], [len(c) for c in junk_cols]
-    okm, jkm = _pad_rows(ok_cols, fill=0), _pad_rows(junk_cols, fill=0)
-    counts = np.stack([npos_h, njunk_h, nres]).astype(np.int32)
-    dev = q.device
-    rep = before.repeat(len(prots), 1) if len(prots) > 1 else before
-    pos_rank = torch.gather(rep, 1, _to_device(okm, dev)).contiguous()
-    junk_rank = torch.gather(rep, 1, _to_device(jkm, dev)).contiguous()
-    cnt = _to_device(counts, dev)
-    try:
-        ap, prk = index.ops.map_eval(pos_rank, junk_rank, cnt[0].contiguous(), cnt[1].contiguous(), list(kappas),
-                                     nres=cnt[2].contiguous())
-    except TypeError:                  # injected test ops with the five-argument signature
-        ap, prk = index.ops.map_eval(pos_rank, junk_rank, cnt[0].contiguous(), cnt[1].contiguous(), list(kappas))
-    ap, prk = ap.cpu().numpy(), prk.cpu().numpy()
-    out = {}
-    for pi, (prot, _) in enumerate(prots):
-        a, pk = ap[pi * nq:(pi + 1) * nq], prk[pi * nq:(pi + 1) * nq]
-        # same accumulation order as the reference loop (evaluate.py:98,106,108-109): sequential, empty queries skipped
-        total, pr, nempty = 0.0, np.zeros(len(kappas)), 0
-        for i in range(nq):
-            if nres[pi * nq + i] == 0:
-                nempty += 1
-                continue
-            total = total + a[i]
-            pr = pr + pk[i, :]
-        nvalid = nq - nempty
-        out[prot] = ((total / nvalid if nvalid else float("nan")), a, (pr / nvalid if nvalid else pr * np.nan), pk)
-    return out
+    return PreparedProtocols(groups, protocols, index.n_total, q.device).evaluate(index, q, kappas)
 
 
 def evaluate_map(index, q, gnd, kappas=()):
@@ -445,19 +464,35 @@ def evaluate_map(index, q, gnd, kappas=()):
     return evaluate_protocols(index, q, groups, {"map": (("ok",), ("junk",))}, kappas)["map"]
 
 
+REVISITED_PROTOCOLS = {"easy": (("easy",), ("junk", "hard")),          # evaluate.py:125-131
+                       "medium": (("easy", "hard"), ("junk",)),         # :133-139
+                       "hard": (("hard",), ("junk", "easy"))}           # :141-147
+
+
+class PreparedGroundTruth:
+    """`gnd` of `compute_map_and_print(dataset, ranks, gnd)` prepared once for repeated evaluations of the same dataset."""
+
+    def __init__(self, dataset, gnd, n_total, device):
+        self.old = "ok" in gnd[0]                                      # old protocol (Oxford/Paris/Tokyo), :117-120
+        if self.old:
+            groups = [{"ok": g["ok"], "junk": g.get("junk", [])} for g in gnd]
+            self.prepared = PreparedProtocols(groups, {"map": (("ok",), ("junk",))}, n_total, device)
+        else:
+            if not (dataset.startswith("roxford5k") or dataset.startswith("rparis6k")):
+                raise ValueError("Unsupported ground-truth format for dataset %s" % dataset)
+            self.prepared = PreparedProtocols(gnd, REVISITED_PROTOCOLS, n_total, device)
+
+
 def compute_map_and_print(dataset, index, q, gnd, kappas=(1, 5, 10), printer=print):
     """Same protocol split, rounding and output dictionaries as evaluate.py:114-152, with (index, q) in place of
-    the precomputed `ranks` matrix."""
-    if "ok" in gnd[0]:                                            # old protocol (Oxford/Paris/Tokyo), :117-120
-        m, aps, _, _ = evaluate_map(index, q, gnd)
+    the precomputed `ranks` matrix. `gnd`: the reference's list of dicts, or a PreparedGroundTruth of it."""
+    prep = gnd if isinstance(gnd, PreparedGroundTruth) else PreparedGroundTruth(dataset, gnd, index.n_total, q.device)
+    if prep.old:
+        m, aps, _, _ = prep.prepared.evaluate(index, q)["map"]
         printer(">> {}: mAP {:.2f}".format(dataset, np.around(m * 100, decimals=2)))
         return {"map": m}, {"ap": aps}
-    if not (dataset.startswith("roxford5k") or dataset.startswith("rparis6k")):
-        raise ValueError("Unsupported ground-truth format for dataset %s" % dataset)
     out_avg, out_aps, mprs = {}, {}, {}
-    res = evaluate_protocols(index, q, gnd, {"easy": (("easy",), ("junk", "hard")),          # :125-131
-                                             "medium": (("easy", "hard"), ("junk",)),         # :133-139
-                                             "hard": (("hard",), ("junk", "easy"))}, kappas)  # :141-147
+    res = prep.prepared.evaluate(index, q, kappas)
     for name in ("easy", "medium", "hard"):
         m, aps, mpr, _ = res[name]
         out_avg["map_" + name], out_aps["ap_" + name], mprs[name] = m, aps, mpr

@@ -1,7 +1,10 @@
 """Learned whitening: apply and learn -- mirrors mdir/external/cirtorch/utils/whiten.py:4-70 and the stage functions of
 mdir/stages/whiten.py:10-107. Float64 like the reference (it is not throughput-critical: it runs once and produces the
-P, m consumed by K2); the linear algebra runs on the GPU through torch.linalg (cuSOLVER / cuBLAS float64), descriptors
-never leave the device. Matrices follow the reference layout: X is D x n, m is D x 1, P is D x D.
+P, m consumed by K2). The O(D^2 n) work -- the three Gram products `df df^T`, `(P(X-m)) (P(X-m))^T`, `Xc Xc^T` over all
+descriptors -- runs in this library's own fp64 kernel (gdt_syrk_f64: triangular tiles, fixed-order split-n reduction,
+bit-reproducible); the O(D^3) factorisations (Cholesky, inverse, symmetric eigendecomposition) go through torch.linalg
+(cuSOLVER) as SURVEY 8(f) N2 prescribes. Descriptors never leave the device. Matrices follow the reference layout: X is
+D x n, m is D x 1, P is D x D.
 
 Eigenvectors are defined up to sign: rows of P may differ from NumPy's `eig` by a factor -1, which leaves every inner
 product between whitened vectors -- hence every ranking -- unchanged.
@@ -23,6 +26,12 @@ def _dev():
 
 def _t(x):
     return x.to(torch.float64) if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), dtype=torch.float64, device=_dev())
+
+
+def _gram(A, alpha=1.0):
+    """alpha * A A^T for a D x n float64 matrix: gdt_syrk_f64 (symmetric by construction)."""
+    from . import _lib
+    return _lib.syrk_f64(A if A.stride(1) == 1 else A.contiguous(), alpha)
 
 
 def whitenapply(X, m, P, dimensions=None):
@@ -58,10 +67,10 @@ def whitenlearn(X, qidxs, pidxs):
     pidxs = torch.as_tensor(np.asarray(pidxs), dtype=torch.long, device=X.device)
     m = X[:, qidxs].mean(dim=1, keepdim=True)
     df = X[:, qidxs] - X[:, pidxs]
-    S = (df @ df.t()) / df.shape[1]
+    S = _gram(df, 1.0 / df.shape[1])
     P = torch.linalg.inv(cholesky(S))
     df = P @ (X - m)
-    D = df @ df.t()
+    D = _gram(df)
     _, eigvec = _eig_desc(D)
     return m, eigvec.t() @ P
 
@@ -71,8 +80,7 @@ def pcawhitenlearn(X, shrink=None):
     N = X.shape[1]
     m = X.mean(dim=1, keepdim=True)
     Xc = X - m
-    Xcov = Xc @ Xc.t()
-    Xcov = (Xcov + Xcov.t()) / (2 * N)
+    Xcov = _gram(Xc, 1.0 / N)                  # symmetric by construction: (Xcov + Xcov.T) / (2 N) of the reference
     eigval, eigvec = _eig_desc(Xcov)
     if shrink:
         b = eigval[shrink - 1]

@@ -322,6 +322,14 @@ size_t gdt_diverse_anchors_workspace_bytes(int n);
 int gdt_diverse_anchors(const float* pool, int n, int d, const int32_t* ranks_dev, int steps, int first,
                         int32_t* picked_dev, float* picked_score_dev, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- N2: whitening learning ------------------------------------------------------------
+ * The symmetric rank-n updates of `whitenlearn` / `pcawhitenlearn` (mdir/external/cirtorch/utils/whiten.py:14-50:
+ * `np.dot(df, df.T)`, `np.dot(Xc, Xc.T)`) in float64:  C [d][d] = alpha * A A^T  for row-major A [d][n] with row stride
+ * lda. Lower-triangular tiles only, mirrored; the split of n is summed in a fixed order (bit-reproducible). */
+size_t gdt_syrk_f64_workspace_bytes(int d, long long n);
+int gdt_syrk_f64(const double* A, int d, long long n, long long lda, double alpha, double* C, void* ws, size_t ws_bytes,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,6 +154,12 @@ def test_duplicated_and_foreign_ground_truth_ids_follow_in1d_semantics():
     for name in ("easy", "medium", "hard"):
         assert np.array_equal(per["ap_" + name], oper["ap_" + name], equal_nan=True)
         assert abs(avg["map_" + name] - oavg["map_" + name]) < 1e-15
+    # ground truth prepared once (validation loops evaluate the same dataset again and again): same numbers
+    from gandtr_b200.retrieval import PreparedGroundTruth
+    prep = PreparedGroundTruth("roxford5k", rg, index.n_total, "cuda")
+    for _ in range(2):
+        avg2, per2 = compute_map_and_print("roxford5k", index, qd, prep, printer=lambda *_: None)
+        assert avg2 == avg and all(np.array_equal(per2[k], per[k], equal_nan=True) for k in per)
 
 
 @pytest.mark.parametrize("d,ndb", [(64, 5000), (512, 20001), (2048, 3000), (130, 4000)])

@@ -361,3 +361,20 @@ def test_descriptor_store_roundtrip_into_sharded_index(tmp_path):
             return int((i[:, 0].cpu() == torch.from_numpy(src)).sum())
         hits = run_ranks(2, rank_fn)
         assert hits[0] == nq                                          # planted neighbours rank first, also from bf16 rows
+
+
+@pytest.mark.parametrize("d,n", [(64, 1000), (70, 333), (512, 30011), (130, 33), (2048, 4100), (1, 5)])
+def test_syrk_f64_gram_products(d, n):
+    """the library's own fp64 rank-n update behind whitenlearn / pcawhitenlearn against the float64
+    product (the reference's np.dot(df, df.T), whiten.py:20,42,47): symmetric, bit-reproducible, strided input."""
+    from gandtr_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(d * 7 + n)
+    A = torch.randn((d, n), generator=g, device="cuda", dtype=torch.float64)
+    C = _lib.syrk_f64(A, 0.5)
+    ref = 0.5 * (A @ A.t())
+    torch.testing.assert_close(C, ref, rtol=1e-12, atol=1e-12)
+    assert torch.equal(C, C.t())
+    assert torch.equal(C, _lib.syrk_f64(A, 0.5))                      # fixed summation order: same bits every run
+    wide = torch.randn((d, n + 9), generator=g, device="cuda", dtype=torch.float64)
+    view = wide[:, 4:4 + n]                                           # row stride != n
+    torch.testing.assert_close(_lib.syrk_f64(view), view @ view.t(), rtol=1e-12, atol=1e-12)

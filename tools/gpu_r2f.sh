@@ -1,8 +1,8 @@
 #!/bin/bash
 # round 2, visit e: K5 dp4a / batch kernels and K4 fp32-bound path: parity + timing
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_resize.py tests/test_gpu_map.py tests/test_gpu_pipeline.py -q -m gpu --timeout 900 > gpurun_out/pytest_r2e.log 2>&1; echo "pytest exit $?" > gpurun_out/summary_r2e.txt
-timeout 600 python - > gpurun_out/k4k5_r2e.log 2>&1 <<'PY'
+timeout 1500 python -m pytest tests/test_gpu_map.py tests/test_gpu_pipeline.py tests/test_gpu_hub.py -q -m gpu --timeout 900 > gpurun_out/pytest_r2f.log 2>&1; echo "pytest exit $?" > gpurun_out/summary_r2f.txt
+timeout 600 python - > gpurun_out/k4k5_r2f.log 2>&1 <<'PY'
 import sys, torch, numpy as np
 sys.path.insert(0, ".")
 from bench import roxford_shaped, synth_images_torch
@@ -46,5 +46,5 @@ out = torch.zeros((70, 110), dtype=torch.int64, device="cuda")
 ms_k = timeit(lambda: _lib.rank_counts(qd, big, probes, ps, out=out), iters=3, warm=1)
 print("70 x 1M x 2048: rank_counts %.3f ms (%.0f GB/s of database reads, 9 passes)" % (ms_k, 9 * 8.192e9 / ms_k / 1e6))
 PY
-echo "k4k5 exit $?" >> gpurun_out/summary_r2e.txt
-cat gpurun_out/summary_r2e.txt; grep -E "passed|failed|FAILED" gpurun_out/pytest_r2e.log | tail -8 | cut -c1-200; cat gpurun_out/k4k5_r2e.log | tail -12
+echo "k4k5 exit $?" >> gpurun_out/summary_r2f.txt
+cat gpurun_out/summary_r2f.txt; grep -E "passed|failed|FAILED" gpurun_out/pytest_r2f.log | tail -8 | cut -c1-200; cat gpurun_out/k4k5_r2f.log | tail -12
