@@ -73,7 +73,10 @@ constexpr int kRankRows = 4;
 
 // Scores are computed in fp32 (FMA, 128 lanes / clk / SM -- the fp64 pipe of this part is >10x slower) together with a
 // rigorous bound on their distance to the library's exact score (fp64-accumulated, rounded once):
-//     |s32 - s_exact| <= tol = 1.1 * (d + 8) * 2^-24 * ||q|| * ||x||      (recursive-summation bound, Cauchy-Schwarz)
+//     |s32 - s_exact| <= tol = 1.1 * (d / 32 + 8) * 2^-24 * ||q|| * ||x||
+// (every lane adds d / 32 products with FMAs, five butterfly levels follow: a summation tree of depth h = d / 32 + 5 has
+// error <= h u / (1 - h u) * sum |q_i x_i| <= ... * ||q|| ||x|| by Cauchy-Schwarz; + 1 for the exact score's own rounding
+// to fp32; the factor 1.1 and the + 2 cover 1 / (1 - h u) and the fp32 norms.)
 // A row is ranked from s32 alone when no probe key lies between the keys of (s32 - tol) and (s32 + tol); only the rare
 // rows that come that close to a probe are re-scored exactly (warp_exact_dot), so the counts are those of the exact
 // kernel. One lane per (row, query) pair does the binary search: all 32 lanes of a warp are busy.
@@ -105,7 +108,7 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
         if (lane == 0) qnorm[warp] = sqrtf(ss) * 1.0001f;
     }
     __syncthreads();
-    const float cd = 1.1f * (float)(d + 8) * 5.9604644775390625e-08f;
+    const float cd = 1.1f * (float)((d + 31) / 32 + 8) * 5.9604644775390625e-08f;
     const bool vec = (d & 3) == 0 && (((uintptr_t)db) & 15) == 0;
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min(r0 + (long long)rows_per_cta, ndb);

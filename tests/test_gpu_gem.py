@@ -9,6 +9,10 @@ from tests.util import golden
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 2e-7
+# Whitened descriptors (3xTF32 projection, tcgen05 or mma.sync): north_star's 1e-5 relative, plus an absolute floor of
+# 5e-7 for the small components of a UNIT vector (5e-7 of the norm; bench.py reports the measured maximum, ~1e-7 at
+# 2048 -> 2048: `roofline_k2.error_vs_float64`)
+W_RTOL, W_ATOL = 1e-5, 5e-7
 
 
 def _run(fmaps, p, **kw):
@@ -58,7 +62,7 @@ def test_oracle_shapes(n, c, sizes, p):
     dim = c - 8
     wh = _run(fm, p, aggregate=True, msp_is_p=multi, P=P, m=m, dim=dim)
     ref = D.descriptor_pipeline(fm, p=p, aggregate=True, msp_is_p=multi, P=P, m=m, dimensions=dim)
-    np.testing.assert_allclose(wh, ref, rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(wh, ref, rtol=W_RTOL, atol=W_ATOL)
     np.testing.assert_allclose(np.linalg.norm(wh, axis=1), 1.0, atol=1e-5)
 
 
@@ -86,6 +90,8 @@ def test_whitening_tcgen05_path(n, c, hw, dim):
     ref = D.descriptor_pipeline(fm, p=3.0, aggregate=True, P=P, m=m, dimensions=dim)
     tc = _run(fm, 3.0, aggregate=True, P=P, m=m, dim=dim, split=True)
     simt = _run(fm, 3.0, aggregate=True, P=P, m=m, dim=dim)
-    np.testing.assert_allclose(tc, ref, rtol=5e-5, atol=5e-6)
-    np.testing.assert_allclose(tc, simt, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(tc, ref, rtol=W_RTOL, atol=W_ATOL)
+    np.testing.assert_allclose(tc, simt, rtol=W_RTOL, atol=W_ATOL)
+    # the contract's 1e-5 read against the vector's norm (unit vectors: SURVEY App. C item 9): measured ~1e-7
+    assert np.abs(tc - ref).max() < 1e-6 * np.linalg.norm(ref, axis=1).max()
     np.testing.assert_allclose(np.linalg.norm(tc, axis=1), 1.0, atol=1e-5)

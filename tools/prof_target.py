@@ -5,7 +5,7 @@ import torch
 from gandtr_b200 import _lib
 from bench import synth_images_torch, MEAN, STD
 
-which = sys.argv[1:] or ["clahe", "resize", "gem", "topk"]
+which = sys.argv[1:] or ["clahe", "resize", "gem", "topk", "map", "chain"]
 dev = torch.device("cuda", 0)
 reps = 3
 if "clahe" in which:
@@ -19,6 +19,9 @@ if "resize" in which:
     ld = DeviceImageLoader(imsize=1024, device=dev)
     for _ in range(reps):
         ld.resize(ph)
+    photos = [synth_images_torch(1, 910 + i, dev, h=2304, w=3072)[0] for i in range(8)]
+    for _ in range(reps):
+        ld.resize_batch(photos)                                   # one launch per pass for 8 images
     big = synth_images_torch(1, 901, dev, h=3456, w=4608)[0]      # pre-reduction by 2, then LANCZOS
     ld.resize(big)
 if "gem" in which:
@@ -41,5 +44,20 @@ if "topk" in which:
     for _ in range(reps):
         s, i, st = _lib.score_topk(q, db, shadow, nmax, 100)
     print("status", st.cpu().tolist())
+if "map" in which:
+    from bench import roxford_shaped
+    from gandtr_b200.retrieval import PreparedGroundTruth, ShardedIndex, compute_map_and_print
+    rq, rdb, rgnd = roxford_shaped()
+    idx = ShardedIndex(torch.from_numpy(rdb).to(dev))
+    qd = torch.from_numpy(rq).to(dev)
+    prep = PreparedGroundTruth("roxford5k", rgnd, idx.n_total, dev)
+    for _ in range(reps):
+        compute_map_and_print("roxford5k", idx, qd, prep, printer=lambda *_: None)
+if "chain" in which:
+    xf = torch.rand((32, 3, 768, 1024), device=dev) * 2 - 1
+    half = [0.5, 0.5, 0.5]
+    for _ in range(reps):
+        y = _lib.clahe_f32(xf, half, half, half, half, clip_limit=1.0)
+        _lib.meanstd_adapt(y, half, half, MEAN, STD, out=y)
 torch.cuda.synchronize()
 print("done")
