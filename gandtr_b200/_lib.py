@@ -36,6 +36,9 @@ SYMBOLS = [
     ("gdt_debug_div_check", _c.c_int, [_c.c_float, _c.c_uint32, _c.c_uint32, _P, _P]),
     ("gdt_debug_k1_config", _c.c_int, [_c.c_int] * 5),
     ("gdt_debug_k1_rows", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_pack", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_persist", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_rec32", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_chunk", _c.c_int, [_c.c_int]),
     ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("gdt_clahe_u8", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _c.c_size_t, _P]),
@@ -174,12 +177,17 @@ def ensure_init(device):
     _initialised_devices.add(idx)
 
 
-K1_DEFAULT_CONFIG = (0, 0, 0, 0, 4)     # texab, spltex, fytex, chroma_a, occ_a -- must match clahe_sm100.cu's statics
+K1_DEFAULT_PACK = 0                     # pass B scalar (1 = packed f32x2); must match g_k1_pack
+K1_DEFAULT_CONFIG = (0, 0, 0, -1, 4)    # texab, spltex, fytex, chroma_a (-1 = automatic), occ_a -- must match clahe_sm100.cu's statics
 
 
 def k1_config_default():
     """Restore K1's built-in work split / pipe choice after an A/B run (debug hook)."""
-    check(load().gdt_debug_k1_config(*K1_DEFAULT_CONFIG), "gdt_debug_k1_config")
+    lib = load()
+    check(lib.gdt_debug_k1_config(*K1_DEFAULT_CONFIG), "gdt_debug_k1_config")
+    check(lib.gdt_debug_k1_rec32(1), "gdt_debug_k1_rec32")
+    check(lib.gdt_debug_k1_persist(1), "gdt_debug_k1_persist")
+    check(lib.gdt_debug_k1_pack(K1_DEFAULT_PACK), "gdt_debug_k1_pack")
 
 
 def _f3(v):

@@ -306,6 +306,250 @@ GDT_HD float normalize_px_fast(float x, float mean, float std, float rstd) {
     return div_by_const<2>(f_sub(x, mean), std, rstd);
 }
 
+// ---- compressed lattice record: all three channels of a cell in ONE 32-byte sector ------------------
+// The trilinear sum over the 8 corners of a cell equals the multilinear polynomial through them:
+//   4096 * v(fr, fg, fb) = 4096 B + 256 (D1 fr + D2 fg + D3 fb) + 16 (M12 fr fg + M13 fr fb + M23 fg fb) + M123 fr fg fb
+// with B the (0,0,0) corner, D the first differences along r / g / b, M the mixed second / third differences (an exact
+// integer identity: expand the weights (16 - f) and f). For the Lab lattice the D are one-signed and fit 10 bits (L, a, b
+// rise or fall monotonically along each RGB axis), the mixed terms are tiny (|M| <= 52): 15 + 3 * 10 + 4 * 7 bits per
+// channel, 219 bits per cell instead of 3 * 128. One gather of one 32-byte sector fetches what took a 16-byte and a
+// 32-byte record in two sectors. pack_lab_rec32() verifies the ranges against the actual table and refuses otherwise.
+//
+// Field placement: every field is extracted by ONE instruction and used where it lies -- low fields (bit 0) and middle
+// fields (bit 7) by a mask, their bit position folded into the per-pixel weight; top fields by a shift.
+//   w[c]     (c = 0, 1, 2 = L, a, b):  M123_c [0,7)   D1_c [7,17)   B_c [17,32)
+//   w[3 + c]:                          M12_c  [0,7)   D2_c [7,17)   top: D3_b [22,32) | M13_L [25,32) | M13_a [25,32)
+//   w[6]:                              M23_L  [0,7)   D3_L [7,17)   M13_b [25,32)
+//   w[7]:                              M23_a  [0,7)   D3_a [7,17)   M23_b [25,32)
+// D fields hold |D| (signs lab_d_sign); M fields hold M + beta_c (one bias per channel, LabRecBias), removed by
+// beta_c * (16 (fr fg + fr fb + fg fb) + fr fg fb).
+struct LabRecBias { int beta[3]; };
+// sign of D1 (r), D2 (g), D3 (b) for L, a, b: a falls with green, b falls with blue
+GDT_HD constexpr int lab_d_sign(int c, int k) { return ((c == 1 && k == 1) || (c == 2 && k == 2)) ? -1 : 1; }
+
+struct LabWeights {      // per pixel, shared by the three channels
+    int r2, g2, b2;      // 2 f       (middle D fields sit at bit 7: 2^7 * 2 f = 256 f)
+    int b256;            // 256 fb    (the one D field in a top slot)
+    int rg16, rb16, gb16;// 16 f f'
+    int rgb;             // fr fg fb
+    int s;               // 16 (fr fg + fr fb + fg fb) + fr fg fb
+};
+GDT_HD LabWeights lab_weights(int fr, int fg, int fb) {
+    LabWeights W;
+    W.r2 = fr * 2; W.g2 = fg * 2; W.b2 = fb * 2;
+    W.b256 = fb * 256;
+    const int rg = fr * fg, rb = fr * fb, gb = fg * fb;
+    W.rg16 = rg * 16; W.rb16 = rb * 16; W.gb16 = gb * 16;
+    W.rgb = rg * fb;
+    W.s = W.rg16 + W.rb16 + W.gb16 + W.rgb;
+    return W;
+}
+// -> Q14 (L, a, b) of the pixel, identical to lab_trilinear() on the uncompressed corners
+GDT_HD void lab_from_rec32(const uint32_t* w, const LabWeights& W, const LabRecBias& bias, int& oL, int& oa, int& ob) {
+    const uint32_t kMid = 0x3ffu << 7, kLow = 0x7fu;
+    int acc[3];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t wa = w[c], wb = w[3 + c];
+        int a = (int)(wa >> 17) * 4096 - bias.beta[c] * W.s;
+        a += (int)(wa & kLow) * W.rgb;
+        a += lab_d_sign(c, 0) * ((int)(wa & kMid) * W.r2);
+        a += (int)(wb & kLow) * W.rg16;
+        a += lab_d_sign(c, 1) * ((int)(wb & kMid) * W.g2);
+        acc[c] = a;
+    }
+    // D3, M13, M23
+    acc[0] += lab_d_sign(0, 2) * ((int)(w[6] & kMid) * W.b2) + (int)(w[4] >> 25) * W.rb16 + (int)(w[6] & kLow) * W.gb16;
+    acc[1] += lab_d_sign(1, 2) * ((int)(w[7] & kMid) * W.b2) + (int)(w[5] >> 25) * W.rb16 + (int)(w[7] & kLow) * W.gb16;
+    acc[2] += lab_d_sign(2, 2) * ((int)(w[3] >> 22) * W.b256) + (int)(w[6] >> 25) * W.rb16 + (int)(w[7] >> 25) * W.gb16;
+    oL = (acc[0] + 2048) >> 12;
+    oa = (acc[1] + 2048) >> 12;
+    ob = (acc[2] + 2048) >> 12;
+}
+
+// lut33: the [33][33][33][3] int16 table. rec: 33^3 * 8 words. Returns false (rec untouched beyond garbage) when a
+// difference does not fit its field or has the wrong sign: the caller then keeps the uncompressed records.
+inline bool pack_lab_rec32(const int16_t* lut33, uint32_t* rec, LabRecBias& bias) {
+    auto at = [&](int r, int g, int b, int c) -> int {
+        r = r < 32 ? r : 32; g = g < 32 ? g : 32; b = b < 32 ? b : 32;   // clamped neighbours carry weight 0
+        return lut33[((r * 33 + g) * 33 + b) * 3 + c];
+    };
+    const int ncell = 33 * 33 * 33;
+    // pass 1: mixed-term minima -> one bias per channel; pass 2: pack and verify
+    int mmin[3] = {0, 0, 0};
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int tr = 0; tr < 33; ++tr)
+            for (int tg = 0; tg < 33; ++tg)
+                for (int tb = 0; tb < 33; ++tb) {
+                    const int cell = (tr * 33 + tg) * 33 + tb;
+                    int B[3], D[3][3], M12[3], M13[3], M23[3], M123[3];
+                    for (int c = 0; c < 3; ++c) {
+                        const int v000 = at(tr, tg, tb, c), v100 = at(tr + 1, tg, tb, c), v010 = at(tr, tg + 1, tb, c),
+                                  v001 = at(tr, tg, tb + 1, c), v110 = at(tr + 1, tg + 1, tb, c),
+                                  v101 = at(tr + 1, tg, tb + 1, c), v011 = at(tr, tg + 1, tb + 1, c),
+                                  v111 = at(tr + 1, tg + 1, tb + 1, c);
+                        B[c] = v000;
+                        D[c][0] = v100 - v000; D[c][1] = v010 - v000; D[c][2] = v001 - v000;
+                        M12[c] = v110 - v100 - v010 + v000;
+                        M13[c] = v101 - v100 - v001 + v000;
+                        M23[c] = v011 - v010 - v001 + v000;
+                        M123[c] = v111 - v110 - v101 - v011 + v100 + v010 + v001 - v000;
+                    }
+                    if (pass == 0) {
+                        for (int c = 0; c < 3; ++c) {
+                            const int m = M12[c] < M13[c] ? M12[c] : M13[c], n = M23[c] < M123[c] ? M23[c] : M123[c];
+                            const int mn = m < n ? m : n;
+                            if (mn < mmin[c]) mmin[c] = mn;
+                        }
+                        continue;
+                    }
+                    uint32_t f_d[3][3], f_m12[3], f_m13[3], f_m23[3], f_m123[3];
+                    for (int c = 0; c < 3; ++c) {
+                        if (B[c] < 0 || B[c] >= (1 << 15)) return false;
+                        for (int k = 0; k < 3; ++k) {
+                            const int mag = D[c][k] * lab_d_sign(c, k);
+                            if (mag < 0 || mag >= (1 << 10)) return false;
+                            f_d[c][k] = (uint32_t)mag;
+                        }
+                        const int beta = bias.beta[c];
+                        const int ms[4] = {M12[c] + beta, M13[c] + beta, M23[c] + beta, M123[c] + beta};
+                        for (int k = 0; k < 4; ++k)
+                            if (ms[k] < 0 || ms[k] >= (1 << 7)) return false;
+                        f_m12[c] = (uint32_t)ms[0]; f_m13[c] = (uint32_t)ms[1]; f_m23[c] = (uint32_t)ms[2]; f_m123[c] = (uint32_t)ms[3];
+                    }
+                    uint32_t* w = rec + (size_t)cell * 8;
+                    for (int c = 0; c < 3; ++c) {
+                        w[c] = f_m123[c] | (f_d[c][0] << 7) | ((uint32_t)B[c] << 17);
+                        w[3 + c] = f_m12[c] | (f_d[c][1] << 7);
+                    }
+                    w[3] |= f_d[2][2] << 22;
+                    w[4] |= f_m13[0] << 25;
+                    w[5] |= f_m13[1] << 25;
+                    w[6] = f_m23[0] | (f_d[0][2] << 7) | (f_m13[2] << 25);
+                    w[7] = f_m23[1] | (f_d[1][2] << 7) | (f_m23[2] << 25);
+                }
+        if (pass == 0)
+            for (int c = 0; c < 3; ++c) bias.beta[c] = -mmin[c];
+    }
+    (void)ncell;
+    return true;
+}
+
+// ---- two pixels per instruction --------------------------------------------------------------------
+// sm_100 has packed fp32 arithmetic (mul / add / fma .rn.f32x2: SASS FMUL2 / FADD2 / FFMA2): both lanes round once per
+// operation exactly like the scalar instruction, so a sequence written lane-wise stays bit-identical while it takes half
+// the issue slots. Every *2 function below is the scalar function of the same name applied to two pixels.
+#if defined(__CUDACC__)
+typedef float2 f2;
+#else
+struct f2 { float x, y; };
+#endif
+GDT_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+GDT_HD f2 bc2(float a) { return mk2(a, a); }
+GDT_HD f2 p_mul(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return mk2(a.x * b.x, a.y * b.y);
+#endif
+}
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (it does not for the scalar .rn forms), which would
+// drop a rounding. The packed addition is therefore issued as fma(a, 1, b) with a 1.0 the assembler cannot see through
+// (a __constant__ it must assume the host may rewrite): exact product, one rounding of a + b, nothing left to contract.
+#if defined(__CUDACC__)
+__constant__ float2 k_opaque_one2 = {1.0f, 1.0f};
+#endif
+GDT_HD f2 p_add(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, k_opaque_one2, b);
+#else
+    return mk2(a.x + b.x, a.y + b.y);
+#endif
+}
+GDT_HD f2 p_fma(f2 a, f2 b, f2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// a - b as fma(b, -1, a): the product is exact, one rounding of the exact difference (signed zeros included)
+GDT_HD f2 p_sub(f2 a, f2 b) { return p_fma(b, bc2(-1.0f), a); }
+GDT_HD f2 p_sel(bool cx, bool cy, f2 a, f2 b) { return mk2(cx ? a.x : b.x, cy ? a.y : b.y); }
+
+template <int ITERS>
+GDT_HD f2 div_by_const2(f2 a, float b, float r) {
+    f2 q = p_mul(a, bc2(r));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int i = 0; i < ITERS; ++i) {
+        const f2 e = p_fma(bc2(-b), q, a);
+        q = p_fma(e, bc2(r), q);
+    }
+    return q;
+}
+GDT_HD f2 lab_chroma_fast2(int o0, int o1) {
+    const f2 x = p_mul(mk2((float)o0, (float)o1), bc2(1.0f / 64.0f));
+    const f2 spc = div_by_const2<1>(x, 255.0f, 1.0f / 255.0f);
+    return p_add(p_mul(spc, bc2(255.0f)), bc2(-128.0f));
+}
+GDT_HD f2 lab_l_from_u8_fast2(int v0, int v1) {
+    return p_mul(div_by_const2<1>(mk2((float)v0, (float)v1), 255.0f, 1.0f / 255.0f), bc2(100.0f));
+}
+GDT_HD void clahe_blend2(const int* l11, const int* l12, const int* l21, const int* l22, f2 xa, f2 xa1, float ya, float ya1,
+                         int& d0, int& d1) {
+    const f2 top = p_add(p_mul(mk2((float)l11[0], (float)l11[1]), xa1), p_mul(mk2((float)l12[0], (float)l12[1]), xa));
+    const f2 bot = p_add(p_mul(mk2((float)l21[0], (float)l21[1]), xa1), p_mul(mk2((float)l22[0], (float)l22[1]), xa));
+    const f2 res = p_add(p_mul(top, bc2(ya1)), p_mul(bot, bc2(ya)));
+    d0 = f_rint(res.x); d1 = f_rint(res.y);
+    d0 = d0 < 0 ? 0 : (d0 > 255 ? 255 : d0);
+    d1 = d1 < 0 ? 0 : (d1 > 255 ? 255 : d1);
+}
+// lab_fy_body for two pixels: both branches are computed lane-wise, the scalar function's branch is selected per lane
+GDT_HD void lab_fy_body2(f2 L, f2& y, f2& fy) {
+    const float c16 = 16.0f / 116.0f;
+    const float r903 = 1.0f / 903.3f, r116 = 1.0f / 116.0f;
+    const f2 ylo = p_mul(L, bc2(r903));
+    const f2 fylo = p_add(p_mul(ylo, bc2(7.787f)), bc2(c16));
+    const f2 fyhi = p_mul(p_add(L, bc2(16.0f)), bc2(r116));
+    const f2 yhi = p_mul(p_mul(fyhi, fyhi), fyhi);
+    const bool lx = L.x <= 8.0f, ly = L.y <= 8.0f;
+    y = p_sel(lx, ly, ylo, yhi);
+    fy = p_sel(lx, ly, fylo, fyhi);
+}
+GDT_HD void lab2lin_body2(f2 fy, f2 y, f2 a, f2 b, const Lab2RgbConst& K, f2& r, f2& g, f2& bl) {
+    const float c16 = 16.0f / 116.0f;
+    const float fth = 6.0f / 29.0f;
+    const float r500 = 1.0f / 500.0f, r200 = 1.0f / 200.0f, r7787 = 1.0f / 7.787f;
+    const f2 fx = p_add(p_mul(a, bc2(r500)), fy);
+    const f2 fz = p_sub(fy, p_mul(b, bc2(r200)));
+    const f2 X = p_sel(fx.x <= fth, fx.y <= fth, p_mul(p_add(fx, bc2(-c16)), bc2(r7787)), p_mul(p_mul(fx, fx), fx));
+    const f2 Z = p_sel(fz.x <= fth, fz.y <= fth, p_mul(p_add(fz, bc2(-c16)), bc2(r7787)), p_mul(p_mul(fz, fz), fz));
+    r = p_add(p_mul(bc2(K.C[0]), X), p_add(p_mul(bc2(K.C[1]), y), p_mul(bc2(K.C[2]), Z)));
+    g = p_add(p_mul(bc2(K.C[3]), X), p_add(p_mul(bc2(K.C[4]), y), p_mul(bc2(K.C[5]), Z)));
+    bl = p_add(p_mul(bc2(K.C[6]), X), p_add(p_mul(bc2(K.C[7]), y), p_mul(bc2(K.C[8]), Z)));
+}
+GDT_HD f2 spline_index2(f2 lin, int& ix0, int& ix1) {
+#if defined(__CUDA_ARCH__)
+    const f2 x = p_mul(mk2(__saturatef(lin.x), __saturatef(lin.y)), bc2(1024.0f));
+#else
+    const f2 x = p_mul(mk2(clamp01(lin.x), clamp01(lin.y)), bc2(1024.0f));
+#endif
+    ix0 = f_trunc(x.x); ix1 = f_trunc(x.y);
+    ix0 = ix0 > 1023 ? 1023 : ix0;
+    ix1 = ix1 > 1023 ? 1023 : ix1;
+    return p_sub(x, mk2((float)ix0, (float)ix1));
+}
+GDT_HD f2 spline_eval2(f2 x, f2 s0, f2 s1, f2 s2, f2 s3) {
+    return p_add(p_mul(p_add(p_mul(p_add(p_mul(s3, x), s2), x), s1), x), s0);
+}
+GDT_HD f2 normalize_px_fast2(f2 x, float mean, float std, float rstd) {
+    return div_by_const2<2>(p_add(x, bc2(-mean)), std, rstd);
+}
+
 // ---- host-side table builders (used by gdt_init; plain C++) --------------------------------------
 
 // Natural cubic spline of the sRGB inverse gamma, built exactly like OpenCV's splineBuild on

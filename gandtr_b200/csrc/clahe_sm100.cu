@@ -27,6 +27,9 @@ namespace gdt {
 struct ClaheTables {
     uint4* lutL = nullptr;     // [33^3]      packed lightness corners
     uint4* lutAB = nullptr;    // [33^3][2]   packed chroma corners (a words, b words)
+    uint32_t* rec32 = nullptr; // [33^3][8]   compressed record of all three channels (clahe_math.cuh), when it fits
+    LabRecBias bias = {{0, 0, 0}};
+    bool rec_ok = false;
     float4* spline = nullptr;  // [1024]
     float4* fytab = nullptr;   // [256]       {fy, C1*y, C4*y, C7*y} per CLAHE output byte (build_fy_table)
     cudaTextureObject_t texL = 0, texAB = 0, texSpline = 0, texFy = 0;   // the same tables behind the texture path
@@ -47,7 +50,14 @@ static ClaheTables g_tables[32];
 //   pass B's arithmetic); occ_a = resident CTAs per SM pass A is compiled for (4 or 6).
 // Defaults = the fastest combination measured on B200 (profiles/k1_v2_ab_r1q.log): chroma in pass B (its gather hides
 // under pass B's arithmetic; in pass A it is exposed: 1.03 vs 1.20 ms per 128 images), everything else recomputed.
-static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_chroma_a = 0, g_k1_occ_a = 4;
+static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_occ_a = 4;
+// chroma_a: -1 = automatic: pass A interpolates all three channels from ONE 32-byte compressed lattice record per pixel
+// (a single sector gather; pass B then touches no lattice at all) whenever the table fits that format, else 0.
+// 1 with g_k1_rec32 == 0 is round 1's uncompressed three-gather variant.
+static int g_k1_chroma_a = -1;
+static int g_k1_rec32 = 1;
+static int g_k1_pack = 0;     // pass B: packed f32x2 arithmetic (two pixels per instruction); 0 = scalar (gdt_debug_k1_pack)
+static int g_k1_persist = 1;  // pass B: persistent 1024-thread CTAs with conflict-free spline copies (gdt_debug_k1_persist)
 static int g_k1_rows = 0;     // > 0: rows per pass-B CTA forced (gdt_debug_k1_rows), 0: pass_b_rows()
 static int g_k1_chunk = 0;    // images per (pass A, pass B) launch pair: 0 whole batch at once (default: measured fastest,
                               // profiles/k1_chunk_ab_r2a.log), -1 sized so that a chunk's scratch stays in L2, > 0 forced
@@ -135,17 +145,33 @@ __device__ __forceinline__ void ld_cell_ab(const uint4* __restrict__ lutAB, int 
                  : "l"(lutAB + cell * 2));
 }
 
+// the 32-byte compressed record of a cell (one sector) as a single 256-bit read-only load
+__device__ __forceinline__ void ld_cell_rec32(const uint32_t* __restrict__ rec32, int cell, uint32_t* w) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(rec32 + (size_t)cell * 8));
+}
+__device__ __forceinline__ void lab_from_rec32_px(const uint32_t* w, int fr, int fg, int fb, const LabRecBias& bias, int& l8,
+                                                  uint32_t& ab) {
+    int oL, oa, ob;
+    lab_from_rec32(w, lab_weights(fr, fg, fb), bias, oL, oa, ob);
+    l8 = lab_l8_int(oL);
+    ab = (uint32_t)oa | ((uint32_t)ob << 16);
+}
+
 // `gq`, `gr` = 256 / gw, 256 % gw (gw = 4-pixel groups per tile row): the vectorised loop walks (row, group) incrementally,
 // no division per step. TEXAB: chroma records through the texture pipe (idle otherwise), lightness through the LSU pipe.
 // TEXL: which lightness-record gathers take the texture pipe instead of the LSU pipe (pass A is bound by the LSU pipe's
 // scattered 16-byte gathers): 0 none, 1 all, 2 every other pixel (both pipes gather in parallel).
-template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL>
+// REC32 (with CHROMA_A): all three channels from the compressed 32-byte record, one gather per pixel.
+template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL, bool REC32>
 __global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w, int pitch,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
                   const uint4* __restrict__ lutL, const uint4* __restrict__ lutAB, Norm3 in_norm,
-                  cudaTextureObject_t texAB, cudaTextureObject_t texL) {
+                  cudaTextureObject_t texAB, cudaTextureObject_t texL, const uint32_t* __restrict__ rec32,
+                  LabRecBias bias) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
@@ -215,7 +241,13 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
             }
             int v[4];
             uint32_t ab[4];
-            if (CHROMA_A) {
+            if (CHROMA_A && REC32) {
+                uint32_t rw[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ld_cell_rec32(rec32, cell[i], rw[i]);      // four sector gathers in flight
+#pragma unroll
+                for (int i = 0; i < 4; ++i) lab_from_rec32_px(rw[i], fr[i], fg[i], fb[i], bias, v[i], ab[i]);
+            } else if (CHROMA_A) {
                 uint4 wl[4], wa[4], wb[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {                                   // twelve gathers in flight
@@ -283,13 +315,18 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                 } else {
                     cell_from_f32(inf[p], inf[plane + p], inf[2 * plane + p], in_norm, cell, fr, fg, fb);
                 }
-                const uint4 wl = __ldg(lutL + cell);
                 uint32_t ab;
-                if (CHROMA_A) {
+                if (CHROMA_A && REC32) {
+                    uint32_t rw[8];
+                    ld_cell_rec32(rec32, cell, rw);
+                    lab_from_rec32_px(rw, fr, fg, fb, bias, v, ab);
+                } else if (CHROMA_A) {
+                    const uint4 wl = __ldg(lutL + cell);
                     uint4 wa, wb;
                     ld_cell_ab(lutAB, cell, wa, wb);
                     lab_from_records(wl, wa, wb, fr, fg, fb, v, ab);
                 } else {
+                    const uint4 wl = __ldg(lutL + cell);
                     v = lab_l8_int(lab_trilinear(wl.x, wl.y, wl.z, wl.w, fr, fg, fb));
                     ab = pack_code(cell, fr, fg, fb);
                 }
@@ -362,45 +399,75 @@ struct NormFast {
 // chroma records are fetched here through the texture pipe.
 // ANYW = widths with scalar-tail pixels (w % 8 != 0) or unaligned planar rows; without it (the common case, chosen by the
 // host) the tail split and the store alignment test are compiled out.
-template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A, bool ANYW>
-__global__ void __launch_bounds__(256, MINB)
+// PACK = two pixels per instruction (packed f32x2 arithmetic, clahe_math.cuh) on every warp without scalar-tail pixels
+// (FAST, SPLTEX == 0, !FYTEX only); bit-identical to the scalar sequence, ~45 fewer issue slots per pixel.
+// PERSIST = one 1024-thread CTA per SM that walks over (image, row band, column chunk) items as four independent
+// 256-thread groups (named barriers), with the inverse-gamma spline held in shared memory EIGHT times: segment i, copy c
+// at [i][c], 16 bytes each, so that a 128-byte row is the same segment for the 8 lanes of a quarter warp. A 16-byte
+// shared-memory load is served one quarter warp at a time; lane l reads copy l & 7, i.e. its own 16-byte bank group,
+// whatever its segment index: the three random spline lookups per pixel are conflict-free (4 wavefronts per request
+// instead of ~18 measured for random 16-byte reads, tools/microbench/gather_rate.cu). 128 KB of shared memory per SM,
+// staged once per launch. (FAST, SPLTEX == 0, !FYTEX only.)
+template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A, bool ANYW, bool PACK, bool PERSIST>
+__global__ void __launch_bounds__(PERSIST ? 1024 : 256, PERSIST ? 1 : MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int pitch, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    const float4* __restrict__ spline, Lab2RgbConst K,
-                   NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy, cudaTextureObject_t texAB) {
+                   NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy, cudaTextureObject_t texAB,
+                   int xchunks, int nbands, int nitems, int lut_area_bytes) {
     if (FAST) on.fast = 1;
     extern __shared__ __align__(16) uint8_t smem[];
-    // inverse-gamma spline segments split into two 8-byte halves: random 8-byte shared-memory gathers conflict far
-    // less than 16-byte ones
+    // !PERSIST: inverse-gamma spline segments split into two 8-byte halves (random 8-byte shared-memory gathers conflict
+    // less than 16-byte ones); PERSIST: eight conflict-free copies of the 16-byte segments
     float2* spl_fb = (float2*)smem;              // [1024] (f, b)
     float2* spl_cd = (float2*)(smem + 1024 * 8); // [1024] (c, d)
-    uint2* luts = (uint2*)(smem + 1024 * 16);    // [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
+    const float4* spl8 = (const float4*)smem;    // [1024][8]
     const int lsh = FAST ? 3 : lut_row_shift(grid);
-    const int tid = threadIdx.x;
-    const int img = blockIdx.z;
-    const int y0 = blockIdx.y * rows_per_cta;
+    const int tid = PERSIST ? (threadIdx.x & 255) : threadIdx.x;      // thread within the 256-thread group
+    const int grp = PERSIST ? (threadIdx.x >> 8) : 0;
+    // LUT rows of the group's current item: [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
+    uint2* luts = (uint2*)(smem + (PERSIST ? 1024 * 128 + (size_t)grp * lut_area_bytes : 1024 * 16));
+    if (PERSIST) {
+        float4* dst = (float4*)smem;
+        for (int i = threadIdx.x; i < 1024; i += 1024) {
+            const float4 sgm = __ldg(spline + i);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[i * 8 + c] = sgm;
+        }
+    } else if (SPLTEX < 3) {
+        for (int i = tid; i < 1024; i += 256) {
+            const float4 sgm = __ldg(spline + i);
+            spl_fb[i] = make_float2(sgm.x, sgm.y);
+            spl_cd[i] = make_float2(sgm.z, sgm.w);
+        }
+    }
+    __syncthreads();
+    auto group_sync = [&]() {
+        if (PERSIST) asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
+        else __syncthreads();
+    };
+    const int lane8 = threadIdx.x & 7;
+
+    for (int item = PERSIST ? (int)blockIdx.x * 4 + grp : (int)blockIdx.x; item < nitems;
+         item += PERSIST ? (int)gridDim.x * 4 : nitems) {
+    const int bx = item % xchunks, by = (item / xchunks) % nbands, img = item / (xchunks * nbands);
+    const int y0 = by * rows_per_cta;
     const int y1 = min(y0 + rows_per_cta, h);
     const int ty_lo = clahe_axis(y0, inv_th, grid).i1;
     const int ty_hi = clahe_axis(y1 - 1, inv_th, grid).i2;
+    if (PERSIST) group_sync();          // the group's previous item no longer reads the LUT rows
     {
         const int nwords = ((ty_hi - ty_lo + 1) * 256) << (lsh - 3);
         const uint2* src = (const uint2*)(lutT + ((((size_t)img * grid + ty_lo) * 256) << lsh));
         for (int i = tid; i < nwords; i += 256) luts[i] = __ldg(src + i);
-        if (SPLTEX < 3) {
-            for (int i = tid; i < 1024; i += 256) {
-                const float4 sgm = __ldg(spline + i);
-                spl_fb[i] = make_float2(sgm.x, sgm.y);
-                spl_cd[i] = make_float2(sgm.z, sgm.w);
-            }
-        }
     }
-    __syncthreads();
+    group_sync();
 
-    const int x0 = (blockIdx.x * 256 + tid) * 4;
+    const int x0 = (bx * 256 + tid) * 4;
     const int wbody = (w >> 3) << 3;  // pixels >= wbody take OpenCV's scalar-tail op sequence
     // does this warp own any scalar-tail pixel? (uniform per warp and constant over the rows)
     const bool tail_warp = ANYW && __any_sync(0xffffffffu, x0 < w && x0 + 4 > wbody);
-    if (x0 >= w) return;
+    if (x0 >= w) continue;
     const int npx = min(4, w - x0);
 
     ClaheAxis ax[4];
@@ -464,6 +531,9 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
             if (c < SPLTEX) {       // texture pipe: no shared-memory bank conflicts
                 const float4 sg = tex1Dfetch<float4>(texSpline, ix[c]);
                 e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
+            } else if (PERSIST) {   // this lane's own copy: conflict-free
+                const float4 sg = spl8[(ix[c] << 3) | lane8];
+                e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
             } else {
                 const float2 s01 = spl_fb[ix[c]], s23 = spl_cd[ix[c]];
                 e[c] = spline_eval(xs[c], s01.x, s01.y, s23.x, s23.y);
@@ -472,6 +542,58 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
         o0 = on.fast ? normalize_px_fast(e[0], on.mean[0], on.std[0], on.rstd[0]) : normalize_px(e[0], on.mean[0], on.std[0]);
         o1 = on.fast ? normalize_px_fast(e[1], on.mean[1], on.std[1], on.rstd[1]) : normalize_px(e[1], on.mean[1], on.std[1]);
         o2 = on.fast ? normalize_px_fast(e[2], on.mean[2], on.std[2], on.rstd[2]) : normalize_px(e[2], on.mean[2], on.std[2]);
+    };
+
+    // two pixels (i, i + 1) per instruction: the same operation sequence as `pixel`, packed lane-wise
+    f2 xa2[2], xa12[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        xa2[j] = mk2(ax[2 * j].a, ax[2 * j + 1].a);
+        xa12[j] = mk2(ax[2 * j].a1, ax[2 * j + 1].a1);
+    }
+    auto pixel_pair = [&](int j, const int* v, const uint32_t* abw, const ClaheAxis& ay, const uint8_t* lrow1,
+                          const uint8_t* lrow2, f2& o0, f2& o1, f2& o2) {
+        int oa[2], ob[2], l11[2], l12[2], l21[2], l22[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (CHROMA_A) {
+                oa[t] = (int)(abw[t] & 0xffffu);
+                ob[t] = (int)(abw[t] >> 16);
+            } else {
+                int cell, fr, fg, fb;
+                unpack_code(abw[t], cell, fr, fg, fb);
+                const uint4 wa = tex1Dfetch<uint4>(texAB, cell * 2), wb = tex1Dfetch<uint4>(texAB, cell * 2 + 1);
+                oa[t] = lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr, fg, fb);
+                ob[t] = lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr, fg, fb);
+            }
+            const uint2 w1 = *(const uint2*)(lrow1 + (v[t] << 3));
+            const uint2 w2 = *(const uint2*)(lrow2 + (v[t] << 3));
+            const uint32_t p1 = __byte_perm(w1.x, w1.y, sel[2 * j + t]), p2 = __byte_perm(w2.x, w2.y, sel[2 * j + t]);
+            l11[t] = p1 & 255; l12[t] = (p1 >> 8) & 255;
+            l21[t] = p2 & 255; l22[t] = (p2 >> 8) & 255;
+        }
+        const f2 a2 = lab_chroma_fast2(oa[0], oa[1]), b2 = lab_chroma_fast2(ob[0], ob[1]);
+        int d0, d1;
+        clahe_blend2(l11, l12, l21, l22, xa2[j], xa12[j], ay.a, ay.a1, d0, d1);
+        f2 y, fy, lin[3];
+        lab_fy_body2(lab_l_from_u8_fast2(d0, d1), y, fy);
+        lab2lin_body2(fy, y, a2, b2, K, lin[0], lin[1], lin[2]);
+        f2 e[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int i0, i1;
+            const f2 xs = spline_index2(lin[c], i0, i1);
+            if (PERSIST) {
+                const float4 s0 = spl8[(i0 << 3) | lane8], s1 = spl8[(i1 << 3) | lane8];
+                e[c] = spline_eval2(xs, mk2(s0.x, s1.x), mk2(s0.y, s1.y), mk2(s0.z, s1.z), mk2(s0.w, s1.w));
+            } else {
+                const float2 f0 = spl_fb[i0], c0 = spl_cd[i0], f1 = spl_fb[i1], c1 = spl_cd[i1];
+                e[c] = spline_eval2(xs, mk2(f0.x, f1.x), mk2(f0.y, f1.y), mk2(c0.x, c1.x), mk2(c0.y, c1.y));
+            }
+        }
+        o0 = normalize_px_fast2(e[0], on.mean[0], on.std[0], on.rstd[0]);
+        o1 = normalize_px_fast2(e[1], on.mean[1], on.std[1], on.rstd[1]);
+        o2 = normalize_px_fast2(e[2], on.mean[2], on.std[2], on.rstd[2]);
     };
 
     // software prefetch: the next row's scratch words are requested before this row's arithmetic
@@ -503,7 +625,16 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
         const uint32_t ab[4] = {cw.x, cw.y, cw.z, cw.w};
 
         float o[3][4];
-        if (tail_warp) {
+        if (PACK && !tail_warp) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                f2 p0, p1, p2;
+                pixel_pair(j, v + 2 * j, ab + 2 * j, ay, lrow1, lrow2, p0, p1, p2);
+                o[0][2 * j] = p0.x; o[0][2 * j + 1] = p0.y;
+                o[1][2 * j] = p1.x; o[1][2 * j + 1] = p1.y;
+                o[2][2 * j] = p2.x; o[2][2 * j + 1] = p2.y;
+            }
+        } else if (tail_warp) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ay, lrow1, lrow2, (x0 + i) >= wbody, o[0][i], o[1][i], o[2][i]);
         } else {
@@ -522,6 +653,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
             }
         }
     }
+    }   // items
 }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -596,24 +728,31 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     else vec_hist = 0;
 
     // A/B switches, see gdt_debug_k1_config (profiles/k1_v2_ab_r1q.log)
-    const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, chroma_a = g_k1_chroma_a, occ_a = g_k1_occ_a;
+    const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, occ_a = g_k1_occ_a;
+    const bool rec32 = g_k1_rec32 != 0 && T->rec_ok;
+    const int chroma_a = g_k1_chroma_a < 0 ? (rec32 ? 1 : 0) : g_k1_chroma_a;
     dim3 gridA(grid * grid, n);
     const int gw = g.tw;                               // scalar path: walk unit = one pixel of a tile row
     const int gq = 256 / gw, gr = 256 % gw;
-#define GDT_HIST(T_, C_, O_, L_)                                                                                       \
-    clahe_hist_kernel<U8, T_, C_, O_, L_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw,   \
-                                                                      g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL,  \
-                                                                      T->lutAB, in_norm, T->texAB, T->texL)
+#define GDT_HIST_R(T_, C_, O_, L_, R_)                                                                                 \
+    clahe_hist_kernel<U8, T_, C_, O_, L_, R_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw, \
+                                                                          g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL, \
+                                                                          T->lutAB, in_norm, T->texAB, T->texL, T->rec32, \
+                                                                          T->bias)
+#define GDT_HIST(T_, C_, O_, L_) GDT_HIST_R(T_, C_, O_, L_, false)
     if (!chroma_a) {
         if (texab & 4) GDT_HIST(false, false, 4, 2);
         else if (texab & 2) GDT_HIST(false, false, 4, 1);
         else if (occ_a >= 6) GDT_HIST(false, false, 6, 0);
         else GDT_HIST(false, false, 4, 0);
+    } else if (rec32) {
+        if (occ_a >= 6) GDT_HIST_R(false, true, 6, 0, true); else GDT_HIST_R(false, true, 4, 0, true);
     } else if (texab & 1) {
         if (occ_a >= 6) GDT_HIST(true, true, 6, 0); else GDT_HIST(true, true, 4, 0);
     } else {
         GDT_HIST(false, true, 4, 0);
     }
+#undef GDT_HIST_R
 #undef GDT_HIST
     GDT_LAUNCH_CHECK();
 
@@ -624,11 +763,15 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     const int xchunks = ceil_div(w, 1024);
     int rows = pass_b_rows(h, (long long)xchunks * n, 4LL * sms);
     if (g_k1_rows > 0) rows = g_k1_rows;
-    dim3 gridB(xchunks, ceil_div(h, rows), n);
+    const int nbands = ceil_div(h, rows);
+    const long long nitems_ll = (long long)xchunks * nbands * n;
+    if (nitems_ll > 0x7fffffffLL) return GDT_ERR_UNSUPPORTED;
+    const int nitems = (int)nitems_ll;
     // spline table + the LUT rows of every tile row a band of `rows` image rows can touch
     int span = (rows + g.th - 1) / g.th + 2;
     if (span > grid) span = grid;
-    const size_t smem = 1024 * 16 + (((size_t)span * 256) << lut_row_shift(grid));
+    const int lut_area = (span * 256) << lut_row_shift(grid);
+    const size_t smem = 1024 * 16 + (size_t)lut_area;
     NormFast on;
     on.fast = 1;
     for (int c = 0; c < 3; ++c) {
@@ -638,23 +781,57 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
         on.rstd[c] = r;
         if (!div_by_const_ok(out_norm.std[c])) on.fast = 0;
     }
-    // 4 resident CTAs per SM (64 registers): measured on B200, 6 and 8 (40 / 32 registers) are no faster -- the kernel is
-    // bound by instruction issue plus the L1 / shared-memory pipeline, not by latency
     // widths with OpenCV scalar-tail pixels or rows of the planar output that are not 16-byte aligned
     const bool anyw = (w & 7) != 0 || (((uintptr_t)out) & 15) != 0;
     if (smem > 48 * 1024) {
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
     }
-#define GDT_APPLY(FAST_, S_, F_, C_, A_)                                                                                 \
-    clahe_apply_kernel<4, FAST_, S_, F_, C_, A_><<<gridB, 256, smem, stream>>>(AB, L8, luts, out, h, w, pitch, grid,        \
-                                                                                g.inv_th, g.inv_tw, rows, T->spline, T->K,  \
-                                                                                on, T->texSpline, T->texFy, T->texAB)
+    // non-persistent form: one 256-thread CTA per item, 4 resident CTAs per SM (64 registers; 6 and 8 CTAs per SM at
+    // 40 / 32 registers measured no faster)
+#define GDT_APPLY_P(FAST_, S_, F_, C_, A_, P_)                                                                            \
+    clahe_apply_kernel<4, FAST_, S_, F_, C_, A_, P_, false><<<nitems, 256, smem, stream>>>(                                \
+        AB, L8, luts, out, h, w, pitch, grid, g.inv_th, g.inv_tw, rows, T->spline, T->K, on, T->texSpline, T->texFy,       \
+        T->texAB, xchunks, nbands, nitems, lut_area)
+#define GDT_APPLY(FAST_, S_, F_, C_, A_) GDT_APPLY_P(FAST_, S_, F_, C_, A_, false)
+    // persistent form (the default for the common configuration): one 1024-thread CTA per SM = four 256-thread groups,
+    // eight conflict-free copies of the spline in shared memory (128 KB) + one LUT area per group
+    const size_t smem_p = 1024 * 128 + 4 * (size_t)lut_area;
+#define GDT_APPLY_PERSIST(C_, A_, P_)                                                                                    \
+    do {                                                                                                                 \
+        auto kern = clahe_apply_kernel<4, true, 0, false, C_, A_, P_, true>;                                             \
+        static bool attr_done[32] = {false};                                                                             \
+        const int slot = current_device_slot();                                                                          \
+        if (!attr_done[slot]) {                                                                                          \
+            GDT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 128 + 4 * 8 * 2048)); \
+            attr_done[slot] = true;                                                                                      \
+        }                                                                                                                \
+        const int ctas = nitems < 4 * sms ? ceil_div(nitems, 4) : sms;                                                   \
+        kern<<<ctas, 1024, smem_p, stream>>>(AB, L8, luts, out, h, w, pitch, grid, g.inv_th, g.inv_tw, rows, T->spline,  \
+                                             T->K, on, T->texSpline, T->texFy, T->texAB, xchunks, nbands, nitems,        \
+                                             lut_area);                                                                  \
+    } while (0)
+    const bool pack = g_k1_pack != 0;
+    const bool persist = g_k1_persist != 0 && spltex == 0 && !fytex;
     if (grid <= 8 && on.fast && smem <= 48 * 1024) {
-        if (anyw) {     // the pipe variants are A/B material for the common case only
-            if (chroma_a) GDT_APPLY(true, 0, false, true, true); else GDT_APPLY(true, 0, false, false, true);
+        if (persist) {
+            switch ((chroma_a ? 4 : 0) + (anyw ? 2 : 0) + (pack ? 1 : 0)) {
+                case 0: GDT_APPLY_PERSIST(false, false, false); break;
+                case 1: GDT_APPLY_PERSIST(false, false, true); break;
+                case 2: GDT_APPLY_PERSIST(false, true, false); break;
+                case 3: GDT_APPLY_PERSIST(false, true, true); break;
+                case 4: GDT_APPLY_PERSIST(true, false, false); break;
+                case 5: GDT_APPLY_PERSIST(true, false, true); break;
+                case 6: GDT_APPLY_PERSIST(true, true, false); break;
+                default: GDT_APPLY_PERSIST(true, true, true); break;
+            }
+        } else if (anyw) {     // the pipe variants are A/B material for the common case only
+            if (chroma_a) { if (pack) GDT_APPLY_P(true, 0, false, true, true, true); else GDT_APPLY(true, 0, false, true, true); }
+            else { if (pack) GDT_APPLY_P(true, 0, false, false, true, true); else GDT_APPLY(true, 0, false, false, true); }
+        } else if (pack && spltex == 0 && !fytex) {
+            if (chroma_a) GDT_APPLY_P(true, 0, false, true, false, true); else GDT_APPLY_P(true, 0, false, false, false, true);
         } else switch ((spltex > 1 ? 1 : spltex) * 4 + fytex * 2 + chroma_a) {
             case 0: GDT_APPLY(true, 0, false, false, false); break;
             case 1: GDT_APPLY(true, 0, false, true, false); break;
@@ -671,6 +848,8 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
         GDT_APPLY(false, 0, false, false, true);
     }
 #undef GDT_APPLY
+#undef GDT_APPLY_PERSIST
+#undef GDT_APPLY_P
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
@@ -805,7 +984,7 @@ extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_
     g_k1_texab = texab & 7;
     g_k1_spltex = spltex;
     g_k1_fytex = fytex ? 1 : 0;
-    g_k1_chroma_a = chroma_a ? 1 : 0;
+    g_k1_chroma_a = chroma_a < 0 ? -1 : (chroma_a ? 1 : 0);
     g_k1_occ_a = occ_a;
     return GDT_OK;
 }
@@ -813,6 +992,21 @@ extern "C" int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_
 extern "C" int gdt_debug_k1_chunk(int images_per_launch_pair) {
     if (images_per_launch_pair < -1) return GDT_ERR_INVALID_ARGUMENT;
     g_k1_chunk = images_per_launch_pair;
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_pack(int packed_f32x2) {
+    g_k1_pack = packed_f32x2 ? 1 : 0;
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_rec32(int compressed_record) {
+    g_k1_rec32 = compressed_record ? 1 : 0;
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_persist(int persistent) {
+    g_k1_persist = persistent ? 1 : 0;
     return GDT_OK;
 }
 
@@ -853,6 +1047,15 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     };
     if (rc == GDT_OK) rc = up((void**)&T.lutL, hL, ncell * 16);
     if (rc == GDT_OK) rc = up((void**)&T.lutAB, hAB, ncell * 32);
+    if (rc == GDT_OK) {
+        uint32_t* hR = (uint32_t*)malloc(ncell * 8 * sizeof(uint32_t));
+        if (hR) {
+            memset(hR, 0, ncell * 8 * sizeof(uint32_t));
+            T.rec_ok = pack_lab_rec32(host_rgb2lab_lut, hR, T.bias);
+            if (T.rec_ok) rc = up((void**)&T.rec32, hR, ncell * 32);
+            free(hR);
+        }
+    }
     if (rc == GDT_OK) rc = up((void**)&T.spline, T.spline_host, 4096 * sizeof(float));
     if (rc == GDT_OK) rc = up((void**)&T.fytab, T.fy_host, 1024 * sizeof(float));
     free(hL);

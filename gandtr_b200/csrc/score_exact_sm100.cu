@@ -199,10 +199,15 @@ topk_pack_kernel(const float* __restrict__ scores, const int64_t* __restrict__ i
     }
 }
 
+// The per-shard lists arrive sorted (key descending, padding at the tail -- what topk_finalize_kernel and
+// gdt_score_topk_exact write), and rank keys are unique across shards (they embed the global row index). So the merged
+// position of an entry is its position in its own list plus, for every other list, the number of larger keys there:
+// g - 1 binary searches per entry, no sort, one barrier. Unsorted input (a caller's own lists) is detected and takes the
+// bitonic sort instead. The merged order is the same either way.
 __global__ void __launch_bounds__(256)
 topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, int np, float* __restrict__ out_s,
                          int64_t* __restrict__ out_i) {
-    extern __shared__ __align__(16) uint64_t keys[];  // [np]
+    extern __shared__ __align__(16) uint64_t keys[];  // [np], list s at [s * k, (s + 1) * k)
     __shared__ int s_overflow;
     const int tid = threadIdx.x, q = blockIdx.x;
     const int total = g * k;
@@ -220,15 +225,59 @@ topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, 
         }
         keys[i] = key;
     }
-    block_bitonic_sort_desc(keys, np, tid, 256);
+    __syncthreads();
     const bool overflow = s_overflow != 0;
-    for (int i = tid; i < k; i += 256) {
+    bool unsorted = false;
+    for (int i = tid; i < total; i += 256) {
+        const int j = i % k;
+        if (j + 1 < k && keys[i] < keys[i + 1]) unsorted = true;
+    }
+    if (__syncthreads_or(unsorted || overflow)) {
+        block_bitonic_sort_desc(keys, np, tid, 256);
+        for (int i = tid; i < k; i += 256) {
+            const uint64_t key = keys[i];
+            const bool valid = key != 0ull;
+            out_s[(size_t)q * k + i] = valid ? key_score(key) : __int_as_float(0xff800000);
+            int64_t id = valid ? (int64_t)key_index(key) : (int64_t)-1;
+            if (overflow && i == 0) id = -2;      // same marker as topk_finalize_kernel: the caller repairs this query
+            out_i[(size_t)q * k + i] = id;
+        }
+        return;
+    }
+    int nvalid = 0;
+    for (int i = tid; i < total; i += 256) {
         const uint64_t key = keys[i];
-        const bool valid = key != 0ull;
-        out_s[(size_t)q * k + i] = valid ? key_score(key) : __int_as_float(0xff800000);
-        int64_t id = valid ? (int64_t)key_index(key) : (int64_t)-1;
-        if (overflow && i == 0) id = -2;      // same marker as topk_finalize_kernel: the caller repairs this query
-        out_i[(size_t)q * k + i] = id;
+        if (key == 0ull) continue;
+        ++nvalid;
+        const int s = i / k;
+        int rank = i - s * k;
+        for (int t = 0; t < g; ++t) {
+            if (t == s) continue;
+            const uint64_t* lst = keys + t * k;
+            // number of entries of list t that sort before `key`: larger keys, and equal ones in earlier lists (a caller
+            // may hand in the same entry twice; the merge stays a stable one)
+            int lo = 0, hi = k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint64_t m = lst[mid];
+                if (m > key || (t < s && m == key)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            out_s[(size_t)q * k + rank] = key_score(key);
+            out_i[(size_t)q * k + rank] = (int64_t)key_index(key);
+        }
+    }
+    // fewer than k valid entries in total: pad the tail
+    __shared__ int s_valid;
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    if (nvalid) atomicAdd(&s_valid, nvalid);
+    __syncthreads();
+    for (int i = s_valid + tid; i < k; i += 256) {
+        out_s[(size_t)q * k + i] = __int_as_float(0xff800000);
+        out_i[(size_t)q * k + i] = (int64_t)-1;
     }
 }
 

@@ -74,11 +74,21 @@ int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, unsigned lo
  *              bit 1 / bit 2: pass A fetches all / every other lightness record through the texture pipe (when !chroma_a)
  *   spltex   : 0..1 of pass B's inverse-gamma spline lookups go through the texture pipe
  *   fytex    : pass B takes the lightness half of Lab->RGB from a 256-entry table through the texture pipe
- *   chroma_a : the chroma is interpolated in pass A (one lattice visit per pixel) instead of pass B
+ *   chroma_a : the chroma is interpolated in pass A (one lattice visit per pixel) instead of pass B; -1 = automatic
+ *              (pass A, from the compressed record, whenever that is available: the default)
  *   occ_a    : resident CTAs per SM pass A is compiled for (4 or 6) */
 int gdt_debug_k1_config(int texab, int spltex, int fytex, int chroma_a, int occ_a);
 /* debug/test hook: force the image rows per pass-B CTA of K1 (1..64; 0 = the built-in wave-quantisation rule) */
 int gdt_debug_k1_rows(int rows_per_cta);
+/* debug/test hook: pass B of K1 with packed f32x2 arithmetic (two pixels per instruction) or scalar (0, the default);
+ * bit-identical results */
+int gdt_debug_k1_pack(int packed_f32x2);
+/* debug/test hook: pass B of K1 as one persistent 1024-thread CTA per SM with eight conflict-free shared-memory copies of
+ * the inverse-gamma spline (default 1) or as one 256-thread CTA per row band (0); bit-identical results */
+int gdt_debug_k1_persist(int persistent);
+/* debug/test hook: pass A interpolates from the compressed 32-byte lattice record (one sector gather per pixel; default 1
+ * when the table fits the format) or from the uncompressed 16 + 32-byte records (0); bit-identical results */
+int gdt_debug_k1_rec32(int compressed_record);
 /* debug/test hook: images per (pass A, pass B) launch pair of K1: 0 = the whole batch at once (default), -1 = sized so
  * that a chunk's 5 B/px scratch stays L2-resident between the passes, > 0 = forced */
 int gdt_debug_k1_chunk(int images_per_launch_pair);

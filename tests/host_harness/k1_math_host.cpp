@@ -7,7 +7,9 @@
 
 using namespace gdt;
 
-static std::vector<uint32_t> g_L, g_AB;
+static std::vector<uint32_t> g_L, g_AB, g_rec;
+static LabRecBias g_bias;
+static bool g_rec_ok = false;
 static Lab2RgbConst g_K;
 static float g_spline[4096], g_fy[1024];
 
@@ -15,6 +17,8 @@ extern "C" void k1h_init(const int16_t* lut33) {
     g_L.assign((size_t)kLabCells * 4, 0u);
     g_AB.assign((size_t)kLabCells * 8, 0u);
     pack_lab_lut(lut33, g_L.data(), g_AB.data());
+    g_rec.assign((size_t)kLabCells * 8, 0u);
+    g_rec_ok = pack_lab_rec32(lut33, g_rec.data(), g_bias);
     build_lab2rgb_const(g_K);
     build_inv_gamma_spline(g_spline);
     build_fy_table(g_K, g_fy);
@@ -58,6 +62,27 @@ extern "C" void k1h_stage_b(const uint8_t* dst, const uint32_t* ab, long n, int 
                             const float* std_, float* out_rgb) {
     float rstd[3];
     for (int c = 0; c < 3; ++c) { volatile float r = 1.0f / std_[c]; rstd[c] = r; }
+    if (use_table == 2 && !tail) {
+        // the packed two-pixel sequence (sm_100 f32x2 on the device), pixels (i, i + 1); an odd last pixel pairs with itself
+        for (long i = 0; i < n; i += 2) {
+            const long j = i + 1 < n ? i + 1 : i;
+            const f2 A = lab_chroma_fast2((int)(ab[i] & 0xffffu), (int)(ab[j] & 0xffffu));
+            const f2 B = lab_chroma_fast2((int)(ab[i] >> 16), (int)(ab[j] >> 16));
+            f2 y, fy, lin[3];
+            lab_fy_body2(lab_l_from_u8_fast2(dst[i], dst[j]), y, fy);
+            lab2lin_body2(fy, y, A, B, g_K, lin[0], lin[1], lin[2]);
+            for (int c = 0; c < 3; ++c) {
+                int i0, i1;
+                const f2 x = spline_index2(lin[c], i0, i1);
+                const float *s = &g_spline[i0 * 4], *t = &g_spline[i1 * 4];
+                const f2 e = spline_eval2(x, mk2(s[0], t[0]), mk2(s[1], t[1]), mk2(s[2], t[2]), mk2(s[3], t[3]));
+                const f2 o = normalize_px_fast2(e, mean[c], std_[c], rstd[c]);
+                out_rgb[i * 3 + c] = o.x;
+                out_rgb[j * 3 + c] = o.y;
+            }
+        }
+        return;
+    }
     for (long i = 0; i < n; ++i) {
         const float a2 = lab_chroma_fast((int)(ab[i] & 0xffffu)), b2 = lab_chroma_fast((int)(ab[i] >> 16));
         float lin[3];
@@ -74,4 +99,28 @@ extern "C" void k1h_stage_b(const uint8_t* dst, const uint32_t* ab, long n, int 
             out_rgb[i * 3 + c] = normalize_px_fast(e, mean[c], std_[c], rstd[c]);
         }
     }
+}
+
+// Compressed 32-byte lattice record against the uncompressed corner records: every cell, every (fr, fg, fb) in
+// [0, 16)^3 with stride `fstep` in each fraction. Returns the number of mismatching (cell, fraction, channel) triples,
+// -1 when the table did not fit the record format.
+extern "C" long k1h_rec32_check(int fstep, int* beta_out) {
+    if (!g_rec_ok) return -1;
+    for (int c = 0; c < 3; ++c) beta_out[c] = g_bias.beta[c];
+    long bad = 0;
+    for (int cell = 0; cell < kLabCells; ++cell) {
+        const uint32_t* wl = &g_L[(size_t)cell * 4];
+        const uint32_t* wc = &g_AB[(size_t)cell * 8];
+        const uint32_t* w = &g_rec[(size_t)cell * 8];
+        for (int fr = 0; fr < 16; fr += fstep)
+            for (int fg = 0; fg < 16; fg += fstep)
+                for (int fb = 0; fb < 16; fb += fstep) {
+                    int oL, oa, ob;
+                    lab_from_rec32(w, lab_weights(fr, fg, fb), g_bias, oL, oa, ob);
+                    bad += oL != lab_trilinear(wl[0], wl[1], wl[2], wl[3], fr, fg, fb);
+                    bad += oa != lab_trilinear(wc[0], wc[1], wc[2], wc[3], fr, fg, fb);
+                    bad += ob != lab_trilinear(wc[4], wc[5], wc[6], wc[7], fr, fg, fb);
+                }
+    }
+    return bad;
 }

@@ -153,11 +153,16 @@ def test_every_pipe_variant_is_bit_identical():
     img = synth_image(11, 96, 128, "smooth")
     ref = O.transform_u8(img, lut, MEAN, STD)
     try:
-        for chroma_a, texab, occ_a in ((1, 1, 4), (1, 0, 4), (1, 1, 6), (0, 0, 4), (0, 0, 6), (0, 2, 4), (0, 4, 4)):
-            for spltex in (0, 1):
-                for fytex in (0, 1):
-                    _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex, chroma_a, occ_a), "gdt_debug_k1_config")
-                    _assert_bits(_run_u8([img])[0], ref, "variant %d %d %d %d %d" % (texab, spltex, fytex, chroma_a, occ_a))
-                    _assert_bits(_run_u8([img[:61, :77]])[0], O.transform_u8(img[:61, :77], lut, MEAN, STD), "generic path")
+        for rec32, persist, pack in ((1, 1, 0), (0, 0, 0), (1, 0, 1), (1, 1, 1), (0, 1, 1)):
+            _lib.check(lib.gdt_debug_k1_rec32(rec32), "rec32")
+            _lib.check(lib.gdt_debug_k1_persist(persist), "persist")
+            _lib.check(lib.gdt_debug_k1_pack(pack), "pack")
+            for chroma_a, texab, occ_a in ((-1, 0, 4), (1, 1, 4), (1, 0, 4), (1, 1, 6), (0, 0, 4), (0, 0, 6), (0, 2, 4), (0, 4, 4)):
+                for spltex in (0, 1):
+                    for fytex in (0, 1):
+                        _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex, chroma_a, occ_a), "gdt_debug_k1_config")
+                        what = "variant %d %d %d %d %d rec32=%d persist=%d pack=%d" % (texab, spltex, fytex, chroma_a, occ_a, rec32, persist, pack)
+                        _assert_bits(_run_u8([img])[0], ref, what)
+                        _assert_bits(_run_u8([img[:61, :77]])[0], O.transform_u8(img[:61, :77], lut, MEAN, STD), "generic path, " + what)
     finally:
         _lib.k1_config_default()

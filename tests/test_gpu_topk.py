@@ -188,3 +188,37 @@ def test_unnormalised_and_tiny_magnitude_vectors():
         assert st[0] == 0
         os_, oi = R.topk(R.scores_exact(q, db), 100)
         _check_lists(s, i, os_, oi, q, db)
+
+
+def test_packed_merge_rank_path_and_sort_fallback():
+    """gdt_topk_merge_packed: sorted per-shard lists take the rank-by-binary-search path, anything else the bitonic sort;
+    both must equal a plain descending sort of the valid keys (short lists, padding, a duplicated entry, unsorted input)."""
+    from gandtr_b200 import _lib
+    rs = np.random.RandomState(5)
+    g, nq, k = 8, 37, 100
+    S = np.full((g, nq, k), -np.inf, np.float32)
+    I = np.full((g, nq, k), -1, np.int64)
+    for s in range(g):
+        for q in range(nq):
+            m = int(rs.randint(0, k + 1)) if q % 3 else k          # ragged valid counts, some lists empty
+            sc = np.sort(rs.standard_normal(m).astype(np.float32))[::-1]
+            if q == 5 and m > 10:
+                sc[3:9] = sc[3]                                     # equal scores inside one list: index breaks the tie
+            ids = s * 1000 + np.sort(rs.choice(1000, m, replace=False))
+            # order inside a list: score desc, index asc
+            o = np.lexsort((ids, -sc.astype(np.float64)))
+            S[s, q, :m], I[s, q, :m] = sc[o], ids[o]
+    S[1, 7], I[1, 7] = S[0, 7], I[0, 7]                             # the same list twice: duplicates across lists
+    unsorted_q = 11
+    S[2, unsorted_q, :k] = S[2, unsorted_q, :k][::-1].copy(); I[2, unsorted_q, :k] = I[2, unsorted_q, :k][::-1].copy()
+    St, It = torch.from_numpy(S).cuda(), torch.from_numpy(I).cuda()
+    ms, mi = _lib.topk_merge_packed(_lib.topk_pack(St, It))
+    ms, mi = ms.cpu().numpy(), mi.cpu().numpy()
+    for q in range(nq):
+        valid = I[:, q, :] >= 0
+        sc, ids = S[:, q, :][valid], I[:, q, :][valid]
+        o = np.lexsort((ids, -sc.astype(np.float64)))[:k]
+        n = len(o)
+        assert np.array_equal(mi[q, :n], ids[o]), q
+        assert np.array_equal(ms[q, :n], sc[o]), q
+        assert (mi[q, n:] == -1).all() and np.isneginf(ms[q, n:]).all(), q

@@ -78,9 +78,10 @@ def test_pass_a_f32_matches_oracle(lib):
         assert np.array_equal((o.astype(f32) * f32(1 / 64.0)) / f32(255), spc[:, ch])
 
 
-@pytest.mark.parametrize("use_table,tail,width", [(1, 0, 8), (0, 0, 8), (0, 1, 1)])
+@pytest.mark.parametrize("use_table,tail,width", [(1, 0, 8), (0, 0, 8), (0, 1, 1), (2, 0, 8)])
 def test_pass_b_matches_oracle(lib, use_table, tail, width):
-    """width 8 -> every pixel takes OpenCV's SIMD-body sequence, width 1 -> every pixel is a scalar-tail pixel."""
+    """width 8 -> every pixel takes OpenCV's SIMD-body sequence, width 1 -> every pixel is a scalar-tail pixel;
+    use_table 2 -> the packed two-pixel (f32x2) sequence the device runs by default."""
     rgb = _colours()
     n = (len(rgb) // 8) * 8
     rgb = rgb[:n]
@@ -98,3 +99,13 @@ def test_pass_b_matches_oracle(lib, use_table, tail, width):
     lab2 = spc * np.array([100.0, 255.0, 255.0], dtype=f32) - np.array([0, 128, 128], dtype=f32)
     ref = (O.lab2rgb_f32(lab2.reshape(-1, width, 3)).reshape(-1, 3) - mean) / std
     assert np.array_equal(out.view(np.uint32), ref.astype(f32).view(np.uint32))
+
+
+def test_compressed_lattice_record_equals_trilinear_exhaustively(lib):
+    """One 32-byte record per cell (base + first differences + mixed differences of the three channels) must reproduce
+    the 8-corner trilinear interpolation for every cell and every 4-bit fraction triple: 35 937 x 4 096 x 3 values."""
+    beta = (ctypes.c_int * 3)()
+    lib.k1h_rec32_check.restype = ctypes.c_long
+    bad = lib.k1h_rec32_check(1, beta)
+    assert bad == 0, "compressed lattice record: %d mismatches (bias %s)" % (bad, list(beta))
+    assert all(0 <= b < 128 for b in beta)

@@ -27,3 +27,14 @@ for r in rows[2:]:
     for k in WANT:
         if k in hdr:
             print("  %-82s %18s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+    # warp stall reasons (cycles a warp waits per issued instruction), largest first
+    stalls = []
+    for i, k in enumerate(hdr):
+        m = re.match(r"smsp__average_warps?_issue_stalled_(\w+)_per_issue_active", k)
+        if m and r[i] not in ("", "n/a"):
+            try:
+                stalls.append((float(r[i].replace(",", "")), m.group(1)))
+            except ValueError:
+                pass
+    for v, n in sorted(stalls, reverse=True)[:8]:
+        print("  stall %-40s %8.2f warps per issue" % (n, v))
