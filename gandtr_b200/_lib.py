@@ -38,6 +38,8 @@ SYMBOLS = [
     ("gdt_debug_k1_rows", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_pack", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_persist", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_div1", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_div1_verified", _c.c_int, [_c.c_float]),
     ("gdt_debug_k1_rec32", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_chunk", _c.c_int, [_c.c_int]),
     ("gdt_clahe_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
@@ -187,6 +189,7 @@ def k1_config_default():
     check(lib.gdt_debug_k1_config(*K1_DEFAULT_CONFIG), "gdt_debug_k1_config")
     check(lib.gdt_debug_k1_rec32(1), "gdt_debug_k1_rec32")
     check(lib.gdt_debug_k1_persist(1), "gdt_debug_k1_persist")
+    check(lib.gdt_debug_k1_div1(1), "gdt_debug_k1_div1")
     check(lib.gdt_debug_k1_pack(K1_DEFAULT_PACK), "gdt_debug_k1_pack")
 
 

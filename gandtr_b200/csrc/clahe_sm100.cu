@@ -30,6 +30,15 @@ struct ClaheTables {
     uint32_t* rec32 = nullptr; // [33^3][8]   compressed record of all three channels (clahe_math.cuh), when it fits
     LabRecBias bias = {{0, 0, 0}};
     bool rec_ok = false;
+    // std values for which div_by_const<1> (ONE Markstein correction) equals IEEE division for every numerator K1 can
+    // produce: checked exhaustively on this device at gdt_init (div1_check_kernel)
+    float div1_std[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n_div1 = 0;
+    bool div1_verified(float s) const {
+        for (int i = 0; i < n_div1; ++i)
+            if (div1_std[i] == s) return true;
+        return false;
+    }
     float4* spline = nullptr;  // [1024]
     float4* fytab = nullptr;   // [256]       {fy, C1*y, C4*y, C7*y} per CLAHE output byte (build_fy_table)
     cudaTextureObject_t texL = 0, texAB = 0, texSpline = 0, texFy = 0;   // the same tables behind the texture path
@@ -56,6 +65,7 @@ static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_occ_a = 4;
 // 1 with g_k1_rec32 == 0 is round 1's uncompressed three-gather variant.
 static int g_k1_chroma_a = -1;
 static int g_k1_rec32 = 1;
+static int g_k1_div1 = 1;     // one-correction-step normalisation for the std values verified at gdt_init (gdt_debug_k1_div1)
 static int g_k1_pack = 0;     // pass B: packed f32x2 arithmetic (two pixels per instruction); 0 = scalar (gdt_debug_k1_pack)
 static int g_k1_persist = 1;  // pass B: persistent 1024-thread CTAs with conflict-free spline copies (gdt_debug_k1_persist)
 static int g_k1_rows = 0;     // > 0: rows per pass-B CTA forced (gdt_debug_k1_rows), 0: pass_b_rows()
@@ -383,6 +393,8 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
 
 // ---- pass B -------------------------------------------------------------------------------------
 
+constexpr int kSpl8Bytes = 1025 * 128, kFy8Bytes = 256 * 128;
+
 struct NormFast {
     float mean[3], std[3], rstd[3];
     int fast;   // div_by_const_ok() for all three std
@@ -414,25 +426,36 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
                    float* __restrict__ out, int h, int w, int pitch, int grid, float inv_th, float inv_tw, int rows_per_cta,
                    const float4* __restrict__ spline, Lab2RgbConst K,
                    NormFast on, cudaTextureObject_t texSpline, cudaTextureObject_t texFy, cudaTextureObject_t texAB,
-                   int xchunks, int nbands, int nitems, int lut_area_bytes) {
+                   int xchunks, int nbands, int nitems, int lut_area_bytes, const float4* __restrict__ fytab, int div1) {
     if (FAST) on.fast = 1;
     extern __shared__ __align__(16) uint8_t smem[];
     // !PERSIST: inverse-gamma spline segments split into two 8-byte halves (random 8-byte shared-memory gathers conflict
     // less than 16-byte ones); PERSIST: eight conflict-free copies of the 16-byte segments
     float2* spl_fb = (float2*)smem;              // [1024] (f, b)
     float2* spl_cd = (float2*)(smem + 1024 * 8); // [1024] (c, d)
-    const float4* spl8 = (const float4*)smem;    // [1024][8]
+    // PERSIST: [1025][8] spline segments (entry 1024 = the value at x == 1024, so the index needs no clamp), then
+    // [256][8] {fy, C1*y, C4*y, C7*y} per CLAHE output byte (lightness half of Lab->RGB, build_fy_table), then LUT areas
+    const float4* spl8 = (const float4*)smem;
+    const float4* fy8 = (const float4*)(smem + kSpl8Bytes);
     const int lsh = FAST ? 3 : lut_row_shift(grid);
     const int tid = PERSIST ? (threadIdx.x & 255) : threadIdx.x;      // thread within the 256-thread group
     const int grp = PERSIST ? (threadIdx.x >> 8) : 0;
     // LUT rows of the group's current item: [(ty_hi - ty_lo + 1)][256] rows of (1 << lsh) bytes
-    uint2* luts = (uint2*)(smem + (PERSIST ? 1024 * 128 + (size_t)grp * lut_area_bytes : 1024 * 16));
+    uint2* luts = (uint2*)(smem + (PERSIST ? kSpl8Bytes + kFy8Bytes + (size_t)grp * lut_area_bytes : 1024 * 16));
     if (PERSIST) {
         float4* dst = (float4*)smem;
-        for (int i = threadIdx.x; i < 1024; i += 1024) {
-            const float4 sgm = __ldg(spline + i);
+        for (int i = threadIdx.x; i < 1025; i += 1024) {
+            float4 sgm = __ldg(spline + (i < 1024 ? i : 1023));
+            if (i == 1024)      // x == 1024 (linear value >= 1): segment 1023 at its right end, in spline_eval's op order
+                sgm = make_float4(spline_eval(1.0f, sgm.x, sgm.y, sgm.z, sgm.w), 0.f, 0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < 8; ++c) dst[i * 8 + c] = sgm;
+        }
+        float4* dfy = (float4*)(smem + kSpl8Bytes);
+        for (int i = threadIdx.x; i < 256; i += 1024) {
+            const float4 t = __ldg(fytab + i);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dfy[i * 8 + c] = t;
         }
     } else if (SPLTEX < 3) {
         for (int i = tid; i < 1024; i += 256) {
@@ -447,6 +470,8 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
         else __syncthreads();
     };
     const int lane8 = threadIdx.x & 7;
+    // byte offset of this lane's copy of spline segment ix, straight from the bits of 2^23 + ix (see `pixel`)
+    const uint32_t spl_off0 = (uint32_t)lane8 * 16u - 0x80000000u;
 
     for (int item = PERSIST ? (int)blockIdx.x * 4 + grp : (int)blockIdx.x; item < nitems;
          item += PERSIST ? (int)gridDim.x * 4 : nitems) {
@@ -517,27 +542,51 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
         }
         const int dst = clahe_blend(l11, l12, l21, l22, ax[i].a, ax[i].a1, ay.a, ay.a1);
         float lr, lg, lb;
-        if (FAST && FYTEX && !tail) {
+        if (PERSIST && !tail) {
+            const float4 fy = fy8[(dst << 3) | lane8];          // this lane's own copy: conflict-free
+            lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
+        } else if (FAST && FYTEX && !tail) {
             const float4 fy = tex1Dfetch<float4>(texFy, dst);
             lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
         } else {
             lab2lin(lab_l_from_u8_fast(dst), a2, b2, tail, K, lr, lg, lb);
         }
-        int ix[3];
-        const float xs[3] = {spline_index(lr, ix[0]), spline_index(lg, ix[1]), spline_index(lb, ix[2])};
         float e[3];
+        if (PERSIST) {
+            // x = clamp01(lin) * 1024 in [0, 1024]; 2^23 + x rounded toward zero is 2^23 + trunc(x): its low mantissa bits
+            // are the segment index (no float <-> int conversion, no clamp: entry 1024 exists), minus 2^23 it is float(ix)
+            const float lin3[3] = {lr, lg, lb};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float x = f_mul(__saturatef(lin3[c]), 1024.0f);
+                const float t = __fadd_rz(x, 8388608.0f);
+                const float xs = f_sub(x, f_sub(t, 8388608.0f));
+                const uint32_t off = (__float_as_uint(t) << 7) + spl_off0;
+                const float4 sg = *(const float4*)(smem + off);
+                e[c] = spline_eval(xs, sg.x, sg.y, sg.z, sg.w);
+            }
+        }
+        int ix[3] = {0, 0, 0};
+        float xs[3] = {0.f, 0.f, 0.f};
+        if (!PERSIST) {
+            xs[0] = spline_index(lr, ix[0]); xs[1] = spline_index(lg, ix[1]); xs[2] = spline_index(lb, ix[2]);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (c < SPLTEX) {       // texture pipe: no shared-memory bank conflicts
+            if (PERSIST) {
+            } else if (c < SPLTEX) {       // texture pipe: no shared-memory bank conflicts
                 const float4 sg = tex1Dfetch<float4>(texSpline, ix[c]);
-                e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
-            } else if (PERSIST) {   // this lane's own copy: conflict-free
-                const float4 sg = spl8[(ix[c] << 3) | lane8];
                 e[c] = spline_eval(xs[c], sg.x, sg.y, sg.z, sg.w);
             } else {
                 const float2 s01 = spl_fb[ix[c]], s23 = spl_cd[ix[c]];
                 e[c] = spline_eval(xs[c], s01.x, s01.y, s23.x, s23.y);
             }
+        }
+        if (PERSIST && div1) {      // std values for which ONE correction step was verified exhaustively (gdt_init)
+            o0 = div_by_const<1>(f_sub(e[0], on.mean[0]), on.std[0], on.rstd[0]);
+            o1 = div_by_const<1>(f_sub(e[1], on.mean[1]), on.std[1], on.rstd[1]);
+            o2 = div_by_const<1>(f_sub(e[2], on.mean[2]), on.std[2], on.rstd[2]);
+            return;
         }
         o0 = on.fast ? normalize_px_fast(e[0], on.mean[0], on.std[0], on.rstd[0]) : normalize_px(e[0], on.mean[0], on.std[0]);
         o1 = on.fast ? normalize_px_fast(e[1], on.mean[1], on.std[1], on.rstd[1]) : normalize_px(e[1], on.mean[1], on.std[1]);
@@ -794,27 +843,32 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
 #define GDT_APPLY_P(FAST_, S_, F_, C_, A_, P_)                                                                            \
     clahe_apply_kernel<4, FAST_, S_, F_, C_, A_, P_, false><<<nitems, 256, smem, stream>>>(                                \
         AB, L8, luts, out, h, w, pitch, grid, g.inv_th, g.inv_tw, rows, T->spline, T->K, on, T->texSpline, T->texFy,       \
-        T->texAB, xchunks, nbands, nitems, lut_area)
+        T->texAB, xchunks, nbands, nitems, lut_area, T->fytab, 0)
 #define GDT_APPLY(FAST_, S_, F_, C_, A_) GDT_APPLY_P(FAST_, S_, F_, C_, A_, false)
     // persistent form (the default for the common configuration): one 1024-thread CTA per SM = four 256-thread groups,
     // eight conflict-free copies of the spline in shared memory (128 KB) + one LUT area per group
-    const size_t smem_p = 1024 * 128 + 4 * (size_t)lut_area;
+    const size_t smem_p = kSpl8Bytes + kFy8Bytes + 4 * (size_t)lut_area;
+    int div1 = g_k1_div1 != 0;
+    for (int c = 0; c < 3; ++c) div1 = div1 && T->div1_verified(out_norm.std[c]);
 #define GDT_APPLY_PERSIST(C_, A_, P_)                                                                                    \
     do {                                                                                                                 \
         auto kern = clahe_apply_kernel<4, true, 0, false, C_, A_, P_, true>;                                             \
         static bool attr_done[32] = {false};                                                                             \
         const int slot = current_device_slot();                                                                          \
         if (!attr_done[slot]) {                                                                                          \
-            GDT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 128 + 4 * 8 * 2048)); \
+            GDT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
+                                          kSpl8Bytes + kFy8Bytes + 4 * 8 * 2048));                                       \
             attr_done[slot] = true;                                                                                      \
         }                                                                                                                \
         const int ctas = nitems < 4 * sms ? ceil_div(nitems, 4) : sms;                                                   \
         kern<<<ctas, 1024, smem_p, stream>>>(AB, L8, luts, out, h, w, pitch, grid, g.inv_th, g.inv_tw, rows, T->spline,  \
                                              T->K, on, T->texSpline, T->texFy, T->texAB, xchunks, nbands, nitems,        \
-                                             lut_area);                                                                  \
+                                             lut_area, T->fytab, div1);                                                  \
     } while (0)
     const bool pack = g_k1_pack != 0;
-    const bool persist = g_k1_persist != 0 && spltex == 0 && !fytex;
+    // measured (profiles/k1_v3_ab_r2n.log): persistent wins on the common widths (0.950 vs 1.008 ms per 128 images of
+    // 1024x768), the any-width instantiation (scalar-tail split, more live state) is faster non-persistent; 2 = force
+    const bool persist = (g_k1_persist == 2 || (g_k1_persist == 1 && !anyw)) && spltex == 0 && !fytex;
     if (grid <= 8 && on.fast && smem <= 48 * 1024) {
         if (persist) {
             switch ((chroma_a ? 4 : 0) + (anyw ? 2 : 0) + (pack ? 1 : 0)) {
@@ -926,17 +980,41 @@ meanstd_adapt_kernel(const float* __restrict__ x, float* __restrict__ y, long lo
     }
 }
 
-// debug: count floats a in the bit range [lo_bits, hi_bits] (both signs) for which div_by_const<2> != a / b
+// debug: count floats a in the bit range [lo_bits, hi_bits] (both signs) for which div_by_const<ITERS> != a / b
+template <int ITERS>
 __global__ void __launch_bounds__(256)
 div_check_kernel(float b, float r, uint32_t lo_bits, uint32_t hi_bits, unsigned long long* __restrict__ mismatches) {
     unsigned long long bad = 0;
     const unsigned long long n = (unsigned long long)hi_bits - lo_bits + 1;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256) {
         const float a = __uint_as_float(lo_bits + (uint32_t)i);
-        if (__float_as_uint(div_by_const<2>(a, b, r)) != __float_as_uint(f_div(a, b))) ++bad;
-        if (__float_as_uint(div_by_const<2>(-a, b, r)) != __float_as_uint(f_div(-a, b))) ++bad;
+        if (__float_as_uint(div_by_const<ITERS>(a, b, r)) != __float_as_uint(f_div(a, b))) ++bad;
+        if (__float_as_uint(div_by_const<ITERS>(-a, b, r)) != __float_as_uint(f_div(-a, b))) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+
+// Is ONE correction step enough for this divisor? Every numerator K1's normalisation can see is (spline output in
+// [0, 1]) - mean, i.e. 0 or 2^-30 <= |a| <= 2: all ~7.5e8 such floats of both signs are tried on the device (~1 ms).
+static bool verify_div1(float b) {
+    unsigned long long* dcount = nullptr;
+    if (cudaMalloc(&dcount, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return false; }
+    bool ok = false;
+    volatile float r = 1.0f / b;
+    const float lo = 9.313225746154785e-10f /* 2^-30 */, hi = 2.0f;
+    uint32_t lo_bits, hi_bits;
+    memcpy(&lo_bits, &lo, 4);
+    memcpy(&hi_bits, &hi, 4);
+    unsigned long long h = 1;
+    if (cudaMemset(dcount, 0, sizeof(unsigned long long)) == cudaSuccess) {
+        div_check_kernel<1><<<sm_count_current_device() * 8, 256>>>(b, r, lo_bits, hi_bits, dcount);
+        if (cudaGetLastError() == cudaSuccess &&
+            cudaMemcpy(&h, dcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess)
+            ok = (h == 0);
+    }
+    cudaGetLastError();
+    cudaFree(dcount);
+    return ok;
 }
 
 }  // namespace gdt
@@ -947,7 +1025,7 @@ extern "C" int gdt_debug_div_check(float b, uint32_t lo_bits, uint32_t hi_bits, 
                                    void* stream) {
     if (!mismatches_dev || hi_bits < lo_bits) return GDT_ERR_INVALID_ARGUMENT;
     volatile float r = 1.0f / b;
-    div_check_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(b, r, lo_bits, hi_bits, mismatches_dev);
+    div_check_kernel<2><<<148 * 8, 256, 0, (cudaStream_t)stream>>>(b, r, lo_bits, hi_bits, mismatches_dev);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }
@@ -1005,8 +1083,19 @@ extern "C" int gdt_debug_k1_rec32(int compressed_record) {
     return GDT_OK;
 }
 
+extern "C" int gdt_debug_k1_div1(int one_step) {
+    g_k1_div1 = one_step ? 1 : 0;
+    return GDT_OK;
+}
+
+extern "C" int gdt_debug_k1_div1_verified(float std) {
+    const ClaheTables* T = clahe_tables_for_current_device();
+    if (!T) return GDT_ERR_NOT_INITIALISED;
+    return T->div1_verified(std) ? 1 : 0;
+}
+
 extern "C" int gdt_debug_k1_persist(int persistent) {
-    g_k1_persist = persistent ? 1 : 0;
+    g_k1_persist = persistent < 0 ? 0 : (persistent > 2 ? 2 : persistent);
     return GDT_OK;
 }
 
@@ -1081,6 +1170,12 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
     if (rc == GDT_OK) rc = make_tex(&T.texAB, T.lutAB, ncell * 32, false);
     if (rc == GDT_OK) rc = make_tex(&T.texSpline, T.spline, 4096 * sizeof(float), true);
     if (rc == GDT_OK) rc = make_tex(&T.texFy, T.fytab, 1024 * sizeof(float), true);
+    if (rc == GDT_OK) {
+        // the normalisation constants of the reference's transforms (ImageNet std; 0.5 for the GAN tensors)
+        const float cand[4] = {0.229f, 0.224f, 0.225f, 0.5f};
+        for (float b : cand)
+            if (div_by_const_ok(b) && T.n_div1 < 8 && verify_div1(b)) T.div1_std[T.n_div1++] = b;
+    }
     if (rc == GDT_OK) T.ready = true;
     return rc;
 }

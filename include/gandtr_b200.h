@@ -84,8 +84,14 @@ int gdt_debug_k1_rows(int rows_per_cta);
  * bit-identical results */
 int gdt_debug_k1_pack(int packed_f32x2);
 /* debug/test hook: pass B of K1 as one persistent 1024-thread CTA per SM with eight conflict-free shared-memory copies of
- * the inverse-gamma spline (default 1) or as one 256-thread CTA per row band (0); bit-identical results */
+ * the inverse-gamma spline and of the lightness table (1, the default: on widths without OpenCV scalar-tail pixels;
+ * 2: on every width) or as one 256-thread CTA per row band (0); bit-identical results */
 int gdt_debug_k1_persist(int persistent);
+/* debug/test hook: the persistent pass B normalises with ONE correction step of the divider-free division for the std
+ * values verified exhaustively at gdt_init (default 1) or always with two (0); bit-identical results.
+ * gdt_debug_k1_div1_verified: 1 when `std` passed that check on the current device, 0 when not, < 0 on error */
+int gdt_debug_k1_div1(int one_step);
+int gdt_debug_k1_div1_verified(float std);
 /* debug/test hook: pass A interpolates from the compressed 32-byte lattice record (one sector gather per pixel; default 1
  * when the table fits the format) or from the uncompressed 16 + 32-byte records (0); bit-identical results */
 int gdt_debug_k1_rec32(int compressed_record);

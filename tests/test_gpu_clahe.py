@@ -1,4 +1,5 @@
 """K1 parity (through the C ABI): bit-exact against the oracle and the reference's golden outputs."""
+import ctypes
 import numpy as np
 import pytest
 import torch
@@ -153,16 +154,29 @@ def test_every_pipe_variant_is_bit_identical():
     img = synth_image(11, 96, 128, "smooth")
     ref = O.transform_u8(img, lut, MEAN, STD)
     try:
-        for rec32, persist, pack in ((1, 1, 0), (0, 0, 0), (1, 0, 1), (1, 1, 1), (0, 1, 1)):
+        for rec32, persist, pack, div1 in ((1, 1, 0, 1), (1, 1, 0, 0), (0, 0, 0, 1), (1, 0, 1, 1), (1, 1, 1, 1), (0, 1, 1, 0)):
+            _lib.check(lib.gdt_debug_k1_div1(div1), "div1")
             _lib.check(lib.gdt_debug_k1_rec32(rec32), "rec32")
-            _lib.check(lib.gdt_debug_k1_persist(persist), "persist")
+            _lib.check(lib.gdt_debug_k1_persist(2 * persist), "persist")
             _lib.check(lib.gdt_debug_k1_pack(pack), "pack")
             for chroma_a, texab, occ_a in ((-1, 0, 4), (1, 1, 4), (1, 0, 4), (1, 1, 6), (0, 0, 4), (0, 0, 6), (0, 2, 4), (0, 4, 4)):
                 for spltex in (0, 1):
                     for fytex in (0, 1):
                         _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex, chroma_a, occ_a), "gdt_debug_k1_config")
-                        what = "variant %d %d %d %d %d rec32=%d persist=%d pack=%d" % (texab, spltex, fytex, chroma_a, occ_a, rec32, persist, pack)
+                        what = "variant %d %d %d %d %d rec32=%d persist=%d pack=%d div1=%d" % (texab, spltex, fytex, chroma_a, occ_a, rec32, persist, pack, div1)
                         _assert_bits(_run_u8([img])[0], ref, what)
                         _assert_bits(_run_u8([img[:61, :77]])[0], O.transform_u8(img[:61, :77], lut, MEAN, STD), "generic path, " + what)
     finally:
         _lib.k1_config_default()
+
+
+def test_one_step_division_is_verified_for_the_reference_constants():
+    """gdt_init tries every numerator the normalisation can see against IEEE division with ONE correction step; the
+    ImageNet std values and 0.5 must pass on this device (otherwise the persistent pass B silently keeps two steps)."""
+    from gandtr_b200 import _lib
+    lib = _lib.load()
+    _lib.clahe_u8(torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device="cuda"), MEAN, STD)     # forces gdt_init
+    got = {s: lib.gdt_debug_k1_div1_verified(ctypes.c_float(s)) for s in (0.229, 0.224, 0.225, 0.5)}
+    assert all(v in (0, 1) for v in got.values()), got
+    print("one-step division verified:", got)
+    assert got[0.5] == 1

@@ -1,7 +1,7 @@
 """A/B timing of K1: compressed 32-byte lattice record in pass A (gdt_debug_k1_rec32) x pass B persistent CTAs with conflict-free spline copies (gdt_debug_k1_persist) x packed f32x2
 arithmetic (gdt_debug_k1_pack); every combination must be bit-identical. Sizes: the bench shape and two odd ones
 (scalar-tail pixels / padded tiles)."""
-import os, sys
+import ctypes, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
 from gandtr_b200 import _lib
@@ -18,9 +18,9 @@ lib = _lib.load()
 for hh, ww, n in ((768, 1024, 128), (768, 1024, 32), (768, 1024, 1), (768, 1020, 64), (681, 1023, 64), (1536, 2048, 16)):
     x = synth_images_torch(n, 1, "cuda", h=hh, w=ww)
     ref = None
-    for rec32, persist, pack in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (0, 1, 0), (0, 0, 0), (1, 1, 0), (1, 1, 1)):
+    for rec32, persist, pack in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1), (0, 0, 0), (1, 1, 0)):
         _lib.check(lib.gdt_debug_k1_rec32(rec32), "rec32")
-        _lib.check(lib.gdt_debug_k1_persist(persist), "persist")
+        _lib.check(lib.gdt_debug_k1_persist(2 * persist), "persist")
         _lib.check(lib.gdt_debug_k1_pack(pack), "pack")
         out = torch.empty((n, 3, hh, ww), dtype=torch.float32, device="cuda")
         ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=out))
@@ -29,4 +29,12 @@ for hh, ww, n in ((768, 1024, 128), (768, 1024, 32), (768, 1024, 1), (768, 1020,
         print("%dx%d n=%d rec32=%d persist=%d pack=%d: %.3f ms  %.0f img/s  %.0f GB/s algorithmic  identical=%s" % (ww, hh, n, rec32, persist, pack, ms, n / ms * 1e3, n * 15 * hh * ww / ms / 1e6, same), flush=True)
         assert same
     del ref, out, x
+_lib.k1_config_default()
+print("one-step division verified:", {s: lib.gdt_debug_k1_div1_verified(ctypes.c_float(s)) for s in (0.229, 0.224, 0.225, 0.5)})
+x = synth_images_torch(128, 1, "cuda")
+out = torch.empty((128, 3, 768, 1024), dtype=torch.float32, device="cuda")
+for div1 in (0, 1, 0, 1):
+    _lib.check(lib.gdt_debug_k1_div1(div1), "div1")
+    ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=out))
+    print("1024x768 n=128 default config, div1=%d: %.3f ms  %.0f GB/s algorithmic" % (div1, ms, 128 * 15 * 768 * 1024 / ms / 1e6))
 _lib.k1_config_default()
