@@ -33,9 +33,9 @@ MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 K1_BYTES_PER_IMG = 15 * H * W
 K2_BYTES_PER_IMG = 4 * C_FEAT * FH * FW + 4 * C_FEAT
 # measured DRAM traffic of K1 per image (dram__bytes_read.sum + dram__bytes_write.sum of clahe_hist + clahe_apply, ncu
-# --set full capture profiles/ncu_k1_r1q.txt at 32 images: 76.1 + 75.0 + 127.7 + 243.9 MB) -- 1.38x the algorithmic
-# bytes: the 5 B/px scratch (lightness byte + cell code) is written by pass A and read by pass B
-K1_TRAFFIC_PER_IMG = (76.089600e6 + 74.962944e6 + 127.656448e6 + 243.922176e6) / 32
+# --set full capture profiles/ncu_k1_v3_r2m.txt at 32 images: 76.7 + 75.1 + 126.4 + 244.0 MB) -- 1.38x the algorithmic
+# bytes: the 5 B/px scratch (lightness byte + Q14 chroma pair) is written by pass A and read by pass B
+K1_TRAFFIC_PER_IMG = (76.685568e6 + 75.133184e6 + 126.411264e6 + 243.973376e6) / 32      # ncu r2m, 32 images
 
 
 def parse():
@@ -460,11 +460,12 @@ def main():
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "K1 clahe_hist_kernel + clahe_apply_kernel (one gdt_clahe_u8 call)", "bound": "hbm",
                      "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r1q, per image x batch",
+                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r2m (dram read + write of both passes), per image x batch",
                      "ms_per_launch_pair": k1_ms,
-                     "note": "nominal bound; ncu shows issue (74 %), the LSU pipe (73 %: shared-memory spline / LUT lookups) and the "
-                             "texture pipe (65 %: scattered lattice records) as the limiters of pass B and the LSU pipe (79 %: "
-                             "scattered lattice records) of pass A; DRAM at ~22 % (profiles/ncu_k1_r1q.txt)",
+                     "note": "nominal bound; ncu (profiles/ncu_k1_v3_r2m.txt): pass A issue 73 % / ALU pipe 70 % / LSU 77 % (one "
+                             "32-byte compressed lattice record per pixel, 139 instructions per pixel), pass B issue 82 % (166 "
+                             "instructions per pixel of bit-exact OpenCV float arithmetic; shared-memory lookups conflict-free); "
+                             "DRAM at 14 - 31 %",
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
                         "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
