@@ -327,6 +327,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     from gandtr_b200 import _lib
@@ -539,6 +540,42 @@ def main():
                          "bound": "tensor", "achieved": flops / world / (r_ms / rK * 1e-3) / 1e12, "peak": tc_peak,
                          "unit": "TFLOP/s", "peak_source": tc_src + " bf16-GEMM burst (fp16 runs at the same tensor rate)", "note": "per GPU; algorithmic flops 2*nq*ndb*d"}}
         block["roofline"]["frac"] = block["roofline"]["achieved"] / tc_peak
+        if world == 1 and db_dim == 2048 and db_rows >= 1_000_000:
+            # K4 at database scale (70 queries x 1 M x 2048, revisited-style easy / hard / junk lists). Two checks, both
+            # outside the timed region: (1) K3 x K4: the rows the search ranks 0..99 must be given exactly the positions
+            # 0..99 by K4's rank counts (independent kernels, full database); (2) the fp32-with-bound counting path must
+            # give the APs of the same kernel forced to re-score every pair exactly (fp64-accumulated).
+            from gandtr_b200.retrieval import PreparedGroundTruth, compute_map_and_print
+            nq4 = 70
+            q4 = q[:nq4].contiguous()
+            pos = index.positions(q4, last["i"][:nq4].contiguous())
+            k34_bad = int((pos != torch.arange(TOPK, device=dev).view(1, -1)).sum())
+            rs4 = np.random.RandomState(11)
+            gnd4 = []
+            for j in range(nq4):
+                ids = rs4.choice(db_rows, 90, replace=False)
+                top = last["i"][j, :40].cpu().numpy()        # true neighbours among the positives, as real lists have
+                gnd4.append({"easy": np.concatenate([top[:10], ids[:20]]), "hard": np.concatenate([top[10:30], ids[20:60]]),
+                             "junk": np.concatenate([top[30:40], ids[60:90]])})
+            prep4 = PreparedGroundTruth("roxford5k", gnd4, index.n_total, dev)
+            res4 = {}
+            def map4():
+                res4["avg"], res4["aps"] = compute_map_and_print("roxford5k", index, q4, prep4, printer=lambda *_: None)
+            k4_ms, w = timed(map4, 5, 2)
+            windows.append(w)
+            fast_aps = {k: np.array(v, copy=True) for k, v in res4["aps"].items()}
+            _lib.check(_lib.load().gdt_debug_k4_exact(1), "gdt_debug_k4_exact")
+            try:
+                map4()
+            finally:
+                _lib.check(_lib.load().gdt_debug_k4_exact(0), "gdt_debug_k4_exact")
+            ap_bad = sum(int((np.asarray(fast_aps[k]).view(np.uint64) != np.asarray(res4["aps"][k]).view(np.uint64)).sum()) for k in fast_aps)
+            block["map_eval_1M"] = {"queries": nq4, "db_rows": db_rows, "dim": db_dim, "map_easy_medium_hard_ms": k4_ms / 5,
+                                    "map": {k: round(float(v), 6) for k, v in res4["avg"].items()},
+                                    "k3_vs_k4_position_mismatches": k34_bad,
+                                    "ap_bits_differing_from_forced_exact_rescoring": ap_bad}
+            if k34_bad or ap_bad:
+                raise SystemExit("bench.py: K4 at 1 M rows disagrees (K3 x K4 positions %d, AP vs exact %d)" % (k34_bad, ap_bad))
         if mism:
             raise SystemExit("bench.py: the timed search disagrees with the exact kernel on %d of %d spot queries" % (mism, sel.numel()))
         del index

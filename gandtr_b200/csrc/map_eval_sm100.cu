@@ -188,10 +188,12 @@ rank_counts_kernel(const float* __restrict__ q, const float* __restrict__ db, in
             const float tol = cd * qnorm[my_q] * (sqrtf(xn) * 1.0001f);
             // keys of the interval ends: (s + tol, best index) is the largest key the row can have, (s - tol, worst
             // index) the smallest; m(K) = number of probe keys >= K is non-increasing in K
+            // ONE search: m_lo counts the probe keys >= the largest key the row can have; the row is ambiguous iff the
+            // next probe key (the largest one below that) is still >= the smallest key the row can have
             const int m_lo = slots_not_after(sk, pp, rank_key(__fadd_ru(s, tol), 0u));
-            const int m_hi = slots_not_after(sk, pp, rank_key(__fadd_rd(s, -tol), 0xffffffffu));
+            const uint64_t k_min = rank_key(__fadd_rd(s, -tol), 0xffffffffu);
             m = m_lo;
-            need_exact = (m_lo != m_hi) || force_exact || !(tol >= 0.f);
+            need_exact = (m_lo < pp && sk[m_lo] >= k_min) || force_exact || !(tol >= 0.f);
         }
         unsigned todo = __ballot_sync(0xffffffffu, need_exact);
         while (todo) {                                    // rare: the whole warp re-scores one pair exactly

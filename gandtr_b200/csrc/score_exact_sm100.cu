@@ -228,9 +228,14 @@ topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, 
     __syncthreads();
     const bool overflow = s_overflow != 0;
     bool unsorted = false;
-    for (int i = tid; i < total; i += 256) {
-        const int j = i % k;
-        if (j + 1 < k && keys[i] < keys[i + 1]) unsorted = true;
+    {
+        int s = tid / k, j = tid - s * k;             // (list, position) of entry i, advanced incrementally
+        const int ds = 256 / k, dj = 256 - ds * k;
+        for (int i = tid; i < total; i += 256) {
+            if (j + 1 < k && keys[i] < keys[i + 1]) unsorted = true;
+            s += ds; j += dj;
+            if (j >= k) { j -= k; ++s; }
+        }
     }
     if (__syncthreads_or(unsorted || overflow)) {
         block_bitonic_sort_desc(keys, np, tid, 256);
@@ -244,29 +249,38 @@ topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, 
         }
         return;
     }
+    // Entry j of a list has at least j entries before it: only the first k positions of the merged order are wanted,
+    // so the walk over the other lists stops as soon as the rank reaches k (most entries stop after one or two lists).
     int nvalid = 0;
-    for (int i = tid; i < total; i += 256) {
-        const uint64_t key = keys[i];
-        if (key == 0ull) continue;
-        ++nvalid;
-        const int s = i / k;
-        int rank = i - s * k;
-        for (int t = 0; t < g; ++t) {
-            if (t == s) continue;
-            const uint64_t* lst = keys + t * k;
-            // number of entries of list t that sort before `key`: larger keys, and equal ones in earlier lists (a caller
-            // may hand in the same entry twice; the merge stays a stable one)
-            int lo = 0, hi = k;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const uint64_t m = lst[mid];
-                if (m > key || (t < s && m == key)) lo = mid + 1; else hi = mid;
+    {
+        int s = tid / k, j = tid - s * k;
+        const int ds = 256 / k, dj = 256 - ds * k;
+        for (int i = tid; i < total; i += 256) {
+            const uint64_t key = keys[i];
+            if (key != 0ull) {
+                ++nvalid;
+                int rank = j;
+                for (int t = 0; t < g && rank < k; ++t) {
+                    if (t == s) continue;
+                    const uint64_t* lst = keys + t * k;
+                    // number of entries of list t that sort before `key`: larger keys, and equal ones in earlier lists
+                    // (a caller may hand in the same entry twice; the merge stays a stable one). Entries at or beyond
+                    // position k - rank cannot change the outcome: the search is confined to the first k - rank.
+                    int lo = 0, hi = k - rank;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const uint64_t m = lst[mid];
+                        if (m > key || (t < s && m == key)) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo;
+                }
+                if (rank < k) {
+                    out_s[(size_t)q * k + rank] = key_score(key);
+                    out_i[(size_t)q * k + rank] = (int64_t)key_index(key);
+                }
             }
-            rank += lo;
-        }
-        if (rank < k) {
-            out_s[(size_t)q * k + rank] = key_score(key);
-            out_i[(size_t)q * k + rank] = (int64_t)key_index(key);
+            s += ds; j += dj;
+            if (j >= k) { j -= k; ++s; }
         }
     }
     // fewer than k valid entries in total: pad the tail

@@ -66,6 +66,7 @@ __host__ __device__ inline int seed_tiles_for(int k) {
     int t = (16 * k + kBlockN - 1) / kBlockN;
     return t < 32 ? 32 : t;
 }
+constexpr int kSeedDiv = 0;      // see topk_plan
 __host__ __device__ inline int stripe_capacity(int k) {
     int c = 8 * k;
     if (c < 1024) c = 1024;
@@ -658,6 +659,23 @@ static TopkPlan topk_plan(int nq, long long ndb, int d, int k) {
     L.n_qtiles = ceil_div(nq, kBlockM);
     L.n_dtiles = (int)ceil_div_ll(ndb, kBlockN);
     L.seed_tiles = seed_tiles_for(k) < L.n_dtiles ? seed_tiles_for(k) : L.n_dtiles;
+    {
+        // Small shards (a row-sharded database on many GPUs): the cold seed pass runs at about half the rate of the main
+        // pass, so it is capped at 1 / kSeedDiv of the shard's tiles (never below 8 tiles = 2048 rows); the main pass
+        // starts from a looser threshold and tightens it from the running histogram. GDT_DEBUG_K3_SEED_DIV overrides
+        // (0 = no cap), for A/B timing.
+        static int div = -1;
+        if (div < 0) {
+            const char* e = getenv("GDT_DEBUG_K3_SEED_DIV");
+            div = e ? atoi(e) : kSeedDiv;
+            if (div < 0) div = 0;
+        }
+        if (div > 0) {
+            int cap = L.n_dtiles / div;
+            if (cap < 8) cap = 8;
+            if (cap < L.seed_tiles) L.seed_tiles = cap;
+        }
+    }
     const int sms = sm_count_current_device();
     L.cluster = topk_cluster_size(L.n_qtiles);
     L.n_qgroups = ceil_div(L.n_qtiles, L.cluster);
