@@ -75,6 +75,8 @@ SYMBOLS = [
     ("gdt_topk_merge", _c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
     ("gdt_topk_pack", _c.c_int, [_P, _P, _c.c_longlong, _P, _P]),
     ("gdt_topk_merge_packed", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P]),
+    ("gdt_topk_merge_packed_keys", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    ("gdt_topk_unpack", _c.c_int, [_P, _c.c_longlong, _P, _P, _P]),
     ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
     ("gdt_rank_counts_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int]),
     ("gdt_debug_k4_exact", _c.c_int, [_c.c_int]),
@@ -104,7 +106,7 @@ launch_count = 0  # number of library compute calls made by this process (bench.
 
 # kernels launched by each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"clahe": 2, "meanstd_adapt": 1, "gem": 2, "gem_whiten": 4, "gem_pool": 1, "l2n_rows": 1, "desc_post": 1, "desc_post_whiten": 3, "db_prepare": 2, "score_topk_exact": 2,
-                    "topk_merge": 1, "topk_pack": 1, "probe_scores": 1, "rank_counts": 3, "map_eval": 1, "resize": 2}
+                    "topk_merge": 1, "topk_pack": 1, "topk_unpack": 1, "probe_scores": 1, "rank_counts": 3, "map_eval": 1, "resize": 2}
 
 
 class GdtError(RuntimeError):
@@ -610,6 +612,28 @@ def topk_merge_packed(keys):
         check(load().gdt_topk_merge_packed(_ptr(keys), g, nq, k, _ptr(out_s), _ptr(out_i), _stream()), "gdt_topk_merge_packed")
     _count("topk_merge")
     return out_s, out_i
+
+
+def topk_merge_packed_keys(keys):
+    """[g, nq, k] packed per-shard lists -> merged packed keys [nq, k] (the query-sharded merge's intermediate form)."""
+    _require(keys, torch.int64, "keys")
+    g, nq, k = keys.shape
+    out = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        check(load().gdt_topk_merge_packed_keys(_ptr(keys), g, nq, k, _ptr(out), _stream()), "gdt_topk_merge_packed_keys")
+    _count("topk_merge")
+    return out
+
+
+def topk_unpack(keys):
+    """packed keys of any shape -> (scores, idx): padding -> (-inf, -1), an overflow marker -> (-inf, -2)."""
+    _require(keys, torch.int64, "keys")
+    s = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    i = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        check(load().gdt_topk_unpack(_ptr(keys), keys.numel(), _ptr(s), _ptr(i), _stream()), "gdt_topk_unpack")
+    _count("topk_unpack")
+    return s, i
 
 
 # ---- K4 ----------------------------------------------------------------------------------------------

@@ -206,7 +206,7 @@ topk_pack_kernel(const float* __restrict__ scores, const int64_t* __restrict__ i
 // bitonic sort instead. The merged order is the same either way.
 __global__ void __launch_bounds__(256)
 topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, int np, float* __restrict__ out_s,
-                         int64_t* __restrict__ out_i) {
+                         int64_t* __restrict__ out_i, uint64_t* __restrict__ out_k) {
     extern __shared__ __align__(16) uint64_t keys[];  // [np], list s at [s * k, (s + 1) * k)
     __shared__ int s_overflow;
     const int tid = threadIdx.x, q = blockIdx.x;
@@ -242,6 +242,10 @@ topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, 
         for (int i = tid; i < k; i += 256) {
             const uint64_t key = keys[i];
             const bool valid = key != 0ull;
+            if (out_k) {                          // keys out (query-sharded merge): the overflow marker travels on
+                out_k[(size_t)q * k + i] = (overflow && i == 0) ? kKeyOverflow : key;
+                continue;
+            }
             out_s[(size_t)q * k + i] = valid ? key_score(key) : __int_as_float(0xff800000);
             int64_t id = valid ? (int64_t)key_index(key) : (int64_t)-1;
             if (overflow && i == 0) id = -2;      // same marker as topk_finalize_kernel: the caller repairs this query
@@ -275,8 +279,12 @@ topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, 
                     rank += lo;
                 }
                 if (rank < k) {
-                    out_s[(size_t)q * k + rank] = key_score(key);
-                    out_i[(size_t)q * k + rank] = (int64_t)key_index(key);
+                    if (out_k) {
+                        out_k[(size_t)q * k + rank] = key;
+                    } else {
+                        out_s[(size_t)q * k + rank] = key_score(key);
+                        out_i[(size_t)q * k + rank] = (int64_t)key_index(key);
+                    }
                 }
             }
             s += ds; j += dj;
@@ -290,8 +298,23 @@ topk_merge_packed_kernel(const uint64_t* __restrict__ in, int g, int nq, int k, 
     if (nvalid) atomicAdd(&s_valid, nvalid);
     __syncthreads();
     for (int i = s_valid + tid; i < k; i += 256) {
-        out_s[(size_t)q * k + i] = __int_as_float(0xff800000);
-        out_i[(size_t)q * k + i] = (int64_t)-1;
+        if (out_k) {
+            out_k[(size_t)q * k + i] = 0ull;
+        } else {
+            out_s[(size_t)q * k + i] = __int_as_float(0xff800000);
+            out_i[(size_t)q * k + i] = (int64_t)-1;
+        }
+    }
+}
+
+// keys -> (score, index): 0 -> (-inf, -1) padding, the overflow key -> (-inf, -2)
+__global__ void __launch_bounds__(256)
+topk_unpack_kernel(const uint64_t* __restrict__ keys, long long n, float* __restrict__ scores, int64_t* __restrict__ idx) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const uint64_t key = keys[i];
+        const bool valid = (key >> 32) != 0ull;
+        scores[i] = valid ? key_score(key) : __int_as_float(0xff800000);
+        idx[i] = valid ? (int64_t)key_index(key) : (key == kKeyOverflow ? (int64_t)-2 : (int64_t)-1);
     }
 }
 
@@ -395,10 +418,9 @@ extern "C" int gdt_topk_pack(const float* scores, const int64_t* idx, long long 
     return GDT_OK;
 }
 
-extern "C" int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k, float* out_scores, int64_t* out_idx,
-                                     void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!keys || !out_scores || !out_idx) return GDT_ERR_INVALID_ARGUMENT;
+static int topk_merge_packed_impl(const uint64_t* keys, int g, int nq, int k, float* out_scores, int64_t* out_idx,
+                                  uint64_t* out_keys, cudaStream_t stream) {
+    if (!keys || (!out_keys && (!out_scores || !out_idx))) return GDT_ERR_INVALID_ARGUMENT;
     if (g <= 0 || nq <= 0 || k <= 0) return GDT_ERR_INVALID_ARGUMENT;
     const long long total = (long long)g * k;
     if (total > 16384) return GDT_ERR_UNSUPPORTED;
@@ -411,7 +433,28 @@ extern "C" int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k,
         GDT_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes = smem;
     }
-    topk_merge_packed_kernel<<<nq, 256, smem, stream>>>(keys, g, nq, k, np, out_scores, out_idx);
+    topk_merge_packed_kernel<<<nq, 256, smem, stream>>>(keys, g, nq, k, np, out_scores, out_idx, out_keys);
+    GDT_LAUNCH_CHECK();
+    return GDT_OK;
+}
+
+extern "C" int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k, float* out_scores, int64_t* out_idx,
+                                     void* stream_) {
+    return topk_merge_packed_impl(keys, g, nq, k, out_scores, out_idx, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int gdt_topk_merge_packed_keys(const uint64_t* keys, int g, int nq, int k, uint64_t* out_keys, void* stream_) {
+    return topk_merge_packed_impl(keys, g, nq, k, nullptr, nullptr, out_keys, (cudaStream_t)stream_);
+}
+
+extern "C" int gdt_topk_unpack(const uint64_t* keys, long long n, float* scores, int64_t* idx, void* stream_) {
+    if (!keys || !scores || !idx || n < 0) return GDT_ERR_INVALID_ARGUMENT;
+    if (!have_device()) return GDT_ERR_NO_DEVICE;
+    if (n == 0) return GDT_OK;
+    long long blocks = ceil_div_ll(n, 256);
+    const long long cap = (long long)sm_count_current_device() * 8;
+    if (blocks > cap) blocks = cap;
+    topk_unpack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(keys, n, scores, idx);
     GDT_LAUNCH_CHECK();
     return GDT_OK;
 }

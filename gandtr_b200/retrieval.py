@@ -79,6 +79,18 @@ class DistComm:
             dist.all_gather(list(out.unbind(0)), t, group=self.group)   # gloo (CPU tests)
         return out
 
+    def all_to_all(self, t):
+        """t: [world, m, ...], chunk r goes to rank r -> [world, m, ...], chunk r came from rank r. None when the backend
+        has no all-to-all (the caller then keeps the all-gather form)."""
+        if self.world == 1:
+            return t.clone()
+        if not self._nccl():
+            return None
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t, group=self.group)
+        return out
+
     def broadcast(self, t, src=0):
         if self.world > 1:
             dist.broadcast(t, src=src, group=self.group)
@@ -239,6 +251,14 @@ class CudaOps:
         from . import _lib
         return _lib.topk_pack(scores.contiguous(), idx.contiguous())
 
+    def merge_packed_keys(self, keys):
+        from . import _lib
+        return _lib.topk_merge_packed_keys(keys.contiguous())
+
+    def unpack(self, keys):
+        from . import _lib
+        return _lib.topk_unpack(keys.contiguous())
+
     def merge_packed(self, keys):
         from . import _lib
         g, nq, k = keys.shape
@@ -327,8 +347,29 @@ class ShardedIndex:
         """Per-shard lists -> the same merged [nq, k] lists on every rank. With the product's ops the lists travel packed
         (8 bytes per entry, ONE all-gather); injected test ops without `pack` use the two-tensor form."""
         if hasattr(self.ops, "pack") and s.shape[1] * self.world <= MERGE_MAX_ENTRIES:
-            return self.ops.merge_packed(self.comm.all_gather(self.ops.pack(s, i)))
+            keys = self.ops.pack(s, i)
+            merged = self._merge_query_sharded(keys) if hasattr(self.ops, "merge_packed_keys") else None
+            return merged if merged is not None else self.ops.merge_packed(self.comm.all_gather(keys))
         return self.ops.merge(self.comm.all_gather(s), self.comm.all_gather(i))
+
+    def _merge_query_sharded(self, keys):
+        """Query-sharded merge: rank r merges the lists of queries [r * m, (r + 1) * m) only. The per-shard lists reach it by
+        ONE all-to-all (1 / world of an all-gather's bytes), the merged slices travel packed in ONE all-gather of
+        nq * k * 8 bytes in total, and every rank unpacks the same [nq, k] result. None when the communicator has no
+        all-to-all or there are fewer queries than ranks."""
+        nq, k = keys.shape
+        w = self.world
+        if w == 1 or nq < w or not hasattr(self.comm, "all_to_all"):
+            return None
+        m = -(-nq // w)
+        if m * w != nq:                                   # pad with empty lists (key 0 = padding)
+            keys = torch.cat([keys, torch.zeros((m * w - nq, k), dtype=keys.dtype, device=keys.device)])
+        recv = self.comm.all_to_all(keys.view(w, m, k))   # [source rank][my m queries][k]
+        if recv is None:
+            return None
+        mine = self.ops.merge_packed_keys(recv)           # [m, k] merged keys of my query slice
+        s, i = self.ops.unpack(self.comm.all_gather(mine).view(w * m, k))
+        return s[:nq], i[:nq]
 
     def search(self, q, k, broadcast=False):
         """q: [nq, d] float32 (identical on every rank, or rank 0's copy with broadcast=True).

@@ -288,6 +288,13 @@ int gdt_topk_merge(const float* scores, const int64_t* idx, int g, int nq, int k
  *                          overflow comes back with idx[q][0] == -2, as gdt_score_topk_finalize marks it. */
 int gdt_topk_pack(const float* scores, const int64_t* idx, long long n, uint64_t* keys, void* stream);
 int gdt_topk_merge_packed(const uint64_t* keys, int g, int nq, int k, float* out_scores, int64_t* out_idx, void* stream);
+/* Query-sharded merge (the row-sharded search on many GPUs): every rank merges only its slice of the queries -- the
+ * per-shard lists reach it by an all-to-all instead of an all-gather (1 / world of the bytes and of the merge work) --
+ * and the merged slices are gathered in packed form:
+ *   gdt_topk_merge_packed_keys  keys [g][nq][k] -> merged KEYS [nq][k] (0 = padding; out[q][0] == 2 marks an overflow)
+ *   gdt_topk_unpack             keys [n] -> (scores, idx) [n]: padding -> (-inf, -1), the overflow key -> (-inf, -2) */
+int gdt_topk_merge_packed_keys(const uint64_t* keys, int g, int nq, int k, uint64_t* out_keys, void* stream);
+int gdt_topk_unpack(const uint64_t* keys, long long n, float* scores, int64_t* idx, void* stream);
 
 /* ---- K4: ranks of ground-truth ids + mAP ------------------------------------------------------------
  * Replaces the use of the full `ranks` matrix inside compute_map

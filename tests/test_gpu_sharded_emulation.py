@@ -142,7 +142,7 @@ def test_sharded_index_with_emulated_ranks(world):
     """ShardedIndex.search / evaluate_map exactly as the NCCL ranks run them, the ranks being threads on one GPU."""
     from gandtr_b200.retrieval import ShardedIndex, evaluate_map
     rs = np.random.RandomState(7)
-    nq, ndb, d, k = 150, 60001, 256, 100
+    nq, ndb, d, k = 151, 60001, 256, 100              # 151 queries: the query-sharded merge pads its last slice
     q, db, src = _planted(rs, nq, ndb, d)
     os_, oi = R.topk(R.scores_exact(q, db), k)
     gnd = [{"ok": np.array([src[j]]), "junk": np.array([(src[j] + 1) % ndb])} for j in range(nq)]
@@ -161,8 +161,10 @@ def test_sharded_index_with_emulated_ranks(world):
         assert abs(m - mo) < 1e-12 and np.array_equal(aps, apo)
         return comm.calls
     calls = run_ranks(world, rank_fn)
-    # per search: 1 broadcast, 1 histogram all-reduce, 1 packed all-gather; index construction: 2 all-reduce(MAX)
+    # per search: 1 broadcast, 1 histogram all-reduce, 1 all-to-all of the packed lists (query-sharded merge), 1 packed
+    # all-gather of the merged slices; index construction: 2 all-reduce(MAX)
     assert calls[0]["all_gather"] == 1 and calls[0]["all_reduce_max"] == 2 and calls[0]["broadcast"] == 1
+    assert calls[0]["all_to_all"] == 1
 
 
 def test_sharded_index_emulated_ranks_empty_shard_and_overflow_repair():

@@ -222,3 +222,21 @@ def test_packed_merge_rank_path_and_sort_fallback():
         assert np.array_equal(mi[q, :n], ids[o]), q
         assert np.array_equal(ms[q, :n], sc[o]), q
         assert (mi[q, n:] == -1).all() and np.isneginf(ms[q, n:]).all(), q
+
+
+def test_merge_to_keys_and_unpack_round_trip():
+    """gdt_topk_merge_packed_keys + gdt_topk_unpack (the query-sharded merge's two halves) == gdt_topk_merge_packed,
+    overflow marker included."""
+    from gandtr_b200 import _lib
+    rs = np.random.RandomState(9)
+    g, nq, k = 4, 19, 50
+    S = np.sort(rs.standard_normal((g, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    I = np.stack([s * 1000 + np.sort(rs.choice(1000, (nq, k)), axis=1) for s in range(g)]).astype(np.int64)
+    S[1, 3, 20:], I[1, 3, 20:] = -np.inf, -1                      # a short list
+    I[2, 5, 0] = -2                                               # shard 2 overflowed on query 5
+    keys = _lib.topk_pack(torch.from_numpy(S).cuda(), torch.from_numpy(I).cuda())
+    ms, mi = _lib.topk_merge_packed(keys)
+    us, ui = _lib.topk_unpack(_lib.topk_merge_packed_keys(keys))
+    assert int(mi[5, 0]) == -2 and int(ui[5, 0]) == -2
+    ok = [q for q in range(nq) if q != 5]
+    assert torch.equal(mi[ok], ui[ok]) and torch.equal(ms[ok], us[ok])

@@ -81,6 +81,10 @@ class ThreadComm:
         self.calls["all_gather"] += 1
         return self._exchange(t.contiguous())
 
+    def all_to_all(self, t):
+        self.calls["all_to_all"] = self.calls.get("all_to_all", 0) + 1
+        return self._exchange(t.contiguous())[:, self.rank].contiguous()       # chunk `rank` of every peer's tensor
+
     def broadcast(self, t, src=0):
         self.calls["broadcast"] += 1
         t.copy_(self._exchange(t)[src])
