@@ -15,7 +15,7 @@ BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libgandtr_b200.so")
 
 SOURCES = ["lib.cu", "clahe_sm100.cu", "gem_whiten_sm100.cu", "score_exact_sm100.cu", "score_topk_sm100.cu",
-           "map_eval_sm100.cu", "resize_sm100.cu", "mining_sm100.cu", "whiten_learn_sm100.cu"]
+           "map_eval_sm100.cu", "resize_sm100.cu", "mining_sm100.cu", "whiten_learn_sm100.cu", "jpeg_nvjpeg.cu"]
 HEADERS = ["common.cuh", "select.cuh", "clahe_math.cuh", "tc_common.cuh", "resize_math.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed for: %s" % ", ".join(failed))
     if force or procs or _stale(LIB_PATH, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout)

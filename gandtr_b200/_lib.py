@@ -80,6 +80,11 @@ SYMBOLS = [
     ("gdt_probe_scores", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _c.c_int, _P, _P]),
     ("gdt_rank_counts_workspace_bytes", _c.c_size_t, [_c.c_int, _c.c_int]),
     ("gdt_debug_k4_exact", _c.c_int, [_c.c_int]),
+    ("gdt_jpeg_available", _c.c_int, []),
+    ("gdt_jpeg_dims", _c.c_int, [_P, _c.c_size_t, _P, _P]),
+    ("gdt_jpeg_decode_batch", _c.c_int, [_P, _P, _c.c_int, _P, _P, _P, _P]),
+    ("gdt_debug_jpeg_last_backend", _c.c_int, []),
+    ("gdt_debug_jpeg_status", _c.c_int, [_P]),
     ("gdt_rank_counts", _c.c_int, [_P, _P, _c.c_int, _c.c_longlong, _c.c_int, _c.c_longlong, _P, _P, _c.c_int, _P, _P,
                                    _c.c_size_t, _P]),
     ("gdt_map_eval", _c.c_int, [_P, _c.c_int, _P, _c.c_int, _P, _P, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
@@ -634,6 +639,36 @@ def topk_unpack(keys):
         check(load().gdt_topk_unpack(_ptr(keys), keys.numel(), _ptr(s), _ptr(i), _stream()), "gdt_topk_unpack")
     _count("topk_unpack")
     return s, i
+
+
+# ---- N1: JPEG decode on the device (nvJPEG library) ---------------------------------------------------
+
+def jpeg_available():
+    return bool(load().gdt_jpeg_available())
+
+
+def jpeg_decode_batch(streams, device):
+    """streams: list of `bytes` (JPEG files) -> list of uint8 CUDA [h, w, 3] tensors, decoded by ONE batched nvJPEG call
+    (hardware JPEG engines when available). Library decode: not bit-identical to libjpeg."""
+    lib = load()
+    dev = torch.device(device)
+    n = len(streams)
+    if n == 0:
+        return []
+    with torch.cuda.device(dev):
+        bufs = [(ctypes.c_ubyte * len(b)).from_buffer_copy(b) for b in streams]
+        ws, hs = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+        for i, b in enumerate(bufs):
+            w, h = ctypes.c_int(), ctypes.c_int()
+            check(lib.gdt_jpeg_dims(ctypes.cast(b, ctypes.c_void_p), len(streams[i]), ctypes.byref(w), ctypes.byref(h)), "gdt_jpeg_dims")
+            ws[i], hs[i] = w.value, h.value
+        outs = [torch.empty((hs[i], ws[i], 3), dtype=torch.uint8, device=dev) for i in range(n)]
+        ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(b, ctypes.c_void_p).value for b in bufs])
+        lens = (ctypes.c_size_t * n)(*[len(b) for b in streams])
+        dsts = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+        check(lib.gdt_jpeg_decode_batch(ptrs, lens, n, dsts, ws, hs, _stream()), "gdt_jpeg_decode_batch")
+        torch.cuda.current_stream().synchronize()        # the host bit-stream buffers must outlive the decode
+    return outs
 
 
 # ---- K4 ----------------------------------------------------------------------------------------------

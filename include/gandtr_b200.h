@@ -129,6 +129,24 @@ int gdt_resize_u8(const gdt_resize_plan* plan, const uint8_t* src, size_t src_st
 size_t gdt_resize_batch_workspace_bytes(const gdt_resize_plan* plan, int n);
 int gdt_resize_u8_batch(const gdt_resize_plan* plan, const uint8_t* const* host_srcs, const size_t* host_strides, int n,
                         uint8_t* dst, void* ws, size_t ws_bytes, void* stream);
+/* N1, decode stage (opt-in): batches of JPEG bit streams decoded on the GPU by the nvJPEG LIBRARY (hardware JPEG engines
+ * when the device exposes them, nvJPEG's default backend otherwise); replaces `pil_loader`
+ * (mdir/external/cirtorch/datasets/datahelpers.py:20-27) for JPEG files. Library code, NOT bit-identical to libjpeg (a few
+ * grey levels): the default loader keeps PIL decoding. libnvjpeg is opened lazily (dlopen); without it these return
+ * GDT_ERR_UNSUPPORTED and everything else works.
+ *   gdt_jpeg_available     1 when libnvjpeg could be loaded
+ *   gdt_jpeg_dims          host-side header parse -> width, height of the decoded image
+ *   gdt_jpeg_decode_batch  jpegs[i] / nbytes[i]: HOST bit streams; dev_rgb[i]: DEVICE buffer of heights[i] x widths[i] x 3
+ *                          bytes (interleaved RGB, what gdt_resize_u8 / gdt_clahe_u8 consume); enqueued on `stream`
+ *   gdt_debug_jpeg_last_backend  backend of the last batch: 1 = hardware engines, 2 = GPU-hybrid (batches of >= 50 baseline
+ *                          streams: Huffman decoding on the GPU), 3 = default (Huffman decoding on the host's threads)
+ *   gdt_debug_jpeg_status  nvjpegStatus_t of {hardware create, hardware batch init, hardware decode, fallback decode} */
+int gdt_jpeg_available(void);
+int gdt_jpeg_dims(const uint8_t* jpeg, size_t nbytes, int* width, int* height);
+int gdt_jpeg_decode_batch(const uint8_t* const* jpegs, const size_t* nbytes, int n, uint8_t* const* dev_rgb,
+                          const int* widths, const int* heights, void* stream);
+int gdt_debug_jpeg_last_backend(void);
+int gdt_debug_jpeg_status(int* out4);
 /* debug/test hook: 1 = K5 runs its byte-wise kernels only (the dp4a kernels off), for A/B timing and parity */
 int gdt_debug_k5_bytewise(int on);
 /* debug/test hook (host only): Pillow's precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter.

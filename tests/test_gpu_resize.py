@@ -76,7 +76,7 @@ def test_loader_matches_host_load_image(tmp_path):
 
 
 def test_nvjpeg_decode_path_is_close_to_libjpeg(tmp_path):
-    """decode='nvjpeg' hands the JPEG bytes to the GPU decoder (library plumbing). It is NOT bit-identical to the
+    """decode='nvjpeg' hands the JPEG bit streams to the nvJPEG library (gdt_jpeg_decode_batch). It is NOT bit-identical to the
     reference's libjpeg decode -- the tolerance here is the documented difference: mean |diff| < 1 grey level after the
     thumbnail, same shape."""
     from PIL import Image
@@ -85,14 +85,24 @@ def test_nvjpeg_decode_path_is_close_to_libjpeg(tmp_path):
     img = synth_image(41, 480, 640, "smooth")
     path = str(tmp_path / "a.jpg")
     Image.fromarray(img).save(path, quality=92)
+    from gandtr_b200 import _lib
+    if not _lib.jpeg_available():                      # no CUDA toolkit libraries on this machine
+        pytest.skip("libnvjpeg could not be loaded")
     ld = DeviceImageLoader(imsize=256, device="cuda", decode="nvjpeg")
-    try:
-        out = ld.load(path).cpu().numpy()
-    except (RuntimeError, ImportError) as e:           # torchvision built without nvjpeg
-        pytest.skip("GPU JPEG decode unavailable: %s" % str(e)[:80])
+    out = ld.load(path).cpu().numpy()
+    print("nvJPEG backend of the last batch (1 = hardware engines, 2 = default):", _lib.load().gdt_debug_jpeg_last_backend())
     ref = load_image(path, 256, None)
     assert out.shape == ref.shape
     assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).mean() < 1.0
+    # batched form: one GPU decode call for the JPEG files of the list, one K5 launch pair per decoded size; a PNG and an
+    # array in the same list take the per-item route
+    path2, png = str(tmp_path / "b.jpg"), str(tmp_path / "c.png")
+    Image.fromarray(img[::-1].copy()).save(path2, quality=92)
+    Image.fromarray(img[:200, :300].copy()).save(png)
+    outs = ld.load_batch([path, png, path2])
+    assert np.array_equal(outs[0].cpu().numpy(), out)
+    assert np.array_equal(outs[1].cpu().numpy(), load_image(png, 256, None))          # PIL decode + K5: bit-exact
+    assert np.array_equal(outs[2].cpu().numpy(), ld.load(path2).cpu().numpy())
 
 
 def test_errors_are_loud():
