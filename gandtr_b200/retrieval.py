@@ -461,7 +461,7 @@ class PreparedProtocols:
         self.jkm = _to_device(_pad_rows(junk_cols, fill=0), device)
         cnt = _to_device(counts, device)
         self.npos, self.njunk, self.nres_dev = cnt[0].contiguous(), cnt[1].contiguous(), cnt[2].contiguous()
-        self._graphs, self._kappa_dev, self._graph_failed = {}, {}, False
+        self._graphs, self._kappa_dev, self._graph_failed, self._evals = {}, {}, False, 0
 
     def _device_part(self, index, q, kappas):
         """Everything of an evaluation that runs on the device -> [nprot * nq, 1 + max(nk, 1)] float64 (AP, P@k)."""
@@ -482,6 +482,9 @@ class PreparedProtocols:
         collectives in the middle; injected test ops; capture failed once)."""
         if (index.world != 1 or not isinstance(index.ops, CudaOps) or not q.is_cuda or self._graph_failed
                 or os.environ.get("GANDTR_B200_NO_GRAPH")):
+            return None
+        self._evals += 1
+        if self._evals < 2:                 # a one-shot evaluation (ground truth prepared per call) is not worth a capture
             return None
         ent = self._graphs.get(key)
         if ent is not None and (ent["index"]() is not index or ent["db_ptr"] != index.shard.db.data_ptr()):
