@@ -22,7 +22,7 @@ from .extract import extract_descriptors
 from .retrieval import ShardedIndex, compute_map_and_print, shard_bounds
 from .transforms import initialize_transforms
 
-__all__ = ["CirDatasetAp", "SCORES", "initialize_score", "configdataset", "validate", "infer", "load_network",
+__all__ = ["CirDatasetAp", "SCORES", "initialize_score", "configdataset", "validate", "print_scores", "infer", "load_network",
            "EmbeddingOutput"]
 
 DATASETS = ["oxford5k", "paris6k", "roxford5k", "rparis6k", "247tokyo1k"]
@@ -155,6 +155,31 @@ def validate(params, data=()):
                         metadata["%s/validation/%s:%s" % (_val, label, k)] = v
             criterion(network, device, logger)
     return ({"eval": metadata},)
+
+
+def print_scores(parameters, _data=()):
+    """mdir/examples/perform_scenario.py:19-41: the scenario step that prints what `validate` returned, same labels and
+    rounding (`round(100 * value, 2)`)."""
+    scores = {
+        "roxford5k/validation/score_avg:map_medium": "roxford.5k medium",
+        "rparis6k/validation/score_avg:map_medium": "rparis.6k medium",
+        "247tokyo1k/validation/score_avg:map": "247tokyo.1k",
+        "val/validation/roxford5k/score_avg:map_medium": "roxford.5k medium",
+        "val/validation/rparis6k/score_avg:map_medium": "rparis.6k medium",
+        "val/validation/val_eccv20/score_avg:map": "validation eccv20",
+    }
+    losses = ["val/validation/loss_avg:dist"]
+    assert parameters.keys() == {"metadata"}, parameters.keys()
+    for heading, section in parameters["metadata"].items():
+        print("\n%s\n" % heading.capitalize())
+        for key, value in section.items():
+            if key in scores:
+                print("    %-20s %s" % (scores[key], round(100 * value, 2)))
+            for loss in losses:
+                if loss in key:
+                    print("    %-20s %s" % (key.split(":")[-1], round(float(value.tolist()), 8)))
+        print()
+    return ({},)
 
 
 class EmbeddingOutput:

@@ -170,3 +170,15 @@ def test_metadata_tensor_and_pass_through_routing():
         assert float(out[i]) == (i + 100 if (i % 2 == 0 and expect[i]) else i) and isinstance(out[i], torch.Tensor)
     rp = N.RandomPassThrough("1.0", "cpu")
     assert rp.preprocess(torch.ones(1), None)[1] is None and repr(rp) == "RandomPassThrough(probability=1.0)"
+
+
+def test_print_scores_mirrors_the_scenario_step(capsys):
+    """mdir/examples/perform_scenario.py:19-41: labels, rounding and the ({},) return of the reference's print_scores."""
+    from gandtr_b200.score import print_scores
+    meta = {"eval": {"roxford5k/validation/score_avg:map_medium": 0.647453, "247tokyo1k/validation/score_avg:map": 0.9,
+                     "roxford5k/validation/score_avg:map_easy": 0.7, "val/validation/loss_avg:dist": np.float32(0.125)}}
+    assert print_scores({"metadata": meta}, ()) == ({},)
+    out = capsys.readouterr().out
+    assert "\nEval\n" in out
+    assert "    %-20s %s" % ("roxford.5k medium", 64.75) in out and "    %-20s %s" % ("247tokyo.1k", 90.0) in out
+    assert "    %-20s %s" % ("dist", 0.125) in out and "map_easy" not in out
