@@ -3,20 +3,22 @@
 // functional.py:28-35,55-63,81-85,140-161}) and the ClahePost wrapper
 // (mdir/components/data/wrapper.py:325-348), bit-exact against the reference's OpenCV 4.13.0 path.
 //
-// Two launches per batch, both streaming with coalesced 16-byte accesses:
+// Two launches per batch, both streaming with coalesced 16-byte accesses (defaults):
 //   pass A  clahe_hist_kernel   one CTA per (image, tile): RGB -> lattice cell + 4-bit fractions (integer arithmetic, one
-//           multiply-shift per channel) -> Q14 lightness (one 16 B gather of the packed lattice record, dp2a trilinear)
-//           -> uint8 L8 scratch (integer formula) + 4-byte cell-code scratch + 256-bin shared-memory histogram
-//           (bank-skewed copies per warp) -> clip, redistribute, prefix sum -> tile LUT (transposed rows).
-//   pass B  clahe_apply_kernel  one CTA per (image, row band, 1024-px column chunk): LUT rows of the band and the
-//           inverse-gamma spline staged in shared memory, per pixel: bilinear LUT blend -> chroma (32 B lattice record
-//           addressed by the cell code, texture pipe) -> Lab->RGB -> spline inverse gamma -> normalise -> planar float4
-//           stores.
+//           multiply-shift per channel) -> ONE 32-byte gather of the cell's compressed record (clahe_math.cuh: base + first
+//           differences + mixed differences of L, a, b) -> Q14 L, a, b by the multilinear form -> uint8 L8 scratch (integer
+//           formula) + 4-byte chroma scratch (a | b << 16) + 256-bin shared-memory histogram (bank-skewed copies per warp)
+//           -> clip, redistribute, prefix sum -> tile LUT (transposed rows).
+//   pass B  clahe_apply_kernel  persistent, one 1024-thread CTA per SM = four 256-thread groups walking over (image, row
+//           band, 1024-px column chunk) items: LUT rows of the band staged per item; the inverse-gamma spline and the
+//           lightness table held in shared memory eight times (conflict-free lookups); per pixel: bilinear LUT blend ->
+//           Lab->RGB -> spline inverse gamma -> normalise -> planar float4 stores. No lattice access, no texture.
 // Algorithmic HBM bytes per pixel: 3 in + 12 out (u8 variant), 12 + 12 (f32 variant). Scratch: 5 B/px written by A and
 // read by B (the input itself is read and quantised once).
-// The alternative work split (CHROMA_A: pass A interpolates all three channels with shared weights, pass B never
-// touches the lattice) is compiled in and bit-identical; it issues 31 % fewer instructions but is slower on B200
-// because the gathers are exposed in pass A (see g_k1_* below and profiles/README.md).
+// Round 1's arrangement (pass A interpolates the lightness only from a 16-byte record and stores a cell code, pass B
+// fetches the 32-byte chroma record through the texture pipe; non-persistent pass B) is compiled in, bit-identical, and
+// selected automatically when the lattice does not fit the compressed record; g_k1_* / gdt_debug_k1_* switch every
+// variant at run time for A/B timing (profiles/README.md).
 #include <stdlib.h>
 
 #include "clahe_math.cuh"
