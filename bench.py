@@ -59,7 +59,7 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------- inputs
 
-def synth_images_torch(n, seed, device, h=None, w=None):
+def synth_images_torch(n, seed, device, h=None, w=None, noise=8.0):
     """Smooth sinusoid + noise family of SURVEY 8(d), generated with torch (host or device)."""
     import torch
     H, W = (h or globals()["H"]), (w or globals()["W"])
@@ -70,9 +70,9 @@ def synth_images_torch(n, seed, device, h=None, w=None):
     base = 128 + 70 * (torch.sin(xx / (37.0 + 5 * cc)) + torch.cos(yy / (23.0 + 3 * cc)))
     out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=device)
     for i in range(n):
-        noise = torch.randn((1, H, W, 3), generator=g, device=device) * 8.0
+        nz = torch.randn((1, H, W, 3), generator=g, device=device) * noise
         gain = 0.6 + 0.8 * torch.rand((1, 1, 1, 1), generator=g, device=device)
-        out[i] = (base * gain + noise).clamp_(0, 255).to(torch.uint8)[0]
+        out[i] = (base * gain + nz).clamp_(0, 255).to(torch.uint8)[0]
     return out
 
 
@@ -450,6 +450,22 @@ def main():
     ms_ms, w = timed(step_ms, K, Wm)
     windows.append(w)
 
+    # ---- context: K1 on images WITHOUT the N(0, 8) pixel noise (the lattice gathers of a warp then fall into a few cells,
+    # as on real photographs) and on uniform-noise images (SURVEY 8(d)'s other family: every gather a different cell) ----
+    k1_content = {}
+    if world == 1:
+        for name, kw in (("smooth_no_noise", {"noise": 0.0}), ("uniform_noise", None)):
+            if kw is None:
+                gx = torch.Generator(device=dev).manual_seed(77)
+                xi = torch.randint(0, 256, (B, H, W, 3), generator=gx, device=dev, dtype=torch.uint8)
+            else:
+                xi = synth_images_torch(B, 5, dev, **kw)
+            c_ms, w = timed(lambda: _lib.clahe_u8(xi, MEAN, STD, out=out), 5, 3)
+            windows.append(w)
+            k1_content[name] = {"ms_per_launch_pair": c_ms / 5, "achieved": B * K1_BYTES_PER_IMG / (c_ms / 5 * 1e-3) / 1e9,
+                                "frac": B * K1_BYTES_PER_IMG / (c_ms / 5 * 1e-3) / 1e9 / hbm_peak}
+            del xi
+
     line = {
         "metric": "images/sec CLAHE+GeM+whiten", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -467,7 +483,8 @@ def main():
                              "32-byte compressed lattice record per pixel, 139 instructions per pixel), pass B issue 82 % (166 "
                              "instructions per pixel of bit-exact OpenCV float arithmetic; shared-memory lookups conflict-free); "
                              "DRAM at 14 - 31 %",
-                     "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG},
+                     "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG,
+                     "other_image_content": k1_content},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
                         "bound": "hbm", "achieved": B * K2_BYTES_PER_IMG / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak,
                         "unit": "GB/s", "ms_per_call": k2_ms,

@@ -311,129 +311,101 @@ GDT_HD float normalize_px_fast(float x, float mean, float std, float rstd) {
 //   4096 * v(fr, fg, fb) = 4096 B + 256 (D1 fr + D2 fg + D3 fb) + 16 (M12 fr fg + M13 fr fb + M23 fg fb) + M123 fr fg fb
 // with B the (0,0,0) corner, D the first differences along r / g / b, M the mixed second / third differences (an exact
 // integer identity: expand the weights (16 - f) and f). For the Lab lattice the D are one-signed and fit 10 bits (L, a, b
-// rise or fall monotonically along each RGB axis), the mixed terms are tiny (|M| <= 52): 15 + 3 * 10 + 4 * 7 bits per
-// channel, 219 bits per cell instead of 3 * 128. One gather of one 32-byte sector fetches what took a 16-byte and a
-// 32-byte record in two sectors. pack_lab_rec32() verifies the ranges against the actual table and refuses otherwise.
+// rise or fall monotonically along each RGB axis), the mixed terms are tiny (|M| <= 52, one signed byte): 15 + 3 * 10 +
+// 4 * 8 bits per channel, 231 bits per cell instead of 3 * 128. One gather of one 32-byte sector fetches what took a
+// 16-byte and a 32-byte record in two sectors. pack_lab_rec32() verifies the ranges against the actual table and refuses
+// otherwise.
 //
-// Field placement: every field is extracted by ONE instruction and used where it lies -- low fields (bit 0) and middle
-// fields (bit 7) by a mask, their bit position folded into the per-pixel weight; top fields by a shift.
-//   w[c]     (c = 0, 1, 2 = L, a, b):  M123_c [0,7)   D1_c [7,17)   B_c [17,32)
-//   w[3 + c]:                          M12_c  [0,7)   D2_c [7,17)   top: D3_b [22,32) | M13_L [25,32) | M13_a [25,32)
-//   w[6]:                              M23_L  [0,7)   D3_L [7,17)   M13_b [25,32)
-//   w[7]:                              M23_a  [0,7)   D3_a [7,17)   M23_b [25,32)
-// D fields hold |D| (signs lab_d_sign); M fields hold M + beta_c (one bias per channel, LabRecBias), removed by
-// beta_c * (16 (fr fg + fr fb + fg fb) + fr fg fb).
-struct LabRecBias { int beta[3]; };
+// Layout: every field costs ONE instruction to extract, and the four mixed terms of a channel cost ONE dp4a.
+//   w[c]     (c = 0, 1, 2 = L, a, b):  signed bytes  M12_c | M13_c | M23_c | M123_c          (dp4a against fr fg | fr fb | fg fb | 0)
+//   w[3 + c]:                          |D1_c| [0,10)   |D2_c| [10,20)   |D3_c| [22,32)        (signs: lab_d_sign)
+//   w[6]:                              B_L [0,15)   B_a [16,31)          w[7]:  B_b [0,15)
+// The sum is accumulated times 4 (acc4 = 4 * 4096 * v + rounding) so that the middle field can be used where it lies:
+// (w & (0x3ff << 10)) = 1024 |D2| is exactly its term per unit of fg; low and top fields take the weights 1024 fr / fb.
 // sign of D1 (r), D2 (g), D3 (b) for L, a, b: a falls with green, b falls with blue
 GDT_HD constexpr int lab_d_sign(int c, int k) { return ((c == 1 && k == 1) || (c == 2 && k == 2)) ? -1 : 1; }
 
 struct LabWeights {      // per pixel, shared by the three channels
-    int r2, g2, b2;      // 2 f       (middle D fields sit at bit 7: 2^7 * 2 f = 256 f)
-    int b256;            // 256 fb    (the one D field in a top slot)
-    int rg16, rb16, gb16;// 16 f f'
-    int rgb;             // fr fg fb
-    int s;               // 16 (fr fg + fr fb + fg fb) + fr fg fb
+    int r1024, g1, b1024;    // 1024 fr, fg, 1024 fb
+    uint32_t m;              // bytes fr fg | fr fb | fg fb | 0   (each <= 225)
+    int rgb4;                // 4 fr fg fb
 };
 GDT_HD LabWeights lab_weights(int fr, int fg, int fb) {
     LabWeights W;
-    W.r2 = fr * 2; W.g2 = fg * 2; W.b2 = fb * 2;
-    W.b256 = fb * 256;
+    W.r1024 = fr * 1024; W.g1 = fg; W.b1024 = fb * 1024;
     const int rg = fr * fg, rb = fr * fb, gb = fg * fb;
-    W.rg16 = rg * 16; W.rb16 = rb * 16; W.gb16 = gb * 16;
-    W.rgb = rg * fb;
-    W.s = W.rg16 + W.rb16 + W.gb16 + W.rgb;
+    W.m = (uint32_t)rg | ((uint32_t)rb << 8) | ((uint32_t)gb << 16);
+    W.rgb4 = rg * (fb * 4);
     return W;
 }
+// signed bytes of `a` times unsigned bytes of `b`, summed, plus c
+GDT_HD int dp4a_su(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)((b >> (8 * i)) & 255u);
+    return c;
+#endif
+}
 // -> Q14 (L, a, b) of the pixel, identical to lab_trilinear() on the uncompressed corners
-GDT_HD void lab_from_rec32(const uint32_t* w, const LabWeights& W, const LabRecBias& bias, int& oL, int& oa, int& ob) {
-    const uint32_t kMid = 0x3ffu << 7, kLow = 0x7fu;
-    int acc[3];
+GDT_HD void lab_from_rec32(const uint32_t* w, const LabWeights& W, int& oL, int& oa, int& ob) {
+    const int base[3] = {(int)(w[6] & 0xffffu), (int)(w[6] >> 16), (int)w[7]};
+    int o[3];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
     for (int c = 0; c < 3; ++c) {
-        const uint32_t wa = w[c], wb = w[3 + c];
-        int a = (int)(wa >> 17) * 4096 - bias.beta[c] * W.s;
-        a += (int)(wa & kLow) * W.rgb;
-        a += lab_d_sign(c, 0) * ((int)(wa & kMid) * W.r2);
-        a += (int)(wb & kLow) * W.rg16;
-        a += lab_d_sign(c, 1) * ((int)(wb & kMid) * W.g2);
-        acc[c] = a;
+        const uint32_t wm = w[c], wd = w[3 + c];
+        int a = base[c] * 16384 + 8192;                                   // 4 * (4096 B + 2048)
+        a += lab_d_sign(c, 0) * ((int)(wd & 0x3ffu) * W.r1024);
+        a += lab_d_sign(c, 1) * ((int)(wd & (0x3ffu << 10)) * W.g1);
+        a += lab_d_sign(c, 2) * ((int)(wd >> 22) * W.b1024);
+        a += dp4a_su(wm, W.m, 0) * 64;
+        a += ((int)wm >> 24) * W.rgb4;
+        o[c] = a >> 14;
     }
-    // D3, M13, M23
-    acc[0] += lab_d_sign(0, 2) * ((int)(w[6] & kMid) * W.b2) + (int)(w[4] >> 25) * W.rb16 + (int)(w[6] & kLow) * W.gb16;
-    acc[1] += lab_d_sign(1, 2) * ((int)(w[7] & kMid) * W.b2) + (int)(w[5] >> 25) * W.rb16 + (int)(w[7] & kLow) * W.gb16;
-    acc[2] += lab_d_sign(2, 2) * ((int)(w[3] >> 22) * W.b256) + (int)(w[6] >> 25) * W.rb16 + (int)(w[7] >> 25) * W.gb16;
-    oL = (acc[0] + 2048) >> 12;
-    oa = (acc[1] + 2048) >> 12;
-    ob = (acc[2] + 2048) >> 12;
+    oL = o[0]; oa = o[1]; ob = o[2];
 }
 
-// lut33: the [33][33][33][3] int16 table. rec: 33^3 * 8 words. Returns false (rec untouched beyond garbage) when a
-// difference does not fit its field or has the wrong sign: the caller then keeps the uncompressed records.
-inline bool pack_lab_rec32(const int16_t* lut33, uint32_t* rec, LabRecBias& bias) {
+// lut33: the [33][33][33][3] int16 table. rec: 33^3 * 8 words. Returns false (rec partially written) when a difference does
+// not fit its field or has the wrong sign: the caller then keeps the uncompressed records.
+inline bool pack_lab_rec32(const int16_t* lut33, uint32_t* rec) {
     auto at = [&](int r, int g, int b, int c) -> int {
         r = r < 32 ? r : 32; g = g < 32 ? g : 32; b = b < 32 ? b : 32;   // clamped neighbours carry weight 0
         return lut33[((r * 33 + g) * 33 + b) * 3 + c];
     };
-    const int ncell = 33 * 33 * 33;
-    // pass 1: mixed-term minima -> one bias per channel; pass 2: pack and verify
-    int mmin[3] = {0, 0, 0};
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int tr = 0; tr < 33; ++tr)
-            for (int tg = 0; tg < 33; ++tg)
-                for (int tb = 0; tb < 33; ++tb) {
-                    const int cell = (tr * 33 + tg) * 33 + tb;
-                    int B[3], D[3][3], M12[3], M13[3], M23[3], M123[3];
-                    for (int c = 0; c < 3; ++c) {
-                        const int v000 = at(tr, tg, tb, c), v100 = at(tr + 1, tg, tb, c), v010 = at(tr, tg + 1, tb, c),
-                                  v001 = at(tr, tg, tb + 1, c), v110 = at(tr + 1, tg + 1, tb, c),
-                                  v101 = at(tr + 1, tg, tb + 1, c), v011 = at(tr, tg + 1, tb + 1, c),
-                                  v111 = at(tr + 1, tg + 1, tb + 1, c);
-                        B[c] = v000;
-                        D[c][0] = v100 - v000; D[c][1] = v010 - v000; D[c][2] = v001 - v000;
-                        M12[c] = v110 - v100 - v010 + v000;
-                        M13[c] = v101 - v100 - v001 + v000;
-                        M23[c] = v011 - v010 - v001 + v000;
-                        M123[c] = v111 - v110 - v101 - v011 + v100 + v010 + v001 - v000;
+    for (int tr = 0; tr < 33; ++tr)
+        for (int tg = 0; tg < 33; ++tg)
+            for (int tb = 0; tb < 33; ++tb) {
+                uint32_t* w = rec + (size_t)((tr * 33 + tg) * 33 + tb) * 8;
+                for (int i = 0; i < 8; ++i) w[i] = 0u;
+                for (int c = 0; c < 3; ++c) {
+                    const int v000 = at(tr, tg, tb, c), v100 = at(tr + 1, tg, tb, c), v010 = at(tr, tg + 1, tb, c),
+                              v001 = at(tr, tg, tb + 1, c), v110 = at(tr + 1, tg + 1, tb, c),
+                              v101 = at(tr + 1, tg, tb + 1, c), v011 = at(tr, tg + 1, tb + 1, c),
+                              v111 = at(tr + 1, tg + 1, tb + 1, c);
+                    const int D[3] = {v100 - v000, v010 - v000, v001 - v000};
+                    const int M[4] = {v110 - v100 - v010 + v000, v101 - v100 - v001 + v000, v011 - v010 - v001 + v000,
+                                      v111 - v110 - v101 - v011 + v100 + v010 + v001 - v000};
+                    if (v000 < 0 || v000 >= (1 << 15)) return false;
+                    uint32_t mag[3];
+                    for (int k = 0; k < 3; ++k) {
+                        const int m = D[k] * lab_d_sign(c, k);
+                        if (m < 0 || m >= (1 << 10)) return false;
+                        mag[k] = (uint32_t)m;
                     }
-                    if (pass == 0) {
-                        for (int c = 0; c < 3; ++c) {
-                            const int m = M12[c] < M13[c] ? M12[c] : M13[c], n = M23[c] < M123[c] ? M23[c] : M123[c];
-                            const int mn = m < n ? m : n;
-                            if (mn < mmin[c]) mmin[c] = mn;
-                        }
-                        continue;
+                    for (int k = 0; k < 4; ++k) {
+                        if (M[k] < -128 || M[k] > 127) return false;
+                        w[c] |= ((uint32_t)M[k] & 255u) << (8 * k);
                     }
-                    uint32_t f_d[3][3], f_m12[3], f_m13[3], f_m23[3], f_m123[3];
-                    for (int c = 0; c < 3; ++c) {
-                        if (B[c] < 0 || B[c] >= (1 << 15)) return false;
-                        for (int k = 0; k < 3; ++k) {
-                            const int mag = D[c][k] * lab_d_sign(c, k);
-                            if (mag < 0 || mag >= (1 << 10)) return false;
-                            f_d[c][k] = (uint32_t)mag;
-                        }
-                        const int beta = bias.beta[c];
-                        const int ms[4] = {M12[c] + beta, M13[c] + beta, M23[c] + beta, M123[c] + beta};
-                        for (int k = 0; k < 4; ++k)
-                            if (ms[k] < 0 || ms[k] >= (1 << 7)) return false;
-                        f_m12[c] = (uint32_t)ms[0]; f_m13[c] = (uint32_t)ms[1]; f_m23[c] = (uint32_t)ms[2]; f_m123[c] = (uint32_t)ms[3];
-                    }
-                    uint32_t* w = rec + (size_t)cell * 8;
-                    for (int c = 0; c < 3; ++c) {
-                        w[c] = f_m123[c] | (f_d[c][0] << 7) | ((uint32_t)B[c] << 17);
-                        w[3 + c] = f_m12[c] | (f_d[c][1] << 7);
-                    }
-                    w[3] |= f_d[2][2] << 22;
-                    w[4] |= f_m13[0] << 25;
-                    w[5] |= f_m13[1] << 25;
-                    w[6] = f_m23[0] | (f_d[0][2] << 7) | (f_m13[2] << 25);
-                    w[7] = f_m23[1] | (f_d[1][2] << 7) | (f_m23[2] << 25);
+                    w[3 + c] = mag[0] | (mag[1] << 10) | (mag[2] << 22);
+                    if (c == 0) w[6] |= (uint32_t)v000;
+                    else if (c == 1) w[6] |= (uint32_t)v000 << 16;
+                    else w[7] = (uint32_t)v000;
                 }
-        if (pass == 0)
-            for (int c = 0; c < 3; ++c) bias.beta[c] = -mmin[c];
-    }
-    (void)ncell;
+            }
     return true;
 }
 

@@ -30,7 +30,6 @@ struct ClaheTables {
     uint4* lutL = nullptr;     // [33^3]      packed lightness corners
     uint4* lutAB = nullptr;    // [33^3][2]   packed chroma corners (a words, b words)
     uint32_t* rec32 = nullptr; // [33^3][8]   compressed record of all three channels (clahe_math.cuh), when it fits
-    LabRecBias bias = {{0, 0, 0}};
     bool rec_ok = false;
     // std values for which div_by_const<1> (ONE Markstein correction) equals IEEE division for every numerator K1 can
     // produce: checked exhaustively on this device at gdt_init (div1_check_kernel)
@@ -163,10 +162,9 @@ __device__ __forceinline__ void ld_cell_rec32(const uint32_t* __restrict__ rec32
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(rec32 + (size_t)cell * 8));
 }
-__device__ __forceinline__ void lab_from_rec32_px(const uint32_t* w, int fr, int fg, int fb, const LabRecBias& bias, int& l8,
-                                                  uint32_t& ab) {
+__device__ __forceinline__ void lab_from_rec32_px(const uint32_t* w, int fr, int fg, int fb, int& l8, uint32_t& ab) {
     int oL, oa, ob;
-    lab_from_rec32(w, lab_weights(fr, fg, fb), bias, oL, oa, ob);
+    lab_from_rec32(w, lab_weights(fr, fg, fb), oL, oa, ob);
     l8 = lab_l8_int(oL);
     ab = (uint32_t)oa | ((uint32_t)ob << 16);
 }
@@ -182,8 +180,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                   uint8_t* __restrict__ lutT, int h, int w, int pitch,
                   int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
                   const uint4* __restrict__ lutL, const uint4* __restrict__ lutAB, Norm3 in_norm,
-                  cudaTextureObject_t texAB, cudaTextureObject_t texL, const uint32_t* __restrict__ rec32,
-                  LabRecBias bias) {
+                  cudaTextureObject_t texAB, cudaTextureObject_t texL, const uint32_t* __restrict__ rec32) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
     __shared__ int warp_tmp[8];
     const int tid = threadIdx.x;
@@ -258,7 +255,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
 #pragma unroll
                 for (int i = 0; i < 4; ++i) ld_cell_rec32(rec32, cell[i], rw[i]);      // four sector gathers in flight
 #pragma unroll
-                for (int i = 0; i < 4; ++i) lab_from_rec32_px(rw[i], fr[i], fg[i], fb[i], bias, v[i], ab[i]);
+                for (int i = 0; i < 4; ++i) lab_from_rec32_px(rw[i], fr[i], fg[i], fb[i], v[i], ab[i]);
             } else if (CHROMA_A) {
                 uint4 wl[4], wa[4], wb[4];
 #pragma unroll
@@ -331,7 +328,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                 if (CHROMA_A && REC32) {
                     uint32_t rw[8];
                     ld_cell_rec32(rec32, cell, rw);
-                    lab_from_rec32_px(rw, fr, fg, fb, bias, v, ab);
+                    lab_from_rec32_px(rw, fr, fg, fb, v, ab);
                 } else if (CHROMA_A) {
                     const uint4 wl = __ldg(lutL + cell);
                     uint4 wa, wb;
@@ -788,8 +785,7 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
 #define GDT_HIST_R(T_, C_, O_, L_, R_)                                                                                 \
     clahe_hist_kernel<U8, T_, C_, O_, L_, R_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw, \
                                                                           g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL, \
-                                                                          T->lutAB, in_norm, T->texAB, T->texL, T->rec32, \
-                                                                          T->bias)
+                                                                          T->lutAB, in_norm, T->texAB, T->texL, T->rec32)
 #define GDT_HIST(T_, C_, O_, L_) GDT_HIST_R(T_, C_, O_, L_, false)
     if (!chroma_a) {
         if (texab & 4) GDT_HIST(false, false, 4, 2);
@@ -1142,7 +1138,7 @@ extern "C" int gdt_init(const int16_t* host_rgb2lab_lut) {
         uint32_t* hR = (uint32_t*)malloc(ncell * 8 * sizeof(uint32_t));
         if (hR) {
             memset(hR, 0, ncell * 8 * sizeof(uint32_t));
-            T.rec_ok = pack_lab_rec32(host_rgb2lab_lut, hR, T.bias);
+            T.rec_ok = pack_lab_rec32(host_rgb2lab_lut, hR);
             if (T.rec_ok) rc = up((void**)&T.rec32, hR, ncell * 32);
             free(hR);
         }

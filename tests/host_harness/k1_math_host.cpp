@@ -8,7 +8,6 @@
 using namespace gdt;
 
 static std::vector<uint32_t> g_L, g_AB, g_rec;
-static LabRecBias g_bias;
 static bool g_rec_ok = false;
 static Lab2RgbConst g_K;
 static float g_spline[4096], g_fy[1024];
@@ -18,7 +17,7 @@ extern "C" void k1h_init(const int16_t* lut33) {
     g_AB.assign((size_t)kLabCells * 8, 0u);
     pack_lab_lut(lut33, g_L.data(), g_AB.data());
     g_rec.assign((size_t)kLabCells * 8, 0u);
-    g_rec_ok = pack_lab_rec32(lut33, g_rec.data(), g_bias);
+    g_rec_ok = pack_lab_rec32(lut33, g_rec.data());
     build_lab2rgb_const(g_K);
     build_inv_gamma_spline(g_spline);
     build_fy_table(g_K, g_fy);
@@ -104,9 +103,8 @@ extern "C" void k1h_stage_b(const uint8_t* dst, const uint32_t* ab, long n, int 
 // Compressed 32-byte lattice record against the uncompressed corner records: every cell, every (fr, fg, fb) in
 // [0, 16)^3 with stride `fstep` in each fraction. Returns the number of mismatching (cell, fraction, channel) triples,
 // -1 when the table did not fit the record format.
-extern "C" long k1h_rec32_check(int fstep, int* beta_out) {
+extern "C" long k1h_rec32_check(int fstep) {
     if (!g_rec_ok) return -1;
-    for (int c = 0; c < 3; ++c) beta_out[c] = g_bias.beta[c];
     long bad = 0;
     for (int cell = 0; cell < kLabCells; ++cell) {
         const uint32_t* wl = &g_L[(size_t)cell * 4];
@@ -116,7 +114,7 @@ extern "C" long k1h_rec32_check(int fstep, int* beta_out) {
             for (int fg = 0; fg < 16; fg += fstep)
                 for (int fb = 0; fb < 16; fb += fstep) {
                     int oL, oa, ob;
-                    lab_from_rec32(w, lab_weights(fr, fg, fb), g_bias, oL, oa, ob);
+                    lab_from_rec32(w, lab_weights(fr, fg, fb), oL, oa, ob);
                     bad += oL != lab_trilinear(wl[0], wl[1], wl[2], wl[3], fr, fg, fb);
                     bad += oa != lab_trilinear(wc[0], wc[1], wc[2], wc[3], fr, fg, fb);
                     bad += ob != lab_trilinear(wc[4], wc[5], wc[6], wc[7], fr, fg, fb);
