@@ -174,11 +174,13 @@ __device__ __forceinline__ void lab_from_rec32_px(const uint32_t* w, int fr, int
 // TEXL: which lightness-record gathers take the texture pipe instead of the LSU pipe (pass A is bound by the LSU pipe's
 // scattered 16-byte gathers): 0 none, 1 all, 2 every other pixel (both pipes gather in parallel).
 // REC32 (with CHROMA_A): all three channels from the compressed 32-byte record, one gather per pixel.
-template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL, bool REC32>
+// VEC1: the host guarantees vec_ok == 1 (every tile a whole number of aligned 4-pixel groups inside the image: the common
+// sizes), so the ragged / reflected / generic paths and their per-group tests are compiled out.
+template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL, bool REC32, bool VEC1>
 __global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w, int pitch,
-                  int grid, int th, int tw, int clip, float lut_scale, int vec_ok, int gq, int gr,
+                  int grid, int th, int tw, int clip, float lut_scale, int vec_ok_, int gq, int gr,
                   const uint4* __restrict__ lutL, const uint4* __restrict__ lutAB, Norm3 in_norm,
                   cudaTextureObject_t texAB, cudaTextureObject_t texL, const uint32_t* __restrict__ rec32) {
     __shared__ int hist_all[8 * kHistCopies * kHistStride];
@@ -197,6 +199,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
     uint8_t* l8img = L8 + (size_t)img * h * pitch;
     uint32_t* abimg = AB + (size_t)img * h * pitch;
 
+    const int vec_ok = VEC1 ? 1 : vec_ok_;
     if (vec_ok) {
         // 4 consecutive pixels per thread, groups aligned to 4 pixels of the image row. vec_ok == 1: the tile is a whole
         // number of groups inside the image. vec_ok == 2 (image padded by OpenCV and / or tile width not a multiple of
@@ -284,7 +287,10 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
             *(uint4*)(abimg + ps) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
             *(uint32_t*)(l8img + ps) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hist_add(hist, (vec_ok == 1 || (x0 + i >= xa && x0 + i < xb)) ? v[i] : 256);
+            for (int i = 0; i < 4; ++i) {
+                if (VEC1) atomicAdd(&hist[v[i]], 1);             // v is a byte by construction: no "no pixel" key to test
+                else hist_add(hist, (vec_ok == 1 || (x0 + i >= xa && x0 + i < xb)) ? v[i] : 256);
+            }
             // next (row, group) of this thread: + 256 groups
             row += vq;
             c4 += vr;
@@ -782,10 +788,11 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     dim3 gridA(grid * grid, n);
     const int gw = g.tw;                               // scalar path: walk unit = one pixel of a tile row
     const int gq = 256 / gw, gr = 256 % gw;
-#define GDT_HIST_R(T_, C_, O_, L_, R_)                                                                                 \
-    clahe_hist_kernel<U8, T_, C_, O_, L_, R_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw, \
+#define GDT_HIST_RV(T_, C_, O_, L_, R_, V_)                                                                            \
+    clahe_hist_kernel<U8, T_, C_, O_, L_, R_, V_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw, \
                                                                           g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL, \
                                                                           T->lutAB, in_norm, T->texAB, T->texL, T->rec32)
+#define GDT_HIST_R(T_, C_, O_, L_, R_) GDT_HIST_RV(T_, C_, O_, L_, R_, false)
 #define GDT_HIST(T_, C_, O_, L_) GDT_HIST_R(T_, C_, O_, L_, false)
     if (!chroma_a) {
         if (texab & 4) GDT_HIST(false, false, 4, 2);
@@ -793,13 +800,16 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
         else if (occ_a >= 6) GDT_HIST(false, false, 6, 0);
         else GDT_HIST(false, false, 4, 0);
     } else if (rec32) {
-        if (occ_a >= 6) GDT_HIST_R(false, true, 6, 0, true); else GDT_HIST_R(false, true, 4, 0, true);
+        if (occ_a >= 6) GDT_HIST_R(false, true, 6, 0, true);
+        else if (vec_hist == 1 && U8) GDT_HIST_RV(false, true, 4, 0, true, true);     // the common sizes: specialised
+        else GDT_HIST_R(false, true, 4, 0, true);
     } else if (texab & 1) {
         if (occ_a >= 6) GDT_HIST(true, true, 6, 0); else GDT_HIST(true, true, 4, 0);
     } else {
         GDT_HIST(false, true, 4, 0);
     }
 #undef GDT_HIST_R
+#undef GDT_HIST_RV
 #undef GDT_HIST
     GDT_LAUNCH_CHECK();
 
