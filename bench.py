@@ -33,9 +33,9 @@ MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 K1_BYTES_PER_IMG = 15 * H * W
 K2_BYTES_PER_IMG = 4 * C_FEAT * FH * FW + 4 * C_FEAT
 # measured DRAM traffic of K1 per image (dram__bytes_read.sum + dram__bytes_write.sum of clahe_hist + clahe_apply, ncu
-# --set full capture profiles/ncu_k1_v3_r2m.txt at 32 images: 76.7 + 75.1 + 126.4 + 244.0 MB) -- 1.38x the algorithmic
+# --set full capture profiles/ncu_k1_v3_r2ac.txt at 32 images: 76.7 + 75.3 + 126.4 + 243.8 MB) -- 1.38x the algorithmic
 # bytes: the 5 B/px scratch (lightness byte + Q14 chroma pair) is written by pass A and read by pass B
-K1_TRAFFIC_PER_IMG = (76.685568e6 + 75.133184e6 + 126.411264e6 + 243.973376e6) / 32      # ncu r2m, 32 images
+K1_TRAFFIC_PER_IMG = (76.662784e6 + 75.250432e6 + 126.394112e6 + 243.810560e6) / 32      # ncu r2ac, 32 images
 
 
 def parse():
@@ -477,12 +477,12 @@ def main():
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "K1 clahe_hist_kernel + clahe_apply_kernel (one gdt_clahe_u8 call)", "bound": "hbm",
                      "achieved": B * K1_BYTES_PER_IMG / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r2m (dram read + write of both passes), per image x batch",
+                     "peak_source": hbm_src, "traffic": B * K1_TRAFFIC_PER_IMG, "traffic_source": "ncu r2ac (dram read + write of both passes), per image x batch",
                      "ms_per_launch_pair": k1_ms,
-                     "note": "nominal bound; ncu (profiles/ncu_k1_v3_r2m.txt): pass A issue 73 % / ALU pipe 70 % / LSU 77 % (one "
-                             "32-byte compressed lattice record per pixel, 139 instructions per pixel), pass B issue 82 % (166 "
-                             "instructions per pixel of bit-exact OpenCV float arithmetic; shared-memory lookups conflict-free); "
-                             "DRAM at 14 - 31 %",
+                     "note": "nominal bound; ncu (profiles/ncu_k1_v3_r2ac.txt): pass A L1 data pipe 83 % (one scattered 32-byte lattice "
+                             "sector per pixel: the SM's ~1 sector/cycle gather floor), issue 57 % (102 instructions per pixel); "
+                             "pass B issue 75 % / shared memory 75 % (147 instructions per pixel of bit-exact OpenCV float "
+                             "arithmetic); DRAM at 15 - 33 %",
                      "algorithmic_bytes_per_call": B * K1_BYTES_PER_IMG,
                      "other_image_content": k1_content},
         "roofline_k2": {"kernel": "K2 gem_pool + finalize + tcgen05 3xTF32 whiten + L2N (one gdt_gem_whiten call, single-scale)",
