@@ -801,7 +801,7 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
         else GDT_HIST(false, false, 4, 0);
     } else if (rec32) {
         if (occ_a >= 6) GDT_HIST_R(false, true, 6, 0, true);
-        else if (vec_hist == 1 && U8) GDT_HIST_RV(false, true, 4, 0, true, true);     // the common sizes: specialised
+        else if (vec_hist == 1) GDT_HIST_RV(false, true, 4, 0, true, true);           // the common sizes: specialised
         else GDT_HIST_R(false, true, 4, 0, true);
     } else if (texab & 1) {
         if (occ_a >= 6) GDT_HIST(true, true, 6, 0); else GDT_HIST(true, true, 4, 0);
