@@ -39,6 +39,7 @@ SYMBOLS = [
     ("gdt_debug_k1_pack", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_persist", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_div1", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k1_chroma_f", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_div1_verified", _c.c_int, [_c.c_float]),
     ("gdt_debug_k1_rec32", _c.c_int, [_c.c_int]),
     ("gdt_debug_k1_chunk", _c.c_int, [_c.c_int]),
@@ -197,6 +198,7 @@ def k1_config_default():
     check(lib.gdt_debug_k1_rec32(1), "gdt_debug_k1_rec32")
     check(lib.gdt_debug_k1_persist(1), "gdt_debug_k1_persist")
     check(lib.gdt_debug_k1_div1(1), "gdt_debug_k1_div1")
+    check(lib.gdt_debug_k1_chroma_f(0), "gdt_debug_k1_chroma_f")
     check(lib.gdt_debug_k1_pack(K1_DEFAULT_PACK), "gdt_debug_k1_pack")
 
 

@@ -257,6 +257,26 @@ GDT_HD void lab2lin_body_from_fy(float fy, float y1, float y4, float y7, float a
     bl = f_add(f_mul(K.C[6], X), f_add(y7, f_mul(K.C[8], Z)));
 }
 
+// The same with the chroma terms already multiplied: ar = a * (1/500), bz = b * (1/200) (pass A's float chroma scratch).
+GDT_HD void lab2lin_body_from_fy_pre(float fy, float y1, float y4, float y7, float ar, float bz, const Lab2RgbConst& K,
+                                     float& r, float& g, float& bl) {
+    const float c16 = 16.0f / 116.0f;
+    const float fth = 6.0f / 29.0f;
+    const float r7787 = 1.0f / 7.787f;
+    const float fx = f_add(ar, fy);
+    const float fz = f_sub(fy, bz);
+    const float X = fx <= fth ? f_mul(f_sub(fx, c16), r7787) : f_mul(f_mul(fx, fx), fx);
+    const float Z = fz <= fth ? f_mul(f_sub(fz, c16), r7787) : f_mul(f_mul(fz, fz), fz);
+    r = f_add(f_mul(K.C[0], X), f_add(y1, f_mul(K.C[2], Z)));
+    g = f_add(f_mul(K.C[3], X), f_add(y4, f_mul(K.C[5], Z)));
+    bl = f_add(f_mul(K.C[6], X), f_add(y7, f_mul(K.C[8], Z)));
+}
+// Q14 chroma pair -> the two products the SIMD-body sequence adds to / subtracts from fy
+GDT_HD void lab_chroma_terms(int oa, int ob, float& ar, float& bz) {
+    ar = f_mul(lab_chroma_fast(oa), 1.0f / 500.0f);
+    bz = f_mul(lab_chroma_fast(ob), 1.0f / 200.0f);
+}
+
 // `tail` selects OpenCV's scalar-tail sequence (last W % 8 pixels of every row): true divisions and
 // ((C0*X + C1*y) + C2*Z); the SIMD body multiplies by f32 reciprocals and uses C0*X + (C1*y + C2*Z).
 // Returns the three *linear* channels, unclipped.

@@ -66,6 +66,9 @@ static int g_k1_texab = 0, g_k1_spltex = 0, g_k1_fytex = 0, g_k1_occ_a = 4;
 // 1 with g_k1_rec32 == 0 is round 1's uncompressed three-gather variant.
 static int g_k1_chroma_a = -1;
 static int g_k1_rec32 = 1;
+static int g_k1_chroma_f = 0; // 1: pass A hands pass B the chroma as float terms (8 B/px scratch; gdt_debug_k1_chroma_f). Measured
+                              // SLOWER (0.999 vs 0.901 ms per 128 images, profiles/k1_chroma_f_ab_r2ae.log): pass A sits on the
+                              // L1 data pipe, the wider stores land exactly there
 static int g_k1_div1 = 1;     // one-correction-step normalisation for the std values verified at gdt_init (gdt_debug_k1_div1)
 static int g_k1_pack = 0;     // pass B: packed f32x2 arithmetic (two pixels per instruction); 0 = scalar (gdt_debug_k1_pack)
 static int g_k1_persist = 1;  // pass B: persistent 1024-thread CTAs with conflict-free spline copies (gdt_debug_k1_persist)
@@ -176,7 +179,9 @@ __device__ __forceinline__ void lab_from_rec32_px(const uint32_t* w, int fr, int
 // REC32 (with CHROMA_A): all three channels from the compressed 32-byte record, one gather per pixel.
 // VEC1: the host guarantees vec_ok == 1 (every tile a whole number of aligned 4-pixel groups inside the image: the common
 // sizes), so the ragged / reflected / generic paths and their per-group tests are compiled out.
-template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL, bool REC32, bool VEC1>
+// CHROMA_F (VEC1, REC32, widths without scalar-tail pixels): the chroma leaves pass A as the two float terms of Lab->RGB
+// (8 B/px: a / 500 | b / 200 in the SIMD-body operation order) instead of the Q14 pair; see clahe_apply_kernel.
+template <bool U8, bool TEXAB, bool CHROMA_A, int MINB, int TEXL, bool REC32, bool VEC1, bool CHROMA_F>
 __global__ void __launch_bounds__(256, MINB)
 clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32_t* __restrict__ AB,
                   uint8_t* __restrict__ lutT, int h, int w, int pitch,
@@ -197,7 +202,7 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
     const float* inf = (const float*)in_ + (size_t)img * plane * 3;
     // scratch rows are `pitch` = align4(w) elements apart: 4-pixel groups are 16-byte aligned for every width
     uint8_t* l8img = L8 + (size_t)img * h * pitch;
-    uint32_t* abimg = AB + (size_t)img * h * pitch;
+    uint32_t* abimg = AB + (size_t)img * h * pitch * (CHROMA_F ? 2 : 1);
 
     const int vec_ok = VEC1 ? 1 : vec_ok_;
     if (vec_ok) {
@@ -284,7 +289,20 @@ clahe_hist_kernel(const void* __restrict__ in_, uint8_t* __restrict__ L8, uint32
                     ab[i] = pack_code(cell[i], fr[i], fg[i], fb[i]);
                 }
             }
-            *(uint4*)(abimg + ps) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
+            if (CHROMA_F) {
+                uint32_t t[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float ar, bz;
+                    lab_chroma_terms((int)(ab[i] & 0xffffu), (int)(ab[i] >> 16), ar, bz);
+                    t[2 * i] = __float_as_uint(ar);
+                    t[2 * i + 1] = __float_as_uint(bz);
+                }
+                *(uint4*)(abimg + ps * 2) = make_uint4(t[0], t[1], t[2], t[3]);
+                *(uint4*)(abimg + ps * 2 + 4) = make_uint4(t[4], t[5], t[6], t[7]);
+            } else {
+                *(uint4*)(abimg + ps) = make_uint4(ab[0], ab[1], ab[2], ab[3]);
+            }
             *(uint32_t*)(l8img + ps) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -425,7 +443,10 @@ struct NormFast {
 // whatever its segment index: the three random spline lookups per pixel are conflict-free (4 wavefronts per request
 // instead of ~18 measured for random 16-byte reads, tools/microbench/gather_rate.cu). 128 KB of shared memory per SM,
 // staged once per launch. (FAST, SPLTEX == 0, !FYTEX only.)
-template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A, bool ANYW, bool PACK, bool PERSIST>
+// CHROMA_F (PERSIST, CHROMA_A, !ANYW, !PACK; A/B variant, off by default): pass A, which has issue slots to spare at its
+// gather floor, already converted the chroma to the two float terms of Lab->RGB (8 B/px scratch: ar | bz); pass B, which is
+// issue-bound, saves the conversion (16 instructions per pixel). Slower in total: see g_k1_chroma_f.
+template <int MINB, bool FAST, int SPLTEX, bool FYTEX, bool CHROMA_A, bool ANYW, bool PACK, bool PERSIST, bool CHROMA_F>
 __global__ void __launch_bounds__(PERSIST ? 1024 : 256, PERSIST ? 1 : MINB)
 clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ L8, const uint8_t* __restrict__ lutT,
                    float* __restrict__ out, int h, int w, int pitch, int grid, float inv_th, float inv_tw, int rows_per_cta,
@@ -509,17 +530,19 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
     }
 
     const size_t plane = (size_t)h * w;
-    const uint32_t* abimg = AB + (size_t)img * h * pitch;     // scratch rows are `pitch` = align4(w) elements apart
+    // scratch rows are `pitch` = align4(w) elements apart (CHROMA_F: two words per element)
+    const uint32_t* abimg = AB + (size_t)img * h * pitch * (CHROMA_F ? 2 : 1);
     const uint8_t* l8img = L8 + (size_t)img * h * pitch;
     float* outimg = out + (size_t)img * plane * 3;
     const uint8_t* lut_bytes = (const uint8_t*)luts;
 
     // one pixel: CLAHE blend of the lightness, chroma, Lab -> RGB, inverse gamma, normalisation
-    auto pixel = [&](int i, int v, uint32_t abw, const ClaheAxis& ay, const uint8_t* lrow1, const uint8_t* lrow2,
-                     bool tail, float& o0, float& o1, float& o2) {
+    auto pixel = [&](int i, int v, uint32_t abw, uint32_t abw2, const ClaheAxis& ay, const uint8_t* lrow1,
+                     const uint8_t* lrow2, bool tail, float& o0, float& o1, float& o2) {
         // chroma: Q14 -> the a / b handed to LAB2RGB
-        int oa, ob;
-        if (CHROMA_A) {
+        int oa = 0, ob = 0;
+        if (CHROMA_F) {
+        } else if (CHROMA_A) {
             oa = (int)(abw & 0xffffu);
             ob = (int)(abw >> 16);
         } else {
@@ -529,7 +552,7 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
             oa = lab_trilinear(wa.x, wa.y, wa.z, wa.w, fr, fg, fb);
             ob = lab_trilinear(wb.x, wb.y, wb.z, wb.w, fr, fg, fb);
         }
-        const float a2 = lab_chroma_fast(oa), b2 = lab_chroma_fast(ob);
+        const float a2 = CHROMA_F ? 0.f : lab_chroma_fast(oa), b2 = CHROMA_F ? 0.f : lab_chroma_fast(ob);
         // lightness through CLAHE: the two LUT rows hold the LUT value of every tile column at level v
         int l11, l12, l21, l22;
         if (lsh == 3) {
@@ -549,7 +572,8 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
         float lr, lg, lb;
         if (PERSIST && !tail) {
             const float4 fy = fy8[(dst << 3) | lane8];          // this lane's own copy: conflict-free
-            lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
+            if (CHROMA_F) lab2lin_body_from_fy_pre(fy.x, fy.y, fy.z, fy.w, __uint_as_float(abw), __uint_as_float(abw2), K, lr, lg, lb);
+            else lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
         } else if (FAST && FYTEX && !tail) {
             const float4 fy = tex1Dfetch<float4>(texFy, dst);
             lab2lin_body_from_fy(fy.x, fy.y, fy.z, fy.w, a2, b2, K, lr, lg, lb);
@@ -651,11 +675,16 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
     };
 
     // software prefetch: the next row's scratch words are requested before this row's arithmetic
-    uint4 nxc;
+    uint4 nxc, nxc2 = make_uint4(0u, 0u, 0u, 0u);
     uint32_t nxl;
     {
         const size_t ps = (size_t)y0 * pitch + x0;
-        nxc = __ldg((const uint4*)(abimg + ps));
+        if (CHROMA_F) {
+            nxc = __ldg((const uint4*)(abimg + ps * 2));
+            nxc2 = __ldg((const uint4*)(abimg + ps * 2 + 4));
+        } else {
+            nxc = __ldg((const uint4*)(abimg + ps));
+        }
         nxl = __ldg((const uint32_t*)(l8img + ps));
     }
     for (int y = y0; y < y1; ++y) {
@@ -665,9 +694,14 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
         const size_t p = (size_t)y * w + x0, ps = (size_t)y * pitch + x0;
 
         uint32_t lw = nxl;
-        uint4 cw = nxc;
+        uint4 cw = nxc, cw2 = nxc2;
         if (y + 1 < y1) {
-            nxc = __ldg((const uint4*)(abimg + ps + pitch));
+            if (CHROMA_F) {
+                nxc = __ldg((const uint4*)(abimg + (ps + pitch) * 2));
+                nxc2 = __ldg((const uint4*)(abimg + (ps + pitch) * 2 + 4));
+            } else {
+                nxc = __ldg((const uint4*)(abimg + ps + pitch));
+            }
             nxl = __ldg((const uint32_t*)(l8img + ps + pitch));
         }
         if (ANYW && npx < 4) {  // slots past the row end are padding (possibly never written): neutral values
@@ -676,7 +710,9 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
             cw.w = 0u; lw &= 0xffffffu;
         }
         const int v[4] = {(int)(lw & 255), (int)((lw >> 8) & 255), (int)((lw >> 16) & 255), (int)(lw >> 24)};
-        const uint32_t ab[4] = {cw.x, cw.y, cw.z, cw.w};
+        // CHROMA_F: pixel i's terms are (ar, bz) = words (2 i, 2 i + 1) of the 8-word group
+        const uint32_t ab[4] = {cw.x, CHROMA_F ? cw.z : cw.y, CHROMA_F ? cw2.x : cw.z, CHROMA_F ? cw2.z : cw.w};
+        const uint32_t ab2[4] = {cw.y, cw.w, cw2.y, cw2.w};
 
         float o[3][4];
         if (PACK && !tail_warp) {
@@ -690,10 +726,10 @@ clahe_apply_kernel(const uint32_t* __restrict__ AB, const uint8_t* __restrict__ 
             }
         } else if (tail_warp) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ay, lrow1, lrow2, (x0 + i) >= wbody, o[0][i], o[1][i], o[2][i]);
+            for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ab2[i], ay, lrow1, lrow2, (x0 + i) >= wbody, o[0][i], o[1][i], o[2][i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ay, lrow1, lrow2, false, o[0][i], o[1][i], o[2][i]);
+            for (int i = 0; i < 4; ++i) pixel(i, v[i], ab[i], ab2[i], ay, lrow1, lrow2, false, o[0][i], o[1][i], o[2][i]);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -768,7 +804,7 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     Workspace W(ws, ws_bytes);
     const int pitch = (w + 3) & ~3;          // scratch row pitch in elements: every 4-pixel group is 16-byte aligned
     uint8_t* L8 = W.take<uint8_t>((size_t)n * h * pitch);
-    uint32_t* AB = W.take<uint32_t>((size_t)n * h * pitch);
+    uint32_t* AB = W.take<uint32_t>((size_t)n * h * pitch * 2);      // 4 B/px (Q14 pair or cell code) or 8 B/px (float terms)
     uint8_t* luts = W.take<uint8_t>(((size_t)n * grid * 256) << lut_row_shift(grid));
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
@@ -785,34 +821,6 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     const int texab = g_k1_texab, spltex = g_k1_spltex, fytex = g_k1_fytex, occ_a = g_k1_occ_a;
     const bool rec32 = g_k1_rec32 != 0 && T->rec_ok;
     const int chroma_a = g_k1_chroma_a < 0 ? (rec32 ? 1 : 0) : g_k1_chroma_a;
-    dim3 gridA(grid * grid, n);
-    const int gw = g.tw;                               // scalar path: walk unit = one pixel of a tile row
-    const int gq = 256 / gw, gr = 256 % gw;
-#define GDT_HIST_RV(T_, C_, O_, L_, R_, V_)                                                                            \
-    clahe_hist_kernel<U8, T_, C_, O_, L_, R_, V_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw, \
-                                                                          g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL, \
-                                                                          T->lutAB, in_norm, T->texAB, T->texL, T->rec32)
-#define GDT_HIST_R(T_, C_, O_, L_, R_) GDT_HIST_RV(T_, C_, O_, L_, R_, false)
-#define GDT_HIST(T_, C_, O_, L_) GDT_HIST_R(T_, C_, O_, L_, false)
-    if (!chroma_a) {
-        if (texab & 4) GDT_HIST(false, false, 4, 2);
-        else if (texab & 2) GDT_HIST(false, false, 4, 1);
-        else if (occ_a >= 6) GDT_HIST(false, false, 6, 0);
-        else GDT_HIST(false, false, 4, 0);
-    } else if (rec32) {
-        if (occ_a >= 6) GDT_HIST_R(false, true, 6, 0, true);
-        else if (vec_hist == 1) GDT_HIST_RV(false, true, 4, 0, true, true);           // the common sizes: specialised
-        else GDT_HIST_R(false, true, 4, 0, true);
-    } else if (texab & 1) {
-        if (occ_a >= 6) GDT_HIST(true, true, 6, 0); else GDT_HIST(true, true, 4, 0);
-    } else {
-        GDT_HIST(false, true, 4, 0);
-    }
-#undef GDT_HIST_R
-#undef GDT_HIST_RV
-#undef GDT_HIST
-    GDT_LAUNCH_CHECK();
-
     // Rows per CTA: as many as possible (amortises the LUT / spline staging) while the grid still fills whole waves of
     // the machine: 4 resident CTAs per SM, and a last wave that is mostly empty costs up to a wave of time (32 rows on
     // 128 images of 768 rows = 5.2 waves; 24 rows = 6.9).
@@ -841,15 +849,15 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     // widths with OpenCV scalar-tail pixels or rows of the planar output that are not 16-byte aligned
     const bool anyw = (w & 7) != 0 || (((uintptr_t)out) & 15) != 0;
     if (smem > 48 * 1024) {
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
-        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GDT_CUDA(cudaFuncSetAttribute(clahe_apply_kernel<4, false, 0, false, false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       1024 * 16 + 16 * 256 * 16));
     }
     // non-persistent form: one 256-thread CTA per item, 4 resident CTAs per SM (64 registers; 6 and 8 CTAs per SM at
     // 40 / 32 registers measured no faster)
 #define GDT_APPLY_P(FAST_, S_, F_, C_, A_, P_)                                                                            \
-    clahe_apply_kernel<4, FAST_, S_, F_, C_, A_, P_, false><<<nitems, 256, smem, stream>>>(                                \
+    clahe_apply_kernel<4, FAST_, S_, F_, C_, A_, P_, false, false><<<nitems, 256, smem, stream>>>(                         \
         AB, L8, luts, out, h, w, pitch, grid, g.inv_th, g.inv_tw, rows, T->spline, T->K, on, T->texSpline, T->texFy,       \
         T->texAB, xchunks, nbands, nitems, lut_area, T->fytab, 0)
 #define GDT_APPLY(FAST_, S_, F_, C_, A_) GDT_APPLY_P(FAST_, S_, F_, C_, A_, false)
@@ -858,9 +866,10 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     const size_t smem_p = kSpl8Bytes + kFy8Bytes + 4 * (size_t)lut_area;
     int div1 = g_k1_div1 != 0;
     for (int c = 0; c < 3; ++c) div1 = div1 && T->div1_verified(out_norm.std[c]);
-#define GDT_APPLY_PERSIST(C_, A_, P_)                                                                                    \
+#define GDT_APPLY_PERSIST(C_, A_, P_) GDT_APPLY_PERSIST_F(C_, A_, P_, false)
+#define GDT_APPLY_PERSIST_F(C_, A_, P_, CF_)                                                                             \
     do {                                                                                                                 \
-        auto kern = clahe_apply_kernel<4, true, 0, false, C_, A_, P_, true>;                                             \
+        auto kern = clahe_apply_kernel<4, true, 0, false, C_, A_, P_, true, CF_>;                                        \
         static bool attr_done[32] = {false};                                                                             \
         const int slot = current_device_slot();                                                                          \
         if (!attr_done[slot]) {                                                                                          \
@@ -877,8 +886,46 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     // measured (profiles/k1_v3_ab_r2n.log): persistent wins on the common widths (0.950 vs 1.008 ms per 128 images of
     // 1024x768), the any-width instantiation (scalar-tail split, more live state) is faster non-persistent; 2 = force
     const bool persist = (g_k1_persist == 2 || (g_k1_persist == 1 && !anyw)) && spltex == 0 && !fytex;
-    if (grid <= 8 && on.fast && smem <= 48 * 1024) {
-        if (persist) {
+    const bool fast_b = grid <= 8 && on.fast && smem <= 48 * 1024;
+    // float chroma scratch: only between the specialised pass A and the persistent scalar pass B, on widths without
+    // OpenCV scalar-tail pixels (those use true divisions for the same terms)
+    const bool chroma_f = g_k1_chroma_f != 0 && rec32 && chroma_a && vec_hist == 1 && fast_b && persist && !anyw && !pack &&
+                          (w & 7) == 0 && occ_a < 6;
+    dim3 gridA(grid * grid, n);
+    const int gw = g.tw;                               // scalar path: walk unit = one pixel of a tile row
+    const int gq = 256 / gw, gr = 256 % gw;
+#define GDT_HIST_RVF(T_, C_, O_, L_, R_, V_, F_)                                                                       \
+    clahe_hist_kernel<U8, T_, C_, O_, L_, R_, V_, F_><<<gridA, 256, 0, stream>>>(in, L8, AB, luts, h, w, pitch, grid, g.th, g.tw, \
+                                                                          g.clip, g.lut_scale, vec_hist, gq, gr, T->lutL, \
+                                                                          T->lutAB, in_norm, T->texAB, T->texL, T->rec32)
+#define GDT_HIST_RV(T_, C_, O_, L_, R_, V_) GDT_HIST_RVF(T_, C_, O_, L_, R_, V_, false)
+#define GDT_HIST_R(T_, C_, O_, L_, R_) GDT_HIST_RV(T_, C_, O_, L_, R_, false)
+#define GDT_HIST(T_, C_, O_, L_) GDT_HIST_R(T_, C_, O_, L_, false)
+    if (!chroma_a) {
+        if (texab & 4) GDT_HIST(false, false, 4, 2);
+        else if (texab & 2) GDT_HIST(false, false, 4, 1);
+        else if (occ_a >= 6) GDT_HIST(false, false, 6, 0);
+        else GDT_HIST(false, false, 4, 0);
+    } else if (rec32) {
+        if (occ_a >= 6) GDT_HIST_R(false, true, 6, 0, true);
+        else if (chroma_f) GDT_HIST_RVF(false, true, 4, 0, true, true, true);         // + float chroma terms for pass B
+        else if (vec_hist == 1) GDT_HIST_RV(false, true, 4, 0, true, true);           // the common sizes: specialised
+        else GDT_HIST_R(false, true, 4, 0, true);
+    } else if (texab & 1) {
+        if (occ_a >= 6) GDT_HIST(true, true, 6, 0); else GDT_HIST(true, true, 4, 0);
+    } else {
+        GDT_HIST(false, true, 4, 0);
+    }
+#undef GDT_HIST_R
+#undef GDT_HIST_RV
+#undef GDT_HIST_RVF
+#undef GDT_HIST
+    GDT_LAUNCH_CHECK();
+
+    if (fast_b) {
+        if (persist && chroma_f) {
+            GDT_APPLY_PERSIST_F(true, false, false, true);
+        } else if (persist) {
             switch ((chroma_a ? 4 : 0) + (anyw ? 2 : 0) + (pack ? 1 : 0)) {
                 case 0: GDT_APPLY_PERSIST(false, false, false); break;
                 case 1: GDT_APPLY_PERSIST(false, false, true); break;
@@ -911,6 +958,7 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     }
 #undef GDT_APPLY
 #undef GDT_APPLY_PERSIST
+#undef GDT_APPLY_PERSIST_F
 #undef GDT_APPLY_P
     GDT_LAUNCH_CHECK();
     return GDT_OK;
@@ -1091,6 +1139,11 @@ extern "C" int gdt_debug_k1_rec32(int compressed_record) {
     return GDT_OK;
 }
 
+extern "C" int gdt_debug_k1_chroma_f(int float_terms) {
+    g_k1_chroma_f = float_terms ? 1 : 0;
+    return GDT_OK;
+}
+
 extern "C" int gdt_debug_k1_div1(int one_step) {
     g_k1_div1 = one_step ? 1 : 0;
     return GDT_OK;
@@ -1202,7 +1255,7 @@ extern "C" int gdt_debug_get_spline_table(float* host_out_4096) {
 extern "C" size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid) {
     if (n <= 0 || h <= 0 || w <= 0 || grid < 1) return 0;
     const size_t pitch = ((size_t)w + 3) & ~(size_t)3;
-    return align_up((size_t)n * h * pitch, 256) + align_up((size_t)n * h * pitch * 4, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 512;
+    return align_up((size_t)n * h * pitch, 256) + align_up((size_t)n * h * pitch * 8, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 512;
 }
 
 extern "C" int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,

@@ -91,6 +91,9 @@ int gdt_debug_k1_persist(int persistent);
  * values verified exhaustively at gdt_init (default 1) or always with two (0); bit-identical results.
  * gdt_debug_k1_div1_verified: 1 when `std` passed that check on the current device, 0 when not, < 0 on error */
 int gdt_debug_k1_div1(int one_step);
+/* debug/test hook: pass A hands pass B the chroma as the two float terms of Lab->RGB (8 B/px scratch; 1, on the common
+ * sizes only) or as the Q14 pair (0, the default: measured faster); bit-identical results */
+int gdt_debug_k1_chroma_f(int float_terms);
 int gdt_debug_k1_div1_verified(float std);
 /* debug/test hook: pass A interpolates from the compressed 32-byte lattice record (one sector gather per pixel; default 1
  * when the table fits the format) or from the uncompressed 16 + 32-byte records (0); bit-identical results */

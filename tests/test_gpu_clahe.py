@@ -154,7 +154,9 @@ def test_every_pipe_variant_is_bit_identical():
     img = synth_image(11, 96, 128, "smooth")
     ref = O.transform_u8(img, lut, MEAN, STD)
     try:
-        for rec32, persist, pack, div1 in ((1, 1, 0, 1), (1, 1, 0, 0), (0, 0, 0, 1), (1, 0, 1, 1), (1, 1, 1, 1), (0, 1, 1, 0)):
+        for rec32, persist, pack, div1, cf in ((1, 1, 0, 1, 1), (1, 1, 0, 1, 0), (1, 1, 0, 0, 1), (0, 0, 0, 1, 1), (1, 0, 1, 1, 1),
+                                               (1, 1, 1, 1, 0), (0, 1, 1, 0, 1)):
+            _lib.check(lib.gdt_debug_k1_chroma_f(cf), "chroma_f")
             _lib.check(lib.gdt_debug_k1_div1(div1), "div1")
             _lib.check(lib.gdt_debug_k1_rec32(rec32), "rec32")
             _lib.check(lib.gdt_debug_k1_persist(2 * persist), "persist")
@@ -163,7 +165,7 @@ def test_every_pipe_variant_is_bit_identical():
                 for spltex in (0, 1):
                     for fytex in (0, 1):
                         _lib.check(lib.gdt_debug_k1_config(texab, spltex, fytex, chroma_a, occ_a), "gdt_debug_k1_config")
-                        what = "variant %d %d %d %d %d rec32=%d persist=%d pack=%d div1=%d" % (texab, spltex, fytex, chroma_a, occ_a, rec32, persist, pack, div1)
+                        what = "variant %d %d %d %d %d rec32=%d persist=%d pack=%d div1=%d chroma_f=%d" % (texab, spltex, fytex, chroma_a, occ_a, rec32, persist, pack, div1, cf)
                         _assert_bits(_run_u8([img])[0], ref, what)
                         _assert_bits(_run_u8([img[:61, :77]])[0], O.transform_u8(img[:61, :77], lut, MEAN, STD), "generic path, " + what)
     finally:

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, visit aa: pass A input prefetch (parity + A/B table), K4 timing after the single-search change
-TAG=r2ab
+TAG=r2ae
 mkdir -p gpurun_out; rm -f gpurun_out/summary_$TAG.txt
 timeout 900 python -m pytest tests/test_gpu_clahe.py tests/test_gpu_map.py -q -m gpu --timeout 600 > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/summary_$TAG.txt
 timeout 300 python tools/k1_pack_ab.py > gpurun_out/k1_pack_ab_$TAG.log 2>&1; echo "pack ab exit $?" >> gpurun_out/summary_$TAG.txt

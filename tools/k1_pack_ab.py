@@ -37,4 +37,13 @@ for div1 in (0, 1, 0, 1):
     _lib.check(lib.gdt_debug_k1_div1(div1), "div1")
     ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=out))
     print("1024x768 n=128 default config, div1=%d: %.3f ms  %.0f GB/s algorithmic" % (div1, ms, 128 * 15 * 768 * 1024 / ms / 1e6))
+ref = None
+for cf in (0, 1, 0, 1):
+    _lib.check(lib.gdt_debug_k1_chroma_f(cf), "chroma_f")
+    o2 = torch.empty_like(out)
+    ms = timeit(lambda: _lib.clahe_u8(x, MEAN, STD, out=o2))
+    same = True if ref is None else bool(torch.equal(ref.view(torch.int32), o2.view(torch.int32)))
+    ref = o2 if ref is None else ref
+    print("1024x768 n=128 default config, chroma_f=%d: %.3f ms  %.0f GB/s algorithmic  identical=%s" % (cf, ms, 128 * 15 * 768 * 1024 / ms / 1e6, same))
+    assert same
 _lib.k1_config_default()
