@@ -1,6 +1,6 @@
 #!/bin/bash
-# round 2, visit ad: smoke + the WHOLE GPU suite + contract bench (own arm and reference arm) on the current binary, launch list
-TAG=r2ad
+# round 2, visit af: smoke + the WHOLE GPU suite + contract bench (own arm and reference arm) on the current binary, launch list
+TAG=r2af
 mkdir -p gpurun_out; rm -f gpurun_out/summary_$TAG.txt
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?" >> gpurun_out/summary_$TAG.txt
 timeout 1800 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest_gpu exit $?" >> gpurun_out/summary_$TAG.txt
