@@ -395,6 +395,23 @@ class ShardedIndex:
                 s[rows], i[rows] = rs, ri
         return s, i
 
+    def search_from_host(self, q_host, k):
+        """The same search for queries that still sit in (pinned) host memory, identical on every rank: instead of every
+        rank pulling the whole [nq, d] matrix through the box's shared host links (world copies of the same bytes), rank r
+        uploads rows [r * m, (r + 1) * m) only and ONE all-gather over NVLink completes the matrix on every device."""
+        dev = self.shard.db.device
+        w = self.world
+        if w == 1:
+            return self.search(q_host.to(dev, non_blocking=True), k)
+        nq, d = q_host.shape
+        m = -(-nq // w)
+        lo, hi = min(self.rank * m, nq), min((self.rank + 1) * m, nq)
+        mine = torch.zeros((m, d), dtype=q_host.dtype, device=dev)
+        if hi > lo:
+            mine[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+        full = self.comm.all_gather(mine).view(w * m, d)[:nq]
+        return self.search(full.contiguous() if not full.is_contiguous() else full, k)
+
     def positions(self, q, probe_idx):
         """0-based position every probe id would take in the full descending ranking of its query
         (= what `np.flatnonzero(np.in1d(ranks[:, i], ids))` reads, evaluate.py:75-76). probe_idx: [nq, pmax] int64, -1 pad."""

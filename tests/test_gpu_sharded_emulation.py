@@ -155,6 +155,8 @@ def test_sharded_index_with_emulated_ranks(world):
         qd = torch.from_numpy(q).cuda() if rank == 0 else torch.zeros((nq, d), device="cuda")
         s, i = index.search(qd, k, broadcast=True)
         _check_lists(s, i, os_, oi, q, db)
+        s2, i2 = index.search_from_host(torch.from_numpy(q).pin_memory(), k)     # sliced upload + all-gather of the queries
+        assert torch.equal(i2, i) and torch.equal(s2, s)
         st = index.shard.last_status
         assert st[0] == 0 and st[1] < k + 40, st              # only this shard's share of the global top k was re-scored
         m, aps, _, _ = evaluate_map(index, qd, gnd)
@@ -163,8 +165,9 @@ def test_sharded_index_with_emulated_ranks(world):
     calls = run_ranks(world, rank_fn)
     # per search: 1 broadcast, 1 histogram all-reduce, 1 all-to-all of the packed lists (query-sharded merge), 1 packed
     # all-gather of the merged slices; index construction: 2 all-reduce(MAX)
-    assert calls[0]["all_gather"] == 1 and calls[0]["all_reduce_max"] == 2 and calls[0]["broadcast"] == 1
-    assert calls[0]["all_to_all"] == 1
+    # (+ the second search through search_from_host: one more all-gather for the queries, one for its merged slices)
+    assert calls[0]["all_gather"] == 3 and calls[0]["all_reduce_max"] == 2 and calls[0]["broadcast"] == 1
+    assert calls[0]["all_to_all"] == 2
 
 
 def test_sharded_index_emulated_ranks_empty_shard_and_overflow_repair():
