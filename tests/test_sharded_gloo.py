@@ -92,6 +92,9 @@ def _worker(rank, world, port, ret):
         s, i = index.search(qr, 100, broadcast=True)
         os_, oi = R.topk(R.scores_exact(g["q"], g["db"]), 100)
         assert np.array_equal(i.numpy(), oi) and np.array_equal(s.numpy(), os_)
+        # queries in host memory on every rank: each rank contributes its slice, one all-gather completes them
+        s2, i2 = index.search_from_host(q, 100)
+        assert torch.equal(i2, i) and torch.equal(s2, s)
         # mAP (medium protocol) through the sharded positions + all_reduce
         ok = [np.concatenate([e[e >= 0], h[h >= 0]]) for e, h in zip(g["easy"], g["hard"])]
         junk = [x[x >= 0] for x in g["junk"]]
