@@ -102,6 +102,7 @@ SYMBOLS = [
     ("gdt_resize_batch_workspace_bytes", _c.c_size_t, [_P, _c.c_int]),
     ("gdt_resize_u8_batch", _c.c_int, [_P, _P, _P, _c.c_int, _P, _P, _c.c_size_t, _P]),
     ("gdt_debug_k5_bytewise", _c.c_int, [_c.c_int]),
+    ("gdt_debug_k5_planar", _c.c_int, [_c.c_int]),
     ("gdt_debug_resize_coeffs", _c.c_int, [_c.c_int, _c.c_float, _c.c_float, _c.c_int, _P, _P, _P, _c.c_size_t]),
 ]
 

@@ -39,6 +39,11 @@ struct ResizePlan {
     uint32_t* kk4_h = nullptr;    // [groups_h][3 planes][out_w]   c0 | c1 (unsigned bytes), c2 (signed bytes), 4 taps per word
     uint32_t* kk4_v = nullptr;    // [out_h][groups_v][3 planes]
     int row_smem = 0;             // bytes of one staged row of the fast horizontal kernel
+    // planar form (resize_h5_kernel): tap groups aligned to 4 INPUT pixels
+    int groups_h5 = 0;            // aligned groups a column's taps can touch
+    int span5 = 0;                // aligned groups a 128-column chunk can touch (shared-memory words per plane and row)
+    int* g0_h = nullptr;          // [out_w] first aligned group of the column's tap window
+    uint32_t* kk5_h = nullptr;    // [groups_h5][3 planes][out_w], coefficients shifted to the aligned groups (zeros outside)
     int device = -1;
 };
 
@@ -239,6 +244,86 @@ resize_h4_kernel(BatchSrc S, int row0, int nrows, uint8_t* __restrict__ dst, siz
     }
 }
 
+// Planar form of the fast horizontal pass (source rows 4-byte aligned). The interleaved RGB bytes are split into three
+// byte planes ONCE, while a row batch is staged in shared memory (12 bytes -> 6 byte permutes -> one word per plane), and
+// the tap groups are aligned to 4 INPUT pixels (the host shifted each column's coefficients accordingly, zeros outside its
+// window): the 4 same-channel bytes of a tap group are then ONE aligned shared-memory word -- no funnel shifts or byte
+// permutes in the tap loop, 3 loads + 9 dp4a per (row, group) instead of 3 + 3 + 6 + 9.
+constexpr int kH5Rows = 4;     // rows per batch (accumulators: 4 x 9 registers)
+constexpr int kH5Band = 32;    // rows per CTA
+
+__global__ void __launch_bounds__(kHCols)
+resize_h5_kernel(BatchSrc S, int row0, int nrows, int in_w, uint8_t* __restrict__ dst, size_t dst_image_stride, size_t dst_stride,
+                 int out_w, const int* __restrict__ g0, const uint32_t* __restrict__ kk5, int groups, int span) {
+    extern __shared__ __align__(16) uint32_t planes[];       // [kH5Rows][3][span]
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z;
+    const uint8_t* __restrict__ src = S.ptr[img];
+    const size_t src_stride = (size_t)S.stride[img];
+    uint8_t* __restrict__ out = dst + (size_t)img * dst_image_stride;
+    const int xx0 = blockIdx.x * kHCols;
+    const int xx = xx0 + tid;
+    const int gcta = __ldg(g0 + xx0);                         // first aligned group of the chunk (g0 is non-decreasing)
+    const int gmine = xx < out_w ? __ldg(g0 + xx) - gcta : 0;
+    const int xl = min(xx0 + kHCols - 1, out_w - 1);
+    const int ngroups_cta = __ldg(g0 + xl) + groups - gcta;   // <= span
+    const int band0 = blockIdx.y * kH5Band, band1 = min(band0 + kH5Band, nrows);
+    for (int rb = band0; rb < band1; rb += kH5Rows) {
+        const int nr = min(kH5Rows, band1 - rb);
+        __syncthreads();                                      // the previous batch's readers are done
+        for (int t = tid; t < nr * ngroups_cta; t += kHCols) {
+            const int r = t / ngroups_cta, gi = t - r * ngroups_cta;
+            const int x = (gcta + gi) << 2;                   // first pixel of the group
+            const uint8_t* row = src + (size_t)(row0 + rb + r) * src_stride;
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u;
+            if (x + 4 <= in_w) {
+                const uint32_t* w = (const uint32_t*)(row + (size_t)x * 3);
+                a0 = __ldg(w); a1 = __ldg(w + 1); a2 = __ldg(w + 2);
+            } else {                                          // the group straddles the row end: zero-weighted taps beyond it
+                uint32_t b[3] = {0u, 0u, 0u};
+                const int nb = max(0, in_w - x) * 3;
+                for (int k = 0; k < nb; ++k) b[k >> 2] |= (uint32_t)__ldg(row + (size_t)x * 3 + k) << (8 * (k & 3));
+                a0 = b[0]; a1 = b[1]; a2 = b[2];
+            }
+            uint32_t* pl = planes + (size_t)r * 3 * span + gi;
+            pl[0] = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);          // b0 b3 b6 b9
+            pl[span] = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);       // b1 b4 b7 b10
+            pl[2 * span] = __byte_perm(__byte_perm(a0, a1, 0x0052), a2, 0x7410);   // b2 b5 b8 b11
+        }
+        __syncthreads();
+        if (xx < out_w) {
+            int acc[kH5Rows][9];
+#pragma unroll
+            for (int r = 0; r < kH5Rows; ++r)
+#pragma unroll
+                for (int a = 0; a < 9; ++a) acc[r][a] = 0;
+            const uint32_t* kc = kk5 + xx;
+            const uint32_t* pm = planes + gmine;
+            for (int g = 0; g < groups; ++g) {
+                const uint32_t c0 = __ldg(kc), c1 = __ldg(kc + out_w), c2 = __ldg(kc + 2 * out_w);
+                kc += 3 * (size_t)out_w;
+#pragma unroll
+                for (int r = 0; r < kH5Rows; ++r) {
+                    // rows past the batch read stale but in-bounds words; their sums are never stored
+                    const uint32_t pr = pm[(r * 3 + 0) * span + g], pg = pm[(r * 3 + 1) * span + g], pb = pm[(r * 3 + 2) * span + g];
+                    acc[r][0] = dp4a_uu(pr, c0, acc[r][0]); acc[r][1] = dp4a_uu(pr, c1, acc[r][1]); acc[r][2] = dp4a_us(pr, c2, acc[r][2]);
+                    acc[r][3] = dp4a_uu(pg, c0, acc[r][3]); acc[r][4] = dp4a_uu(pg, c1, acc[r][4]); acc[r][5] = dp4a_us(pg, c2, acc[r][5]);
+                    acc[r][6] = dp4a_uu(pb, c0, acc[r][6]); acc[r][7] = dp4a_uu(pb, c1, acc[r][7]); acc[r][8] = dp4a_us(pb, c2, acc[r][8]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kH5Rows; ++r) {
+                if (r < nr) {
+                    uint8_t* o = out + (size_t)(rb + r) * dst_stride + (size_t)xx * 3;
+                    o[0] = clip8_planes(acc[r][0], acc[r][1], acc[r][2]);
+                    o[1] = clip8_planes(acc[r][3], acc[r][4], acc[r][5]);
+                    o[2] = clip8_planes(acc[r][6], acc[r][7], acc[r][8]);
+                }
+            }
+        }
+    }
+}
+
 // Aligned layouts only: src rows 4-byte aligned and padded to whole words, dst rows 4-byte aligned.
 __global__ void __launch_bounds__(256)
 resize_v4_kernel(const uint8_t* __restrict__ src, size_t src_image_stride, size_t src_stride, int src_rows,
@@ -361,6 +446,8 @@ extern "C" void gdt_resize_plan_destroy(gdt_resize_plan* plan_) {
     cudaFree(p->kk_v);
     cudaFree(p->kk4_h);
     cudaFree(p->kk4_v);
+    cudaFree(p->g0_h);
+    cudaFree(p->kk5_h);
     delete p;
 }
 
@@ -433,6 +520,30 @@ extern "C" int gdt_resize_plan_create(int in_w, int in_h, double imsize, gdt_res
             for (int k = 0; k < bv[(size_t)yy * 2 + 1]; ++k)
                 for (int pl = 0; pl < 3; ++pl)
                     k4v[((size_t)yy * p->groups_v + k / 4) * 3 + pl] |= plane(kv[(size_t)yy * p->ksize_v + k], pl) << (8 * (k & 3));
+        // planar form: tap groups aligned to 4 input pixels
+        std::vector<int> g0v((size_t)g.out_w);
+        p->groups_h5 = 1;
+        for (int xx = 0; xx < g.out_w; ++xx) {
+            const int xmin = bh[(size_t)xx * 2], cnt = bh[(size_t)xx * 2 + 1];
+            g0v[xx] = xmin >> 2;
+            const int ng = ((xmin + cnt + 3) >> 2) - (xmin >> 2);
+            if (ng > p->groups_h5) p->groups_h5 = ng;
+        }
+        std::vector<uint32_t> k5h((size_t)p->groups_h5 * 3 * g.out_w, 0u);
+        for (int xx = 0; xx < g.out_w; ++xx) {
+            const int xmin = bh[(size_t)xx * 2], cnt = bh[(size_t)xx * 2 + 1];
+            for (int k = 0; k < cnt; ++k) {
+                const int pos = xmin + k - (g0v[xx] << 2);           // tap position inside the column's aligned groups
+                for (int pl = 0; pl < 3; ++pl)
+                    k5h[((size_t)(pos >> 2) * 3 + pl) * g.out_w + xx] |= plane(kh[(size_t)xx * p->ksize_h + k], pl) << (8 * (pos & 3));
+            }
+        }
+        p->span5 = 1;
+        for (int xx0 = 0; xx0 < g.out_w; xx0 += kHCols) {
+            const int xl = xx0 + kHCols - 1 < g.out_w ? xx0 + kHCols - 1 : g.out_w - 1;
+            const int sg = g0v[xl] + p->groups_h5 - g0v[xx0];
+            if (sg > p->span5) p->span5 = sg;
+        }
         // one staged row: the span, up to 3 bytes of misalignment, the over-read of the last (zero-weighted) tap groups
         p->row_smem = (int)align_up((size_t)span * 3 + 8 + (size_t)p->groups_h * 12 + 16, 16);
         int rc = up((void**)&p->bounds_h, bh.data(), bh.size() * sizeof(int));
@@ -441,6 +552,8 @@ extern "C" int gdt_resize_plan_create(int in_w, int in_h, double imsize, gdt_res
         if (rc == GDT_OK) rc = up((void**)&p->kk_v, kv.data(), kv.size() * sizeof(int32_t));
         if (rc == GDT_OK) rc = up((void**)&p->kk4_h, k4h.data(), k4h.size() * sizeof(uint32_t));
         if (rc == GDT_OK) rc = up((void**)&p->kk4_v, k4v.data(), k4v.size() * sizeof(uint32_t));
+        if (rc == GDT_OK) rc = up((void**)&p->g0_h, g0v.data(), g0v.size() * sizeof(int));
+        if (rc == GDT_OK) rc = up((void**)&p->kk5_h, k5h.data(), k5h.size() * sizeof(uint32_t));
         if (rc != GDT_OK) {
             gdt_resize_plan_destroy((gdt_resize_plan*)p);
             return rc;
@@ -477,6 +590,12 @@ extern "C" size_t gdt_resize_batch_workspace_bytes(const gdt_resize_plan* plan_,
 extern "C" size_t gdt_resize_workspace_bytes(const gdt_resize_plan* plan_) { return gdt_resize_batch_workspace_bytes(plan_, 1); }
 
 static int g_k5_force_bytewise = 0;      // debug (gdt_debug_k5_bytewise): 1 = always the byte-wise kernels (A/B, parity)
+static int g_k5_planar = 1;              // debug (gdt_debug_k5_planar): 0 = the interleaved dp4a kernel instead of the planar one
+
+extern "C" int gdt_debug_k5_planar(int on) {
+    g_k5_planar = on ? 1 : 0;
+    return GDT_OK;
+}
 
 extern "C" int gdt_debug_k5_bytewise(int on) {
     g_k5_force_bytewise = on ? 1 : 0;
@@ -528,7 +647,19 @@ static int resize_chunk(const ResizePlan* p, const uint8_t* const* srcs, const s
             if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
         }
         const size_t smem4 = (size_t)p->row_smem * kH4Rows;
-        if (!g_k5_force_bytewise && smem4 <= 200 * 1024) {
+        const size_t smem5 = (size_t)kH5Rows * 3 * p->span5 * sizeof(uint32_t);
+        bool aligned_src = true;                         // planar form: 12-byte groups are read as three aligned words
+        for (int i = 0; i < n; ++i) aligned_src = aligned_src && (((uintptr_t)cur.ptr[i]) & 3) == 0 && (cur.stride[i] & 3) == 0;
+        if (!g_k5_force_bytewise && g_k5_planar && aligned_src && smem5 <= 200 * 1024) {
+            static size_t attr5[32] = {0};
+            size_t& a5 = attr5[current_device_slot()];
+            if (smem5 > 48 * 1024 && smem5 > a5) {
+                GDT_CUDA(cudaFuncSetAttribute(resize_h5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+                a5 = smem5;
+            }
+            resize_h5_kernel<<<dim3(ceil_div(g.out_w, kHCols), ceil_div(nrows, kH5Band), n), kHCols, smem5, stream>>>(
+                cur, p->ybox_first, nrows, p->red_w, hdst, himage, hstride, g.out_w, p->g0_h, p->kk5_h, p->groups_h5, p->span5);
+        } else if (!g_k5_force_bytewise && smem4 <= 200 * 1024) {
             static size_t attr4[32] = {0};
             size_t& a4 = attr4[current_device_slot()];
             if (smem4 > 48 * 1024 && smem4 > a4) {

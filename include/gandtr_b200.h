@@ -152,6 +152,8 @@ int gdt_debug_jpeg_last_backend(void);
 int gdt_debug_jpeg_status(int* out4);
 /* debug/test hook: 1 = K5 runs its byte-wise kernels only (the dp4a kernels off), for A/B timing and parity */
 int gdt_debug_k5_bytewise(int on);
+/* debug/test hook: 0 = K5's horizontal pass runs the interleaved dp4a kernel instead of the planar one (A/B, parity) */
+int gdt_debug_k5_planar(int on);
 /* debug/test hook (host only): Pillow's precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter.
  * bounds: out_size x (first input index, tap count); kk: out_size x ksize int32 (capacity in elements). */
 int gdt_debug_resize_coeffs(int in_size, float in0, float in1, int out_size, int* ksize, int* bounds, int32_t* kk,

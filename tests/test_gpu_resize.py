@@ -145,3 +145,13 @@ def test_batched_launch_equals_per_image_and_bytewise_kernels(h, w, imsize, n):
         _lib.check(lib.gdt_debug_k5_bytewise(0), "bytewise")
     assert torch.equal(slow, batch)
     assert torch.equal(ld.resize(dev[1]), batch[1])
+    # sources that are all 4-byte aligned (base and row stride) take the planar horizontal kernel (resize_h5_kernel);
+    # with it switched off the interleaved dp4a kernel gives the same bits
+    if n > 1:
+        fast = ld.resize_batch(dev[1:])
+        assert torch.equal(fast, batch[1:])
+        try:
+            _lib.check(lib.gdt_debug_k5_planar(0), "planar")
+            assert torch.equal(ld.resize_batch(dev[1:]), fast)
+        finally:
+            _lib.check(lib.gdt_debug_k5_planar(1), "planar")
