@@ -245,17 +245,30 @@ resize_h4_kernel(BatchSrc S, int row0, int nrows, uint8_t* __restrict__ dst, siz
 }
 
 // Planar form of the fast horizontal pass (source rows 4-byte aligned). The interleaved RGB bytes are split into three
-// byte planes ONCE, while a row batch is staged in shared memory (12 bytes -> 6 byte permutes -> one word per plane), and
+// byte planes ONCE per row batch in shared memory (12 bytes -> 6 byte permutes -> one word per plane), and
 // the tap groups are aligned to 4 INPUT pixels (the host shifted each column's coefficients accordingly, zeros outside its
 // window): the 4 same-channel bytes of a tap group are then ONE aligned shared-memory word -- no funnel shifts or byte
 // permutes in the tap loop, 3 loads + 9 dp4a per (row, group) instead of 3 + 3 + 6 + 9.
 constexpr int kH5Rows = 4;     // rows per batch (accumulators: 4 x 9 registers)
 constexpr int kH5Band = 32;    // rows per CTA
 
+// The raw bytes of the NEXT row batch travel global -> shared memory with cp.async (no registers, double-buffered) while
+// the current batch is split into planes and runs its tap loop, so the DRAM latency of the staging hides under the dp4a
+// work.
+__device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const void* gptr, bool valid) {
+    const int n = valid ? 4 : 0;          // src-size 0: the destination word is zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(kHCols)
 resize_h5_kernel(BatchSrc S, int row0, int nrows, int in_w, uint8_t* __restrict__ dst, size_t dst_image_stride, size_t dst_stride,
                  int out_w, const int* __restrict__ g0, const uint32_t* __restrict__ kk5, int groups, int span) {
-    extern __shared__ __align__(16) uint32_t planes[];       // [kH5Rows][3][span]
+    extern __shared__ __align__(16) uint32_t h5smem[];       // planes [kH5Rows][3][span], then raw [2][kH5Rows][3 * span]
+    uint32_t* planes = h5smem;
+    uint32_t* raw = h5smem + kH5Rows * 3 * span;
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const uint8_t* __restrict__ src = S.ptr[img];
@@ -268,27 +281,39 @@ resize_h5_kernel(BatchSrc S, int row0, int nrows, int in_w, uint8_t* __restrict_
     const int xl = min(xx0 + kHCols - 1, out_w - 1);
     const int ngroups_cta = __ldg(g0 + xl) + groups - gcta;   // <= span
     const int band0 = blockIdx.y * kH5Band, band1 = min(band0 + kH5Band, nrows);
-    for (int rb = band0; rb < band1; rb += kH5Rows) {
+    const int nwords = ngroups_cta * 3;                       // raw words per row: 12 bytes per aligned group
+    const int row_words = (in_w * 3 + 3) >> 2;                // words that hold bytes of the row (rows are word-aligned)
+    const int w0 = gcta * 3;                                  // first raw word of the chunk inside a row
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
+
+    auto issue = [&](int rb, int buf) {                       // raw bytes of rows [rb, rb + kH5Rows) -> raw[buf]
+        for (int r = 0; r < kH5Rows; ++r) {
+            if (rb + r >= band1) break;
+            const uint32_t* rp = (const uint32_t*)(src + (size_t)(row0 + rb + r) * src_stride) + w0;
+            const uint32_t sbase = raw_s + (uint32_t)(((buf * kH5Rows + r) * 3 * span) << 2);
+            for (int i = tid; i < nwords; i += kHCols)        // words past the row end are zero-filled (zero-weighted taps)
+                cp_async_4(sbase + (uint32_t)(i << 2), rp + i, w0 + i < row_words);
+        }
+        cp_async_commit();
+    };
+
+    issue(band0, 0);
+    int buf = 0;
+    for (int rb = band0; rb < band1; rb += kH5Rows, buf ^= 1) {
         const int nr = min(kH5Rows, band1 - rb);
-        __syncthreads();                                      // the previous batch's readers are done
-        for (int t = tid; t < nr * ngroups_cta; t += kHCols) {
-            const int r = t / ngroups_cta, gi = t - r * ngroups_cta;
-            const int x = (gcta + gi) << 2;                   // first pixel of the group
-            const uint8_t* row = src + (size_t)(row0 + rb + r) * src_stride;
-            uint32_t a0 = 0u, a1 = 0u, a2 = 0u;
-            if (x + 4 <= in_w) {
-                const uint32_t* w = (const uint32_t*)(row + (size_t)x * 3);
-                a0 = __ldg(w); a1 = __ldg(w + 1); a2 = __ldg(w + 2);
-            } else {                                          // the group straddles the row end: zero-weighted taps beyond it
-                uint32_t b[3] = {0u, 0u, 0u};
-                const int nb = max(0, in_w - x) * 3;
-                for (int k = 0; k < nb; ++k) b[k >> 2] |= (uint32_t)__ldg(row + (size_t)x * 3 + k) << (8 * (k & 3));
-                a0 = b[0]; a1 = b[1]; a2 = b[2];
+        const bool more = rb + kH5Rows < band1;
+        if (more) issue(rb + kH5Rows, buf ^ 1);              // its buffer was split into planes two barriers ago
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();                                      // this batch's bytes have landed; the previous tap loop is done
+        for (int r = 0; r < nr; ++r) {
+            const uint32_t* rr = raw + (size_t)(buf * kH5Rows + r) * 3 * span;
+            for (int gi = tid; gi < ngroups_cta; gi += kHCols) {
+                const uint32_t a0 = rr[gi * 3], a1 = rr[gi * 3 + 1], a2 = rr[gi * 3 + 2];
+                uint32_t* pl = planes + (size_t)r * 3 * span + gi;
+                pl[0] = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);          // b0 b3 b6 b9
+                pl[span] = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);       // b1 b4 b7 b10
+                pl[2 * span] = __byte_perm(__byte_perm(a0, a1, 0x0052), a2, 0x7410);   // b2 b5 b8 b11
             }
-            uint32_t* pl = planes + (size_t)r * 3 * span + gi;
-            pl[0] = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);          // b0 b3 b6 b9
-            pl[span] = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);       // b1 b4 b7 b10
-            pl[2 * span] = __byte_perm(__byte_perm(a0, a1, 0x0052), a2, 0x7410);   // b2 b5 b8 b11
         }
         __syncthreads();
         if (xx < out_w) {
@@ -647,8 +672,8 @@ static int resize_chunk(const ResizePlan* p, const uint8_t* const* srcs, const s
             if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
         }
         const size_t smem4 = (size_t)p->row_smem * kH4Rows;
-        const size_t smem5 = (size_t)kH5Rows * 3 * p->span5 * sizeof(uint32_t);
-        bool aligned_src = true;                         // planar form: 12-byte groups are read as three aligned words
+        const size_t smem5 = (size_t)3 * kH5Rows * 3 * p->span5 * sizeof(uint32_t);      // planes + two raw buffers
+        bool aligned_src = true;                         // planar form: rows are copied and read as aligned words
         for (int i = 0; i < n; ++i) aligned_src = aligned_src && (((uintptr_t)cur.ptr[i]) & 3) == 0 && (cur.stride[i] & 3) == 0;
         if (!g_k5_force_bytewise && g_k5_planar && aligned_src && smem5 <= 200 * 1024) {
             static size_t attr5[32] = {0};
