@@ -717,7 +717,7 @@ def main():
             per = g_ms / 5 / len(photos)
             oh, ow = ld.resize(photos[0]).shape[:2]
             alg = 3.0 * gh * gw + 3.0 * oh * ow
-            line["image_geometry"] = {"kernel": "K5 resize_h4_kernel + resize_v4_kernel (Pillow LANCZOS thumbnail, bit-exact; dp4a, batch of 8)",
+            line["image_geometry"] = {"kernel": "K5 resize_h5_kernel + resize_v4_kernel (Pillow LANCZOS thumbnail, bit-exact; planar dp4a, cp.async staging, batch of 8)",
                                       "workload": "%dx%d uint8 RGB -> %dx%d" % (gw, gh, ow, oh), "ms_per_image": per,
                                       "images_per_s": 1e3 / per, "bound": "hbm", "achieved": alg / per / 1e6, "peak": hbm_peak,
                                       "unit": "GB/s", "frac": alg / per / 1e6 / hbm_peak,

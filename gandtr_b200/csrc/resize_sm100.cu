@@ -5,7 +5,10 @@
 // Integer / byte work, HBM- and L1-bound; the filter coefficients are computed on the host in double precision with the
 // same libm calls Pillow makes (resize_math.h) when a plan is created, one plan per image geometry.
 //   reduce_kernel     one thread per reduced pixel
-//   resize_h4_kernel  one CTA per (image, 128 output columns, band of rows): the input spans of 4 rows are staged in
+//   resize_h5_kernel  the default horizontal pass (source rows 4-byte aligned): raw bytes of the next row batch arrive by
+//                     cp.async while the current batch, split once into three byte planes, runs its tap loop; tap groups
+//                     aligned to 4 input pixels: one aligned shared-memory word per channel and group, 9 dp4a per group
+//   resize_h4_kernel  (any alignment) one CTA per (image, 128 output columns, band of rows): the input spans of 4 rows are staged in
 //                     shared memory as aligned words; a thread owns one output pixel of each row and walks its taps four
 //                     at a time: 3 word loads + funnel shifts + byte permutes gather the 4 same-channel bytes, and the
 //                     22-bit coefficients, split on the host into three byte planes (c = c2 * 65536 + c1 * 256 + c0),
