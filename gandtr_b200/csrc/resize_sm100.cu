@@ -266,9 +266,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// NG > 0: the number of aligned tap groups is a compile-time constant (5 ... 8 cover every LANCZOS scale after Pillow's box
+// pre-reduction): the tap loop is unrolled and the coefficient words of the next group load under the current group's dp4a.
+template <int NG>
 __global__ void __launch_bounds__(kHCols)
 resize_h5_kernel(BatchSrc S, int row0, int nrows, int in_w, uint8_t* __restrict__ dst, size_t dst_image_stride, size_t dst_stride,
-                 int out_w, const int* __restrict__ g0, const uint32_t* __restrict__ kk5, int groups, int span) {
+                 int out_w, const int* __restrict__ g0, const uint32_t* __restrict__ kk5, int groups_, int span) {
+    const int groups = NG > 0 ? NG : groups_;
     extern __shared__ __align__(16) uint32_t h5smem[];       // planes [kH5Rows][3][span], then raw [2][kH5Rows][3 * span]
     uint32_t* planes = h5smem;
     uint32_t* raw = h5smem + kH5Rows * 3 * span;
@@ -327,7 +331,8 @@ resize_h5_kernel(BatchSrc S, int row0, int nrows, int in_w, uint8_t* __restrict_
                 for (int a = 0; a < 9; ++a) acc[r][a] = 0;
             const uint32_t* kc = kk5 + xx;
             const uint32_t* pm = planes + gmine;
-            for (int g = 0; g < groups; ++g) {
+#pragma unroll
+            for (int g = 0; g < (NG > 0 ? NG : groups); ++g) {
                 const uint32_t c0 = __ldg(kc), c1 = __ldg(kc + out_w), c2 = __ldg(kc + 2 * out_w);
                 kc += 3 * (size_t)out_w;
 #pragma unroll
@@ -681,12 +686,24 @@ static int resize_chunk(const ResizePlan* p, const uint8_t* const* srcs, const s
         if (!g_k5_force_bytewise && g_k5_planar && aligned_src && smem5 <= 200 * 1024) {
             static size_t attr5[32] = {0};
             size_t& a5 = attr5[current_device_slot()];
-            if (smem5 > 48 * 1024 && smem5 > a5) {
-                GDT_CUDA(cudaFuncSetAttribute(resize_h5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-                a5 = smem5;
+            const dim3 grid5(ceil_div(g.out_w, kHCols), ceil_div(nrows, kH5Band), n);
+#define GDT_H5(NG_)                                                                                                       \
+    do {                                                                                                                  \
+        if (smem5 > 48 * 1024 && smem5 > a5) {                                                                            \
+            GDT_CUDA(cudaFuncSetAttribute(resize_h5_kernel<NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5)); \
+        }                                                                                                                 \
+        resize_h5_kernel<NG_><<<grid5, kHCols, smem5, stream>>>(cur, p->ybox_first, nrows, p->red_w, hdst, himage, hstride, \
+                                                                g.out_w, p->g0_h, p->kk5_h, p->groups_h5, p->span5);       \
+    } while (0)
+            switch (p->groups_h5) {
+                case 5: GDT_H5(5); break;
+                case 6: GDT_H5(6); break;
+                case 7: GDT_H5(7); break;
+                case 8: GDT_H5(8); break;
+                default: GDT_H5(0); break;
             }
-            resize_h5_kernel<<<dim3(ceil_div(g.out_w, kHCols), ceil_div(nrows, kH5Band), n), kHCols, smem5, stream>>>(
-                cur, p->ybox_first, nrows, p->red_w, hdst, himage, hstride, g.out_w, p->g0_h, p->kk5_h, p->groups_h5, p->span5);
+#undef GDT_H5
+            (void)a5;
         } else if (!g_k5_force_bytewise && smem4 <= 200 * 1024) {
             static size_t attr4[32] = {0};
             size_t& a4 = attr4[current_device_slot()];
