@@ -543,7 +543,12 @@ def main():
         # parity spot (outside the timed regions): 64 fixed queries re-scored by the exact CUDA-core kernel on every
         # rank's whole shard, merged across the ranks, compared with the lists the timed search returned
         sel = torch.arange(0, args.queries, max(1, args.queries // 64), device=dev)[:64]
+        ex0, ex1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ex0.record()
         es, ei = index.ops.exact_topk(q[sel].contiguous(), index.shard, TOPK)
+        ex1.record()
+        torch.cuda.synchronize()
+        exact_ms_per_query = ex0.elapsed_time(ex1) / max(1, int(sel.numel()))      # the repair path's price, per shard
         if world > 1:
             es, ei = index._exchange_and_merge(es, ei)
         mism = int((ei != last["i"][sel]).any(dim=1).sum())
@@ -559,6 +564,7 @@ def main():
                             "split evenly over the ranks"},
             "status": status,
             "parity_spot": {"queries": int(sel.numel()), "mismatch": mism, "max_abs_score_diff": smax,
+                            "exact_kernel_ms_per_query": exact_ms_per_query,
                             "checker": "gdt_score_topk_exact over every shard + merge (index lists must be identical)"},
             "roofline": {"kernel": "K3 score_filter_kernel (tcgen05 fp16 coarse pass) + exact re-score/finalise",
                          "bound": "tensor", "achieved": flops / world / (r_ms / rK * 1e-3) / 1e12, "peak": tc_peak,
