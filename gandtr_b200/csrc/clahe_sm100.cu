@@ -804,7 +804,8 @@ static int clahe_launch_chunk(const void* in, int n, int h, int w, double clip_l
     Workspace W(ws, ws_bytes);
     const int pitch = (w + 3) & ~3;          // scratch row pitch in elements: every 4-pixel group is 16-byte aligned
     uint8_t* L8 = W.take<uint8_t>((size_t)n * h * pitch);
-    uint32_t* AB = W.take<uint32_t>((size_t)n * h * pitch * 2);      // 4 B/px (Q14 pair or cell code) or 8 B/px (float terms)
+    // 4 B/px (Q14 pair or cell code); 8 B/px only while the float-terms variant is switched on
+    uint32_t* AB = W.take<uint32_t>((size_t)n * h * pitch * (g_k1_chroma_f ? 2 : 1));
     uint8_t* luts = W.take<uint8_t>(((size_t)n * grid * 256) << lut_row_shift(grid));
     if (!W.ok()) return GDT_ERR_WORKSPACE_TOO_SMALL;
 
@@ -1255,7 +1256,8 @@ extern "C" int gdt_debug_get_spline_table(float* host_out_4096) {
 extern "C" size_t gdt_clahe_workspace_bytes(int n, int h, int w, int grid) {
     if (n <= 0 || h <= 0 || w <= 0 || grid < 1) return 0;
     const size_t pitch = ((size_t)w + 3) & ~(size_t)3;
-    return align_up((size_t)n * h * pitch, 256) + align_up((size_t)n * h * pitch * 8, 256) + align_up((size_t)n * grid * 256 * 16, 256) + 512;
+    return align_up((size_t)n * h * pitch, 256) + align_up((size_t)n * h * pitch * (gdt::g_k1_chroma_f ? 8 : 4), 256) +
+           align_up((size_t)n * grid * 256 * 16, 256) + 512;
 }
 
 extern "C" int gdt_clahe_u8(const uint8_t* rgb_hwc, int n, int h, int w, double clip_limit, int grid,
