@@ -83,13 +83,12 @@ class DistComm:
         return out
 
     def all_to_all(self, t):
-        """t: [world, m, ...], chunk r goes to rank r -> [world, m, ...], chunk r came from rank r. None when the backend
-        has no all-to-all (the caller then keeps the all-gather form)."""
+        """t: [world, m, ...], chunk r goes to rank r -> [world, m, ...], chunk r came from rank r."""
         if self.world == 1:
             return t.clone()
-        if not self._nccl():
-            return None
         t = t.contiguous()
+        if not self._nccl():       # gloo (CPU tests of the host logic): the same exchange through an all-gather
+            return self.all_gather(t)[:, self.rank].contiguous()
         out = torch.empty_like(t)
         dist.all_to_all_single(out, t, group=self.group)
         return out

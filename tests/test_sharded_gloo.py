@@ -1,6 +1,6 @@
 """Host logic of the row-sharded retrieval path on CPU: world_size-2 gloo, with the oracle standing in for the
-CUDA kernels (the product's CudaOps needs a GPU; here only the sharding / broadcast / all_gather / all_reduce
-plumbing of gandtr_b200.retrieval is under test)."""
+CUDA kernels (the product's CudaOps needs a GPU; here only the sharding / broadcast / all_gather / all_reduce /
+packed query-sharded merge plumbing of gandtr_b200.retrieval is under test)."""
 import os
 import socket
 
@@ -31,6 +31,36 @@ class OracleOps:
         key_i = np.where(i < 0, np.iinfo(np.int64).max, i)
         order = np.lexsort((key_i, -s), axis=1)[:, :k]
         return torch.from_numpy(np.take_along_axis(s, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
+
+    # the packed exchange format and the query-sharded merge (ShardedIndex._merge_query_sharded), restated in NumPy:
+    # key = order-preserving bits of the fp32 score << 32 | ~index (larger sorts first), 0 = padding
+    @staticmethod
+    def _keys(s, i):
+        s = np.ascontiguousarray(s, dtype=np.float32) + np.float32(0)
+        u = s.view(np.uint32).astype(np.uint64)
+        ob = np.where(u & np.uint64(0x80000000), ~u & np.uint64(0xffffffff), u | np.uint64(0x80000000))
+        key = (ob << np.uint64(32)) | (~i.astype(np.uint64) & np.uint64(0xffffffff))
+        return np.where(i >= 0, key, np.uint64(0))
+
+    def pack(self, scores, idx):
+        return torch.from_numpy(self._keys(scores.numpy(), idx.numpy()).view(np.int64))
+
+    def merge_packed_keys(self, keys):
+        self.slice_merges = getattr(self, "slice_merges", 0) + 1
+        g, nq, k = keys.shape
+        u = keys.numpy().view(np.uint64).transpose(1, 0, 2).reshape(nq, g * k)
+        return torch.from_numpy(np.sort(u, axis=1)[:, ::-1][:, :k].copy().view(np.int64))
+
+    def merge_packed(self, keys):
+        return self.unpack(self.merge_packed_keys(keys))
+
+    def unpack(self, keys):
+        u = keys.numpy().view(np.uint64)
+        ob = (u >> np.uint64(32)).astype(np.uint32)
+        bits = np.where(ob & np.uint32(0x80000000), ob & np.uint32(0x7fffffff), ~ob)
+        s = np.where(u != 0, bits.view(np.float32), np.float32(-np.inf)).astype(np.float32)
+        i = np.where(u != 0, (~u & np.uint64(0xffffffff)).astype(np.int64), np.int64(-1))
+        return torch.from_numpy(s), torch.from_numpy(i)
 
     def probe_scores(self, q, shard, probe_idx, out):
         qn, dbn, pi = q.numpy().astype(np.float64), shard.db.numpy().astype(np.float64), probe_idx.numpy()
@@ -95,6 +125,7 @@ def _worker(rank, world, port, ret):
         # queries in host memory on every rank: each rank contributes its slice, one all-gather completes them
         s2, i2 = index.search_from_host(q, 100)
         assert torch.equal(i2, i) and torch.equal(s2, s)
+        assert index.ops.slice_merges == 2                    # both searches went through the query-sharded packed merge
         # mAP (medium protocol) through the sharded positions + all_reduce
         ok = [np.concatenate([e[e >= 0], h[h >= 0]]) for e, h in zip(g["easy"], g["hard"])]
         junk = [x[x >= 0] for x in g["junk"]]
