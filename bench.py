@@ -540,6 +540,14 @@ def main():
             res_i[qlo:qhi].copy_(i[qlo:qhi], non_blocking=True)
         re_ms, w = timed(search_e2e, rK, rW)
         windows.append(w)
+        torch.cuda.synchronize()
+        # what came back over the host link must be what the device-resident search returned (this rank's slice)
+        e2e_bad = int((res_i[qlo:qhi] != last["i"][qlo:qhi].cpu()).any(dim=1).sum()) + \
+            int((res_s[qlo:qhi] != last["s"][qlo:qhi].cpu()).any(dim=1).sum())
+        if world > 1:
+            tb = torch.tensor([e2e_bad], dtype=torch.int64, device=dev)
+            dist.all_reduce(tb)
+            e2e_bad = int(tb.item())
         # parity spot (outside the timed regions): 64 fixed queries re-scored by the exact CUDA-core kernel on every
         # rank's whole shard, merged across the ranks, compared with the lists the timed search returned
         sel = torch.arange(0, args.queries, max(1, args.queries // 64), device=dev)[:64]
@@ -560,6 +568,7 @@ def main():
             "ms_per_search": r_ms / rK, "steps": rK, "warmup": rW, "gpu_launches": r_launches,
             "e2e": {"value": args.queries * rK / (re_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": args.queries * db_dim * 4, "d2h_bytes_per_step": args.queries * TOPK * 12,
+                    "mismatching_rows_vs_device_resident_search": e2e_bad,
                     "note": "bytes of the whole job per step: every query is uploaded once and every result row read once, "
                             "split evenly over the ranks"},
             "status": status,
@@ -606,6 +615,8 @@ def main():
                                     "ap_bits_differing_from_forced_exact_rescoring": ap_bad}
             if k34_bad or ap_bad:
                 raise SystemExit("bench.py: K4 at 1 M rows disagrees (K3 x K4 positions %d, AP vs exact %d)" % (k34_bad, ap_bad))
+        if e2e_bad:
+            raise SystemExit("bench.py: the end-to-end search returned %d rows that differ from the device-resident search" % e2e_bad)
         if mism:
             raise SystemExit("bench.py: the timed search disagrees with the exact kernel on %d of %d spot queries" % (mism, sel.numel()))
         del index
